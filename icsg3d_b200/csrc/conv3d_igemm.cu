@@ -1,0 +1,359 @@
+// Conv3D 3x3x3 "same" as an implicit GEMM on tcgen05 / TMEM, operands fetched by TMA (sm_100a).
+//
+// Replaces the TF ops behind Keras Conv3D(kernel_size=3, padding="same") in the reference graphs
+// (vae/lattice_vae.py:173,178,213,219-224; unet/unet.py:276-336): Conv3D + BiasAdd (+ the ReLU that
+// follows it in the U-Net ordering), and Conv3DBackpropInputV2 when called with mirrored weights.
+//
+// GEMM view:  Y[M = B*D*H*W, N = Cout] = sum over 27 taps of  X_tap[M, Cin] * Wp[tap][N, Cin]^T
+//   * one CTA tile = 128 consecutive output voxels (a box bw x bh x bd x bn of the NDHWC tensor) x NT
+//     output channels; accumulator 128 lanes x NT fp32 columns in TMEM, double buffered so the epilogue
+//     of tile i overlaps the MMAs of tile i+1;
+//   * the A operand of tap (kd,kh,kw) is the same box shifted by (kd-1,kh-1,kw-1): one 5-D tiled TMA
+//     load whose out-of-bounds zero fill IS the "same" padding (also across sample boundaries);
+//   * both operands are K-major with the hardware swizzle matching the channel-chunk width
+//     (KC = 16/32/64 channels -> 32/64/128-byte swizzle), so TMA output == UMMA canonical layout;
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
+//     warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> global);
+//   * persistent CTAs, static round-robin tile scheduler.
+#include "common.cuh"
+
+namespace icsg3d {
+
+struct ConvIgemmParams {
+  int m_total;          // B*D*H*W
+  int D, H, W;          // spatial extents
+  int bw, bh, bd, bn;   // TMA box (product == 128)
+  int chunks;           // cin / KC
+  int kc;               // channels per k-unit: 16, 32 or 64
+  int nt;               // N tile
+  int tiles_n, tiles_m;
+  int ups;              // k-units per pipeline stage
+  int iters;            // 27*chunks/ups
+  int stages;
+  uint32_t a_unit_bytes;  // 128*kc*2
+  uint32_t b_unit_bytes;  // nt*kc*2
+  uint32_t stage_bytes;   // multiple of 1024
+  uint32_t sbo;           // 8 rows * kc*2 bytes
+  uint32_t layout;        // UMMA swizzle code
+  uint32_t idesc;
+  uint32_t tmem_cols;     // power of two >= 32, >= 2*nt
+  // epilogue
+  void* y;
+  int ldy;
+  int y_dtype;
+  int n_store;
+  const float* bias;
+  int act;
+  float alpha;
+};
+
+static constexpr int kConvThreads = 192;
+static constexpr int kMaxStages = 8;
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const ConvIgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // 1024-byte aligned operand ring (128B swizzle atoms repeat every 1024 bytes).
+  const uint32_t ring_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* ring = smem_raw + (ring_base - smem_u32(smem_raw));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int total_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.ups) * (p.a_unit_bytes + p.b_unit_bytes);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n;
+        const int tn = tile - tm * p.tiles_n;
+        int pix = tm * 128;
+        const int w0 = pix % p.W;
+        pix /= p.W;
+        const int h0 = pix % p.H;
+        pix /= p.H;
+        const int d0 = pix % p.D;
+        const int n0 = pix / p.D;
+        for (int it = 0; it < p.iters; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
+          uint8_t* sb = sa + static_cast<size_t>(p.ups) * p.a_unit_bytes;
+          for (int j = 0; j < p.ups; ++j) {
+            const int u = it * p.ups + j;
+            const int tap = u / p.chunks;
+            const int ch = u - tap * p.chunks;
+            const int kd = tap / 9;
+            const int kh = (tap - kd * 9) / 3;
+            const int kw = tap - kd * 9 - kh * 3;
+            tma_load_5d(sa + static_cast<size_t>(j) * p.a_unit_bytes, &tmA, &full_bar[stage], ch * p.kc,
+                        w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, n0);
+            tma_load_3d(sb + static_cast<size_t>(j) * p.b_unit_bytes, &tmB, &full_bar[stage], ch * p.kc,
+                        tn * p.nt, tap);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      const int ksteps = p.kc / 16;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = static_cast<uint32_t>(local >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.nt);
+        for (int it = 0; it < p.iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = ring_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+          const uint32_t sb = sa + static_cast<uint32_t>(p.ups) * p.a_unit_bytes;
+          for (int j = 0; j < p.ups; ++j) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc =
+                  umma_smem_desc(sa + static_cast<uint32_t>(j) * p.a_unit_bytes + k * 32u, 16u, p.sbo, p.layout);
+              const uint64_t bdesc =
+                  umma_smem_desc(sb + static_cast<uint32_t>(j) * p.b_unit_bytes + k * 32u, 16u, p.sbo, p.layout);
+              umma_bf16(d_tmem, adesc, bdesc, p.idesc, (it | j | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local >> 1) & 1u;
+      const int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      const long long pixel = static_cast<long long>(tm) * 128 + row;
+      const bool row_ok = pixel < p.m_total;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.nt);
+      for (int c0 = 0; c0 < p.nt; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
+        tmem_ld_wait();
+        const int col0 = tn * p.nt + c0;
+        if (!row_ok || col0 >= p.n_store) continue;
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = __uint_as_float(v[i]);
+          if (p.bias != nullptr) x += __ldg(p.bias + col0 + i);
+          if (p.act == ICSG3D_ACT_RELU) {
+            x = fmaxf(x, 0.f);
+          } else if (p.act == ICSG3D_ACT_LEAKY) {
+            x = x > 0.f ? x : p.alpha * x;
+          }
+          f[i] = x;
+        }
+        const int nvalid = min(16, p.n_store - col0);
+        if (p.y_dtype == ICSG3D_DT_BF16) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + col0;
+          if (nvalid == 16 && (p.ldy & 7) == 0) {
+            uint4 q0, q1;
+            q0.x = pack_bf16x2(f[0], f[1]);
+            q0.y = pack_bf16x2(f[2], f[3]);
+            q0.z = pack_bf16x2(f[4], f[5]);
+            q0.w = pack_bf16x2(f[6], f[7]);
+            q1.x = pack_bf16x2(f[8], f[9]);
+            q1.y = pack_bf16x2(f[10], f[11]);
+            q1.z = pack_bf16x2(f[12], f[13]);
+            q1.w = pack_bf16x2(f[14], f[15]);
+            reinterpret_cast<uint4*>(dst)[0] = q0;
+            reinterpret_cast<uint4*>(dst)[1] = q1;
+          } else {
+            for (int i = 0; i < nvalid; ++i) dst[i] = f2bf(f[i]);
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + col0;
+          if (nvalid == 16 && (p.ldy & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else if (nvalid == 4 && (p.ldy & 3) == 0) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
+          } else {
+            for (int i = 0; i < nvalid; ++i) dst[i] = f[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Decompose a 128-voxel tile into a TMA box over (W, H, D, B).
+static void tile_box(int B, int D, int H, int W, int* bw, int* bh, int* bd, int* bn) {
+  int rem = 128;
+  *bw = W < rem ? W : rem;
+  rem /= *bw;
+  *bh = H < rem ? H : rem;
+  rem /= *bh;
+  *bd = D < rem ? D : rem;
+  rem /= *bd;
+  *bn = rem;  // may exceed B for tiny problems: out-of-bounds samples are zero filled and never stored
+  (void)B;
+}
+
+int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H, int W, int c_extent, int kc) {
+  int bw, bh, bd, bn;
+  tile_box(B, D, H, W, &bw, &bh, &bd, &bn);
+  uint64_t dims[5] = {static_cast<uint64_t>(c_extent), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                      static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
+  uint64_t strides[4] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(W) * ldx * 2,
+                         static_cast<uint64_t>(H) * W * ldx * 2, static_cast<uint64_t>(D) * H * W * ldx * 2};
+  uint32_t box[5] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh),
+                     static_cast<uint32_t>(bd), static_cast<uint32_t>(bn)};
+  return encode_tiled_bf16(map, x, 5, dims, strides, box, kc * 2);
+}
+
+}  // namespace icsg3d
+
+using namespace icsg3d;
+
+extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const float* bias, void* y,
+                                      int ldy, int y_dtype, int n_store, int B, int D, int H, int W, int cin,
+                                      int nout, int act, float leaky_alpha, void* stream) {
+  ICSG_REQUIRE(x && wpack && y, "conv3d_k3_igemm: null pointer");
+  ICSG_REQUIRE(B > 0 && is_pow2(D) && is_pow2(H) && is_pow2(W) && D >= 2 && H >= 2 && W >= 2 && W <= 128,
+               "conv3d_k3_igemm: D,H,W must be powers of two in [2,128] (got %d %d %d)", D, H, W);
+  ICSG_REQUIRE(cin >= 16 && cin % 16 == 0, "conv3d_k3_igemm: cin must be a multiple of 16 (got %d)", cin);
+  ICSG_REQUIRE(nout >= 16 && nout % 16 == 0, "conv3d_k3_igemm: nout must be a multiple of 16 (got %d)", nout);
+  ICSG_REQUIRE(ldx % 8 == 0 && ldx >= cin, "conv3d_k3_igemm: ldx must be >= cin and a multiple of 8 (got %d)", ldx);
+  ICSG_REQUIRE(n_store > 0 && n_store <= nout && ldy >= n_store, "conv3d_k3_igemm: bad n_store/ldy (%d/%d)", n_store, ldy);
+  ICSG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0,
+               "conv3d_k3_igemm: x and wpack must be 16-byte aligned");
+  ICSG_REQUIRE(y_dtype == ICSG3D_DT_BF16 || y_dtype == ICSG3D_DT_F32, "conv3d_k3_igemm: bad y_dtype");
+  const long long m_total = static_cast<long long>(B) * D * H * W;
+  ICSG_REQUIRE(m_total < (1ll << 31), "conv3d_k3_igemm: too many voxels");
+
+  ConvIgemmParams p{};
+  p.m_total = static_cast<int>(m_total);
+  p.D = D;
+  p.H = H;
+  p.W = W;
+  tile_box(B, D, H, W, &p.bw, &p.bh, &p.bd, &p.bn);
+  p.kc = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+  p.chunks = cin / p.kc;
+  p.tiles_m = static_cast<int>((m_total + 127) / 128);
+  const int sms = sm_count();
+  if (sms <= 0) return cuda_fail(cudaGetLastError(), "sm_count", __FILE__, __LINE__);
+  // N tile: the widest tile (best operand reuse) that still yields at least one tile per SM; never
+  // below 64 unless the layer itself is narrower.
+  int nt = nout < 256 ? nout : 256;
+  while (nt > 64 && nout % nt != 0) nt -= 16;
+  while (nt > 64 && (nt % 2 == 0) && nout % (nt / 2) == 0 &&
+         static_cast<long long>(p.tiles_m) * (nout / nt) < sms)
+    nt /= 2;
+  ICSG_REQUIRE(nout % nt == 0, "conv3d_k3_igemm: unsupported nout %d", nout);
+  p.nt = nt;
+  p.tiles_n = nout / nt;
+  p.ups = (p.kc == 64) ? 1 : 3;
+  p.iters = 27 * p.chunks / p.ups;
+  p.a_unit_bytes = 128u * p.kc * 2u;
+  p.b_unit_bytes = static_cast<uint32_t>(nt) * p.kc * 2u;
+  p.stage_bytes = (static_cast<uint32_t>(p.ups) * (p.a_unit_bytes + p.b_unit_bytes) + 1023u) & ~1023u;
+  const uint32_t smem_budget = 200u * 1024u;
+  int stages = static_cast<int>(smem_budget / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  ICSG_REQUIRE(stages >= 2, "conv3d_k3_igemm: stage too large (%u bytes)", p.stage_bytes);
+  p.stages = stages;
+  p.sbo = 8u * p.kc * 2u;
+  p.layout = umma_layout_for_swizzle(p.kc * 2);
+  p.idesc = umma_idesc_bf16(nt, 0, 0);
+  uint32_t cols = 32;
+  while (cols < 2u * nt) cols <<= 1;
+  p.tmem_cols = cols;
+  p.y = y;
+  p.ldy = ldy;
+  p.y_dtype = y_dtype;
+  p.n_store = n_store;
+  p.bias = bias;
+  p.act = act;
+  p.alpha = leaky_alpha;
+
+  CUtensorMap tmA, tmB;
+  int rc = encode_act_map(&tmA, x, ldx, B, D, H, W, cin, p.kc);
+  if (rc) return rc;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(nout), 27};
+    uint64_t strides[2] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(nout) * cin * 2};
+    uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(nt), 1};
+    rc = encode_tiled_bf16(&tmB, wpack, 3, dims, strides, box, p.kc * 2);
+    if (rc) return rc;
+  }
+
+  const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
+  static size_t configured_smem = 0;
+  if (smem > configured_smem) {
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(210 * 1024)));
+    configured_smem = 210 * 1024;
+  }
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int grid = total_tiles < sms ? total_tiles : sms;
+  conv3d_k3_igemm_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}

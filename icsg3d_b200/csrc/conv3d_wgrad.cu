@@ -1,0 +1,286 @@
+// Conv3D 3x3x3 filter gradient (Conv3DBackpropFilterV2) on tcgen05 / TMEM (sm_100a).
+//
+//   dW[tap][ci][co] = sum over voxels v of  x[v + off(tap), ci] * dy[v, co]
+//
+// GEMM view (per 128-voxel tile, accumulated over all tiles a CTA owns):
+//   D[(tap,ci) = 128 rows, co = NT cols] += A^T[128 x 16 voxels] * B[16 voxels x NT]     (8 k-steps / tile)
+// Both operands are the NDHWC tiles exactly as TMA delivers them ([voxel][channel], channel contiguous),
+// i.e. MN-major UMMA operands: no transposed copies of x or dy are ever materialised.
+// The 128 MMA rows of one "group" are 128/KCA row-blocks, each row-block = one (tap, channel-chunk) and one
+// TMA box (the tap shift and the "same" zero padding come from the box coordinates / OOB fill).
+// Every group owns NT TMEM columns; a CTA keeps up to 512/NT groups resident for its whole voxel range,
+// then dumps fp32 partials to the workspace; a second kernel reduces the voxel splits in a fixed order
+// (deterministic: needed for the 1-rank vs N-rank data-parallel equivalence test).
+#include "common.cuh"
+
+namespace icsg3d {
+
+struct WgradParams {
+  int m_total;
+  int D, H, W;
+  int tiles_m;
+  int cin, cout;
+  int kca, chunks_a, bpg;      // channels per row-block, chunks per tap, row-blocks per group
+  int total_blocks, total_groups;
+  int groups_per_cta;
+  int kcb, ntw, nb_boxes;      // B operand: channels per box, N tile, boxes per tile
+  int splits;
+  int stages;
+  uint32_t a_box_bytes, b_box_bytes, a_bytes, stage_bytes;
+  uint32_t sbo_a, lbo_a, sbo_b, lbo_b, layout_a, layout_b, idesc, tmem_cols;
+  float* ws;                   // [splits][27*cin*cout]
+};
+
+static constexpr int kWgradThreads = 192;
+static constexpr int kWgradMaxStages = 6;
+
+__global__ void __launch_bounds__(kWgradThreads, 1)
+conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kWgradMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWgradMaxStages];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t ring_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* ring = smem_raw + (ring_base - smem_u32(smem_raw));
+
+  const int split = blockIdx.x;
+  const int g_begin = blockIdx.y * p.groups_per_cta;
+  const int g_end = min(g_begin + p.groups_per_cta, p.total_groups);
+  const int nz = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = split; tile < p.tiles_m; tile += p.splits) {
+        int pix = tile * 128;
+        const int w0 = pix % p.W;
+        pix /= p.W;
+        const int h0 = pix % p.H;
+        pix /= p.H;
+        const int d0 = pix % p.D;
+        const int n0 = pix / p.D;
+        for (int g = g_begin; g < g_end; ++g) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const int blk0 = g * p.bpg;
+          int nblk = p.total_blocks - blk0;
+          if (nblk > p.bpg) nblk = p.bpg;
+          mbar_expect_tx(&full_bar[stage],
+                         static_cast<uint32_t>(nblk) * p.a_box_bytes + static_cast<uint32_t>(p.nb_boxes) * p.b_box_bytes);
+          uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
+          uint8_t* sb = sa + p.a_bytes;
+          for (int b = 0; b < nblk; ++b) {
+            const int blk = blk0 + b;
+            const int tap = blk / p.chunks_a;
+            const int ch = blk - tap * p.chunks_a;
+            const int kd = tap / 9;
+            const int kh = (tap - kd * 9) / 3;
+            const int kw = tap - kd * 9 - kh * 3;
+            tma_load_5d(sa + static_cast<size_t>(b) * p.a_box_bytes, &tmX, &full_bar[stage], ch * p.kca, w0 + kw - 1,
+                        h0 + kh - 1, d0 + kd - 1, n0);
+          }
+          for (int j = 0; j < p.nb_boxes; ++j)
+            tma_load_5d(sb + static_cast<size_t>(j) * p.b_box_bytes, &tmDY, &full_bar[stage], nz * p.ntw + j * p.kcb, w0,
+                        h0, d0, n0);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int ti = 0;
+      for (int tile = split; tile < p.tiles_m; tile += p.splits, ++ti) {
+        for (int g = g_begin; g < g_end; ++g) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = ring_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+          const uint32_t sb = sa + p.a_bytes;
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((g - g_begin) * p.ntw);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 8 x 16 voxels
+            const uint64_t adesc = umma_smem_desc(sa + k * 2u * p.sbo_a, p.lbo_a, p.sbo_a, p.layout_a);
+            const uint64_t bdesc = umma_smem_desc(sb + k * 2u * p.sbo_b, p.lbo_b, p.sbo_b, p.layout_b);
+            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (ti | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      umma_commit(&done_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    float* ws = p.ws + static_cast<size_t>(split) * 27 * p.cin * p.cout;
+    for (int g = g_begin; g < g_end; ++g) {
+      const int blk = g * p.bpg + row / p.kca;
+      const int tap = blk / p.chunks_a;
+      const int ci = (blk - tap * p.chunks_a) * p.kca + row % p.kca;
+      const bool ok = blk < p.total_blocks;
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((g - g_begin) * p.ntw);
+      for (int c0 = 0; c0 < p.ntw; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
+        tmem_ld_wait();
+        if (!ok) continue;
+        float4* dst = reinterpret_cast<float4*>(ws + (static_cast<size_t>(tap) * p.cin + ci) * p.cout + nz * p.ntw + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                               __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int splits) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[static_cast<long long>(s) * n + i];
+    dw[i] = acc;
+  }
+}
+
+int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H, int W, int c_extent, int kc);
+
+static bool wg_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static int wgrad_plan(int B, int D, int H, int W, int cin, int cout, WgradParams* p) {
+  const long long m_total = static_cast<long long>(B) * D * H * W;
+  p->m_total = static_cast<int>(m_total);
+  p->D = D;
+  p->H = H;
+  p->W = W;
+  p->tiles_m = static_cast<int>((m_total + 127) / 128);
+  p->cin = cin;
+  p->cout = cout;
+  p->kca = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+  p->chunks_a = cin / p->kca;
+  p->bpg = 128 / p->kca;
+  p->total_blocks = 27 * p->chunks_a;
+  p->total_groups = (p->total_blocks + p->bpg - 1) / p->bpg;
+  p->kcb = (cout % 64 == 0) ? 64 : (cout % 32 == 0 ? 32 : 16);
+  p->ntw = cout < 128 ? cout : 128;
+  if (cout % p->ntw != 0) p->ntw = p->kcb;
+  p->nb_boxes = p->ntw / p->kcb;
+  int gpc = 512 / p->ntw;
+  if (gpc > p->total_groups) gpc = p->total_groups;
+  p->groups_per_cta = gpc;
+  p->a_box_bytes = 128u * p->kca * 2u;
+  p->b_box_bytes = 128u * p->kcb * 2u;
+  p->a_bytes = static_cast<uint32_t>(p->bpg) * p->a_box_bytes;  // 32 KB
+  p->stage_bytes = p->a_bytes + static_cast<uint32_t>(p->nb_boxes) * p->b_box_bytes;
+  int stages = static_cast<int>((200u * 1024u) / p->stage_bytes);
+  if (stages > kWgradMaxStages) stages = kWgradMaxStages;
+  p->stages = stages;
+  p->sbo_a = 8u * p->kca * 2u;
+  p->lbo_a = p->a_box_bytes;
+  p->sbo_b = 8u * p->kcb * 2u;
+  p->lbo_b = p->b_box_bytes;
+  p->layout_a = umma_layout_for_swizzle(p->kca * 2);
+  p->layout_b = umma_layout_for_swizzle(p->kcb * 2);
+  p->idesc = umma_idesc_bf16(p->ntw, 1, 1);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(gpc * p->ntw)) cols <<= 1;
+  p->tmem_cols = cols;
+  const int gy = (p->total_groups + gpc - 1) / gpc;
+  const int gz = cout / p->ntw;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int splits = sms / (gy * gz);
+  if (splits < 1) splits = 1;
+  if (splits > p->tiles_m) splits = p->tiles_m;
+  p->splits = splits;
+  return ICSG3D_OK;
+}
+
+}  // namespace icsg3d
+
+using namespace icsg3d;
+
+extern "C" int64_t icsg3d_conv3d_k3_wgrad_workspace(int B, int D, int H, int W, int cin, int cout) {
+  if (B <= 0 || cin <= 0 || cout <= 0 || cin % 16 || cout % 16) return -1;
+  WgradParams p{};
+  wgrad_plan(B, D, H, W, cin, cout, &p);
+  return static_cast<int64_t>(p.splits) * 27 * cin * cout * 4;
+}
+
+extern "C" int icsg3d_conv3d_k3_wgrad(const void* x, int ldx, const void* dy, int ldy, float* dw, int B, int D, int H,
+                                      int W, int cin, int cout, void* workspace, int64_t workspace_bytes,
+                                      void* stream) {
+  ICSG_REQUIRE(x && dy && dw && workspace, "conv3d_k3_wgrad: null pointer");
+  ICSG_REQUIRE(B > 0 && wg_pow2(D) && wg_pow2(H) && wg_pow2(W) && D >= 2 && H >= 2 && W >= 2 && W <= 128,
+               "conv3d_k3_wgrad: D,H,W must be powers of two in [2,128]");
+  ICSG_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && cin >= 16 && cout >= 16,
+               "conv3d_k3_wgrad: cin/cout must be multiples of 16 (got %d/%d)", cin, cout);
+  ICSG_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cin && ldy >= cout, "conv3d_k3_wgrad: bad ldx/ldy");
+  WgradParams p{};
+  wgrad_plan(B, D, H, W, cin, cout, &p);
+  ICSG_REQUIRE(p.stages >= 2, "conv3d_k3_wgrad: stage too large");
+  const int64_t need = static_cast<int64_t>(p.splits) * 27 * cin * cout * 4;
+  ICSG_REQUIRE(workspace_bytes >= need, "conv3d_k3_wgrad: workspace too small (%lld < %lld)",
+               static_cast<long long>(workspace_bytes), static_cast<long long>(need));
+  p.ws = static_cast<float*>(workspace);
+
+  CUtensorMap tmX, tmDY;
+  int rc = encode_act_map(&tmX, x, ldx, B, D, H, W, cin, p.kca);
+  if (rc) return rc;
+  rc = encode_act_map(&tmDY, dy, ldy, B, D, H, W, cout, p.kcb);
+  if (rc) return rc;
+
+  static bool configured = false;
+  if (!configured) {
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    configured = true;
+  }
+  const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
+  dim3 grid(p.splits, (p.total_groups + p.groups_per_cta - 1) / p.groups_per_cta, cout / p.ntw);
+  conv3d_k3_wgrad_kernel<<<grid, kWgradThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmDY, p);
+  ICSG_CHECK_LAUNCH();
+  const long long n = 27ll * cin * cout;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p.ws, dw, n, p.splits);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}

@@ -1,0 +1,104 @@
+// Weight packing between the Keras master layout (kd,kh,kw,Cin,Cout) fp32 and the bf16 GEMM
+// operand layouts of the tcgen05 conv kernels, incl. channel padding to multiples of 16 and the
+// fold of the encoder's tiled condition channels (vae/lattice_vae.py:167-169).
+#include "common.cuh"
+
+namespace icsg3d {
+
+__global__ void pack_w_fprop_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int cin, int cout,
+                                    int cin_pad, int cout_pad, int cin_lead, int fold, int fold_c) {
+  const long long total = 27ll * cout_pad * cin_pad;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(idx % cin_pad);
+    const int co = static_cast<int>((idx / cin_pad) % cout_pad);
+    const int tap = static_cast<int>(idx / (static_cast<long long>(cin_pad) * cout_pad));
+    float v = 0.f;
+    if (co < cout) {
+      const float* wt = w + static_cast<long long>(tap) * cin * cout;
+      if (fold <= 1) {
+        if (ci < cin) v = wt[static_cast<long long>(ci) * cout + co];
+      } else if (ci < cin_lead) {
+        v = wt[static_cast<long long>(ci) * cout + co];
+      } else if (ci < cin_lead + fold_c) {
+        for (int r = 0; r < fold; ++r) v += wt[static_cast<long long>(cin_lead + r * fold_c + (ci - cin_lead)) * cout + co];
+      }
+    }
+    wp[idx] = f2bf(v);
+  }
+}
+
+__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int cin, int cout,
+                                    int cin_pad, int cout_pad) {
+  const long long total = 27ll * cin_pad * cout_pad;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(idx % cout_pad);
+    const int ci = static_cast<int>((idx / cout_pad) % cin_pad);
+    const int tap = static_cast<int>(idx / (static_cast<long long>(cin_pad) * cout_pad));
+    float v = 0.f;
+    if (ci < cin && co < cout) v = w[(static_cast<long long>(26 - tap) * cin + ci) * cout + co];
+    wp[idx] = f2bf(v);
+  }
+}
+
+__global__ void unpack_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int cin, int cout, int cin_pad,
+                                 int cout_pad, int cin_lead, int fold, int fold_c) {
+  const long long total = 27ll * cin * cout;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(idx % cout);
+    const int ci = static_cast<int>((idx / cout) % cin);
+    const int tap = static_cast<int>(idx / (static_cast<long long>(cin) * cout));
+    int src = ci;
+    if (fold > 1 && ci >= cin_lead) src = cin_lead + (ci - cin_lead) % fold_c;
+    dw[idx] = dwp[(static_cast<long long>(tap) * cin_pad + src) * cout_pad + co];
+  }
+}
+
+static int grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace icsg3d
+
+using namespace icsg3d;
+
+extern "C" int icsg3d_pack_conv_w_fprop(const float* w, void* wpack, int cin, int cout, int cin_pad, int cout_pad,
+                                        int cin_lead, int fold, int fold_c, void* stream) {
+  ICSG_REQUIRE(w && wpack, "pack_conv_w_fprop: null pointer");
+  ICSG_REQUIRE(cout_pad >= cout && cin_pad > 0, "pack_conv_w_fprop: bad padding");
+  if (fold > 1) {
+    ICSG_REQUIRE(cin == cin_lead + fold * fold_c && cin_pad >= cin_lead + fold_c,
+                 "pack_conv_w_fprop: fold %d x %d + lead %d does not match cin %d / cin_pad %d", fold, fold_c, cin_lead,
+                 cin, cin_pad);
+  } else {
+    ICSG_REQUIRE(cin_pad >= cin, "pack_conv_w_fprop: cin_pad < cin");
+  }
+  pack_w_fprop_kernel<<<grid_for(27ll * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(wpack), cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, int cout, int cin_pad, int cout_pad,
+                                        void* stream) {
+  ICSG_REQUIRE(w && wpack, "pack_conv_w_dgrad: null pointer");
+  ICSG_REQUIRE(cin_pad >= cin && cout_pad >= cout, "pack_conv_w_dgrad: bad padding");
+  pack_w_dgrad_kernel<<<grid_for(27ll * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(wpack), cin, cout, cin_pad, cout_pad);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_unpack_conv_dw(const float* dw_pad, float* dw, int cin, int cout, int cin_pad, int cout_pad,
+                                     int cin_lead, int fold, int fold_c, void* stream) {
+  ICSG_REQUIRE(dw_pad && dw, "unpack_conv_dw: null pointer");
+  unpack_dw_kernel<<<grid_for(27ll * cin * cout), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dw_pad, dw, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
