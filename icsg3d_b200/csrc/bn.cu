@@ -1,0 +1,669 @@
+// BatchNormalization (batch-statistics mode) fused with its neighbouring activation / MaxPool3D(2) /
+// UpSampling3D(2), forward and backward.  HBM-bound passes: 16-byte vector loads/stores, fp32 math,
+// fp64 statistics, deterministic two-stage reductions (partials per block, fixed-order final sum).
+//
+// Reference layers: keras BatchNormalization() after every Conv3D (lattice_vae.py:174,214,225;
+// unet.py:278-338), LeakyReLU/ReLU (lattice_vae.py:175,215,226), MaxPool3D (lattice_vae.py:176;
+// unet.py:282,291,300), UpSampling3D (lattice_vae.py:217; unet.py:309,319,329).
+// Semantics register: SURVEY.md §8c R3 (eps 1e-3, momentum 0.99, biased variance, moving-variance
+// factor n/(n-(1+eps))), R4 (LeakyReLU alpha, gradient at 0), R6 (max-pool gradient -> first maximum).
+//
+// Layouts: x, dy are [B,D,H,W,ld] channels-last with C used channels; T = bf16 (C % 8 == 0) or
+// fp32 (C % 4 == 0).  "post" describes what follows BN+activation in the forward graph:
+//   NONE : y has the shape of x;  POOL2 : y is [B,D/2,H/2,W/2,C] (+ uint8 argmax);  UP2 : y is [B,2D,2H,2W,C].
+#include "common.cuh"
+
+namespace icsg3d {
+
+template <typename T>
+struct VecIO;
+template <>
+struct VecIO<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+};
+template <>
+struct VecIO<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+  __device__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <int N>
+__device__ __forceinline__ void store_bf16_vec(__nv_bfloat16* p, const float (&v)[N]) {
+  if constexpr (N == 8) {
+    VecIO<__nv_bfloat16>::store(p, v);
+  } else {
+    uint2 q;
+    q.x = pack_bf16x2(v[0], v[1]);
+    q.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = q;
+  }
+}
+
+__device__ __forceinline__ float act_fwd(float z, int act, float alpha) {
+  if (act == ICSG3D_ACT_RELU) return z > 0.f ? z : 0.f;
+  if (act == ICSG3D_ACT_LEAKY) return z > 0.f ? z : alpha * z;
+  return z;
+}
+__device__ __forceinline__ float act_grad(float z, int act, float alpha) {
+  if (act == ICSG3D_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (act == ICSG3D_ACT_LEAKY) return z > 0.f ? 1.f : alpha;
+  return 1.f;
+}
+
+static constexpr int kBnThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// statistics: partials[blk][0][c] = sum x, partials[blk][1][c] = sum x^2 (fp64)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, int ldx, long long M, int C,
+                                                             double* __restrict__ partials) {
+  constexpr int V = VecIO<T>::N;
+  extern __shared__ double sred[];  // [2][rows_per_iter][C] would be too big: reduce per channel group instead
+  const int cg = C / V;
+  const int rpi = kBnThreads / cg;  // rows per iteration handled by this block
+  const int g = threadIdx.x % cg;
+  const int rl = threadIdx.x / cg;
+  float s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
+  double ds[V], dq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) ds[i] = dq[i] = 0.0;
+  if (rl < rpi) {
+    int n = 0;
+    for (long long r = static_cast<long long>(blockIdx.x) * rpi + rl; r < M; r += static_cast<long long>(gridDim.x) * rpi) {
+      float v[V];
+      VecIO<T>::load(x + r * ldx + g * V, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s[i] += v[i];
+        q[i] += v[i] * v[i];
+      }
+      if (++n == 32) {  // flush fp32 partials to fp64 regularly
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          ds[i] += s[i];
+          dq[i] += q[i];
+          s[i] = q[i] = 0.f;
+        }
+        n = 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      ds[i] += s[i];
+      dq[i] += q[i];
+    }
+  }
+  // block reduction over the row lanes: smem [rpi][cg*V] doubles, two passes (sum, sumsq)
+  double* out = partials + static_cast<size_t>(blockIdx.x) * 2 * C;
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+    if (rl < rpi) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) sred[rl * C + g * V + i] = pass == 0 ? ds[i] : dq[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kBnThreads) {
+      double a = 0.0;
+      for (int r = 0; r < rpi; ++r) a += sred[r * C + c];
+      out[pass * C + c] = a;
+    }
+  }
+}
+
+__global__ void bn_reduce_partials_kernel(const double* __restrict__ partials, int nparts, int C2,
+                                          double* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C2) return;
+  double a = 0.0;
+  for (int p = 0; p < nparts; ++p) a += partials[static_cast<size_t>(p) * C2 + c];
+  sums[c] = a;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var, float momentum,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
+  const double g = gamma ? static_cast<double>(gamma[c]) : 1.0;
+  const double b = beta ? static_cast<double>(beta[c]) : 0.0;
+  mean_out[c] = static_cast<float>(mean);
+  rstd_out[c] = static_cast<float>(rstd);
+  scale[c] = static_cast<float>(g * rstd);
+  shift[c] = static_cast<float>(b - mean * g * rstd);
+  if (moving_mean) {
+    // keras 2.3.1 / TF backend: mov -= (mov - value) * (1 - momentum); variance * n / (n - (1 + eps))
+    const double var_unbiased = var * (count / (count - (1.0 + static_cast<double>(eps))));
+    moving_mean[c] = static_cast<float>(moving_mean[c] - (moving_mean[c] - mean) * (1.0 - momentum));
+    moving_var[c] = static_cast<float>(moving_var[c] - (moving_var[c] - var_unbiased) * (1.0 - momentum));
+  }
+}
+
+__global__ void bn_inference_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           const float* __restrict__ mm, const float* __restrict__ mv, float eps,
+                                           float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double rstd = 1.0 / sqrt(static_cast<double>(mv[c]) + static_cast<double>(eps));
+  const double g = gamma ? gamma[c] : 1.0;
+  scale[c] = static_cast<float>(g * rstd);
+  shift[c] = static_cast<float>((beta ? beta[c] : 0.0) - mm[c] * g * rstd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward apply
+// ------------------------------------------------------------------------------------------------
+struct BnFwdParams {
+  const void* x;
+  int ldx;
+  const float* scale;
+  const float* shift;
+  int act;
+  float alpha;
+  int post;
+  int B, D, H, W, C;  // extents of x
+  __nv_bfloat16* y;
+  int ldy;
+  float* y32;
+  int ldy32;
+  uint8_t* pool_idx;  // [B*D/2*H/2*W/2][C]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_fwd_kernel(const BnFwdParams p) {
+  constexpr int V = VecIO<T>::N;
+  const T* x = static_cast<const T*>(p.x);
+  const int cg = p.C / V;
+  if (p.post == ICSG3D_POST_POOL2) {
+    const int Do = p.D / 2, Ho = p.H / 2, Wo = p.W / 2;
+    const long long total = static_cast<long long>(p.B) * Do * Ho * Wo * cg;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int g = static_cast<int>(idx % cg);
+      long long o = idx / cg;
+      const int wo = static_cast<int>(o % Wo);
+      long long t = o / Wo;
+      const int ho = static_cast<int>(t % Ho);
+      t /= Ho;
+      const int dz = static_cast<int>(t % Do);
+      const int n = static_cast<int>(t / Do);
+      float sc[V], sh[V], best[V];
+      int bi[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        sc[i] = p.scale[g * V + i];
+        sh[i] = p.shift[g * V + i];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int dd = 2 * dz + (k >> 2), hh = 2 * ho + ((k >> 1) & 1), ww = 2 * wo + (k & 1);
+        const long long r = ((static_cast<long long>(n) * p.D + dd) * p.H + hh) * p.W + ww;
+        float v[V];
+        VecIO<T>::load(x + r * p.ldx + g * V, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float z = act_fwd(fmaf(sc[i], v[i], sh[i]), p.act, p.alpha);
+          if (k == 0 || z > best[i]) {  // strict '>' keeps the FIRST maximum in (d,h,w) scan order
+            best[i] = z;
+            bi[i] = k;
+          }
+        }
+      }
+      store_bf16_vec<V>(p.y + o * p.ldy + g * V, best);
+      if (p.pool_idx) {
+        uint8_t* ip = p.pool_idx + o * p.C + g * V;
+        if constexpr (V == 8) {
+          uint2 q;
+          q.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+          q.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+          *reinterpret_cast<uint2*>(ip) = q;
+        } else {
+          *reinterpret_cast<uint32_t*>(ip) = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+        }
+      }
+    }
+    return;
+  }
+  const long long M = static_cast<long long>(p.B) * p.D * p.H * p.W;
+  const long long total = M * cg;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % cg);
+    const long long r = idx / cg;
+    float v[V];
+    VecIO<T>::load(x + r * p.ldx + g * V, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = act_fwd(fmaf(p.scale[g * V + i], v[i], p.shift[g * V + i]), p.act, p.alpha);
+    if (p.post == ICSG3D_POST_UP2) {
+      const int w = static_cast<int>(r % p.W);
+      long long t = r / p.W;
+      const int h = static_cast<int>(t % p.H);
+      t /= p.H;
+      const int d = static_cast<int>(t % p.D);
+      const int n = static_cast<int>(t / p.D);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long long ro = ((static_cast<long long>(n) * 2 * p.D + 2 * d + (k >> 2)) * 2 * p.H + 2 * h + ((k >> 1) & 1)) *
+                                 2 * p.W + 2 * w + (k & 1);
+        store_bf16_vec<V>(p.y + ro * p.ldy + g * V, v);
+      }
+    } else {
+      if (p.y) store_bf16_vec<V>(p.y + r * p.ldy + g * V, v);
+      if (p.y32) {
+        float* d32 = p.y32 + r * p.ldy32 + g * V;
+#pragma unroll
+        for (int i = 0; i < V; ++i) d32[i] = v[i];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct BnBwdParams {
+  const void* dy;   // gradient w.r.t. the forward output (post domain)
+  int lddy;
+  const void* x;    // BN input (pre-normalisation)
+  int ldx;
+  const float* mean;
+  const float* rstd;
+  const float* scale;  // gamma * rstd
+  const float* shift;
+  int act;
+  float alpha;
+  int post;
+  const uint8_t* pool_idx;
+  int B, D, H, W, C;   // extents of x
+  double* partials;    // reduce: [nblk][2][C]
+  const double* sums;  // apply:  [2][C] (sum g, sum g*xhat)
+  double count;
+  int pre_relu;        // U-Net ordering: x = ReLU(conv); multiply dx by (x > 0)
+  const __nv_bfloat16* tap_other;  // DFC tap: dx += tap_coef * (x - tap_other) before the ReLU mask
+  int ld_other;
+  float tap_coef;
+  __nv_bfloat16* dx;
+  int lddx;
+};
+
+// g for one x row given the matching dy vector: g_i = dyv_i * act'(scale*x+shift)
+template <int V>
+__device__ __forceinline__ void g_from(const float (&xv)[V], const float (&dyv)[V], const float (&sc)[V],
+                                       const float (&sh)[V], int act, float alpha, float (&g)[V]) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) g[i] = dyv[i] * act_grad(fmaf(sc[i], xv[i], sh[i]), act, alpha);
+}
+
+template <typename T, bool kApply>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_kernel(const BnBwdParams p) {
+  constexpr int V = VecIO<T>::N;
+  const T* x = static_cast<const T*>(p.x);
+  const T* dy = static_cast<const T*>(p.dy);
+  const int cg = p.C / V;
+  // Thread -> channel group is fixed for the whole kernel (grid-stride keeps idx % cg constant when the
+  // stride is a multiple of cg; enforce it by striding in units of whole rows).
+  const int rpi = kBnThreads / cg;
+  const int g = threadIdx.x % cg;
+  const int rl = threadIdx.x / cg;
+  float sc[V], sh[V], mu[V], rs[V];
+  float s1[V], s2[V], k1[V], k2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sc[i] = p.scale[g * V + i];
+    sh[i] = p.shift[g * V + i];
+    mu[i] = p.mean[g * V + i];
+    rs[i] = p.rstd[g * V + i];
+    s1[i] = s2[i] = 0.f;
+    if (kApply) {
+      k1[i] = static_cast<float>(p.sums[g * V + i] / p.count);
+      k2[i] = static_cast<float>(p.sums[p.C + g * V + i] / p.count);
+    }
+  }
+  double d1[V], d2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) d1[i] = d2[i] = 0.0;
+  int nacc = 0;
+
+  auto emit = [&](long long r, const float (&xv)[V], const float (&gv)[V]) {
+    if (kApply) {
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xh = (xv[i] - mu[i]) * rs[i];
+        o[i] = sc[i] * (gv[i] - k1[i] - xh * k2[i]);
+      }
+      if (p.tap_other) {
+        float ov[8];
+        const uint4 q = *reinterpret_cast<const uint4*>(p.tap_other + r * p.ld_other + g * V);
+        float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+        ov[0] = a.x; ov[1] = a.y; ov[2] = b.x; ov[3] = b.y; ov[4] = c.x; ov[5] = c.y; ov[6] = d.x; ov[7] = d.y;
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] += p.tap_coef * (xv[i] - ov[i < 8 ? i : 0]);
+      }
+      if (p.pre_relu) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = xv[i] > 0.f ? o[i] : 0.f;
+      }
+      store_bf16_vec<V>(p.dx + r * p.lddx + g * V, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s1[i] += gv[i];
+        s2[i] += gv[i] * (xv[i] - mu[i]) * rs[i];
+      }
+      if (++nacc == 32) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          d1[i] += s1[i];
+          d2[i] += s2[i];
+          s1[i] = s2[i] = 0.f;
+        }
+        nacc = 0;
+      }
+    }
+  };
+
+  if (rl < rpi) {
+    if (p.post == ICSG3D_POST_POOL2) {
+      const int Do = p.D / 2, Ho = p.H / 2, Wo = p.W / 2;
+      const long long Mo = static_cast<long long>(p.B) * Do * Ho * Wo;
+      for (long long o = static_cast<long long>(blockIdx.x) * rpi + rl; o < Mo; o += static_cast<long long>(gridDim.x) * rpi) {
+        const int wo = static_cast<int>(o % Wo);
+        long long t = o / Wo;
+        const int ho = static_cast<int>(t % Ho);
+        t /= Ho;
+        const int dz = static_cast<int>(t % Do);
+        const int n = static_cast<int>(t / Do);
+        float dyv[V];
+        VecIO<T>::load(dy + o * p.lddy + g * V, dyv);
+        int bi[V];
+        {
+          const uint8_t* ip = p.pool_idx + o * p.C + g * V;
+          if constexpr (V == 8) {
+            const uint2 q = *reinterpret_cast<const uint2*>(ip);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              bi[i] = (q.x >> (8 * i)) & 0xff;
+              bi[4 + i] = (q.y >> (8 * i)) & 0xff;
+            }
+          } else {
+            const uint32_t q = *reinterpret_cast<const uint32_t*>(ip);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bi[i] = (q >> (8 * i)) & 0xff;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int dd = 2 * dz + (k >> 2), hh = 2 * ho + ((k >> 1) & 1), ww = 2 * wo + (k & 1);
+          const long long r = ((static_cast<long long>(n) * p.D + dd) * p.H + hh) * p.W + ww;
+          float xv[V], sel[V], gv[V];
+          VecIO<T>::load(x + r * p.ldx + g * V, xv);
+#pragma unroll
+          for (int i = 0; i < V; ++i) sel[i] = bi[i] == k ? dyv[i] : 0.f;
+          g_from<V>(xv, sel, sc, sh, p.act, p.alpha, gv);
+          emit(r, xv, gv);
+        }
+      }
+    } else {
+      const long long M = static_cast<long long>(p.B) * p.D * p.H * p.W;
+      for (long long r = static_cast<long long>(blockIdx.x) * rpi + rl; r < M; r += static_cast<long long>(gridDim.x) * rpi) {
+        float xv[V], dyv[V], gv[V];
+        VecIO<T>::load(x + r * p.ldx + g * V, xv);
+        if (p.post == ICSG3D_POST_UP2) {
+          const int w = static_cast<int>(r % p.W);
+          long long t = r / p.W;
+          const int h = static_cast<int>(t % p.H);
+          t /= p.H;
+          const int d = static_cast<int>(t % p.D);
+          const int n = static_cast<int>(t / p.D);
+#pragma unroll
+          for (int i = 0; i < V; ++i) dyv[i] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const long long ro = ((static_cast<long long>(n) * 2 * p.D + 2 * d + (k >> 2)) * 2 * p.H + 2 * h + ((k >> 1) & 1)) *
+                                     2 * p.W + 2 * w + (k & 1);
+            float c[V];
+            VecIO<T>::load(dy + ro * p.lddy + g * V, c);
+#pragma unroll
+            for (int i = 0; i < V; ++i) dyv[i] += c[i];
+          }
+        } else {
+          VecIO<T>::load(dy + r * p.lddy + g * V, dyv);
+        }
+        g_from<V>(xv, dyv, sc, sh, p.act, p.alpha, gv);
+        emit(r, xv, gv);
+      }
+    }
+  }
+  if (!kApply) {
+    extern __shared__ double sred[];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      d1[i] += s1[i];
+      d2[i] += s2[i];
+    }
+    double* out = p.partials + static_cast<size_t>(blockIdx.x) * 2 * p.C;
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+      if (rl < rpi) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) sred[rl * p.C + g * V + i] = pass == 0 ? d1[i] : d2[i];
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < p.C; c += kBnThreads) {
+        double a = 0.0;
+        for (int r = 0; r < rpi; ++r) a += sred[r * p.C + c];
+        out[pass * p.C + c] = a;
+      }
+    }
+  }
+}
+
+// dgamma = sum g*xhat, dbeta = sum g  (fp64 sums -> fp32 gradient slots)
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] = static_cast<float>(sums[c]);
+  if (dgamma) dgamma[c] = static_cast<float>(sums[C + c]);
+}
+
+static int bn_grid(long long rows, int C, int V) {
+  const int cg = C / V;
+  const int rpi = kBnThreads / cg;
+  long long blocks = (rows + rpi - 1) / rpi;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  const long long cap = static_cast<long long>(sms) * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+static size_t bn_red_smem(int C, int V) {
+  const int cg = C / V;
+  const int rpi = kBnThreads / cg;
+  return static_cast<size_t>(rpi) * C * sizeof(double);
+}
+
+static bool bn_shape_ok(int C, int dtype) {
+  const int V = dtype == ICSG3D_DT_BF16 ? 8 : 4;
+  return C > 0 && C % V == 0 && C / V <= kBnThreads;
+}
+
+}  // namespace icsg3d
+
+using namespace icsg3d;
+
+extern "C" int icsg3d_bn_nparts(int64_t rows, int C, int dtype) {
+  if (!bn_shape_ok(C, dtype)) return -1;
+  return bn_grid(rows, C, dtype == ICSG3D_DT_BF16 ? 8 : 4);
+}
+
+extern "C" int icsg3d_bn_stats(const void* x, int ldx, int dtype, int64_t rows, int C, double* partials, int nparts,
+                               void* stream) {
+  ICSG_REQUIRE(x && partials, "bn_stats: null pointer");
+  ICSG_REQUIRE(bn_shape_ok(C, dtype), "bn_stats: unsupported C=%d for dtype %d", C, dtype);
+  const int V = dtype == ICSG3D_DT_BF16 ? 8 : 4;
+  ICSG_REQUIRE(ldx % V == 0, "bn_stats: ldx must be a multiple of %d", V);
+  ICSG_REQUIRE(nparts == bn_grid(rows, C, V), "bn_stats: nparts %d != icsg3d_bn_nparts() %d", nparts, bn_grid(rows, C, V));
+  const size_t smem = bn_red_smem(C, V);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == ICSG3D_DT_BF16) {
+    if (smem > 48 * 1024) ICSG_CUDA(cudaFuncSetAttribute(bn_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    bn_stats_kernel<__nv_bfloat16><<<nparts, kBnThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, rows, C, partials);
+  } else {
+    bn_stats_kernel<float><<<nparts, kBnThreads, smem, st>>>(static_cast<const float*>(x), ldx, rows, C, partials);
+  }
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_bn_reduce_partials(const double* partials, int nparts, int C, double* sums, void* stream) {
+  ICSG_REQUIRE(partials && sums && nparts > 0, "bn_reduce_partials: bad arguments");
+  bn_reduce_partials_kernel<<<ceil_div(2 * C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(partials, nparts, 2 * C, sums);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
+                                  float* mean, float* rstd, float* scale, float* shift, float* moving_mean,
+                                  float* moving_var, float momentum, int C, void* stream) {
+  ICSG_REQUIRE(sums && mean && rstd && scale && shift && count > 0, "bn_finalize: bad arguments");
+  ICSG_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize: moving_mean/var must both be given");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, count, gamma, beta, eps, mean, rstd, scale, shift, moving_mean, moving_var, momentum, C);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_bn_inference_coeffs(const float* gamma, const float* beta, const float* moving_mean,
+                                          const float* moving_var, float eps, float* scale, float* shift, int C,
+                                          void* stream) {
+  ICSG_REQUIRE(moving_mean && moving_var && scale && shift, "bn_inference_coeffs: null pointer");
+  bn_inference_coeffs_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, moving_mean, moving_var,
+                                                                                        eps, scale, shift, C);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_bn_apply_fwd(const void* x, int ldx, int x_dtype, const float* scale, const float* shift, int act,
+                                   float alpha, int post, int B, int D, int H, int W, int C, void* y, int ldy,
+                                   float* y32, int ldy32, uint8_t* pool_idx, void* stream) {
+  ICSG_REQUIRE(x && scale && shift && (y || y32), "bn_apply_fwd: null pointer");
+  ICSG_REQUIRE(bn_shape_ok(C, x_dtype), "bn_apply_fwd: unsupported C=%d for dtype %d", C, x_dtype);
+  const int V = x_dtype == ICSG3D_DT_BF16 ? 8 : 4;
+  ICSG_REQUIRE(ldx % V == 0 && (!y || ldy % V == 0), "bn_apply_fwd: ld must be a multiple of the vector width %d", V);
+  ICSG_REQUIRE(post == ICSG3D_POST_NONE || y, "bn_apply_fwd: pool/upsample need the bf16 output");
+  ICSG_REQUIRE(post != ICSG3D_POST_POOL2 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "bn_apply_fwd: odd extent for pool");
+  BnFwdParams p{x, ldx, scale, shift, act, alpha, post, B, D, H, W, C, static_cast<__nv_bfloat16*>(y), ldy, y32, ldy32, pool_idx};
+  long long items = static_cast<long long>(B) * D * H * W * (C / V);
+  if (post == ICSG3D_POST_POOL2) items /= 8;
+  long long blocks = (items + kBnThreads - 1) / kBnThreads;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  if (blocks > static_cast<long long>(sms) * 8) blocks = static_cast<long long>(sms) * 8;
+  if (blocks < 1) blocks = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_dtype == ICSG3D_DT_BF16) bn_apply_fwd_kernel<__nv_bfloat16><<<static_cast<int>(blocks), kBnThreads, 0, st>>>(p);
+  else bn_apply_fwd_kernel<float><<<static_cast<int>(blocks), kBnThreads, 0, st>>>(p);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+                         const float* rstd, const float* scale, const float* shift, int act, float alpha, int post,
+                         const uint8_t* pool_idx, int B, int D, int H, int W, int C, double* partials, int nparts,
+                         const double* sums, double count, int pre_relu, const void* tap_other, int ld_other,
+                         float tap_coef, void* dx, int lddx, void* stream) {
+  ICSG_REQUIRE(dy && x && mean && rstd && scale && shift, "bn_bwd: null pointer");
+  ICSG_REQUIRE(bn_shape_ok(C, dtype), "bn_bwd: unsupported C=%d for dtype %d", C, dtype);
+  const int V = dtype == ICSG3D_DT_BF16 ? 8 : 4;
+  ICSG_REQUIRE(ldx % V == 0 && lddy % V == 0, "bn_bwd: ld must be a multiple of %d", V);
+  ICSG_REQUIRE(post != ICSG3D_POST_POOL2 || pool_idx, "bn_bwd: pool needs pool_idx");
+  ICSG_REQUIRE(!tap_other || dtype == ICSG3D_DT_BF16, "bn_bwd: tap gradient needs bf16 activations");
+  long long rows = static_cast<long long>(B) * D * H * W;
+  if (post == ICSG3D_POST_POOL2) rows /= 8;
+  const int grid = bn_grid(rows, C, V);
+  BnBwdParams p{};
+  p.dy = dy; p.lddy = lddy; p.x = x; p.ldx = ldx; p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
+  p.act = act; p.alpha = alpha; p.post = post; p.pool_idx = pool_idx; p.B = B; p.D = D; p.H = H; p.W = W; p.C = C;
+  p.partials = partials; p.sums = sums; p.count = count; p.pre_relu = pre_relu;
+  p.tap_other = static_cast<const __nv_bfloat16*>(tap_other); p.ld_other = ld_other; p.tap_coef = tap_coef;
+  p.dx = static_cast<__nv_bfloat16*>(dx); p.lddx = lddx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!apply) {
+    ICSG_REQUIRE(partials && nparts == grid, "bn_bwd_reduce: nparts %d != expected %d", nparts, grid);
+    const size_t smem = bn_red_smem(C, V);
+    if (dtype == ICSG3D_DT_BF16) {
+      if (smem > 48 * 1024) ICSG_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      bn_bwd_kernel<__nv_bfloat16, false><<<grid, kBnThreads, smem, st>>>(p);
+    } else {
+      bn_bwd_kernel<float, false><<<grid, kBnThreads, smem, st>>>(p);
+    }
+  } else {
+    ICSG_REQUIRE(sums && dx && count > 0, "bn_bwd_apply: bad arguments");
+    ICSG_REQUIRE(lddx % 4 == 0, "bn_bwd_apply: lddx must be a multiple of 4");
+    const int g2 = grid * 2 < 148 * 8 ? grid * 2 : grid;
+    if (dtype == ICSG3D_DT_BF16) bn_bwd_kernel<__nv_bfloat16, true><<<g2, kBnThreads, 0, st>>>(p);
+    else bn_bwd_kernel<float, true><<<g2, kBnThreads, 0, st>>>(p);
+  }
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_bn_bwd_nparts(int B, int D, int H, int W, int C, int dtype, int post) {
+  if (!bn_shape_ok(C, dtype)) return -1;
+  long long rows = static_cast<long long>(B) * D * H * W;
+  if (post == ICSG3D_POST_POOL2) rows /= 8;
+  return bn_grid(rows, C, dtype == ICSG3D_DT_BF16 ? 8 : 4);
+}
+
+extern "C" int icsg3d_bn_bwd_reduce(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+                                    const float* rstd, const float* scale, const float* shift, int act, float alpha,
+                                    int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C,
+                                    double* partials, int nparts, void* stream) {
+  return bn_bwd_launch(false, dy, lddy, x, ldx, dtype, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D, H, W, C,
+                       partials, nparts, nullptr, 0.0, 0, nullptr, 0, 0.f, nullptr, 0, stream);
+}
+
+extern "C" int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+                                   const float* rstd, const float* scale, const float* shift, int act, float alpha,
+                                   int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C,
+                                   const double* sums, double count, int pre_relu, const void* tap_other, int ld_other,
+                                   float tap_coef, void* dx, int lddx, void* stream) {
+  return bn_bwd_launch(true, dy, lddy, x, ldx, dtype, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D, H, W, C,
+                       nullptr, 0, sums, count, pre_relu, tap_other, ld_other, tap_coef, dx, lddx, stream);
+}
+
+extern "C" int icsg3d_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream) {
+  ICSG_REQUIRE(sums, "bn_param_grads: null pointer");
+  bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, dgamma, dbeta, C);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}

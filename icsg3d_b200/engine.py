@@ -1,0 +1,469 @@
+"""Step executors: the sequence of C-ABI kernel launches that make up one forward / backward / update
+of the reference's two graphs, over pre-allocated device buffers (so a whole step can be captured in a
+CUDA graph and replayed).
+
+    VAEEngine  — conditional DFC-VAE (vae/lattice_vae.py:127-158, 160-270, 296-310) trained against the
+                 frozen U-Net prefix c1..c10 used as perceptual model (lattice_vae.py:257-270)
+
+Every FLOP runs in libicsg3d.so (icsg3d_b200/ops.py); this file only orders launches and owns buffers.
+Data-parallel mode: batch sharded over ranks; BatchNorm statistic sums (forward and backward)
+and the flat gradient buffer are summed with NCCL all-reduce; nothing else is exchanged.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, POST_NONE, POST_POOL2, POST_UP2, pad16
+from .params import LATENT, VAE_FILTERS, ParamStore, unet_specs, vae_specs
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+F64 = torch.float64
+
+PM_BLOCKS = [  # U-Net prefix evaluated by the perceptual loss: (name, cin, cout, level, pool_after, dfc_tap)
+    ("c1", 4, 32, 0, False, False), ("c2", 32, 64, 0, True, True), ("c3", 64, 64, 1, False, False),
+    ("c4", 64, 128, 1, True, True), ("c5", 128, 128, 2, False, False), ("c6", 128, 256, 2, True, True),
+    ("c9", 256, 512, 3, False, False), ("c10", 512, 512, 3, False, True),
+]
+
+
+class Dist:
+    """Thin view of torch.distributed for the two collectives the path needs."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class _BN:
+    """Per-layer BatchNorm scratch: batch mean/rstd, folded scale/shift, fp64 statistic sums."""
+
+    def __init__(self, C, dev):
+        self.C = C
+        self.mean = torch.zeros(C, dtype=F32, device=dev)
+        self.rstd = torch.zeros(C, dtype=F32, device=dev)
+        self.scale = torch.zeros(C, dtype=F32, device=dev)
+        self.shift = torch.zeros(C, dtype=F32, device=dev)
+        self.sums = torch.zeros(2 * C, dtype=F64, device=dev)
+        self.bsums = torch.zeros(2 * C, dtype=F64, device=dev)
+        self.bsums_g = torch.zeros(2 * C, dtype=F64, device=dev)
+
+
+class _Ctx:
+    """Scratch shared by the launches of one stream."""
+
+    def __init__(self, dev, max_partials=148 * 4 * 2 * 1024, max_dw=27 * 512 * 512):
+        self.partials = torch.zeros(max_partials, dtype=F64, device=dev)
+        self.dw_pad = torch.zeros(max_dw, dtype=F32, device=dev)
+
+
+class VAEEngine:
+    def __init__(self, batch, d=32, channels=4, ncond=10, latent=LATENT, filters=VAE_FILTERS, device="cuda",
+                 vae_params: ParamStore | None = None, pm_params: ParamStore | None = None, alpha=0.5, beta=3e-4,
+                 pm_layer_weights=(1.0, 1.0, 1.0, 1.0), lr=5e-4, dist: Dist | None = None, seed=1):
+        assert channels == 4, "the reference hard-wires 4 input channels (lattice_vae.py:90)"
+        assert d % 16 == 0 and d & (d - 1) == 0, "grid edge must be a power of two >= 16"
+        self.B, self.d, self.ncond, self.latent, self.filters = batch, d, ncond, latent, list(filters)
+        self.dev = torch.device(device)
+        self.alpha, self.beta, self.lr = float(alpha), float(beta), float(lr)
+        self.pm_w = [float(w) for w in pm_layer_weights]
+        self.dist = dist
+        self.world = dist.world if dist else 1
+        dev = self.dev
+        self.vp = vae_params or ParamStore(vae_specs(channels, ncond, d, latent, filters), dev).init(seed)
+        self.pp = pm_params or ParamStore(unet_specs(channels), dev, with_grads=False, with_adam=False).init(seed + 1)
+        self.ctx = _Ctx(dev)
+        B = batch
+        z = lambda *s, dt=BF16: torch.zeros(*s, dtype=dt, device=dev)
+
+        # ---- static inputs ----
+        self.M = z(B, d, d, d, 4, dt=F32)
+        self.cond = z(B, ncond, dt=F32)
+        self.eps = z(B, latent, dt=F32)
+        self.xe = z(B, d, d, d, 16)
+        self.xp = z(B, d, d, d, 16)
+
+        # ---- encoder ----
+        self.enc = []
+        cin_pad, D = 16, d
+        for i, f in enumerate(self.filters, 1):
+            L = dict(name=f"enc_conv{i}", bn=f"enc_bn{i}", cin_pad=cin_pad, cout=f, D=D,
+                     c=z(B, D, D, D, f), y=z(B, D // 2, D // 2, D // 2, f), idx=z(B, D // 2, D // 2, D // 2, f, dt=torch.uint8),
+                     dc=z(B, D, D, D, f), dy=z(B, D // 2, D // 2, D // 2, f), bns=_BN(f, dev),
+                     wf=z(27, f, cin_pad), wd=z(27, cin_pad, f) if i > 1 else None)
+            self.enc.append(L)
+            cin_pad, D = f, D // 2
+        self.e_s = D  # spatial edge at enc_conv5 (d/16)
+        c4 = self.filters[-1]
+        self.e5 = z(B, D, D, D, 4, dt=F32)
+        self.e5_wf, self.e5_wd = z(27, 16, c4), z(27, c4, 16)
+        self.de5 = z(B, D * D * D * 4, dt=F32)
+        self.dc_e5 = z(B, D, D, D, 16)
+        # ---- bottleneck ----
+        self.h, self.mu, self.lv, self.z, self.kl = (z(B, latent, dt=F32), z(B, latent, dt=F32), z(B, latent, dt=F32),
+                                                      z(B, latent, dt=F32), z(B, dt=F32))
+        self.dh, self.dmu, self.dlv, self.dz = (z(B, latent, dt=F32), z(B, latent, dt=F32), z(B, latent, dt=F32),
+                                                  z(B, latent, dt=F32))
+        s0 = d // 8
+        self.s0 = s0
+        self.dd = z(B, s0 * s0 * s0 * 4, dt=F32)
+        self.ddd = z(B, s0 * s0 * s0 * 4, dt=F32)
+        self.d0 = z(B, s0, s0, s0, 16)
+        self.dy_d0 = z(B, s0, s0, s0, 16)
+        # ---- decoder ----
+        self.dec = []
+        cin_pad, S = 16, s0
+        for i, f in enumerate(self.filters[::-1], 1):
+            up = i < len(self.filters)
+            So = S * 2 if up else S
+            L = dict(name=f"dec_conv{i}", bn=f"dec_bn{i}", cin_pad=cin_pad, cout=f, D=S, up=up,
+                     c=z(B, S, S, S, f), u=z(B, So, So, So, f), dc=z(B, S, S, S, f), du=z(B, So, So, So, f),
+                     bns=_BN(f, dev), wf=z(27, f, cin_pad), wd=z(27, cin_pad, f))
+            self.dec.append(L)
+            cin_pad, S = f, So
+        cl = self.filters[0]
+        self.c5 = z(B, d, d, d, 4, dt=F32)
+        self.xhat = z(B, d, d, d, 4, dt=F32)
+        self.xhat16 = z(B, d, d, d, 16)
+        self.dxhat = z(B, d, d, d, 4, dt=F32)
+        self.dc5 = z(B, d, d, d, 16)
+        self.out_wf, self.out_wd = z(27, 16, cl), z(27, cl, 16)
+        self.bn5 = _BN(4, dev)
+        # ---- perceptual model (two branches: 0 = x, 1 = x_hat) ----
+        self.pm = []
+        for name, cin, cout, lvl, pool, tap in PM_BLOCKS:
+            D = d >> lvl
+            cp = pad16(cin)
+            L = dict(name=name, cin_pad=cp, cout=cout, D=D, pool=pool, tap=tap, has_bn=name != "c10",
+                     wf=ops.pack_conv_w_fprop(self.pp.p[name + "/kernel"]),
+                     wd=ops.pack_conv_w_dgrad(self.pp.p[name + "/kernel"]),
+                     a=[z(B, D, D, D, cout), z(B, D, D, D, cout)], bnst=[_BN(cout, dev), _BN(cout, dev)])
+            Do = D // 2 if pool else D
+            if L["has_bn"]:
+                L["y"] = [z(B, Do, Do, Do, cout), z(B, Do, Do, Do, cout)]
+                L["idx"] = [z(B, Do, Do, Do, cout, dt=torch.uint8) if pool else None for _ in range(2)]
+                L["dy"] = z(B, Do, Do, Do, cout)   # gradient w.r.t. y (x_hat branch only)
+            L["dc"] = z(B, D, D, D, cout)
+            self.pm.append(L)
+        self.dxh16 = z(B, d, d, d, 16)
+        # ---- losses ----
+        self.n_terms = 1 + sum(1 for b in PM_BLOCKS if b[5])
+        self.loss_stride = 148 * 4
+        self.loss_partials = torch.zeros(self.n_terms, self.loss_stride, dtype=F64, device=dev)
+        self.loss_nparts = torch.zeros(self.n_terms, dtype=torch.int32, device=dev)
+        self.loss_scales = torch.zeros(self.n_terms, dtype=F64, device=dev)
+        self.metrics = torch.zeros(4, dtype=F32, device=dev)
+        self._loss_meta_ready = False
+        self._graph = None
+        self.use_graph = False
+
+    # ------------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------------
+    def _bn_fwd(self, x, C, st: _BN, gamma, beta, mm, mv, training, act, post, y=None, y32=None, idx=None):
+        if training:
+            rows = x.numel() // x.shape[-1]
+            n = ops.bn_nparts(rows, C, x.dtype)
+            part = self.ctx.partials[: n * 2 * C].view(n, 2, C)
+            ops.bn_stats(x, C, part)
+            ops.bn_reduce_partials(part, st.sums)
+            if self.world > 1:
+                self.dist.all_reduce_sum(st.sums)
+            ops.bn_finalize(st.sums, float(rows * self.world), gamma, beta, st.mean, st.rstd, st.scale, st.shift, mm, mv)
+        else:
+            ops.bn_inference_coeffs(gamma, beta, mm, mv, st.scale, st.shift)
+        ops.bn_apply_fwd(x, C, st.scale, st.shift, act, post, y=y, y32=y32, pool_idx=idx)
+
+    def _bn_bwd(self, dy, x, C, st: _BN, act, post, idx, dx, pre_relu=False, tap_other=None, tap_coef=0.0, dgamma=None,
+                dbeta=None):
+        n = ops.bn_bwd_nparts(x, C, post)
+        part = self.ctx.partials[: n * 2 * C].view(n, 2, C)
+        ops.bn_bwd_reduce(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, part)
+        ops.bn_reduce_partials(part, st.bsums)
+        if dgamma is not None:
+            ops.bn_param_grads(st.bsums, dgamma, dbeta)  # local sums: the gradient all-reduce adds the ranks
+        sums = st.bsums
+        if self.world > 1:
+            st.bsums_g.copy_(st.bsums)
+            self.dist.all_reduce_sum(st.bsums_g)
+            sums = st.bsums_g
+        rows = x.numel() // x.shape[-1]
+        ops.bn_bwd_apply(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, sums, float(rows * self.world), dx,
+                         pre_relu=pre_relu, tap_other=tap_other, tap_coef=tap_coef)
+
+    def _wgrad(self, x, dy, name, cin, cout, cin_pad, cout_pad, fold=None):
+        """dW of conv `name` into the flat gradient buffer (Keras layout)."""
+        g = self.vp.g[name + "/kernel"]
+        if cin == cin_pad and cout == cout_pad and fold is None:
+            ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=g.view(27, cin, cout))
+            return
+        scratch = self.ctx.dw_pad[: 27 * cin_pad * cout_pad].view(27, cin_pad, cout_pad)
+        ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=scratch)
+        if fold is None:
+            ops.unpack_conv_dw(scratch, cin, cout, out=g)
+        else:
+            ops.unpack_conv_dw(scratch, cin, cout, cin_lead=fold[0], fold=fold[1], fold_c=fold[2], out=g)
+
+    def pack_weights(self):
+        """fp32 master weights -> bf16 GEMM operand layouts (after every optimiser step)."""
+        p = self.vp.p
+        for i, L in enumerate(self.enc):
+            if i == 0:
+                ops.pack_conv_w_fprop(p[L["name"] + "/kernel"], cin_pad=16, cin_lead=4, fold=4, fold_c=self.ncond, out=L["wf"])
+            else:
+                ops.pack_conv_w_fprop(p[L["name"] + "/kernel"], out=L["wf"])
+                ops.pack_conv_w_dgrad(p[L["name"] + "/kernel"], out=L["wd"])
+        ops.pack_conv_w_fprop(p["enc_conv5/kernel"], out=self.e5_wf)
+        ops.pack_conv_w_dgrad(p["enc_conv5/kernel"], out=self.e5_wd)
+        for L in self.dec:
+            ops.pack_conv_w_fprop(p[L["name"] + "/kernel"], out=L["wf"])
+            ops.pack_conv_w_dgrad(p[L["name"] + "/kernel"], out=L["wd"])
+        ops.pack_conv_w_fprop(p["decoder_output/kernel"], out=self.out_wf)
+        ops.pack_conv_w_dgrad(p["decoder_output/kernel"], out=self.out_wd)
+
+    def repack_pm(self):
+        for L in self.pm:
+            ops.pack_conv_w_fprop(self.pp.p[L["name"] + "/kernel"], out=L["wf"])
+            ops.pack_conv_w_dgrad(self.pp.p[L["name"] + "/kernel"], out=L["wd"])
+
+    # ------------------------------------------------------------------------------------------
+    # forward pieces
+    # ------------------------------------------------------------------------------------------
+    def encode(self, training):
+        """build_encoder (lattice_vae.py:160-195) on self.xe / self.eps -> self.mu, self.lv, self.z."""
+        p = self.vp.p
+        x = self.xe
+        for L in self.enc:
+            ops.conv3d_k3(x, L["wf"], p[L["name"] + "/bias"], out=L["c"])
+            bn = L["bn"]
+            self._bn_fwd(L["c"], L["cout"], L["bns"], p[bn + "/gamma"], p[bn + "/beta"],
+                         p[bn + "/moving_mean"], p[bn + "/moving_variance"], training, ACT_LEAKY, POST_POOL2, y=L["y"],
+                         idx=L["idx"])
+            x = L["y"]
+        ops.conv3d_k3(x, self.e5_wf, p["enc_conv5/bias"], out=self.e5, n_store=4, act=ACT_LEAKY)
+        ops.dense_fwd(self.e5.view(self.B, -1), p["enc_dense/kernel"], p["enc_dense/bias"], self.h, act=ACT_RELU)
+        ops.dense_fwd(self.h, p["z_mean/kernel"], p["z_mean/bias"], self.mu)
+        ops.dense_fwd(self.h, p["z_log_var/kernel"], p["z_log_var/bias"], self.lv)
+        ops.reparam_fwd(self.mu, self.lv, self.eps, self.z, self.kl)
+
+    def decode(self, training):
+        """build_decoder (lattice_vae.py:197-230) on self.z / self.cond -> self.xhat (fp32) and self.xhat16 (bf16)."""
+        p = self.vp.p
+        ops.dense_fwd(self.z, p["dec_dense/kernel"], p["dec_dense/bias"], self.dd, x2=self.cond)
+        ops.f32_to_bf16_rows(self.dd, 4, self.d0)
+        x = self.d0
+        for L in self.dec:
+            ops.conv3d_k3(x, L["wf"], p[L["name"] + "/bias"], out=L["c"])
+            bn = L["bn"]
+            self._bn_fwd(L["c"], L["cout"], L["bns"], p[bn + "/gamma"], p[bn + "/beta"], p[bn + "/moving_mean"],
+                         p[bn + "/moving_variance"], training, ACT_LEAKY, POST_UP2 if L["up"] else POST_NONE, y=L["u"])
+            x = L["u"]
+        ops.conv3d_k3(x, self.out_wf, p["decoder_output/bias"], out=self.c5, n_store=4)
+        self._bn_fwd(self.c5, 4, self.bn5, p["dec_bn5/gamma"], p["dec_bn5/beta"], p["dec_bn5/moving_mean"],
+                     p["dec_bn5/moving_variance"], training, ACT_RELU, POST_NONE, y=self.xhat16, y32=self.xhat)
+
+    def pm_forward(self, branch, training):
+        """U-Net prefix c1..c10 (unet.py:276-306) on x (branch 0) or x_hat (branch 1); BN follows the learning
+        phase and its moving averages are never updated from here."""
+        p = self.pp.p
+        x = self.xp if branch == 0 else self.xhat16
+        for L in self.pm:
+            n = L["name"]
+            ops.conv3d_k3(x, L["wf"], p[n + "/bias"], out=L["a"][branch], act=ACT_RELU)
+            if not L["has_bn"]:
+                break
+            bn = "bn_" + n
+            self._bn_fwd(L["a"][branch], L["cout"], L["bnst"][branch], p[bn + "/gamma"], p[bn + "/beta"],
+                         p[bn + "/moving_mean"] if not training else None,
+                         p[bn + "/moving_variance"] if not training else None, training, ACT_NONE,
+                         POST_POOL2 if L["pool"] else POST_NONE, y=L["y"][branch], idx=L["idx"][branch])
+            x = L["y"][branch]
+
+    def _loss_meta(self):
+        if self._loss_meta_ready:
+            return
+        nparts, scales = [], []
+        n_mse = self.M.numel()
+        nparts.append(ops.sqdiff_nparts(n_mse))
+        scales.append(1.0 / n_mse)  # local batch means; metrics_host() averages the ranks
+        k = 0
+        for L in self.pm:
+            if L["tap"]:
+                n = L["a"][0].numel()
+                nparts.append(ops.sqdiff_nparts(n))
+                scales.append(self.pm_w[k] / n)
+                k += 1
+        assert max(nparts) <= self.loss_stride
+        self.loss_nparts.copy_(torch.tensor(nparts, dtype=torch.int32))
+        self.loss_scales.copy_(torch.tensor(scales, dtype=F64))
+        self._nparts_host = nparts
+        self._loss_meta_ready = True
+
+    def losses(self):
+        """[loss, pm, mse, kld] (lattice_vae.py:241-255) into self.metrics (local batch means)."""
+        self._loss_meta()
+        ops.sqdiff_partials(self.M, self.xhat, self.loss_partials[0], self._nparts_host[0])
+        k = 1
+        for L in self.pm:
+            if L["tap"]:
+                ops.sqdiff_partials(L["a"][0], L["a"][1], self.loss_partials[k], self._nparts_host[k])
+                k += 1
+        ops.vae_loss_assemble(self.loss_partials, self.loss_nparts, self.loss_scales, self.kl, 1.0 / self.B, self.alpha,
+                              self.beta, self.metrics)
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def backward(self):
+        p, g = self.vp.p, self.vp.g
+        Bg = self.B * self.world
+        # ---- perceptual branch on x_hat: dgrad only (pm is frozen) ----
+        taps = [L for L in self.pm if L["tap"]]
+        coef = {}
+        for k, L in enumerate(taps):
+            feat = L["a"][0].numel() // self.B
+            coef[L["name"]] = self.alpha * self.pm_w[k] * 2.0 / (feat * Bg)
+        last = self.pm[-1]
+        ops.tap_grad_relu(last["a"][1], last["a"][0], coef[last["name"]], last["dc"])
+        dy = self.pm[-2]["dy"]
+        ops.conv3d_k3(last["dc"], last["wd"], None, out=dy)
+        for li in range(len(self.pm) - 2, -1, -1):
+            L = self.pm[li]
+            self._bn_bwd(dy, L["a"][1], L["cout"], L["bnst"][1], ACT_NONE, POST_POOL2 if L["pool"] else POST_NONE,
+                         L["idx"][1], L["dc"], pre_relu=True, tap_other=L["a"][0] if L["tap"] else None,
+                         tap_coef=coef.get(L["name"], 0.0))
+            if li > 0:
+                dy = self.pm[li - 1]["dy"]
+                ops.conv3d_k3(L["dc"], L["wd"], None, out=dy)
+            else:
+                ops.conv3d_k3(L["dc"], L["wd"], None, out=self.dxh16)
+        # ---- decoder ----
+        ops.xhat_grad(self.M, self.xhat, 2.0 / (self.M.numel() // self.B * Bg), self.dxh16, self.dxhat)
+        self._bn_bwd(self.dxhat, self.c5, 4, self.bn5, ACT_RELU, POST_NONE, None, self.dc5, dgamma=g["dec_bn5/gamma"],
+                     dbeta=g["dec_bn5/beta"])
+        lastd = self.dec[-1]
+        self._wgrad(lastd["u"], self.dc5, "decoder_output", lastd["cout"], 4, lastd["cout"], 16)
+        ops.conv3d_k3(self.dc5, self.out_wd, None, out=lastd["du"])
+        for li in range(len(self.dec) - 1, -1, -1):
+            L = self.dec[li]
+            bn = L["bn"]
+            self._bn_bwd(L["du"], L["c"], L["cout"], L["bns"], ACT_LEAKY, POST_UP2 if L["up"] else POST_NONE, None, L["dc"],
+                         dgamma=g[bn + "/gamma"], dbeta=g[bn + "/beta"])
+            xin = self.dec[li - 1]["u"] if li > 0 else self.d0
+            cin = self.dec[li - 1]["cout"] if li > 0 else 4
+            self._wgrad(xin, L["dc"], L["name"], cin, L["cout"], L["cin_pad"], L["cout"])
+            ops.conv3d_k3(L["dc"], L["wd"], None, out=self.dec[li - 1]["du"] if li > 0 else self.dy_d0)
+        # ---- bottleneck ----
+        ops.bf16_rows_to_f32(self.dy_d0, 4, self.ddd)
+        ops.dense_bwd(self.z, p["dec_dense/kernel"], None, self.ddd, g["dec_dense/kernel"], g["dec_dense/bias"], x2=self.cond,
+                      dx1=self.dz)
+        ops.reparam_bwd(self.dz, self.mu, self.lv, self.eps, self.beta / Bg, self.dmu, self.dlv)
+        ops.dense_bwd(self.h, p["z_mean/kernel"], None, self.dmu, g["z_mean/kernel"], g["z_mean/bias"], dx1=self.dh)
+        ops.dense_bwd(self.h, p["z_log_var/kernel"], None, self.dlv, g["z_log_var/kernel"], g["z_log_var/bias"], dx1=self.dh,
+                      accumulate_dx=True)
+        ops.dense_bwd(self.e5.view(self.B, -1), p["enc_dense/kernel"], self.h, self.dh, g["enc_dense/kernel"],
+                      g["enc_dense/bias"], act=ACT_RELU, dx1=self.de5)
+        ops.leaky_bwd_rows(self.de5, self.e5, 4, self.dc_e5)
+        # ---- encoder ----
+        e4 = self.enc[-1]
+        ops.bias_grad(self.dc_e5, 4, g["enc_conv5/bias"])
+        self._wgrad(e4["y"], self.dc_e5, "enc_conv5", e4["cout"], 4, e4["cout"], 16)
+        ops.conv3d_k3(self.dc_e5, self.e5_wd, None, out=e4["dy"])
+        for li in range(len(self.enc) - 1, -1, -1):
+            L = self.enc[li]
+            bn = L["bn"]
+            self._bn_bwd(L["dy"], L["c"], L["cout"], L["bns"], ACT_LEAKY, POST_POOL2, L["idx"], L["dc"],
+                         dgamma=g[bn + "/gamma"], dbeta=g[bn + "/beta"])
+            if li > 0:
+                self._wgrad(self.enc[li - 1]["y"], L["dc"], L["name"], L["cin_pad"], L["cout"], L["cin_pad"], L["cout"])
+                ops.conv3d_k3(L["dc"], L["wd"], None, out=self.enc[li - 1]["dy"])
+            else:
+                self._wgrad(self.xe, L["dc"], L["name"], 4 + 4 * self.ncond, L["cout"], 16, L["cout"], fold=(4, 4, self.ncond))
+
+    def optimizer_step(self):
+        if self.world > 1:
+            self.dist.all_reduce_sum(self.vp.grad)
+        ops.adam_keras_step(self.vp.theta, self.vp.grad, self.vp.adam_m, self.vp.adam_v, self.vp.adam_state, self.lr)
+
+    # ------------------------------------------------------------------------------------------
+    # whole steps
+    # ------------------------------------------------------------------------------------------
+    def set_inputs(self, M, cond, eps=None):
+        self.M.copy_(M, non_blocking=True)
+        self.cond.copy_(cond, non_blocking=True)
+        if eps is not None:
+            self.eps.copy_(eps, non_blocking=True)
+        else:
+            self.eps.normal_()
+
+    def _train_body(self):
+        self.pack_weights()
+        ops.pack_vae_input(self.M, self.cond, self.xe, self.xp)
+        self.encode(True)
+        self.decode(True)
+        self.pm_forward(0, True)
+        self.pm_forward(1, True)
+        self.losses()
+        self.backward()
+        self.optimizer_step()
+
+    def train_step(self):
+        """train_on_batch (lattice_vae.py:296-298) on the static input buffers; returns the device metrics tensor."""
+        if self.use_graph:
+            if self._graph is None:
+                self._train_body()  # warm-up: attribute setup, lazy allocations
+                torch.cuda.synchronize()
+                raise RuntimeError("call capture_train_graph() before train_step() with use_graph")
+            self._graph.replay()
+        else:
+            self._train_body()
+        return self.metrics
+
+    def capture_train_graph(self, snapshot=True):
+        """Capture one full train step in a CUDA graph.  The warm-up + capture executes optimiser steps, so the
+        parameter/optimiser state is snapshotted and restored around it."""
+        saved = None
+        if snapshot:
+            saved = [t.clone() for t in (self.vp.theta, self.vp.state, self.vp.adam_m, self.vp.adam_v, self.vp.adam_state)]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._train_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._train_body()
+        torch.cuda.synchronize()
+        if saved is not None:
+            for t, sv in zip((self.vp.theta, self.vp.state, self.vp.adam_m, self.vp.adam_v, self.vp.adam_state), saved):
+                t.copy_(sv)
+        self._graph = g
+        self.use_graph = True
+
+    def eval_step(self):
+        """test_on_batch (lattice_vae.py:305-310): learning phase 0 -> moving-statistics BN everywhere."""
+        self.pack_weights()
+        ops.pack_vae_input(self.M, self.cond, self.xe, self.xp)
+        self.encode(False)
+        self.decode(False)
+        self.pm_forward(0, False)
+        self.pm_forward(1, False)
+        self.losses()
+        return self.metrics
+
+    def metrics_host(self):
+        m = self.metrics.clone()
+        if self.world > 1:
+            self.dist.all_reduce_sum(m)
+            m /= self.world
+        return m.cpu().tolist()

@@ -96,9 +96,9 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
         raise ValueError(f"conv3d_k3: cin {cin} does not match packed weights {cin_w}")
     n_store = n_store or nout
     if bias is not None:
+        # a bias shorter than the padded nout is fine: it is a view into a flat parameter buffer with slack
+        # (params.ParamStore.PAD) and the columns >= n_store it would feed are never stored.
         _chk(bias, torch.float32, "bias")
-        if bias.numel() < nout:
-            raise ValueError("bias must be padded to nout")
     if ref:
         y = torch.empty((B, D, H, W, nout), dtype=torch.float32, device=x.device) if out is None else out
         _lib.call("icsg3d_ref_conv3d_k3", _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(y), y.shape[-1], B, D, H, W, cin,
@@ -139,3 +139,166 @@ def conv3d_k3_wgrad(x, dy, *, cin=None, cout=None, out=None, ref=False):
     _lib.call("icsg3d_conv3d_k3_wgrad", _ptr(x), ldx, _ptr(dy), ldy, _ptr(out), B, D, H, W, cin, cout, _ptr(ws),
               ctypes.c_int64(ws.numel()), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm (+activation, +pool/upsample)
+# ------------------------------------------------------------------------------------------------
+BN_EPS = 1e-3
+BN_MOMENTUM = 0.99
+
+
+def _dt(t):
+    return DT_BF16 if t.dtype == torch.bfloat16 else DT_F32
+
+
+def bn_nparts(rows, C, dtype):
+    n = _lib.lib().icsg3d_bn_nparts(ctypes.c_int64(rows), C, DT_BF16 if dtype == torch.bfloat16 else DT_F32)
+    if n <= 0:
+        raise _lib.Icsg3dError(f"bn_nparts: unsupported C={C} for {dtype}")
+    return n
+
+
+def bn_stats(x, C, partials):
+    """x: [..., ld]; partials: float64 [nparts, 2, C]."""
+    rows = x.numel() // x.shape[-1]
+    _lib.call("icsg3d_bn_stats", _ptr(x), x.shape[-1], _dt(x), ctypes.c_int64(rows), C, _ptr(partials),
+              partials.shape[0], _stream())
+
+
+def bn_reduce_partials(partials, sums):
+    _lib.call("icsg3d_bn_reduce_partials", _ptr(partials), partials.shape[0], partials.shape[2], _ptr(sums), _stream())
+
+
+def bn_finalize(sums, count, gamma, beta, mean, rstd, scale, shift, moving_mean=None, moving_var=None, eps=BN_EPS,
+                momentum=BN_MOMENTUM):
+    C = mean.numel()
+    _lib.call("icsg3d_bn_finalize", _ptr(sums), ctypes.c_double(count), _ptr(gamma), _ptr(beta), eps, _ptr(mean),
+              _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(moving_mean), _ptr(moving_var), momentum, C, _stream())
+
+
+def bn_inference_coeffs(gamma, beta, moving_mean, moving_var, scale, shift, eps=BN_EPS):
+    _lib.call("icsg3d_bn_inference_coeffs", _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), eps,
+              _ptr(scale), _ptr(shift), scale.numel(), _stream())
+
+
+def bn_apply_fwd(x, C, scale, shift, act, post, y=None, y32=None, pool_idx=None, alpha=LEAKY_ALPHA):
+    B, D, H, W, ldx = x.shape
+    _lib.call("icsg3d_bn_apply_fwd", _ptr(x), ldx, _dt(x), _ptr(scale), _ptr(shift), act, alpha, post, B, D, H, W, C,
+              _ptr(y), y.shape[-1] if y is not None else 0, _ptr(y32), y32.shape[-1] if y32 is not None else 0,
+              _ptr(pool_idx), _stream())
+
+
+def bn_bwd_nparts(x, C, post):
+    B, D, H, W, _ = x.shape
+    n = _lib.lib().icsg3d_bn_bwd_nparts(B, D, H, W, C, _dt(x), post)
+    if n <= 0:
+        raise _lib.Icsg3dError("bn_bwd_nparts: unsupported shape")
+    return n
+
+
+def bn_bwd_reduce(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, partials, alpha=LEAKY_ALPHA):
+    B, D, H, W, ldx = x.shape
+    _lib.call("icsg3d_bn_bwd_reduce", _ptr(dy), dy.shape[-1], _ptr(x), ldx, _dt(x), _ptr(mean), _ptr(rstd), _ptr(scale),
+              _ptr(shift), act, alpha, post, _ptr(pool_idx), B, D, H, W, C, _ptr(partials), partials.shape[0], _stream())
+
+
+def bn_bwd_apply(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums, count, dx, pre_relu=False,
+                 tap_other=None, tap_coef=0.0, alpha=LEAKY_ALPHA):
+    B, D, H, W, ldx = x.shape
+    _lib.call("icsg3d_bn_bwd_apply", _ptr(dy), dy.shape[-1], _ptr(x), ldx, _dt(x), _ptr(mean), _ptr(rstd), _ptr(scale),
+              _ptr(shift), act, alpha, post, _ptr(pool_idx), B, D, H, W, C, _ptr(sums), ctypes.c_double(count),
+              1 if pre_relu else 0, _ptr(tap_other), tap_other.shape[-1] if tap_other is not None else 0,
+              tap_coef, _ptr(dx), dx.shape[-1], _stream())
+
+
+def bn_param_grads(sums, dgamma, dbeta):
+    C = sums.numel() // 2
+    _lib.call("icsg3d_bn_param_grads", _ptr(sums), _ptr(dgamma), _ptr(dbeta), C, _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE glue
+# ------------------------------------------------------------------------------------------------
+def pack_vae_input(m, cond, xe, xp):
+    B = m.shape[0]
+    vox = m.numel() // (B * 4)
+    _lib.call("icsg3d_pack_vae_input", _ptr(m), _ptr(cond), cond.shape[1] if cond is not None else 0, B,
+              ctypes.c_int64(vox), _ptr(xe), _ptr(xp), _stream())
+
+
+def f32_to_bf16_rows(src, c, dst):
+    rows = src.numel() // c
+    _lib.call("icsg3d_f32_to_bf16_rows", _ptr(src), c, ctypes.c_int64(rows), _ptr(dst), dst.shape[-1], _stream())
+
+
+def bf16_rows_to_f32(src, c, dst):
+    rows = src.numel() // src.shape[-1]
+    _lib.call("icsg3d_bf16_rows_to_f32", _ptr(src), src.shape[-1], c, ctypes.c_int64(rows), _ptr(dst), _stream())
+
+
+def dense_fwd(x1, w, bias, y, act=ACT_NONE, x2=None):
+    B = x1.shape[0]
+    k1 = x1.numel() // B
+    k2 = x2.numel() // B if x2 is not None else 0
+    _lib.call("icsg3d_dense_fwd", _ptr(x1), k1, _ptr(x2), k2, _ptr(w), _ptr(bias), act, B, w.shape[1], _ptr(y), _stream())
+
+
+def dense_bwd(x1, w, y, dy, dw, db, act=ACT_NONE, x2=None, dx1=None, accumulate_dx=False):
+    B = x1.shape[0]
+    k1 = x1.numel() // B
+    k2 = x2.numel() // B if x2 is not None else 0
+    _lib.call("icsg3d_dense_bwd", _ptr(x1), k1, _ptr(x2), k2, _ptr(w), _ptr(y), act, _ptr(dy), B, w.shape[1], _ptr(dx1),
+              1 if accumulate_dx else 0, _ptr(dw), _ptr(db), _stream())
+
+
+def reparam_fwd(mu, lv, eps, z, kl):
+    _lib.call("icsg3d_reparam_fwd", _ptr(mu), _ptr(lv), _ptr(eps), mu.shape[0], mu.shape[1], _ptr(z), _ptr(kl), _stream())
+
+
+def reparam_bwd(dz, mu, lv, eps, kl_coef, dmu, dlv):
+    _lib.call("icsg3d_reparam_bwd", _ptr(dz), _ptr(mu), _ptr(lv), _ptr(eps), kl_coef, mu.shape[0], mu.shape[1], _ptr(dmu),
+              _ptr(dlv), _stream())
+
+
+def leaky_bwd_rows(dy, y, c, dst, alpha=LEAKY_ALPHA):
+    rows = y.numel() // c
+    _lib.call("icsg3d_leaky_bwd_rows", _ptr(dy), _ptr(y), alpha, c, ctypes.c_int64(rows), _ptr(dst), dst.shape[-1],
+              _stream())
+
+
+def sqdiff_nparts(n):
+    return _lib.lib().icsg3d_sqdiff_nparts(ctypes.c_int64(n))
+
+
+def sqdiff_partials(a, b, partials, nparts):
+    """partials: float64 view with at least nparts entries."""
+    _lib.call("icsg3d_sqdiff_partials", _ptr(a), _ptr(b), _dt(a), ctypes.c_int64(a.numel()), _ptr(partials), nparts,
+              _stream())
+
+
+def vae_loss_assemble(partials, nparts, scales, kl, kl_scale, alpha, beta, out, raw=None):
+    """partials: float64 [nterms, stride]; nparts: int32 [nterms]; scales: float64 [nterms]."""
+    _lib.call("icsg3d_vae_loss_assemble", _ptr(partials), _ptr(nparts), partials.shape[1], partials.shape[0],
+              _ptr(scales), _ptr(kl), kl.numel(), ctypes.c_double(kl_scale), alpha, beta, _ptr(out), _ptr(raw), _stream())
+
+
+def xhat_grad(x, xhat, mse_coef, dpm, dy):
+    rows = x.numel() // 4
+    _lib.call("icsg3d_xhat_grad", _ptr(x), _ptr(xhat), mse_coef, _ptr(dpm), dpm.shape[-1] if dpm is not None else 0,
+              ctypes.c_int64(rows), _ptr(dy), _stream())
+
+
+def tap_grad_relu(a, other, coef, dc):
+    _lib.call("icsg3d_tap_grad_relu", _ptr(a), _ptr(other), coef, ctypes.c_int64(a.numel()), _ptr(dc), _stream())
+
+
+def bias_grad(dy, C, db):
+    rows = dy.numel() // dy.shape[-1]
+    _lib.call("icsg3d_bias_grad", _ptr(dy), dy.shape[-1], ctypes.c_int64(rows), C, _ptr(db), _stream())
+
+
+def adam_keras_step(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-7, grad_scale=1.0):
+    _lib.call("icsg3d_adam_keras_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(state), ctypes.c_double(lr),
+              ctypes.c_double(beta1), ctypes.c_double(beta2), ctypes.c_double(eps), grad_scale,
+              ctypes.c_int64(p.numel()), _stream())

@@ -100,6 +100,91 @@ int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, int cout, int
 int icsg3d_unpack_conv_dw(const float* dw_pad, float* dw, int cin, int cout, int cin_pad, int cout_pad,
                           int cin_lead, int fold, int fold_c, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * BatchNormalization in batch-statistics mode, fused with the activation and the MaxPool3D(2) /
+ * UpSampling3D(2) that follow it — keras BatchNormalization() (lattice_vae.py:174,214,225;
+ * unet.py:278-338; eps 1e-3, momentum 0.99 — SURVEY R3), LeakyReLU/ReLU, MaxPool3D, UpSampling3D.
+ * Tensors are [B,D,H,W,ld] with C used channels, dtype bf16 (C % 8 == 0) or fp32 (C % 4 == 0).
+ *
+ * Forward:   bn_stats (per-block fp64 partials of sum x, sum x^2)  ->  bn_reduce_partials -> sums[2][C]
+ *            [data parallel: all-reduce `sums` here]  ->  bn_finalize (mean, rstd, scale = gamma*rstd,
+ *            shift = beta - mean*scale, moving-average update)  ->  bn_apply_fwd.
+ * Backward:  bn_bwd_reduce (partials of sum g, sum g*xhat, g = act'(.) * un-post(dy)) -> bn_reduce_partials
+ *            [all-reduce] -> bn_bwd_apply (dx = scale*(g - mean(g) - xhat*mean(g*xhat))), bn_param_grads.
+ * All reductions are two-stage with a fixed summation order (deterministic).
+ * ---------------------------------------------------------------------------------------------- */
+int icsg3d_bn_nparts(int64_t rows, int C, int dtype);
+int icsg3d_bn_stats(const void* x, int ldx, int dtype, int64_t rows, int C, double* partials, int nparts,
+                    void* stream);
+int icsg3d_bn_reduce_partials(const double* partials, int nparts, int C, double* sums, void* stream);
+int icsg3d_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
+                       float* mean, float* rstd, float* scale, float* shift, float* moving_mean,
+                       float* moving_var, float momentum, int C, void* stream);
+/* learning phase 0 (predict / test_on_batch): scale/shift from the moving statistics */
+int icsg3d_bn_inference_coeffs(const float* gamma, const float* beta, const float* moving_mean,
+                               const float* moving_var, float eps, float* scale, float* shift, int C,
+                               void* stream);
+/* y = post(act(scale*x + shift)); post POOL2 also writes the uint8 index of the FIRST maximum of every
+ * 2x2x2 window; y32 (fp32 copy, ld ldy32) is optional and only valid with POST_NONE. */
+int icsg3d_bn_apply_fwd(const void* x, int ldx, int x_dtype, const float* scale, const float* shift, int act,
+                        float alpha, int post, int B, int D, int H, int W, int C, void* y, int ldy, float* y32,
+                        int ldy32, uint8_t* pool_idx, void* stream);
+int icsg3d_bn_bwd_nparts(int B, int D, int H, int W, int C, int dtype, int post);
+int icsg3d_bn_bwd_reduce(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+                         const float* rstd, const float* scale, const float* shift, int act, float alpha,
+                         int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C, double* partials,
+                         int nparts, void* stream);
+/* pre_relu: U-Net ordering Conv->ReLU->BN (unet.py:276-278): x is the ReLU output and dx is masked by x>0.
+ * tap_other/tap_coef: DFC feature-loss gradient tap_coef*(x - tap_other) added before the mask
+ * (lattice_vae.py:257-270).  dx is bf16 with stride lddx. */
+int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+                        const float* rstd, const float* scale, const float* shift, int act, float alpha,
+                        int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C, const double* sums,
+                        double count, int pre_relu, const void* tap_other, int ld_other, float tap_coef,
+                        void* dx, int lddx, void* stream);
+int icsg3d_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VAE glue: input packing, bottleneck Dense / sampling / KL, losses, loss-gradient seeds, Adam.
+ * ---------------------------------------------------------------------------------------------- */
+/* m fp32 [B*vox][4], cond fp32 [B][ncond] -> xe bf16 [B*vox][16] = (M, one-hot cond, 0) (encoder input:
+ * Reshape+K.tile+Concatenate of lattice_vae.py:167-169 with the 4 replicas folded into the weights) and
+ * xp bf16 [B*vox][16] = (M, 0...) (perceptual U-Net input).  Either output may be NULL. */
+int icsg3d_pack_vae_input(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe, void* xp,
+                          void* stream);
+int icsg3d_f32_to_bf16_rows(const float* src, int c, int64_t rows, void* dst, int ld, void* stream);
+int icsg3d_bf16_rows_to_f32(const void* src, int ld, int c, int64_t rows, float* dst, void* stream);
+/* Dense (+ preceding Concatenate of two inputs): y = act([x1|x2] W + b); W fp32 (k1+k2, N) Keras layout
+ * (lattice_vae.py:183-185, 207-208). */
+int icsg3d_dense_fwd(const float* x1, int k1, const float* x2, int k2, const float* w, const float* bias,
+                     int act, int B, int N, float* y, void* stream);
+/* dy is masked in place by relu'(y) when act == RELU; dx1 (w.r.t. x1, may be NULL), dw (k1+k2,N), db (N). */
+int icsg3d_dense_bwd(const float* x1, int k1, const float* x2, int k2, const float* w, const float* y, int act,
+                     float* dy, int B, int N, float* dx1, int accumulate_dx, float* dw, float* db, void* stream);
+/* sampling (lattice_vae.py:53-66) with an explicit eps, and the per-sample KL term (lattice_vae.py:235-239) */
+int icsg3d_reparam_fwd(const float* mu, const float* lv, const float* eps, int B, int L, float* z, float* kl,
+                       void* stream);
+int icsg3d_reparam_bwd(const float* dz, const float* mu, const float* lv, const float* eps, float kl_coef, int B,
+                       int L, float* dmu, float* dlv, void* stream);
+int icsg3d_leaky_bwd_rows(const float* dy, const float* y, float alpha, int c, int64_t rows, void* dst, int ld,
+                          void* stream);
+/* sum (a-b)^2 as per-block fp64 partials (MSE and DFC feature losses, lattice_vae.py:232-233,266-269) */
+int icsg3d_sqdiff_nparts(int64_t n);
+int icsg3d_sqdiff_partials(const void* a, const void* b, int dtype, int64_t n, double* partials, int nparts,
+                           void* stream);
+/* out = [loss, pm, mse, kld] exactly as train_on_batch reports them (lattice_vae.py:124-125, 241-255) */
+int icsg3d_vae_loss_assemble(const double* partials, const int* nparts, int stride, int nterms,
+                             const double* scales, const float* kl, int B, double kl_scale, float alpha,
+                             float beta, float* out, double* raw, void* stream);
+int icsg3d_xhat_grad(const float* x, const float* xhat, float mse_coef, const void* dpm, int ld, int64_t rows,
+                     float* dy, void* stream);
+int icsg3d_tap_grad_relu(const void* a, const void* other, float coef, int64_t n, void* dc, void* stream);
+int icsg3d_bias_grad(const void* dy, int ld, int64_t rows, int C, float* db, void* stream);
+/* keras.optimizers.Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps).
+ * state: double[2] on the device = {t, lr_t}; advanced on the device so the step is CUDA-graph replayable. */
+int icsg3d_adam_keras_step(float* p, const float* g, float* m, float* v, double* state, double lr, double beta1,
+                           double beta2, double eps, float grad_scale, int64_t n, void* stream);
+
 /* Hardware probe (tools/tests only): UMMA K-major swizzled descriptors with row-shifted start addresses.
  * out: fp32 [2][nshift][128][n]; see csrc/probe.cu. */
 int icsg3d_probe_shifted_desc(const void* a, const void* b, float* out, int rows, int kc, int n, int nshift,

@@ -1,0 +1,102 @@
+"""T1 kernel-local parity: tcgen05 Conv3D fprop / dgrad / wgrad through the C ABI against the
+oracle's Keras-semantics conv (oracle/keras_ops.py::conv3d_same, torch CPU fp32) on the same bf16-rounded
+operands, plus the on-device CUDA-core cross-check.  bf16 outputs: rel-L2 <= 1e-2 (north_star tolerance);
+fp32 outputs only differ by accumulation order."""
+import pytest
+import torch
+
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (B, D, cin, cout) — the layer shapes of SURVEY §8a at reduced batch
+    (2, 32, 16, 16), (2, 32, 32, 64), (1, 32, 64, 32), (2, 16, 64, 128), (2, 8, 128, 256), (4, 4, 256, 512),
+    (8, 2, 128, 16), (1, 2, 16, 16),
+]
+
+
+def _mk(B, D, cin, cout, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, D, D, D, cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(3, 3, 3, cin, cout, generator=g) / (27 * cin) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(cout, generator=g)
+    return x, w, b
+
+
+@pytest.mark.parametrize("B,D,cin,cout", SHAPES)
+def test_fprop_matches_oracle(B, D, cin, cout):
+    from icsg3d_b200 import ops
+    from oracle import keras_ops as K
+    x, w, b = _mk(B, D, cin, cout)
+    ref = torch.relu(K.conv3d_same(x.float(), w, b))
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    wp = ops.pack_conv_w_fprop(wd)
+    y = ops.conv3d_k3(xd, wp, bd, act=ops.ACT_RELU)
+    y32 = ops.conv3d_k3(xd, wp, bd, act=ops.ACT_RELU, out_dtype=torch.float32)
+    yr = ops.conv3d_k3(xd, wp, bd, act=ops.ACT_RELU, ref=True)
+    torch.cuda.synchronize()
+    assert rel_l2(y32, ref) < 2e-5
+    assert rel_l2(yr, ref) < 2e-5
+    assert rel_l2(y.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,D,cin,cout", SHAPES[:6])
+def test_dgrad_matches_oracle(B, D, cin, cout):
+    """Conv3DBackpropInput = the same kernel on mirrored/transposed weights."""
+    from icsg3d_b200 import ops
+    from oracle import keras_ops as K
+    x, w, _ = _mk(B, D, cin, cout, seed=1)
+    g = torch.Generator().manual_seed(2)
+    dy = torch.randn(B, D, D, D, cout, generator=g).to(torch.bfloat16)
+    xr = x.float().requires_grad_(True)
+    K.conv3d_same(xr, w).backward(dy.float())
+    wp = ops.pack_conv_w_dgrad(w.cuda())
+    dx = ops.conv3d_k3(dy.cuda(), wp, None, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_l2(dx, xr.grad) < 2e-5
+
+
+@pytest.mark.parametrize("B,D,cin,cout", [(2, 32, 16, 16), (1, 32, 32, 16), (2, 16, 64, 32), (2, 8, 128, 64),
+                                          (4, 4, 64, 128), (8, 2, 128, 16), (4, 4, 16, 128), (2, 8, 256, 256)])
+def test_wgrad_matches_oracle(B, D, cin, cout):
+    from icsg3d_b200 import ops
+    from oracle import keras_ops as K
+    x, w, _ = _mk(B, D, cin, cout, seed=3)
+    g = torch.Generator().manual_seed(4)
+    dy = torch.randn(B, D, D, D, cout, generator=g).to(torch.bfloat16)
+    wr = w.clone().requires_grad_(True)
+    K.conv3d_same(x.float(), wr).backward(dy.float())
+    dw = ops.conv3d_k3_wgrad(x.cuda(), dy.cuda())
+    dw2 = ops.conv3d_k3_wgrad(x.cuda(), dy.cuda())
+    torch.cuda.synchronize()
+    assert rel_l2(dw.view(3, 3, 3, cin, cout), wr.grad) < 2e-5
+    assert torch.equal(dw, dw2), "wgrad must be deterministic (fixed-order split reduction)"
+
+
+def test_condition_fold_equals_tiled_concat():
+    """Encoder conv1 on [M | one-hot tiled 4x] (lattice_vae.py:167-173, Cin=44) == 16-channel conv on
+    [M | one-hot | 0 0] with the 4 replicas folded into the weights, borders included."""
+    from icsg3d_b200 import ops
+    from oracle import keras_ops as K, nets
+    B, D = 2, 16
+    g = torch.Generator().manual_seed(5)
+    M = torch.randn(B, D, D, D, 4, generator=g)
+    cond = torch.eye(10)[torch.tensor([3, 7])]
+    w = (torch.randn(3, 3, 3, 44, 16, generator=g) / (27 * 44) ** 0.5)
+    full = torch.cat([M, nets.tile_cond(cond, (D, D, D), reps=4)], dim=-1)
+    ref = K.conv3d_same(full.to(torch.bfloat16).float(), w.to(torch.bfloat16).float())
+    xe = torch.zeros(B, D, D, D, 16, dtype=torch.bfloat16, device="cuda")
+    ops.pack_vae_input(M.cuda(), cond.cuda(), xe, None)
+    wp = ops.pack_conv_w_fprop(w.cuda(), cin_pad=16, cin_lead=4, fold=4, fold_c=10)
+    y = ops.conv3d_k3(xe, wp, None, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_l2(y, ref) < 5e-3  # folded weights are rounded to bf16 after the sum of 4 replicas
+    # wgrad un-fold: gradient of the 4 replicas is identical
+    dy = torch.randn(B, D, D, D, 16, generator=g).to(torch.bfloat16)
+    dwp = ops.conv3d_k3_wgrad(xe, dy.cuda())
+    dw = ops.unpack_conv_dw(dwp, 44, 16, cin_lead=4, fold=4, fold_c=10)
+    fr = full.to(torch.bfloat16).float()
+    wr = w.clone().requires_grad_(True)
+    K.conv3d_same(fr, wr).backward(dy.float())
+    torch.cuda.synchronize()
+    assert rel_l2(dw, wr.grad) < 2e-5

@@ -1,0 +1,126 @@
+"""T2/T3 end-to-end parity of the VAE+DFC train step (SURVEY §8c protocol): the CUDA path (VAEEngine ->
+C ABI -> sm_100a kernels) against the oracle (oracle/nets.py, torch CPU fp32) on identical inputs, weights
+and eps.  bf16 operand mode: losses |delta| <= 1e-3 (relative to max(1,|value|)), activations reported and
+bounded, gradients reported (rel-L2, cosine) and bounded by cosine."""
+import json
+import os
+
+import pytest
+import torch
+
+from tests.util import cosine, rel_l2, synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(B=2, d=32, seed=0):
+    from icsg3d_b200.engine import VAEEngine
+    eng = VAEEngine(B, d=d, seed=3)
+    M, cond, _ = synthetic_batch(B, d=d, seed=seed)
+    eps = torch.randn(B, 256, generator=torch.Generator().manual_seed(7))
+    eng.set_inputs(M.cuda(), cond.cuda(), eps.cuda())
+    pv = {k: torch.from_numpy(v) for k, v in eng.vp.to_dict().items()}
+    pu = {k: torch.from_numpy(v) for k, v in eng.pp.to_dict().items()}
+    return eng, M, cond, eps, pv, pu
+
+
+def test_train_step_matches_oracle():
+    from oracle import nets
+    eng, M, cond, eps, pv, pu = _setup()
+    names = nets.trainable_names(pv)
+    leaves = {k: pv[k].clone().requires_grad_(True) for k in names}
+    p = dict(pv)
+    p.update(leaves)
+    taps = {}
+    (loss, pm, mse, kl), xhat = nets.vae_dfc_step(p, pu, M, cond, eps, training=True, taps=taps)
+    grads = dict(zip(names, torch.autograd.grad(loss, [leaves[k] for k in names])))
+
+    theta0 = eng.vp.theta.clone()
+    eng.train_step()
+    torch.cuda.synchronize()
+    got = eng.metrics_host()
+    want = [float(loss), float(pm), float(mse), float(kl)]
+    report = {"metrics_cuda": got, "metrics_oracle": want, "act": {}, "grad": {}}
+
+    # ---- activations (T2: reported; bounded loosely — bf16 drift grows with depth) ----
+    act = report["act"]
+    for i, L in enumerate(eng.enc, 1):
+        act[f"enc_conv{i}"] = rel_l2(L["c"].float(), taps[f"enc_conv{i}"])
+        act[f"enc_pool{i}"] = rel_l2(L["y"].float(), taps[f"enc_pool{i}"])
+    act["z_mean"] = rel_l2(eng.mu, taps["z_mean"])
+    act["z_log_var"] = rel_l2(eng.lv, taps["z_log_var"])
+    act["z"] = rel_l2(eng.z, taps["z"])
+    for i, L in enumerate(eng.dec, 1):
+        act[f"dec_conv{i}"] = rel_l2(L["c"].float(), taps[f"dec_conv{i}"])
+    act["decoder_output"] = rel_l2(eng.c5, taps["decoder_output"])
+    act["x_hat"] = rel_l2(eng.xhat, taps["x_hat"])
+    for L in eng.pm:
+        act["pm_x/" + L["name"]] = rel_l2(L["a"][0].float(), taps["pm_x/" + L["name"]])
+        act["pm_xhat/" + L["name"]] = rel_l2(L["a"][1].float(), taps["pm_xhat/" + L["name"]])
+    # ---- gradients (T3: reported) ----
+    for k in names:
+        g = eng.vp.g[k]
+        if k.endswith("/bias") and (k.startswith("enc_conv") or k.startswith("dec_conv") or k.startswith("decoder_output")) \
+                and k != "enc_conv5/bias":
+            continue  # bias directly followed by BatchNorm: gradient is analytically zero
+        report["grad"][k] = {"rel_l2": rel_l2(g, grads[k]), "cos": cosine(g, grads[k])}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/vae_step_parity.json", "w") as f:
+        json.dump(report, f, indent=1)
+    print(json.dumps(report, indent=1))
+
+    for g_, w_ in zip(got, want):
+        assert abs(g_ - w_) <= 1e-3 * max(1.0, abs(w_)), (got, want)
+    assert act["enc_conv1"] < 1e-2 and act["z_mean"] < 3e-2 and act["x_hat"] < 3e-2
+    assert act["pm_x/c2"] < 1e-2 and act["pm_x/c10"] < 5e-2
+    bad = {k: v for k, v in report["grad"].items() if v["cos"] < 0.95 and k.endswith("kernel")}
+    assert not bad, bad
+    # the optimiser moved every kernel
+    assert float((eng.vp.theta - theta0).abs().max()) > 0
+
+
+def test_eval_step_matches_oracle():
+    """test_on_batch: learning phase 0 -> moving-statistics BatchNorm everywhere."""
+    from oracle import nets
+    eng, M, cond, eps, pv, pu = _setup(seed=1)
+    # non-trivial moving statistics
+    g = torch.Generator().manual_seed(11)
+    for store, d in ((eng.vp, pv), (eng.pp, pu)):
+        for k in list(d):
+            if k.endswith("moving_mean"):
+                d[k] = torch.randn(d[k].shape, generator=g) * 0.05
+            if k.endswith("moving_variance"):
+                d[k] = torch.rand(d[k].shape, generator=g) * 0.5 + 0.75
+        store.load_dict(d)
+    eng.repack_pm()
+    (loss, pm, mse, kl), _ = nets.vae_dfc_step(pv, pu, M, cond, eps, training=False)
+    eng.eval_step()
+    torch.cuda.synchronize()
+    got = eng.metrics_host()
+    want = [float(loss), float(pm), float(mse), float(kl)]
+    print(got, want)
+    for g_, w_ in zip(got, want):
+        assert abs(g_ - w_) <= 2e-3 * max(1.0, abs(w_)), (got, want)
+
+
+def test_graph_replay_equals_eager():
+    """A CUDA-graph replay of the whole step must produce the same numbers as eager launches."""
+    eng, M, cond, eps, _, _ = _setup(seed=2)
+    theta0 = eng.vp.theta.clone()
+    eng.train_step()
+    torch.cuda.synchronize()
+    m_eager = eng.metrics.clone()
+    theta_eager = eng.vp.theta.clone()
+    # reset and replay through a graph
+    eng.vp.theta.copy_(theta0)
+    eng.vp.adam_m.zero_(); eng.vp.adam_v.zero_(); eng.vp.adam_state.zero_(); eng.vp.grad.zero_()
+    for k, v in eng.vp.p.items():
+        if k.endswith("moving_mean"):
+            v.zero_()
+        if k.endswith("moving_variance"):
+            v.fill_(1.0)
+    eng.capture_train_graph()
+    eng.train_step()
+    torch.cuda.synchronize()
+    assert torch.allclose(eng.metrics, m_eager, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(eng.vp.theta, theta_eager, rtol=1e-4, atol=1e-6)
