@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Headline benchmark: VAE+DFC train samples/s @32^3 (BASELINE.json `metric`, configs[1]: batch 32 per GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # the sm_100a path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+One "step" = one full train_on_batch of the conditional DFC-VAE against the frozen perceptual U-Net prefix
+(forward, DFC/MSE/KL losses, backward, Keras-Adam) on a batch of synthetic voxelised perovskite grids made on
+the device by the CUDA voxeliser.  N>1: one process per GPU (torchrun), batch 32 per GPU (weak scaling; global
+batch 256 at N=8 = configs[2]), NCCL all-reduce of BatchNorm statistic sums and of the flat gradient buffer.
+
+Prints ONE JSON line (rank 0).  Keys: see the round contract — `value` is device-timed with inputs resident in
+HBM (CUDA-graph replay); `e2e` goes through the public API (LatticeDFCVAE.model.train_on_batch) with pinned
+host inputs copied H2D and the metrics read back D2H every step; `roofline` is the tcgen05 implicit-GEMM conv
+kernel (all fprop/dgrad launches of a step) timed live with CUDA events; `cpu_baseline` is the oracle port
+timed on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 32
+D = 32
+METRIC = "vae_dfc_train_samples_per_sec_32cubed"
+GFLOP_PER_SAMPLE = 36.05  # algorithmic conv FLOPs of one VAE+DFC train step per sample @32^3
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:  # noqa: BLE001
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the Keras graphs on the host cores
+# --------------------------------------------------------------------------------------------------
+def oracle_cpu_steps(batch, steps, warmup, seed=0):
+    """Times `steps` oracle train steps (torch CPU fp32, all host threads) on `batch` synthetic samples."""
+    import numpy as np
+    import torch
+    from oracle import nets, voxelizer as vox
+
+    rng = np.random.default_rng(seed)
+    M = np.zeros((batch, D, D, D, 4), dtype=np.float32)
+    for b in range(batch):
+        N, z, l, sigma = vox.synthetic_cell(rng)
+        dens, _ = vox.density_matrix(N, z, l, dims=(D, D, D), sigma=sigma)
+        M[b, ..., 0] = dens
+        M[b, ..., 1:] = vox.coordinate_grid(l, dim=D)
+    M = torch.from_numpy(M)
+    cond = torch.eye(10)[torch.from_numpy(rng.integers(0, 10, size=batch))]
+    pv, pu = nets.init_vae_params(1), nets.init_unet_params(2)
+    opt = nets.KerasAdam(5e-4)
+    gen = torch.Generator().manual_seed(seed)
+    for _ in range(warmup):
+        nets.vae_train_step(pv, pu, opt, M, cond, torch.randn(batch, 256, generator=gen))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        nets.vae_train_step(pv, pu, opt, M, cond, torch.randn(batch, 256, generator=gen))
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cpu_batch = 4  # bounded sample of the batch-32 workload; per-sample cost is batch independent on CPU
+    sps, ms, cores = oracle_cpu_steps(cpu_batch, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "VAE+DFC train step @32^3, batch 32/GPU (configs[1])", "grid": D,
+                   "note": "reference CPU arm: oracle port of the Keras graphs (TF/Keras not installable), torch CPU fp32"},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} train steps at batch {cpu_batch} of the batch-32 workload"},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# the sm_100a arm
+# --------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the icsg3d hot path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from icsg3d_b200 import ops, utils
+    from icsg3d_b200.engine import Dist
+    from icsg3d_b200.vae.lattice_vae import LatticeDFCVAE
+
+    peaks = load_peaks()
+    B = args.batch
+    vae = LatticeDFCVAE(perceptual_model=None, device=dev, dist=Dist() if world > 1 else None, seed=1,
+                        use_cuda_graph=not args.no_graph)
+    vae._set_model(batch_size=B)
+    eng = vae.engine(B)
+    M, cond, _ = utils.synthetic_batch(B, d=D, seed=1000 + rank, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(2)
+    eps = torch.randn(B, 256, device=dev, generator=gen)
+    eng.set_inputs(M, cond, eps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm (value) ----
+    l0 = ops.launch_count()
+    eng._train_body()  # eager once (also the launch count of one step)
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() - l0
+    if not args.no_graph:
+        eng.capture_train_graph(snapshot=False)
+    for _ in range(max(args.warmup, 3)):
+        eng.train_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.train_step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = B * world / (ms_step * 1e-3)
+    metrics = eng.metrics_host()
+
+    # ---- end-to-end arm through the public API with host buffers ----
+    Mh = M.cpu().pin_memory()
+    ch = cond.cpu().pin_memory()
+    for _ in range(3):
+        vae.model.train_on_batch([Mh, ch], Mh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vae.model.train_on_batch([Mh, ch], Mh)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / float(dt.item())
+    h2d = Mh.numel() * 4 + ch.numel() * 4
+    d2h = 4 * 4
+
+    # ---- roofline pass: per-launch CUDA-event timing of the conv kernels (eager, same stream) ----
+    roof, per_layer = None, None
+    if rank == 0:
+        for _ in range(2):
+            eng._train_body()
+        torch.cuda.synchronize()
+        ops.TIMING = []
+        reps = 3
+        for _ in range(reps):
+            eng._train_body()
+        torch.cuda.synchronize()
+        rec, ops.TIMING = ops.TIMING, None
+        agg = {}
+        for (kind, tag), fl, a, b in rec:
+            d = agg.setdefault((kind, tag), [0.0, 0.0, 0])
+            d[0] += fl
+            d[1] += a.elapsed_time(b)
+            d[2] += 1
+        ig_f = sum(v[0] for (k, _), v in agg.items() if k == "igemm")
+        ig_ms = sum(v[1] for (k, _), v in agg.items() if k == "igemm")
+        wg_f = sum(v[0] for (k, _), v in agg.items() if k == "wgrad")
+        wg_ms = sum(v[1] for (k, _), v in agg.items() if k == "wgrad")
+        n_ig = sum(v[2] for (k, _), v in agg.items() if k == "igemm")
+        achieved = ig_f / (ig_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv3d_k3_igemm_kernel (tcgen05 implicit GEMM, fprop+dgrad)",
+                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["src"] + " (sustained)",
+                "algorithmic_gflop_per_launch": ig_f / n_ig / 1e9, "avg_launch_ms": ig_ms / n_ig,
+                "launches_per_step": n_ig // reps, "kernel_ms_per_step": ig_ms / reps,
+                "wgrad": {"achieved": wg_f / (wg_ms * 1e-3) / 1e12 if wg_ms else None, "kernel_ms_per_step": wg_ms / reps}}
+        per_layer = {f"{k}:{t}": {"gflop": v[0] / v[2] / 1e9, "ms": v[1] / v[2], "tflops": v[0] / (v[1] * 1e-3) / 1e12}
+                     for (k, t), v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "bench_per_layer.json"), "w") as f:
+            json.dump({"ms_per_step_graph": ms_step, "per_layer": per_layer}, f, indent=1)
+
+    # ---- CPU baseline (rank 0, N == 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sps, ms, cores = oracle_cpu_steps(2, 2, 1)
+        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "2 oracle train steps at batch 2 of the batch-32 workload (per-sample cost is batch independent)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "VAE+DFC train step @32^3, batch 32/GPU (configs[1]); N>1 = configs[2] data parallel",
+                       "grid": D, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": "per-step working set (~2 GB of activations) exceeds the 126 MB L2; no flush needed",
+                       "cuda_graph": not args.no_graph, "gflop_per_sample": GFLOP_PER_SAMPLE},
+            "conv_tflops_whole_step": GFLOP_PER_SAMPLE * value / 1e3,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "loss": {"loss": metrics[0], "pm": metrics[1], "mse": metrics[2], "kld": metrics[3]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

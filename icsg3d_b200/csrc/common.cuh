@@ -27,7 +27,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (_e != cudaSuccess) return ::icsg3d::cuda_fail(_e, #expr, __FILE__, __LINE__); \
   } while (0)
 
-#define ICSG_CHECK_LAUNCH() ICSG_CUDA(cudaPeekAtLastError())
+// Every kernel launch of the library goes through this macro: it also feeds icsg3d_launch_count().
+extern unsigned long long g_launches;
+#define ICSG_CHECK_LAUNCH()              \
+  do {                                   \
+    ++::icsg3d::g_launches;              \
+    ICSG_CUDA(cudaPeekAtLastError());    \
+  } while (0)
 
 #define ICSG_REQUIRE(cond, ...)                 \
   do {                                          \

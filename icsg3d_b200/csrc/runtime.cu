@@ -8,6 +8,7 @@
 namespace icsg3d {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -95,5 +96,7 @@ const char* icsg3d_last_error(void) { return icsg3d::g_err; }
 int icsg3d_version(void) { return 100; }
 
 int icsg3d_sm_count(void) { return icsg3d::sm_count(); }
+
+int64_t icsg3d_launch_count(void) { return static_cast<int64_t>(icsg3d::g_launches); }
 
 }  // extern "C"

@@ -1,0 +1,158 @@
+// Gaussian atomic-density voxeliser on the device — replaces utils.py:88-144 of the reference
+// (coordinate_grid, density_matrix; called from create_matrices.py:142-155).
+//
+// One thread per voxel, the (<= 64) sites of the cell staged in shared memory.  The species predicate
+// D[v,s] < sigma_s*label_frac is evaluated in fp64 in EXACTLY the operation order of numpy/scipy
+// (np.linspace: i*step + start; + dv/2; cdist: sqrt of the left-to-right sum of squares) — this file is
+// compiled with --fmad=false and without fast-math so no multiply-add is contracted — which makes the
+// integer species grid bit-exact against the reference.  Species rule in closed form:
+// |Q|=0 -> 0, |Q|=1 -> z of that site, |Q|>=2 -> z[argmin_s D] over all sites, first index on ties.
+//
+// Per-site record (8 doubles): x, y, z (Cartesian), thr = sigma*label_frac, zs = Z/sigma^3, two_s2 = 2*sigma^2,
+// Z, unused.  The host wrapper computes thr/zs/two_s2 with numpy for parity runs (np.power is libm pow);
+// icsg3d_synth_perovskite_sites produces them on the device for the benchmark generator.
+#include "common.cuh"
+
+namespace icsg3d {
+
+static constexpr int kMaxSites = 64;
+static constexpr int kSiteRec = 8;
+
+__global__ void __launch_bounds__(256) voxelize_kernel(const double* __restrict__ sites, const int* __restrict__ nsites,
+                                                       const double* __restrict__ lattice, int max_sites, int d,
+                                                       double eps_frac, float* __restrict__ m32,
+                                                       double* __restrict__ m64, uint8_t* __restrict__ species,
+                                                       double* __restrict__ species64) {
+  __shared__ double s_site[kMaxSites * kSiteRec];
+  const int cell = blockIdx.y;
+  const int n = nsites[cell];
+  for (int i = threadIdx.x; i < n * kSiteRec; i += blockDim.x)
+    s_site[i] = sites[static_cast<size_t>(cell) * max_sites * kSiteRec + i];
+  __syncthreads();
+  const long long vox = static_cast<long long>(d) * d * d;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= vox) return;
+  const int k = static_cast<int>(v % d);
+  const int j = static_cast<int>((v / d) % d);
+  const int i = static_cast<int>(v / (static_cast<long long>(d) * d));
+  const int ijk[3] = {i, j, k};
+  double c[3], p[3];
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const double a = lattice[cell * 3 + ax];
+    // density_matrix (utils.py:101-115)
+    const double dv = (a + ((2.0 * a) * eps_frac)) / static_cast<double>(d);
+    const double start = -a * eps_frac;
+    const double stop = a + (a * eps_frac);
+    const double step = (stop - start) / static_cast<double>(d);
+    const double corner = static_cast<double>(ijk[ax]) * step + start;
+    c[ax] = corner + dv / 2.0;
+    // coordinate_grid (utils.py:88-94)
+    const double stop2 = a + ((2.0 * eps_frac) * a);
+    const double step2 = (stop2 - 0.0) / static_cast<double>(d);
+    p[ax] = static_cast<double>(ijk[ax]) * step2 + 0.0;
+  }
+  int count = 0, first_in = 0, nearest = 0;
+  double dmin = 0.0, acc = 0.0;
+  for (int s = 0; s < n; ++s) {
+    const double* r = s_site + s * kSiteRec;
+    const double dx = c[0] - r[0], dy = c[1] - r[1], dz = c[2] - r[2];
+    double ss = dx * dx;
+    ss = ss + dy * dy;
+    ss = ss + dz * dz;
+    const double D = sqrt(ss);
+    if (D < r[3]) {
+      if (count == 0) first_in = s;
+      ++count;
+    }
+    if (s == 0 || D < dmin) {
+      dmin = D;
+      nearest = s;
+    }
+    const double D2 = D * D;                       // utils.py:135  D ** 2
+    const double g = exp((-1.0 * D2) / r[5]);      // utils.py:137
+    acc = acc + g * r[4];                          // utils.py:138  np.dot(D, z/sigma^3)
+  }
+  const double norm = 1.0 / 15.749609945722419;    // 1/(2*pi)^1.5 (utils.py:139)
+  const double dens = norm * acc;
+  double spec = 0.0;
+  if (count == 1) spec = s_site[first_in * kSiteRec + 6];
+  else if (count >= 2) spec = s_site[nearest * kSiteRec + 6];
+  const size_t o = static_cast<size_t>(cell) * vox + v;
+  if (m32) reinterpret_cast<float4*>(m32)[o] = make_float4(static_cast<float>(dens), static_cast<float>(p[0]),
+                                                           static_cast<float>(p[1]), static_cast<float>(p[2]));
+  if (m64) m64[o] = dens;
+  if (species) species[o] = static_cast<uint8_t>(spec);
+  if (species64) species64[o] = spec;
+}
+
+// splitmix64: stateless per-cell random numbers for the synthetic ABX3 generator
+__device__ __forceinline__ uint64_t splitmix(uint64_t& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(uint64_t& s) { return static_cast<double>(splitmix(s) >> 11) * (1.0 / 9007199254740992.0); }
+
+// Cubic-perovskite-like ABX3 cells: A(0,0,0) B(.5,.5,.5) X(.5,.5,0),(.5,0,.5),(0,.5,.5);
+// a,b,c ~ U(3.7,4.3) A; Z_A in {20,38,56,57,58,59,60}, Z_B in 22..30, Z_X in {8,9,17}; radii plausible.
+__global__ void synth_sites_kernel(uint64_t seed, int ncells, int max_sites, double label_frac, double* __restrict__ sites,
+                                   int* __restrict__ nsites, double* __restrict__ lattice) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncells) return;
+  uint64_t s = seed * 0xD1342543DE82EF95ull + static_cast<uint64_t>(cell) * 0x2545F4914F6CDD1Dull + 1;
+  double l[3];
+  for (int ax = 0; ax < 3; ++ax) l[ax] = 3.7 + 0.6 * u01(s);
+  const int za_tab[7] = {20, 38, 56, 57, 58, 59, 60};
+  const int zx_tab[3] = {8, 9, 17};
+  const double za = za_tab[splitmix(s) % 7];
+  const double zb = 22 + static_cast<int>(splitmix(s) % 9);
+  const double zx = zx_tab[splitmix(s) % 3];
+  const double ra = 1.0 + 0.6 * u01(s), rb = 0.5 + 0.4 * u01(s), rx = 1.1 + 0.4 * u01(s);
+  const double frac[5][3] = {{0, 0, 0}, {0.5, 0.5, 0.5}, {0.5, 0.5, 0}, {0.5, 0, 0.5}, {0, 0.5, 0.5}};
+  const double zz[5] = {za, zb, zx, zx, zx};
+  const double rr[5] = {ra, rb, rx, rx, rx};
+  double* out = sites + static_cast<size_t>(cell) * max_sites * kSiteRec;
+  for (int i = 0; i < 5; ++i) {
+    out[i * kSiteRec + 0] = frac[i][0] * l[0];
+    out[i * kSiteRec + 1] = frac[i][1] * l[1];
+    out[i * kSiteRec + 2] = frac[i][2] * l[2];
+    out[i * kSiteRec + 3] = rr[i] * label_frac;
+    out[i * kSiteRec + 4] = zz[i] / (rr[i] * rr[i] * rr[i]);
+    out[i * kSiteRec + 5] = 2.0 * (rr[i] * rr[i]);
+    out[i * kSiteRec + 6] = zz[i];
+    out[i * kSiteRec + 7] = rr[i];
+  }
+  nsites[cell] = 5;
+  for (int ax = 0; ax < 3; ++ax) lattice[cell * 3 + ax] = l[ax];
+}
+
+}  // namespace icsg3d
+
+using namespace icsg3d;
+
+extern "C" int icsg3d_voxelize(const double* sites, const int* nsites, const double* lattice, int ncells, int max_sites,
+                               int d, double eps_frac, float* m32, double* m64, uint8_t* species, double* species64,
+                               void* stream) {
+  ICSG_REQUIRE(sites && nsites && lattice, "voxelize: null pointer");
+  ICSG_REQUIRE(m32 || m64 || species || species64, "voxelize: no output requested");
+  ICSG_REQUIRE(max_sites >= 1 && max_sites <= kMaxSites, "voxelize: max_sites must be in [1,%d]", kMaxSites);
+  ICSG_REQUIRE(ncells >= 1 && ncells <= 65535 && d >= 1 && d <= 512, "voxelize: bad ncells/d");
+  const long long vox = static_cast<long long>(d) * d * d;
+  dim3 grid(static_cast<unsigned>((vox + 255) / 256), ncells);
+  voxelize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(sites, nsites, lattice, max_sites, d, eps_frac, m32,
+                                                                      m64, species, species64);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_synth_perovskite_sites(uint64_t seed, int ncells, int max_sites, double label_frac, double* sites,
+                                             int* nsites, double* lattice, void* stream) {
+  ICSG_REQUIRE(sites && nsites && lattice && max_sites >= 5 && max_sites <= kMaxSites, "synth_perovskite_sites: bad arguments");
+  synth_sites_kernel<<<ceil_div(ncells, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(seed, ncells, max_sites, label_frac,
+                                                                                         sites, nsites, lattice);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}

@@ -203,10 +203,10 @@ class VAEEngine:
         """dW of conv `name` into the flat gradient buffer (Keras layout)."""
         g = self.vp.g[name + "/kernel"]
         if cin == cin_pad and cout == cout_pad and fold is None:
-            ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=g.view(27, cin, cout))
+            ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=g.view(27, cin, cout), tag=name + ".wgrad")
             return
         scratch = self.ctx.dw_pad[: 27 * cin_pad * cout_pad].view(27, cin_pad, cout_pad)
-        ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=scratch)
+        ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=scratch, tag=name + ".wgrad", nominal=(cin, cout))
         if fold is None:
             ops.unpack_conv_dw(scratch, cin, cout, out=g)
         else:
@@ -242,13 +242,15 @@ class VAEEngine:
         p = self.vp.p
         x = self.xe
         for L in self.enc:
-            ops.conv3d_k3(x, L["wf"], p[L["name"] + "/bias"], out=L["c"])
+            ops.conv3d_k3(x, L["wf"], p[L["name"] + "/bias"], out=L["c"], tag=L["name"] + ".fprop",
+                          nominal=(4 + 4 * self.ncond, L["cout"]) if L is self.enc[0] else None)
             bn = L["bn"]
             self._bn_fwd(L["c"], L["cout"], L["bns"], p[bn + "/gamma"], p[bn + "/beta"],
                          p[bn + "/moving_mean"], p[bn + "/moving_variance"], training, ACT_LEAKY, POST_POOL2, y=L["y"],
                          idx=L["idx"])
             x = L["y"]
-        ops.conv3d_k3(x, self.e5_wf, p["enc_conv5/bias"], out=self.e5, n_store=4, act=ACT_LEAKY)
+        ops.conv3d_k3(x, self.e5_wf, p["enc_conv5/bias"], out=self.e5, n_store=4, act=ACT_LEAKY, tag="enc_conv5.fprop",
+                      nominal=(self.filters[-1], 4))
         ops.dense_fwd(self.e5.view(self.B, -1), p["enc_dense/kernel"], p["enc_dense/bias"], self.h, act=ACT_RELU)
         ops.dense_fwd(self.h, p["z_mean/kernel"], p["z_mean/bias"], self.mu)
         ops.dense_fwd(self.h, p["z_log_var/kernel"], p["z_log_var/bias"], self.lv)
@@ -261,12 +263,14 @@ class VAEEngine:
         ops.f32_to_bf16_rows(self.dd, 4, self.d0)
         x = self.d0
         for L in self.dec:
-            ops.conv3d_k3(x, L["wf"], p[L["name"] + "/bias"], out=L["c"])
+            ops.conv3d_k3(x, L["wf"], p[L["name"] + "/bias"], out=L["c"], tag=L["name"] + ".fprop",
+                          nominal=(4, L["cout"]) if L is self.dec[0] else None)
             bn = L["bn"]
             self._bn_fwd(L["c"], L["cout"], L["bns"], p[bn + "/gamma"], p[bn + "/beta"], p[bn + "/moving_mean"],
                          p[bn + "/moving_variance"], training, ACT_LEAKY, POST_UP2 if L["up"] else POST_NONE, y=L["u"])
             x = L["u"]
-        ops.conv3d_k3(x, self.out_wf, p["decoder_output/bias"], out=self.c5, n_store=4)
+        ops.conv3d_k3(x, self.out_wf, p["decoder_output/bias"], out=self.c5, n_store=4, tag="decoder_output.fprop",
+                      nominal=(self.filters[0], 4))
         self._bn_fwd(self.c5, 4, self.bn5, p["dec_bn5/gamma"], p["dec_bn5/beta"], p["dec_bn5/moving_mean"],
                      p["dec_bn5/moving_variance"], training, ACT_RELU, POST_NONE, y=self.xhat16, y32=self.xhat)
 
@@ -277,7 +281,8 @@ class VAEEngine:
         x = self.xp if branch == 0 else self.xhat16
         for L in self.pm:
             n = L["name"]
-            ops.conv3d_k3(x, L["wf"], p[n + "/bias"], out=L["a"][branch], act=ACT_RELU)
+            ops.conv3d_k3(x, L["wf"], p[n + "/bias"], out=L["a"][branch], act=ACT_RELU, tag=f"pm{branch}.{n}.fprop",
+                          nominal=(4, L["cout"]) if n == "c1" else None)
             if not L["has_bn"]:
                 break
             bn = "bn_" + n
@@ -334,7 +339,7 @@ class VAEEngine:
         last = self.pm[-1]
         ops.tap_grad_relu(last["a"][1], last["a"][0], coef[last["name"]], last["dc"])
         dy = self.pm[-2]["dy"]
-        ops.conv3d_k3(last["dc"], last["wd"], None, out=dy)
+        ops.conv3d_k3(last["dc"], last["wd"], None, out=dy, tag="pm1.c10.dgrad")
         for li in range(len(self.pm) - 2, -1, -1):
             L = self.pm[li]
             self._bn_bwd(dy, L["a"][1], L["cout"], L["bnst"][1], ACT_NONE, POST_POOL2 if L["pool"] else POST_NONE,
@@ -342,16 +347,16 @@ class VAEEngine:
                          tap_coef=coef.get(L["name"], 0.0))
             if li > 0:
                 dy = self.pm[li - 1]["dy"]
-                ops.conv3d_k3(L["dc"], L["wd"], None, out=dy)
+                ops.conv3d_k3(L["dc"], L["wd"], None, out=dy, tag=f"pm1.{L['name']}.dgrad")
             else:
-                ops.conv3d_k3(L["dc"], L["wd"], None, out=self.dxh16)
+                ops.conv3d_k3(L["dc"], L["wd"], None, out=self.dxh16, tag="pm1.c1.dgrad", nominal=(L["cout"], 4))
         # ---- decoder ----
         ops.xhat_grad(self.M, self.xhat, 2.0 / (self.M.numel() // self.B * Bg), self.dxh16, self.dxhat)
         self._bn_bwd(self.dxhat, self.c5, 4, self.bn5, ACT_RELU, POST_NONE, None, self.dc5, dgamma=g["dec_bn5/gamma"],
                      dbeta=g["dec_bn5/beta"])
         lastd = self.dec[-1]
         self._wgrad(lastd["u"], self.dc5, "decoder_output", lastd["cout"], 4, lastd["cout"], 16)
-        ops.conv3d_k3(self.dc5, self.out_wd, None, out=lastd["du"])
+        ops.conv3d_k3(self.dc5, self.out_wd, None, out=lastd["du"], tag="decoder_output.dgrad", nominal=(4, lastd["cout"]))
         for li in range(len(self.dec) - 1, -1, -1):
             L = self.dec[li]
             bn = L["bn"]
@@ -360,7 +365,8 @@ class VAEEngine:
             xin = self.dec[li - 1]["u"] if li > 0 else self.d0
             cin = self.dec[li - 1]["cout"] if li > 0 else 4
             self._wgrad(xin, L["dc"], L["name"], cin, L["cout"], L["cin_pad"], L["cout"])
-            ops.conv3d_k3(L["dc"], L["wd"], None, out=self.dec[li - 1]["du"] if li > 0 else self.dy_d0)
+            ops.conv3d_k3(L["dc"], L["wd"], None, out=self.dec[li - 1]["du"] if li > 0 else self.dy_d0,
+                          tag=L["name"] + ".dgrad", nominal=(L["cout"], 4) if li == 0 else None)
         # ---- bottleneck ----
         ops.bf16_rows_to_f32(self.dy_d0, 4, self.ddd)
         ops.dense_bwd(self.z, p["dec_dense/kernel"], None, self.ddd, g["dec_dense/kernel"], g["dec_dense/bias"], x2=self.cond,
@@ -376,7 +382,7 @@ class VAEEngine:
         e4 = self.enc[-1]
         ops.bias_grad(self.dc_e5, 4, g["enc_conv5/bias"])
         self._wgrad(e4["y"], self.dc_e5, "enc_conv5", e4["cout"], 4, e4["cout"], 16)
-        ops.conv3d_k3(self.dc_e5, self.e5_wd, None, out=e4["dy"])
+        ops.conv3d_k3(self.dc_e5, self.e5_wd, None, out=e4["dy"], tag="enc_conv5.dgrad", nominal=(4, e4["cout"]))
         for li in range(len(self.enc) - 1, -1, -1):
             L = self.enc[li]
             bn = L["bn"]
@@ -384,7 +390,7 @@ class VAEEngine:
                          dgamma=g[bn + "/gamma"], dbeta=g[bn + "/beta"])
             if li > 0:
                 self._wgrad(self.enc[li - 1]["y"], L["dc"], L["name"], L["cin_pad"], L["cout"], L["cin_pad"], L["cout"])
-                ops.conv3d_k3(L["dc"], L["wd"], None, out=self.enc[li - 1]["dy"])
+                ops.conv3d_k3(L["dc"], L["wd"], None, out=self.enc[li - 1]["dy"], tag=L["name"] + ".dgrad")
             else:
                 self._wgrad(self.xe, L["dc"], L["name"], 4 + 4 * self.ncond, L["cout"], 16, L["cout"], fold=(4, 4, self.ncond))
 

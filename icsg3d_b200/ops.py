@@ -37,6 +37,10 @@ def _chk(t, dtype, name):
         raise ValueError(f"{name}: tensor must be contiguous")
 
 
+def launch_count() -> int:
+    return int(_lib.lib().icsg3d_launch_count())
+
+
 def pad16(c: int) -> int:
     return (c + 15) // 16 * 16
 
@@ -81,8 +85,29 @@ def unpack_conv_dw(dw_pad, cin, cout, cin_lead=0, fold=1, fold_c=0, out=None):
     return out
 
 
+# Optional per-launch timing of the dominant kernel (bench.py's roofline pass): when TIMING is a list, every
+# tcgen05 conv launch appends (tag, algorithmic_flops, start_event, end_event).
+TIMING = None
+
+
+def _timed(tag, flops):
+    class _T:
+        def __enter__(self):
+            if TIMING is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            return self
+
+        def __exit__(self, *a):
+            if TIMING is not None:
+                self.e1.record()
+                TIMING.append((tag, flops, self.e0, self.e1))
+    return _T()
+
+
 def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alpha=LEAKY_ALPHA, out=None,
-              out_dtype=torch.bfloat16, ref=False):
+              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv"):
     """x: bf16 [B,D,H,W,ldx]; wpack: bf16 [27][nout][cin]; returns y [B,D,H,W,n_store].
 
     `ref=True` runs the CUDA-core cross-check kernel (fp32 output) instead of the tcgen05 kernel.
@@ -107,15 +132,17 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
     if out is None:
         out = torch.empty((B, D, H, W, n_store), dtype=out_dtype, device=x.device)
     ydt = DT_BF16 if out.dtype == torch.bfloat16 else DT_F32
-    _lib.call("icsg3d_conv3d_k3_igemm", _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), out.shape[-1], ydt, n_store,
-              B, D, H, W, cin, nout, act, alpha, _stream())
+    nc, no = nominal if nominal else (cin, nout)
+    with _timed(("igemm", tag), 2.0 * B * D * H * W * 27 * nc * no):
+        _lib.call("icsg3d_conv3d_k3_igemm", _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), out.shape[-1], ydt,
+                  n_store, B, D, H, W, cin, nout, act, alpha, _stream())
     return out
 
 
 _wgrad_ws = {}
 
 
-def conv3d_k3_wgrad(x, dy, *, cin=None, cout=None, out=None, ref=False):
+def conv3d_k3_wgrad(x, dy, *, cin=None, cout=None, out=None, ref=False, nominal=None, tag="wgrad"):
     """dW[27][cin][cout] (fp32) = sum_v x[v+tap, ci] * dy[v, co]; x,dy bf16 NDHWC."""
     _chk(x, torch.bfloat16, "x")
     _chk(dy, torch.bfloat16, "dy")
@@ -136,8 +163,10 @@ def conv3d_k3_wgrad(x, dy, *, cin=None, cout=None, out=None, ref=False):
     if ws is None or ws.numel() < need:
         ws = torch.empty(int(need), dtype=torch.uint8, device=x.device)
         _wgrad_ws[key] = ws
-    _lib.call("icsg3d_conv3d_k3_wgrad", _ptr(x), ldx, _ptr(dy), ldy, _ptr(out), B, D, H, W, cin, cout, _ptr(ws),
-              ctypes.c_int64(ws.numel()), _stream())
+    nc, no = nominal if nominal else (cin, cout)
+    with _timed(("wgrad", tag), 2.0 * B * D * H * W * 27 * nc * no):
+        _lib.call("icsg3d_conv3d_k3_wgrad", _ptr(x), ldx, _ptr(dy), ldy, _ptr(out), B, D, H, W, cin, cout, _ptr(ws),
+                  ctypes.c_int64(ws.numel()), _stream())
     return out
 
 

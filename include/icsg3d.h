@@ -46,6 +46,8 @@ const char* icsg3d_last_error(void);
 int icsg3d_version(void);
 /* Number of SMs of the current device (148 on B200); <0 on error. */
 int icsg3d_sm_count(void);
+/* Number of kernels this library has launched (or captured into a CUDA graph) in this process. */
+int64_t icsg3d_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv3D 3x3x3, stride 1, "same" — Keras Conv3D(kernel_size=(3,3,3), padding="same")
@@ -184,6 +186,23 @@ int icsg3d_bias_grad(const void* dy, int ld, int64_t rows, int C, float* db, voi
  * state: double[2] on the device = {t, lr_t}; advanced on the device so the step is CUDA-graph replayable. */
 int icsg3d_adam_keras_step(float* p, const float* g, float* m, float* v, double* state, double lr, double beta1,
                            double beta2, double eps, float grad_scale, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gaussian atomic-density voxeliser — utils.py:97-144 density_matrix + utils.py:88-94 coordinate_grid
+ * (create_matrices.py:142-155).  sites: fp64 [ncells][max_sites][8] records
+ * (x, y, z Cartesian, thr = sigma*label_frac, zs = Z/sigma^3, two_s2 = 2*sigma^2, Z, unused);
+ * nsites int32 [ncells]; lattice fp64 [ncells][3] = (a,b,c).  Outputs (each optional):
+ *   m32       fp32  [ncells][d][d][d][4]  network input (density, p_x, p_y, p_z)
+ *   m64       fp64  [ncells][d][d][d]     density M exactly as the reference returns it
+ *   species   uint8 [ncells][d][d][d]     species grid S (bit-exact; fp64 predicate, no FMA contraction)
+ *   species64 fp64  [ncells][d][d][d]     S in the reference's dtype
+ * ---------------------------------------------------------------------------------------------- */
+int icsg3d_voxelize(const double* sites, const int* nsites, const double* lattice, int ncells, int max_sites,
+                    int d, double eps_frac, float* m32, double* m64, uint8_t* species, double* species64,
+                    void* stream);
+/* On-device synthetic perovskite-like ABX3 cells (benchmark inputs); 5 sites per cell. */
+int icsg3d_synth_perovskite_sites(uint64_t seed, int ncells, int max_sites, double label_frac, double* sites,
+                                  int* nsites, double* lattice, void* stream);
 
 /* Hardware probe (tools/tests only): UMMA K-major swizzled descriptors with row-shifted start addresses.
  * out: fp32 [2][nshift][128][n]; see csrc/probe.cu. */
