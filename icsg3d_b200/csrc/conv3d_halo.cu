@@ -1,0 +1,365 @@
+// Conv3D 3x3x3 "same" — halo-reuse implicit GEMM on tcgen05 / TMEM (sm_100a).  Second-generation kernel
+// for layers with W >= 8: the per-tap re-fetch of the A operand (27x L2->SM traffic in conv3d_igemm.cu)
+// is replaced by ONE TMA load of a halo'd activation block; every tap is the same block read through a
+// UMMA descriptor whose start address is shifted by a whole number of rows.
+//
+//   * work item = output region TD x TH x W (full width) of one sample (x one N tile);
+//   * A block in smem = (TD+2) x (TH+2) x (W+1) voxels x KC channels per channel chunk, row pitch KC*2 bytes
+//     (hardware swizzle = row pitch), delivered by one 5-D tiled TMA box per chunk starting at
+//     (w,h,d) = (-1, h0-1, d0-1): out-of-bounds zero fill = "same" padding.  The row pitch in W is W+1:
+//     column 0 of every row is the zero pad w=-1 and doubles as the pad w=W of the previous row;
+//   * flat row index f = (dl*HP + hl)*WP + wl addresses the block; output voxel (dl,hl,wl) has its
+//     (kd,kh,kw) input at f + kd*HP*WP + kh*WP + kw, so an M tile of 128 consecutive f and a tap shift are
+//     both plain row offsets of the descriptor start address (measured on B200: K-major swizzled
+//     descriptors accept arbitrary row-shifted starts, profiles/r01_conv_probe_bringup.jsonl "shift");
+//     rows with hl >= TH or wl == W are junk and are skipped by the epilogue;
+//   * loop order is tap-outer: each weight tile B[tap][N x KC] streams through a small TMA ring once per
+//     work item and is applied to all G = ceil(TD*HP*WP/128) M tiles, whose accumulators live side by side
+//     in TMEM (G*NT <= 512 columns);
+//   * the epilogue drains tile g as soon as the item completes and hands the accumulator back per tile, so the
+//     next item's first taps overlap with the previous item's drain; the A block is double buffered when
+//     shared memory allows.
+#include "common.cuh"
+#include "conv3d_halo.cuh"
+
+namespace icsg3d {
+
+
+
+static constexpr int kHaloThreads = 192;
+static constexpr int kHaloMaxG = 32;
+static constexpr int kHaloMaxBStages = 8;
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const ConvHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2];
+  __shared__ __align__(8) uint64_t b_full[kHaloMaxBStages], b_empty[kHaloMaxBStages];
+  __shared__ __align__(8) uint64_t acc_full;
+  __shared__ __align__(8) uint64_t acc_empty[kHaloMaxG];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t b_ring_off = static_cast<uint32_t>(p.a_bufs) * p.a_buf_bytes;
+
+  // Zero the guard row that follows every A chunk block: it is the w=W pad of the block's last row.
+  {
+    const int words = p.row_bytes / 4;
+    for (int i = threadIdx.x; i < p.a_bufs * p.chunks * words; i += blockDim.x) {
+      const int buf = i / (p.chunks * words);
+      const int ch = (i / words) % p.chunks;
+      const int w = i % words;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sm + static_cast<size_t>(buf) * p.a_buf_bytes +
+                                                  static_cast<size_t>(ch) * p.a_chunk_bytes +
+                                                  static_cast<size_t>(p.block_rows) * p.row_bytes);
+      dst[w] = 0u;
+    }
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    for (int g = 0; g < p.G; ++g) mbar_init(&acc_empty[g], 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int units = 27 * p.chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int bstage = 0;
+      uint32_t bphase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        int t = item;
+        const int tn = t % p.tiles_n;
+        t /= p.tiles_n;
+        const int hb = t % p.n_hblk;
+        t /= p.n_hblk;
+        const int db = t % p.n_dblk;
+        const int n = t / p.n_dblk;
+        const int buf = it % p.a_bufs;
+        const uint32_t aph = static_cast<uint32_t>(it / p.a_bufs) & 1u;
+        mbar_wait(&a_empty[buf], aph ^ 1u);
+        mbar_expect_tx(&a_full[buf], p.a_tx_bytes);
+        for (int ch = 0; ch < p.chunks; ++ch)
+          tma_load_5d(sm + static_cast<size_t>(buf) * p.a_buf_bytes + static_cast<size_t>(ch) * p.a_chunk_bytes, &tmA,
+                      &a_full[buf], ch * p.kc, -1, hb * p.TH - 1, db * p.TD - 1, n);
+        for (int u = 0; u < units; ++u) {
+          const int tap = u / p.chunks;
+          const int ch = u - tap * p.chunks;
+          mbar_wait(&b_empty[bstage], bphase ^ 1u);
+          mbar_expect_tx(&b_full[bstage], p.b_unit_bytes);
+          tma_load_3d(sm + b_ring_off + static_cast<size_t>(bstage) * p.b_unit_bytes, &tmB, &b_full[bstage], ch * p.kc,
+                      tn * p.nt, tap);
+          if (++bstage == p.b_stages) {
+            bstage = 0;
+            bphase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      int bstage = 0;
+      uint32_t bphase = 0;
+      int it = 0;
+      const int ksteps = p.kc / 16;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        const int buf = it % p.a_bufs;
+        const uint32_t aph = static_cast<uint32_t>(it / p.a_bufs) & 1u;
+        const uint32_t eph = static_cast<uint32_t>(it) & 1u;
+        mbar_wait(&a_full[buf], aph);
+        tc_fence_after();
+        const uint32_t a_base = base + static_cast<uint32_t>(buf) * p.a_buf_bytes;
+        for (int u = 0; u < units; ++u) {
+          const int tap = u / p.chunks;
+          const int ch = u - tap * p.chunks;
+          const int kd = tap / 9;
+          const int kh = (tap - kd * 9) / 3;
+          const int kw = tap - kd * 9 - kh * 3;
+          const uint32_t shift = static_cast<uint32_t>(kd * p.plane_rows + kh * p.WP + kw);
+          mbar_wait(&b_full[bstage], bphase);
+          tc_fence_after();
+          const uint32_t b_addr = base + b_ring_off + static_cast<uint32_t>(bstage) * p.b_unit_bytes;
+          const uint32_t a_tap = a_base + static_cast<uint32_t>(ch) * p.a_chunk_bytes + shift * p.row_bytes;
+          for (int g = 0; g < p.G; ++g) {
+            if (u == 0) {
+              mbar_wait(&acc_empty[g], eph ^ 1u);
+              tc_fence_after();
+            }
+            const uint32_t a_addr = a_tap + static_cast<uint32_t>(g) * 128u * p.row_bytes;
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * p.nt);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = umma_smem_desc(a_addr + k * 32u, 16u, p.sbo, p.layout);
+              const uint64_t bdesc = umma_smem_desc(b_addr + k * 32u, 16u, p.sbo, p.layout);
+              umma_bf16(d_tmem, adesc, bdesc, p.idesc, (u | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&b_empty[bstage]);
+          if (++bstage == p.b_stages) {
+            bstage = 0;
+            bphase ^= 1u;
+          }
+        }
+        umma_commit(&a_empty[buf]);
+        umma_commit(&acc_full);
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      int t = item;
+      const int tn = t % p.tiles_n;
+      t /= p.tiles_n;
+      const int hb = t % p.n_hblk;
+      t /= p.n_hblk;
+      const int db = t % p.n_dblk;
+      const int n = t / p.n_dblk;
+      mbar_wait(&acc_full, static_cast<uint32_t>(it) & 1u);
+      tc_fence_after();
+      for (int g = 0; g < p.G; ++g) {
+        const int f = g * 128 + quarter * 32 + lane;
+        const int dl = f / p.plane_rows;
+        const int rem = f - dl * p.plane_rows;
+        const int hl = rem / p.WP;
+        const int wl = rem - hl * p.WP;
+        const int d = db * p.TD + dl;
+        const bool ok = dl < p.TD && hl < p.TH && wl < p.W && d < p.D;
+        const long long pixel = ((static_cast<long long>(n) * p.D + d) * p.H + hb * p.TH + hl) * p.W + wl;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(g * p.nt);
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
+          tmem_ld_wait();
+          const int col0 = tn * p.nt + c0;
+          if (!ok || col0 >= p.n_store) continue;
+          float fv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x = __uint_as_float(v[i]);
+            if (p.bias != nullptr) x += __ldg(p.bias + col0 + i);
+            if (p.act == ICSG3D_ACT_RELU) x = fmaxf(x, 0.f);
+            else if (p.act == ICSG3D_ACT_LEAKY) x = x > 0.f ? x : p.alpha * x;
+            fv[i] = x;
+          }
+          const int nvalid = min(16, p.n_store - col0);
+          if (p.y_dtype == ICSG3D_DT_BF16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + col0;
+            if (nvalid == 16 && (p.ldy & 7) == 0) {
+              uint4 q0, q1;
+              q0.x = pack_bf16x2(fv[0], fv[1]);
+              q0.y = pack_bf16x2(fv[2], fv[3]);
+              q0.z = pack_bf16x2(fv[4], fv[5]);
+              q0.w = pack_bf16x2(fv[6], fv[7]);
+              q1.x = pack_bf16x2(fv[8], fv[9]);
+              q1.y = pack_bf16x2(fv[10], fv[11]);
+              q1.z = pack_bf16x2(fv[12], fv[13]);
+              q1.w = pack_bf16x2(fv[14], fv[15]);
+              reinterpret_cast<uint4*>(dst)[0] = q0;
+              reinterpret_cast<uint4*>(dst)[1] = q1;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) dst[i] = f2bf(fv[i]);
+            }
+          } else {
+            float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + col0;
+            if (nvalid == 16 && (p.ldy & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(dst)[i] = make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
+            } else if (nvalid == 4 && (p.ldy & 3) == 0) {
+              reinterpret_cast<float4*>(dst)[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) dst[i] = fv[i];
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[g]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static bool halo_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Pick (TD, TH, NT) minimising a simple time-per-output model; returns false when no configuration fits.
+bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvHaloParams* out) {
+  if (W < 8 || W > 64 || !halo_pow2(W) || !halo_pow2(H) || !halo_pow2(D)) return false;
+  const int kc = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+  const int chunks = cin / kc;
+  const int row_bytes = kc * 2;
+  const int WP = W + 1;
+  const uint32_t smem_budget = 198u * 1024u;
+  double best = 1e30;
+  bool found = false;
+  ConvHaloParams bp{};
+  for (int nt = (nout < 256 ? nout : 256); nt >= 16; nt -= 16) {
+    if (nout % nt != 0) continue;
+    if (nt < 64 && nt != nout) continue;  // never split a narrow layer
+    for (int TH = H; TH >= 2; TH /= 2) {
+      const int HP = TH + 2;
+      const int plane_rows = HP * WP;
+      for (int TD = 1; TD <= 8 && TD <= D; ++TD) {
+        const int out_rows = TD * plane_rows;
+        const int G = (out_rows + 127) / 128;
+        if (G > kHaloMaxG || G * nt > 512) continue;
+        const int block_rows = (TD + 2) * plane_rows;
+        const int rows_alloc = G * 128 + 2 * plane_rows + 2 * WP + 3;
+        const uint32_t a_chunk = (static_cast<uint32_t>((rows_alloc > block_rows + 1 ? rows_alloc : block_rows + 1)) * row_bytes + 1023u) & ~1023u;
+        const uint32_t a_buf = a_chunk * chunks;
+        const uint32_t b_unit = static_cast<uint32_t>(nt) * row_bytes;
+        if (a_buf + 3 * b_unit > smem_budget) continue;
+        const int a_bufs = (2 * a_buf + 4 * b_unit <= smem_budget) ? 2 : 1;
+        int b_stages = static_cast<int>((smem_budget - a_bufs * a_buf) / b_unit);
+        if (b_stages > kHaloMaxBStages) b_stages = kHaloMaxBStages;
+        if (b_stages < 3) continue;
+        const int n_dblk = (D + TD - 1) / TD;
+        const long long items = static_cast<long long>(B) * n_dblk * (H / TH) * (nout / nt);
+        // cycles per item: MMA pipe (A smem read floor ~32 clk / MMA, N/2 clk tensor floor) vs L2->SM fill
+        const double mma_clk = static_cast<double>(G) * 27 * chunks * (kc / 16) * (nt / 2 > 32 ? nt / 2 : 32);
+        const double a_rows = static_cast<double>(block_rows) * chunks;
+        const double fill_bytes = a_rows * row_bytes + 27.0 * chunks * nt * row_bytes;
+        double fill_clk = fill_bytes / 28.0;
+        if (fill_clk < a_rows * 2.5) fill_clk = a_rows * 2.5;
+        double t = (a_bufs == 2) ? (mma_clk > fill_clk ? mma_clk : fill_clk) : (mma_clk + a_rows * row_bytes / 28.0);
+        t += 2000.0;  // per-item fixed overhead (barrier round trips, accumulator drain)
+        const double waves = static_cast<double>((items + sms - 1) / sms);
+        const double score = waves * t;  // modelled cycles for the whole layer
+        if (score < best) {
+          best = score;
+          found = true;
+          bp = ConvHaloParams{};
+          bp.B = B; bp.D = D; bp.H = H; bp.W = W;
+          bp.TD = TD; bp.TH = TH; bp.HP = HP; bp.WP = WP;
+          bp.plane_rows = plane_rows; bp.block_rows = block_rows; bp.out_rows = out_rows; bp.G = G;
+          bp.kc = kc; bp.chunks = chunks; bp.row_bytes = row_bytes;
+          bp.nt = nt; bp.tiles_n = nout / nt;
+          bp.n_dblk = n_dblk; bp.n_hblk = H / TH;
+          bp.total_items = static_cast<int>(items);
+          bp.a_bufs = a_bufs; bp.b_stages = b_stages;
+          bp.a_chunk_bytes = a_chunk; bp.a_buf_bytes = a_buf;
+          bp.a_tx_bytes = static_cast<uint32_t>(block_rows) * row_bytes * chunks;
+          bp.b_unit_bytes = b_unit;
+        }
+      }
+    }
+  }
+  if (!found) return false;
+  bp.sbo = 8u * bp.row_bytes;
+  bp.layout = umma_layout_for_swizzle(bp.row_bytes);
+  bp.idesc = umma_idesc_bf16(bp.nt, 0, 0);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(bp.G * bp.nt)) cols <<= 1;
+  bp.tmem_cols = cols;
+  *out = bp;
+  return true;
+}
+
+int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
+                     int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
+                        static_cast<uint64_t>(p.D), static_cast<uint64_t>(p.B)};
+    uint64_t strides[4] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(p.W) * ldx * 2,
+                           static_cast<uint64_t>(p.H) * p.W * ldx * 2, static_cast<uint64_t>(p.D) * p.H * p.W * ldx * 2};
+    uint32_t box[5] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.WP), static_cast<uint32_t>(p.HP),
+                       static_cast<uint32_t>(p.TD + 2), 1};
+    int rc = encode_tiled_bf16(&tmA, x, 5, dims, strides, box, p.row_bytes);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(nout), 27};
+    uint64_t strides[2] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(nout) * cin * 2};
+    uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.nt), 1};
+    int rc = encode_tiled_bf16(&tmB, wpack, 3, dims, strides, box, p.row_bytes);
+    if (rc) return rc;
+  }
+  p.y = y; p.ldy = ldy; p.y_dtype = y_dtype; p.n_store = n_store; p.bias = bias; p.act = act; p.alpha = alpha;
+  static bool configured = false;
+  if (!configured) {
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    configured = true;
+  }
+  const size_t smem = static_cast<size_t>(p.a_bufs) * p.a_buf_bytes + static_cast<size_t>(p.b_stages) * p.b_unit_bytes + 1024;
+  const int grid = p.total_items < sms ? p.total_items : sms;
+  conv3d_k3_halo_kernel<<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+}  // namespace icsg3d

@@ -1,0 +1,29 @@
+// Shared declarations of the halo-reuse Conv3D kernel (conv3d_halo.cu), used by the dispatcher in conv3d_igemm.cu.
+#pragma once
+#include "common.cuh"
+
+namespace icsg3d {
+
+struct ConvHaloParams {
+  int B, D, H, W;
+  int TD, TH, HP, WP;
+  int plane_rows, block_rows, out_rows, G;
+  int kc, chunks, row_bytes;
+  int nt, tiles_n;
+  int n_dblk, n_hblk, total_items;
+  int a_bufs, b_stages;
+  uint32_t a_chunk_bytes, a_buf_bytes, a_tx_bytes, b_unit_bytes;
+  uint32_t sbo, layout, idesc, tmem_cols;
+  void* y;
+  int ldy, y_dtype, n_store;
+  const float* bias;
+  int act;
+  float alpha;
+};
+
+// Pick (TD, TH, NT) from a simple cycle model; false when the layer shape does not fit the halo scheme.
+bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvHaloParams* out);
+int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
+                     int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st);
+
+}  // namespace icsg3d

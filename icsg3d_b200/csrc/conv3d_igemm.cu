@@ -270,6 +270,22 @@ int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H
 
 }  // namespace icsg3d
 
+#include <stdlib.h>
+#include <string.h>
+
+#include "conv3d_halo.cuh"
+namespace icsg3d {
+// ICSG3D_CONV_IMPL=v1 forces the per-tap TMA kernel (A/B comparisons); default picks the halo kernel when it applies.
+static int conv_impl_choice() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ICSG3D_CONV_IMPL");
+    v = (e && strcmp(e, "v1") == 0) ? 1 : 0;
+  }
+  return v;
+}
+}  // namespace icsg3d
+
 using namespace icsg3d;
 
 extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const float* bias, void* y,
@@ -288,6 +304,13 @@ extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack,
   const long long m_total = static_cast<long long>(B) * D * H * W;
   ICSG_REQUIRE(m_total < (1ll << 31), "conv3d_k3_igemm: too many voxels");
 
+  {
+    const int sms0 = sm_count();
+    ConvHaloParams hp;
+    if (sms0 > 0 && conv_impl_choice() == 0 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp))
+      return launch_conv_halo(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, hp, sms0,
+                              static_cast<cudaStream_t>(stream));
+  }
   ConvIgemmParams p{};
   p.m_total = static_cast<int>(m_total);
   p.D = D;
@@ -355,5 +378,19 @@ extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack,
   const int grid = total_tiles < sms ? total_tiles : sms;
   conv3d_k3_igemm_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+// Diagnostic: which kernel and tiling the dispatcher picks for a layer shape (host only; no device needed).
+// out[0..9] = {impl (0 = per-tap TMA kernel, 1 = halo kernel), TD, TH, G, NT, a_bufs, b_stages, items, kc, smem_bytes}
+extern "C" int icsg3d_conv3d_k3_plan(int B, int D, int H, int W, int cin, int nout, int sms, int* out) {
+  ICSG_REQUIRE(out && sms > 0, "conv3d_k3_plan: bad arguments");
+  for (int i = 0; i < 10; ++i) out[i] = 0;
+  ConvHaloParams hp;
+  if (conv_impl_choice() == 0 && conv_halo_plan(B, D, H, W, cin, nout, sms, &hp)) {
+    out[0] = 1; out[1] = hp.TD; out[2] = hp.TH; out[3] = hp.G; out[4] = hp.nt; out[5] = hp.a_bufs; out[6] = hp.b_stages;
+    out[7] = hp.total_items; out[8] = hp.kc;
+    out[9] = static_cast<int>(hp.a_bufs * hp.a_buf_bytes + hp.b_stages * hp.b_unit_bytes);
+  }
   return ICSG3D_OK;
 }

@@ -69,6 +69,10 @@ int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const floa
                            int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                            float leaky_alpha, void* stream);
 
+/* Diagnostic (host only): kernel/tiling choice of the dispatcher for a layer shape.
+ * out[0..9] = {impl (0 per-tap TMA kernel, 1 halo-reuse kernel), TD, TH, G, NT, a_bufs, b_stages, items, kc, smem} */
+int icsg3d_conv3d_k3_plan(int B, int D, int H, int W, int cin, int nout, int sms, int* out);
+
 /* Conv3DBackpropFilterV2: dW[tap][ci][co] = sum_voxels x[voxel+tap, ci] * dy[voxel, co]
  * (gradient of the layers above w.r.t. their kernels).  tcgen05 GEMM with both operands MN-major,
  * the voxel range split over CTAs; partials are reduced in a fixed order (deterministic).
