@@ -30,6 +30,7 @@ static constexpr int kHaloThreads = 192;
 static constexpr int kHaloMaxG = 32;
 static constexpr int kHaloMaxBStages = 8;
 
+template <int KSTEPS>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const ConvHaloParams p) {
@@ -80,36 +81,38 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  const int units = 27 * p.chunks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      int bstage = 0;
-      uint32_t bphase = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-        int t = item;
-        const int tn = t % p.tiles_n;
-        t /= p.tiles_n;
-        const int hb = t % p.n_hblk;
-        t /= p.n_hblk;
-        const int db = t % p.n_dblk;
-        const int n = t / p.n_dblk;
-        const int buf = it % p.a_bufs;
-        const uint32_t aph = static_cast<uint32_t>(it / p.a_bufs) & 1u;
-        mbar_wait(&a_empty[buf], aph ^ 1u);
+    // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
+    const bool leader = elect_one();
+    int bstage = 0;
+    uint32_t bphase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      int t = item;
+      const int tn = t % p.tiles_n;
+      t /= p.tiles_n;
+      const int hb = t % p.n_hblk;
+      t /= p.n_hblk;
+      const int db = t % p.n_dblk;
+      const int n = t / p.n_dblk;
+      const int buf = it % p.a_bufs;
+      const uint32_t aph = static_cast<uint32_t>(it / p.a_bufs) & 1u;
+      mbar_wait(&a_empty[buf], aph ^ 1u);
+      if (leader) {
         mbar_expect_tx(&a_full[buf], p.a_tx_bytes);
         for (int ch = 0; ch < p.chunks; ++ch)
           tma_load_5d(sm + static_cast<size_t>(buf) * p.a_buf_bytes + static_cast<size_t>(ch) * p.a_chunk_bytes, &tmA,
                       &a_full[buf], ch * p.kc, -1, hb * p.TH - 1, db * p.TD - 1, n);
-        for (int u = 0; u < units; ++u) {
-          const int tap = u / p.chunks;
-          const int ch = u - tap * p.chunks;
+      }
+      for (int tap = 0; tap < 27; ++tap) {
+        for (int ch = 0; ch < p.chunks; ++ch) {
           mbar_wait(&b_empty[bstage], bphase ^ 1u);
-          mbar_expect_tx(&b_full[bstage], p.b_unit_bytes);
-          tma_load_3d(sm + b_ring_off + static_cast<size_t>(bstage) * p.b_unit_bytes, &tmB, &b_full[bstage], ch * p.kc,
-                      tn * p.nt, tap);
+          if (leader) {
+            mbar_expect_tx(&b_full[bstage], p.b_unit_bytes);
+            tma_load_3d(sm + b_ring_off + static_cast<size_t>(bstage) * p.b_unit_bytes, &tmB, &b_full[bstage], ch * p.kc,
+                        tn * p.nt, tap);
+          }
           if (++bstage == p.b_stages) {
             bstage = 0;
             bphase ^= 1u;
@@ -118,49 +121,57 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      int bstage = 0;
-      uint32_t bphase = 0;
-      int it = 0;
-      const int ksteps = p.kc / 16;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-        const int buf = it % p.a_bufs;
-        const uint32_t aph = static_cast<uint32_t>(it / p.a_bufs) & 1u;
-        const uint32_t eph = static_cast<uint32_t>(it) & 1u;
-        mbar_wait(&a_full[buf], aph);
-        tc_fence_after();
-        const uint32_t a_base = base + static_cast<uint32_t>(buf) * p.a_buf_bytes;
-        for (int u = 0; u < units; ++u) {
-          const int tap = u / p.chunks;
-          const int ch = u - tap * p.chunks;
-          const int kd = tap / 9;
-          const int kh = (tap - kd * 9) / 3;
-          const int kw = tap - kd * 9 - kh * 3;
-          const uint32_t shift = static_cast<uint32_t>(kd * p.plane_rows + kh * p.WP + kw);
-          mbar_wait(&b_full[bstage], bphase);
-          tc_fence_after();
-          const uint32_t b_addr = base + b_ring_off + static_cast<uint32_t>(bstage) * p.b_unit_bytes;
-          const uint32_t a_tap = a_base + static_cast<uint32_t>(ch) * p.a_chunk_bytes + shift * p.row_bytes;
-          for (int g = 0; g < p.G; ++g) {
-            if (u == 0) {
-              mbar_wait(&acc_empty[g], eph ^ 1u);
+    // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
+    const bool leader = elect_one();
+    int bstage = 0;
+    uint32_t bphase = 0;
+    int it = 0;
+    const uint32_t desc_hi = umma_desc_hi(p.sbo, p.layout);
+    const uint32_t tile_lo = (128u * static_cast<uint32_t>(p.row_bytes)) >> 4;  // descriptor-lo step between M tiles
+    const uint32_t b_ring_lo = umma_desc_lo(base + b_ring_off, 16u);
+    const uint32_t b_unit_lo = p.b_unit_bytes >> 4;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      const int buf = it % p.a_bufs;
+      const uint32_t aph = static_cast<uint32_t>(it / p.a_bufs) & 1u;
+      const uint32_t eph = static_cast<uint32_t>(it) & 1u;
+      mbar_wait(&a_full[buf], aph);
+      tc_fence_after();
+      const uint32_t a_buf_lo = umma_desc_lo(base + static_cast<uint32_t>(buf) * p.a_buf_bytes, 16u);
+      bool first = true;
+      for (int kd = 0; kd < 3; ++kd) {
+        for (int kh = 0; kh < 3; ++kh) {
+          for (int kw = 0; kw < 3; ++kw) {
+            const uint32_t shift_lo = (static_cast<uint32_t>(kd * p.plane_rows + kh * p.WP + kw) * static_cast<uint32_t>(p.row_bytes)) >> 4;
+            for (int ch = 0; ch < p.chunks; ++ch) {
+              mbar_wait(&b_full[bstage], bphase);
               tc_fence_after();
+              const uint32_t b_lo = b_ring_lo + static_cast<uint32_t>(bstage) * b_unit_lo;
+              uint32_t a_lo = a_buf_lo + static_cast<uint32_t>(ch) * (p.a_chunk_bytes >> 4) + shift_lo;
+              uint32_t d_tmem = tmem_base;
+              for (int g = 0; g < p.G; ++g) {
+                if (first) {
+                  mbar_wait(&acc_empty[g], eph ^ 1u);
+                  tc_fence_after();
+                }
+                if (leader) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_bf16_lohi(d_tmem, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, p.idesc, (!first || k != 0) ? 1u : 0u);
+                }
+                a_lo += tile_lo;
+                d_tmem += static_cast<uint32_t>(p.nt);
+              }
+              if (leader) umma_commit(&b_empty[bstage]);
+              first = false;
+              if (++bstage == p.b_stages) {
+                bstage = 0;
+                bphase ^= 1u;
+              }
             }
-            const uint32_t a_addr = a_tap + static_cast<uint32_t>(g) * 128u * p.row_bytes;
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * p.nt);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = umma_smem_desc(a_addr + k * 32u, 16u, p.sbo, p.layout);
-              const uint64_t bdesc = umma_smem_desc(b_addr + k * 32u, 16u, p.sbo, p.layout);
-              umma_bf16(d_tmem, adesc, bdesc, p.idesc, (u | k) != 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(&b_empty[bstage]);
-          if (++bstage == p.b_stages) {
-            bstage = 0;
-            bphase ^= 1u;
           }
         }
+      }
+      if (leader) {
         umma_commit(&a_empty[buf]);
         umma_commit(&acc_full);
       }
@@ -352,12 +363,16 @@ int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bia
   p.y = y; p.ldy = ldy; p.y_dtype = y_dtype; p.n_store = n_store; p.bias = bias; p.act = act; p.alpha = alpha;
   static bool configured = false;
   if (!configured) {
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     configured = true;
   }
   const size_t smem = static_cast<size_t>(p.a_bufs) * p.a_buf_bytes + static_cast<size_t>(p.b_stages) * p.b_unit_bytes + 1024;
   const int grid = p.total_items < sms ? p.total_items : sms;
-  conv3d_k3_halo_kernel<<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
+  if (p.kc == 16) conv3d_k3_halo_kernel<1><<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.kc == 32) conv3d_k3_halo_kernel<2><<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
+  else conv3d_k3_halo_kernel<4><<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -50,6 +50,7 @@ struct ConvIgemmParams {
 static constexpr int kConvThreads = 192;
 static constexpr int kMaxStages = 8;
 
+template <int KSTEPS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const ConvIgemmParams p) {
@@ -88,80 +89,83 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int total_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.ups) * (p.a_unit_bytes + p.b_unit_bytes);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tm = tile / p.tiles_n;
-        const int tn = tile - tm * p.tiles_n;
-        int pix = tm * 128;
-        const int w0 = pix % p.W;
-        pix /= p.W;
-        const int h0 = pix % p.H;
-        pix /= p.H;
-        const int d0 = pix % p.D;
-        const int n0 = pix / p.D;
-        for (int it = 0; it < p.iters; ++it) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
-          uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
-          uint8_t* sb = sa + static_cast<size_t>(p.ups) * p.a_unit_bytes;
-          for (int j = 0; j < p.ups; ++j) {
-            const int u = it * p.ups + j;
-            const int tap = u / p.chunks;
-            const int ch = u - tap * p.chunks;
-            const int kd = tap / 9;
-            const int kh = (tap - kd * 9) / 3;
-            const int kw = tap - kd * 9 - kh * 3;
-            tma_load_5d(sa + static_cast<size_t>(j) * p.a_unit_bytes, &tmA, &full_bar[stage], ch * p.kc,
-                        w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, n0);
-            tma_load_3d(sb + static_cast<size_t>(j) * p.b_unit_bytes, &tmB, &full_bar[stage], ch * p.kc,
-                        tn * p.nt, tap);
+    // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>(p.ups) * (p.a_unit_bytes + p.b_unit_bytes);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      int pix = tm * 128;
+      const int w0 = pix % p.W;
+      pix /= p.W;
+      const int h0 = pix % p.H;
+      pix /= p.H;
+      const int d0 = pix % p.D;
+      const int n0 = pix / p.D;
+      int tap = 0, ch = 0;
+      for (int it = 0; it < p.iters; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
+        uint8_t* sb = sa + static_cast<size_t>(p.ups) * p.a_unit_bytes;
+        if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
+        for (int j = 0; j < p.ups; ++j) {
+          const int kd = tap / 9;
+          const int kh = (tap - kd * 9) / 3;
+          const int kw = tap - kd * 9 - kh * 3;
+          if (leader) {
+            tma_load_5d(sa + static_cast<size_t>(j) * p.a_unit_bytes, &tmA, &full_bar[stage], ch * p.kc, w0 + kw - 1,
+                        h0 + kh - 1, d0 + kd - 1, n0);
+            tma_load_3d(sb + static_cast<size_t>(j) * p.b_unit_bytes, &tmB, &full_bar[stage], ch * p.kc, tn * p.nt, tap);
           }
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
+          if (++ch == p.chunks) {
+            ch = 0;
+            ++tap;
           }
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      const int ksteps = p.kc / 16;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = static_cast<uint32_t>(local >> 1) & 1u;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+    // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    const uint32_t desc_hi = umma_desc_hi(p.sbo, p.layout);
+    const uint32_t ring_lo = umma_desc_lo(ring_base, 16u);
+    const uint32_t stage_lo = p.stage_bytes >> 4, a_unit_lo = p.a_unit_bytes >> 4, b_unit_lo = p.b_unit_bytes >> 4;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local >> 1) & 1u;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.nt);
+      for (int it = 0; it < p.iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.nt);
-        for (int it = 0; it < p.iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = ring_base + static_cast<uint32_t>(stage) * p.stage_bytes;
-          const uint32_t sb = sa + static_cast<uint32_t>(p.ups) * p.a_unit_bytes;
-          for (int j = 0; j < p.ups; ++j) {
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc =
-                  umma_smem_desc(sa + static_cast<uint32_t>(j) * p.a_unit_bytes + k * 32u, 16u, p.sbo, p.layout);
-              const uint64_t bdesc =
-                  umma_smem_desc(sb + static_cast<uint32_t>(j) * p.b_unit_bytes + k * 32u, 16u, p.sbo, p.layout);
-              umma_bf16(d_tmem, adesc, bdesc, p.idesc, (it | j | k) != 0 ? 1u : 0u);
-            }
+        uint32_t a_lo = ring_lo + static_cast<uint32_t>(stage) * stage_lo;
+        uint32_t b_lo = a_lo + static_cast<uint32_t>(p.ups) * a_unit_lo;
+        for (int j = 0; j < p.ups; ++j) {
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              umma_bf16_lohi(d_tmem, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, p.idesc, (it | j | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          a_lo += a_unit_lo;
+          b_lo += b_unit_lo;
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (leader) umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
+      if (leader) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
@@ -368,15 +372,19 @@ extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack,
   }
 
   const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
-  static size_t configured_smem = 0;
-  if (smem > configured_smem) {
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(210 * 1024)));
-    configured_smem = 210 * 1024;
+  static bool configured = false;
+  if (!configured) {
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    configured = true;
   }
   const int total_tiles = p.tiles_m * p.tiles_n;
   const int grid = total_tiles < sms ? total_tiles : sms;
-  conv3d_k3_igemm_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p.kc == 16) conv3d_k3_igemm_kernel<1><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.kc == 32) conv3d_k3_igemm_kernel<2><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
+  else conv3d_k3_igemm_kernel<4><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

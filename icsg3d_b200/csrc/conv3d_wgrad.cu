@@ -70,26 +70,28 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = split; tile < p.tiles_m; tile += p.splits) {
-        int pix = tile * 128;
-        const int w0 = pix % p.W;
-        pix /= p.W;
-        const int h0 = pix % p.H;
-        pix /= p.H;
-        const int d0 = pix % p.D;
-        const int n0 = pix / p.D;
-        for (int g = g_begin; g < g_end; ++g) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          const int blk0 = g * p.bpg;
-          int nblk = p.total_blocks - blk0;
-          if (nblk > p.bpg) nblk = p.bpg;
+    // TMA producer: whole warp runs the loop, one elected lane issues
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = split; tile < p.tiles_m; tile += p.splits) {
+      int pix = tile * 128;
+      const int w0 = pix % p.W;
+      pix /= p.W;
+      const int h0 = pix % p.H;
+      pix /= p.H;
+      const int d0 = pix % p.D;
+      const int n0 = pix / p.D;
+      for (int g = g_begin; g < g_end; ++g) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        const int blk0 = g * p.bpg;
+        int nblk = p.total_blocks - blk0;
+        if (nblk > p.bpg) nblk = p.bpg;
+        uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
+        uint8_t* sb = sa + p.a_bytes;
+        if (leader) {
           mbar_expect_tx(&full_bar[stage],
                          static_cast<uint32_t>(nblk) * p.a_box_bytes + static_cast<uint32_t>(p.nb_boxes) * p.b_box_bytes);
-          uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
-          uint8_t* sb = sa + p.a_bytes;
           for (int b = 0; b < nblk; ++b) {
             const int blk = blk0 + b;
             const int tap = blk / p.chunks_a;
@@ -103,40 +105,44 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           for (int j = 0; j < p.nb_boxes; ++j)
             tma_load_5d(sb + static_cast<size_t>(j) * p.b_box_bytes, &tmDY, &full_bar[stage], nz * p.ntw + j * p.kcb, w0,
                         h0, d0, n0);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int ti = 0;
-      for (int tile = split; tile < p.tiles_m; tile += p.splits, ++ti) {
-        for (int g = g_begin; g < g_end; ++g) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = ring_base + static_cast<uint32_t>(stage) * p.stage_bytes;
-          const uint32_t sb = sa + p.a_bytes;
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((g - g_begin) * p.ntw);
+    // MMA issuer: whole warp runs the loop, one elected lane issues; descriptor high words are loop invariant
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int ti = 0;
+    const uint32_t a_hi = umma_desc_hi(p.sbo_a, p.layout_a), b_hi = umma_desc_hi(p.sbo_b, p.layout_b);
+    const uint32_t ring_lo_a = umma_desc_lo(ring_base, p.lbo_a);
+    const uint32_t ring_lo_b = umma_desc_lo(ring_base + p.a_bytes, p.lbo_b);
+    const uint32_t stage_lo = p.stage_bytes >> 4;
+    const uint32_t ka = (2u * p.sbo_a) >> 4, kb = (2u * p.sbo_b) >> 4;
+    for (int tile = split; tile < p.tiles_m; tile += p.splits, ++ti) {
+      for (int g = g_begin; g < g_end; ++g) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_lo = ring_lo_a + static_cast<uint32_t>(stage) * stage_lo;
+        const uint32_t b_lo = ring_lo_b + static_cast<uint32_t>(stage) * stage_lo;
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((g - g_begin) * p.ntw);
+        if (leader) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 8 x 16 voxels
-            const uint64_t adesc = umma_smem_desc(sa + k * 2u * p.sbo_a, p.lbo_a, p.sbo_a, p.layout_a);
-            const uint64_t bdesc = umma_smem_desc(sb + k * 2u * p.sbo_b, p.lbo_b, p.sbo_b, p.layout_b);
-            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (ti | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 8; ++k)  // 8 x 16 voxels
+            umma_bf16_lohi(d_tmem, a_lo + k * ka, a_hi, b_lo + k * kb, b_hi, p.idesc, (ti | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
-      umma_commit(&done_bar);
     }
+    if (leader) umma_commit(&done_bar);
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;

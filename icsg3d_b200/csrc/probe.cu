@@ -107,3 +107,73 @@ extern "C" int icsg3d_probe_shifted_desc(const void* a, const void* b, float* ou
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Probe 2: tensor-pipe occupancy of one tcgen05.mma (SS mode, bf16, K=16) as a function of (M, N):
+// one CTA issues `reps` MMAs back to back (alternating `nacc` accumulators), commits, waits, and reports
+// elapsed SM cycles.  Operand contents are irrelevant (zeros).
+// ------------------------------------------------------------------------------------------------------
+namespace icsg3d {
+__global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(long long* out, int m, int n, int reps, int nacc, int swz,
+                                                                int a_step, int b_step) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0u;
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t row_bytes = static_cast<uint32_t>(swz);
+    const uint32_t layout = umma_layout_for_swizzle(swz);
+    const uint32_t sbo = 8u * row_bytes;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+                           (static_cast<uint32_t>(m >> 4) << 24);
+    const uint64_t adesc = umma_smem_desc(base, 16u, sbo, layout);
+    const uint64_t bdesc = umma_smem_desc(base + 48 * 1024, 16u, sbo, layout);
+    const long long t0 = clock64();
+    const uint32_t mask = static_cast<uint32_t>(nacc - 1);  // nacc is a power of two
+    // a_step / b_step (bytes, multiples of 16): operand start address advances by that much per MMA, cycling
+    // through 8 positions, so consecutive MMAs read DIFFERENT shared-memory operands (no operand reuse).
+    const uint64_t astep = static_cast<uint64_t>(a_step >> 4), bstep = static_cast<uint64_t>(b_step >> 4);
+#pragma unroll 8
+    for (int r = 0; r < reps; ++r) {
+      const uint64_t j = static_cast<uint64_t>(r & 7);
+      umma_bf16(tmem + (static_cast<uint32_t>(r) & mask) * static_cast<uint32_t>(n), adesc + j * astep, bdesc + j * bstep, idesc, 1u);
+    }
+    umma_commit(&bar);
+    const long long t1 = clock64();
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+}  // namespace icsg3d
+
+extern "C" int icsg3d_probe_mma_rate(int64_t* out, int m, int n, int reps, int nacc, int swizzle_bytes, int a_step,
+                                     int b_step, void* stream) {
+  ICSG_REQUIRE(out && (m == 64 || m == 128) && n % 16 == 0 && n >= 16 && n <= 256 && nacc >= 1 && nacc * n <= 512,
+               "probe_mma_rate: bad arguments");
+  ICSG_CUDA(cudaFuncSetAttribute(icsg3d::probe_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  icsg3d::probe_mma_rate_kernel<<<1, 128, 98 * 1024, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<long long*>(out), m, n,
+                                                                                         reps, nacc, swizzle_bytes, a_step, b_step);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
