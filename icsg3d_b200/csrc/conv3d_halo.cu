@@ -16,9 +16,10 @@
 //   * loop order is tap-outer: each weight tile B[tap][N x KC] streams through a small TMA ring once per
 //     work item and is applied to all G = ceil(TD*HP*WP/128) M tiles, whose accumulators live side by side
 //     in TMEM (G*NT <= 512 columns);
-//   * the epilogue drains tile g as soon as the item completes and hands the accumulator back per tile, so the
-//     next item's first taps overlap with the previous item's drain; the A block is double buffered when
-//     shared memory allows.
+//   * two accumulator sets (2*G*NT <= 512 TMEM columns) alternate between consecutive items, so the epilogue
+//     of item i (TMEM -> bias/activation -> global) overlaps all MMAs of item i+1; the A block is double
+//     buffered when shared memory allows, and when all 27*chunks weight tiles fit beside it they are loaded
+//     once and stay resident (every 32^3 layer of the VAE+DFC step).
 #include "common.cuh"
 #include "conv3d_halo.cuh"
 
@@ -26,7 +27,11 @@ namespace icsg3d {
 
 
 
-static constexpr int kHaloThreads = 192;
+// warp 0: TMA producer | warps 1..kHaloIssuers: MMA issuers (accumulator g is owned by issuer g % kHaloIssuers;
+// measured: one issuing thread sustains only ~100-150 cycles per tcgen05.mma because of its own uniform-register
+// dependency chains, vs a 55-cycle tensor floor at N <= 64 — profiles/r01_halo_pattern_probe.json) | last 4 warps: epilogue
+static constexpr int kHaloIssuers = 3;
+static constexpr int kHaloThreads = (1 + kHaloIssuers + 4) * 32;
 static constexpr int kHaloMaxG = 32;
 static constexpr int kHaloMaxBStages = 8;
 
@@ -37,8 +42,9 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2];
   __shared__ __align__(8) uint64_t b_full[kHaloMaxBStages], b_empty[kHaloMaxBStages];
-  __shared__ __align__(8) uint64_t acc_full;
-  __shared__ __align__(8) uint64_t acc_empty[kHaloMaxG];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t b_all_full;
+  __shared__ float s_bias[512];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -66,16 +72,20 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], kHaloIssuers);
     }
-    for (int s = 0; s < p.b_stages; ++s) {
+    for (int s = 0; s < (p.b_resident ? 0 : p.b_stages); ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], kHaloIssuers);
     }
-    mbar_init(&acc_full, 1);
-    for (int g = 0; g < p.G; ++g) mbar_init(&acc_empty[g], 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], kHaloIssuers);
+      mbar_init(&acc_empty[i], 4);
+    }
+    mbar_init(&b_all_full, 1);
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < p.nt * p.tiles_n && i < 512; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -105,6 +115,16 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tma_load_5d(sm + static_cast<size_t>(buf) * p.a_buf_bytes + static_cast<size_t>(ch) * p.a_chunk_bytes, &tmA,
                       &a_full[buf], ch * p.kc, -1, hb * p.TH - 1, db * p.TD - 1, n);
       }
+      if (p.b_resident) {
+        if (it == 0 && leader) {  // tiles_n == 1 in resident mode: one load of all weight tiles for the whole kernel
+          mbar_expect_tx(&b_all_full, static_cast<uint32_t>(27 * p.chunks) * p.b_unit_bytes);
+          for (int tap = 0; tap < 27; ++tap)
+            for (int ch = 0; ch < p.chunks; ++ch)
+              tma_load_3d(sm + b_ring_off + static_cast<size_t>(tap * p.chunks + ch) * p.b_unit_bytes, &tmB, &b_all_full,
+                          ch * p.kc, 0, tap);
+        }
+        continue;
+      }
       for (int tap = 0; tap < 27; ++tap) {
         for (int ch = 0; ch < p.chunks; ++ch) {
           mbar_wait(&b_empty[bstage], bphase ^ 1u);
@@ -120,8 +140,9 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
+  } else if (warp <= kHaloIssuers) {
+    // ===================== MMA issuers (whole warp runs the loop; one elected lane issues) =====================
+    const int issuer = warp - 1;
     const bool leader = elect_one();
     int bstage = 0;
     uint32_t bphase = 0;
@@ -133,39 +154,48 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
       const int buf = it % p.a_bufs;
       const uint32_t aph = static_cast<uint32_t>(it / p.a_bufs) & 1u;
-      const uint32_t eph = static_cast<uint32_t>(it) & 1u;
+      const int set = it & 1;
+      const uint32_t sph = static_cast<uint32_t>(it >> 1) & 1u;
       mbar_wait(&a_full[buf], aph);
+      if (p.b_resident && it == 0) mbar_wait(&b_all_full, 0);
+      mbar_wait(&acc_empty[set], sph ^ 1u);
       tc_fence_after();
       const uint32_t a_buf_lo = umma_desc_lo(base + static_cast<uint32_t>(buf) * p.a_buf_bytes, 16u);
+      const uint32_t tmem_set = tmem_base + static_cast<uint32_t>(set * p.G * p.nt);
       bool first = true;
+      int unit = 0;
       for (int kd = 0; kd < 3; ++kd) {
         for (int kh = 0; kh < 3; ++kh) {
           for (int kw = 0; kw < 3; ++kw) {
             const uint32_t shift_lo = (static_cast<uint32_t>(kd * p.plane_rows + kh * p.WP + kw) * static_cast<uint32_t>(p.row_bytes)) >> 4;
-            for (int ch = 0; ch < p.chunks; ++ch) {
-              mbar_wait(&b_full[bstage], bphase);
-              tc_fence_after();
-              const uint32_t b_lo = b_ring_lo + static_cast<uint32_t>(bstage) * b_unit_lo;
-              uint32_t a_lo = a_buf_lo + static_cast<uint32_t>(ch) * (p.a_chunk_bytes >> 4) + shift_lo;
-              uint32_t d_tmem = tmem_base;
-              for (int g = 0; g < p.G; ++g) {
-                if (first) {
-                  mbar_wait(&acc_empty[g], eph ^ 1u);
-                  tc_fence_after();
-                }
-                if (leader) {
+            for (int ch = 0; ch < p.chunks; ++ch, ++unit) {
+              uint32_t b_lo;
+              if (p.b_resident) {
+                b_lo = b_ring_lo + static_cast<uint32_t>(unit) * b_unit_lo;
+              } else {
+                mbar_wait(&b_full[bstage], bphase);
+                tc_fence_after();
+                b_lo = b_ring_lo + static_cast<uint32_t>(bstage) * b_unit_lo;
+              }
+              uint32_t a_lo = a_buf_lo + static_cast<uint32_t>(ch) * (p.a_chunk_bytes >> 4) + shift_lo +
+                              static_cast<uint32_t>(issuer) * tile_lo;
+              uint32_t d_tmem = tmem_set + static_cast<uint32_t>(issuer * p.nt);
+              if (leader) {
+                for (int g = issuer; g < p.G; g += kHaloIssuers) {
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k)
                     umma_bf16_lohi(d_tmem, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, p.idesc, (!first || k != 0) ? 1u : 0u);
+                  a_lo += kHaloIssuers * tile_lo;
+                  d_tmem += static_cast<uint32_t>(kHaloIssuers * p.nt);
                 }
-                a_lo += tile_lo;
-                d_tmem += static_cast<uint32_t>(p.nt);
               }
-              if (leader) umma_commit(&b_empty[bstage]);
               first = false;
-              if (++bstage == p.b_stages) {
-                bstage = 0;
-                bphase ^= 1u;
+              if (!p.b_resident) {
+                if (leader) umma_commit(&b_empty[bstage]);
+                if (++bstage == p.b_stages) {
+                  bstage = 0;
+                  bphase ^= 1u;
+                }
               }
             }
           }
@@ -173,7 +203,7 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
       if (leader) {
         umma_commit(&a_empty[buf]);
-        umma_commit(&acc_full);
+        umma_commit(&acc_full[set]);
       }
     }
   } else {
@@ -188,7 +218,8 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       t /= p.n_hblk;
       const int db = t % p.n_dblk;
       const int n = t / p.n_dblk;
-      mbar_wait(&acc_full, static_cast<uint32_t>(it) & 1u);
+      const int set = it & 1;
+      mbar_wait(&acc_full[set], static_cast<uint32_t>(it >> 1) & 1u);
       tc_fence_after();
       for (int g = 0; g < p.G; ++g) {
         const int f = g * 128 + quarter * 32 + lane;
@@ -199,7 +230,8 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int d = db * p.TD + dl;
         const bool ok = dl < p.TD && hl < p.TH && wl < p.W && d < p.D;
         const long long pixel = ((static_cast<long long>(n) * p.D + d) * p.H + hb * p.TH + hl) * p.W + wl;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(g * p.nt);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>((set * p.G + g) * p.nt);
         for (int c0 = 0; c0 < p.nt; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
@@ -209,8 +241,7 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           float fv[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(v[i]);
-            if (p.bias != nullptr) x += __ldg(p.bias + col0 + i);
+            float x = __uint_as_float(v[i]) + s_bias[col0 + i];
             if (p.act == ICSG3D_ACT_RELU) x = fmaxf(x, 0.f);
             else if (p.act == ICSG3D_ACT_LEAKY) x = x > 0.f ? x : p.alpha * x;
             fv[i] = x;
@@ -250,10 +281,10 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[g]);
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[set]);
     }
   }
 
@@ -274,7 +305,7 @@ bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, Conv
   const int chunks = cin / kc;
   const int row_bytes = kc * 2;
   const int WP = W + 1;
-  const uint32_t smem_budget = 198u * 1024u;
+  const uint32_t smem_budget = 216u * 1024u;
   double best = 1e30;
   bool found = false;
   ConvHaloParams bp{};
@@ -287,23 +318,32 @@ bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, Conv
       for (int TD = 1; TD <= 8 && TD <= D; ++TD) {
         const int out_rows = TD * plane_rows;
         const int G = (out_rows + 127) / 128;
-        if (G > kHaloMaxG || G * nt > 512) continue;
+        if (G > kHaloMaxG || 2 * G * nt > 512) continue;  // two accumulator sets
         const int block_rows = (TD + 2) * plane_rows;
         const int rows_alloc = G * 128 + 2 * plane_rows + 2 * WP + 3;
         const uint32_t a_chunk = (static_cast<uint32_t>((rows_alloc > block_rows + 1 ? rows_alloc : block_rows + 1)) * row_bytes + 1023u) & ~1023u;
         const uint32_t a_buf = a_chunk * chunks;
         const uint32_t b_unit = static_cast<uint32_t>(nt) * row_bytes;
         if (a_buf + 3 * b_unit > smem_budget) continue;
-        const int a_bufs = (2 * a_buf + 4 * b_unit <= smem_budget) ? 2 : 1;
-        int b_stages = static_cast<int>((smem_budget - a_bufs * a_buf) / b_unit);
-        if (b_stages > kHaloMaxBStages) b_stages = kHaloMaxBStages;
-        if (b_stages < 3) continue;
+        const uint32_t b_all = 27u * chunks * b_unit;
+        int a_bufs, b_stages, b_resident = 0;
+        if (nt == nout && nout <= 512 && 2 * a_buf + b_all <= smem_budget) {
+          a_bufs = 2; b_resident = 1; b_stages = 27 * chunks;
+        } else if (nt == nout && nout <= 512 && a_buf + b_all <= smem_budget) {
+          a_bufs = 1; b_resident = 1; b_stages = 27 * chunks;
+        } else {
+          a_bufs = (2 * a_buf + 4 * b_unit <= smem_budget) ? 2 : 1;
+          b_stages = static_cast<int>((smem_budget - a_bufs * a_buf) / b_unit);
+          if (b_stages > kHaloMaxBStages) b_stages = kHaloMaxBStages;
+          if (b_stages < 3) continue;
+        }
         const int n_dblk = (D + TD - 1) / TD;
         const long long items = static_cast<long long>(B) * n_dblk * (H / TH) * (nout / nt);
         // cycles per item: MMA pipe (A smem read floor ~32 clk / MMA, N/2 clk tensor floor) vs L2->SM fill
-        const double mma_clk = static_cast<double>(G) * 27 * chunks * (kc / 16) * (nt / 2 > 32 ? nt / 2 : 32);
+        // measured on B200 (profiles/r01_mma_rate_probe.json): SS-mode tcgen05.mma K=16 costs max(54.7, N/2) cycles
+        const double mma_clk = static_cast<double>(G) * 27 * chunks * (kc / 16) * (nt / 2 > 55 ? nt / 2 : 55);
         const double a_rows = static_cast<double>(block_rows) * chunks;
-        const double fill_bytes = a_rows * row_bytes + 27.0 * chunks * nt * row_bytes;
+        const double fill_bytes = a_rows * row_bytes + (b_resident ? 0.0 : 27.0 * chunks * nt * row_bytes);
         double fill_clk = fill_bytes / 28.0;
         if (fill_clk < a_rows * 2.5) fill_clk = a_rows * 2.5;
         double t = (a_bufs == 2) ? (mma_clk > fill_clk ? mma_clk : fill_clk) : (mma_clk + a_rows * row_bytes / 28.0);
@@ -321,7 +361,7 @@ bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, Conv
           bp.nt = nt; bp.tiles_n = nout / nt;
           bp.n_dblk = n_dblk; bp.n_hblk = H / TH;
           bp.total_items = static_cast<int>(items);
-          bp.a_bufs = a_bufs; bp.b_stages = b_stages;
+          bp.a_bufs = a_bufs; bp.b_stages = b_stages; bp.b_resident = b_resident;
           bp.a_chunk_bytes = a_chunk; bp.a_buf_bytes = a_buf;
           bp.a_tx_bytes = static_cast<uint32_t>(block_rows) * row_bytes * chunks;
           bp.b_unit_bytes = b_unit;
@@ -334,7 +374,7 @@ bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, Conv
   bp.layout = umma_layout_for_swizzle(bp.row_bytes);
   bp.idesc = umma_idesc_bf16(bp.nt, 0, 0);
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(bp.G * bp.nt)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(2 * bp.G * bp.nt)) cols <<= 1;
   bp.tmem_cols = cols;
   *out = bp;
   return true;
@@ -363,9 +403,9 @@ int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bia
   p.y = y; p.ldy = ldy; p.y_dtype = y_dtype; p.n_store = n_store; p.bias = bias; p.act = act; p.alpha = alpha;
   static bool configured = false;
   if (!configured) {
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured = true;
   }
   const size_t smem = static_cast<size_t>(p.a_bufs) * p.a_buf_bytes + static_cast<size_t>(p.b_stages) * p.b_unit_bytes + 1024;

@@ -12,6 +12,7 @@ struct ConvHaloParams {
   int nt, tiles_n;
   int n_dblk, n_hblk, total_items;
   int a_bufs, b_stages;
+  int b_resident;  // all 27*chunks weight tiles stay in shared memory for the whole kernel (loaded once)
   uint32_t a_chunk_bytes, a_buf_bytes, a_tx_bytes, b_unit_bytes;
   uint32_t sbo, layout, idesc, tmem_cols;
   void* y;

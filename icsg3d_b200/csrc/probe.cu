@@ -177,3 +177,93 @@ extern "C" int icsg3d_probe_mma_rate(int64_t* out, int m, int n, int reps, int n
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Probe 3: the halo kernel's exact MMA issue pattern (tap-outer, G accumulators, KSTEPS k-steps, per-tap row
+// shifts into a resident A block, resident B tiles) with NO TMA, NO barriers and NO epilogue: isolates the
+// tensor-pipe cost of the pattern itself.  out[0] = cycles for `items` items, out[1] = MMAs issued.
+// ------------------------------------------------------------------------------------------------------
+namespace icsg3d {
+__global__ void __launch_bounds__(192, 1) probe_halo_pattern_kernel(long long* out, int G, int nt, int plane_rows, int WP,
+                                                                    int row_bytes, int ksteps, int items, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0u;
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  // variant A (mode < 4): whole warp runs the loop, elected lane issues (the production kernels' structure)
+  // variant B (mode >= 4): ONE thread (threadIdx.x == 32) runs the whole loop
+  const bool single = mode >= 4;
+  mode &= 3;
+  if (warp == 1 && (!single || threadIdx.x == 32)) {
+    const bool leader = single ? true : elect_one();
+    const uint32_t desc_hi = umma_desc_hi(8u * row_bytes, umma_layout_for_swizzle(row_bytes));
+    const uint32_t idesc = umma_idesc_bf16(nt, 0, 0);
+    const uint32_t a_base_lo = umma_desc_lo(base, 16u);
+    const uint32_t b_base_lo = umma_desc_lo(base + 96 * 1024, 16u);
+    const uint32_t b_unit_lo = (static_cast<uint32_t>(nt) * row_bytes) >> 4;
+    const uint32_t tile_lo = (128u * row_bytes) >> 4;
+    long long n_mma = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < items; ++it) {
+      const uint32_t tmem_set = tmem + static_cast<uint32_t>((it & 1) * G * nt);
+      bool first = true;
+      int unit = 0;
+      for (int kd = 0; kd < 3; ++kd)
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw, ++unit) {
+            uint32_t shift_rows = static_cast<uint32_t>(kd * plane_rows + kh * WP + kw);
+            if (mode == 1) shift_rows = 0;
+            if (mode == 2) shift_rows &= ~7u;
+            const uint32_t b_lo = b_base_lo + static_cast<uint32_t>(mode == 3 ? 0 : unit) * b_unit_lo;
+            uint32_t a_lo = a_base_lo + ((shift_rows * static_cast<uint32_t>(row_bytes)) >> 4);
+            uint32_t d_tmem = tmem_set;
+            if (leader) {
+              for (int g = 0; g < G; ++g) {
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16_lohi(d_tmem, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc, (!first || k != 0) ? 1u : 0u);
+                a_lo += tile_lo;
+                d_tmem += static_cast<uint32_t>(nt);
+              }
+            }
+            n_mma += G * ksteps;
+            first = false;
+          }
+    }
+    if (leader) {
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      out[0] = clock64() - t0;
+      out[1] = n_mma;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+}  // namespace icsg3d
+
+extern "C" int icsg3d_probe_halo_pattern(int64_t* out, int G, int nt, int plane_rows, int WP, int row_bytes, int ksteps,
+                                         int items, int mode, void* stream) {
+  ICSG_REQUIRE(out && 2 * G * nt <= 512 && 27 * nt * row_bytes <= 112 * 1024, "probe_halo_pattern: bad arguments");
+  ICSG_CUDA(cudaFuncSetAttribute(icsg3d::probe_halo_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  icsg3d::probe_halo_pattern_kernel<<<1, 192, 210 * 1024, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<long long*>(out), G, nt, plane_rows, WP, row_bytes, ksteps, items, mode);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}

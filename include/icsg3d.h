@@ -218,6 +218,10 @@ int icsg3d_probe_shifted_desc(const void* a, const void* b, float* out, int rows
 int icsg3d_probe_mma_rate(int64_t* out, int m, int n, int reps, int nacc, int swizzle_bytes, int a_step, int b_step,
                           void* stream);
 
+/* Hardware probe: the halo kernel's MMA issue pattern without TMA/barriers/epilogue (see csrc/probe.cu). */
+int icsg3d_probe_halo_pattern(int64_t* out, int G, int nt, int plane_rows, int WP, int row_bytes, int ksteps, int items,
+                              int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
