@@ -130,13 +130,32 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
   }
 }
 
-__global__ void bn_reduce_partials_kernel(const double* __restrict__ partials, int nparts, int C2,
-                                          double* __restrict__ sums) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C2) return;
-  double a = 0.0;
-  for (int p = 0; p < nparts; ++p) a += partials[static_cast<size_t>(p) * C2 + c];
-  sums[c] = a;
+// sums[c] = sum_p partials[p][c] in a FIXED order (deterministic): 8 warps stride over the partials with
+// coalesced 32-column reads, then the 8 warp partials are added in warp order.  Block = 32 columns.
+__global__ void __launch_bounds__(256) bn_reduce_partials_kernel(const double* __restrict__ partials, int nparts, int C2,
+                                                                 double* __restrict__ sums) {
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (c < C2) {
+    int p = w;
+    for (; p + 24 < nparts; p += 32) {
+      a0 += partials[static_cast<size_t>(p) * C2 + c];
+      a1 += partials[static_cast<size_t>(p + 8) * C2 + c];
+      a2 += partials[static_cast<size_t>(p + 16) * C2 + c];
+      a3 += partials[static_cast<size_t>(p + 24) * C2 + c];
+    }
+    for (; p < nparts; p += 8) a0 += partials[static_cast<size_t>(p) * C2 + c];
+  }
+  red[w][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (w == 0 && c < C2) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    sums[c] = t;
+  }
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
@@ -546,7 +565,7 @@ extern "C" int icsg3d_bn_stats(const void* x, int ldx, int dtype, int64_t rows, 
 
 extern "C" int icsg3d_bn_reduce_partials(const double* partials, int nparts, int C, double* sums, void* stream) {
   ICSG_REQUIRE(partials && sums && nparts > 0, "bn_reduce_partials: bad arguments");
-  bn_reduce_partials_kernel<<<ceil_div(2 * C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(partials, nparts, 2 * C, sums);
+  bn_reduce_partials_kernel<<<ceil_div(2 * C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, nparts, 2 * C, sums);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

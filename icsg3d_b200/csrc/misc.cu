@@ -70,17 +70,27 @@ __global__ void bf16_rows_to_f32_kernel(const __nv_bfloat16* __restrict__ src, i
 
 // ---- Dense ----------------------------------------------------------------------------------------
 // y[b,n] = act( sum_k x1[b,k] W[k,n] + sum_k x2[b,k] W[K1+k,n] + bias[n] )   (Concatenate + Dense)
-__global__ void dense_fwd_kernel(const float* __restrict__ x1, int k1, const float* __restrict__ x2, int k2,
-                                 const float* __restrict__ w, const float* __restrict__ bias, int act, int B, int N,
-                                 float* __restrict__ y) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * N) return;
-  const int b = idx / N, n = idx % N;
-  float acc = bias ? bias[n] : 0.f;
-  for (int k = 0; k < k1; ++k) acc = fmaf(x1[b * k1 + k], w[static_cast<size_t>(k) * N + n], acc);
-  for (int k = 0; k < k2; ++k) acc = fmaf(x2[b * k2 + k], w[static_cast<size_t>(k1 + k) * N + n], acc);
-  if (act == ICSG3D_ACT_RELU) acc = fmaxf(acc, 0.f);
-  y[idx] = acc;
+// Block = 32 outputs (n) x 8 k-slices; the 8 slice partials are added in slice order (deterministic).
+__global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict__ x1, int k1, const float* __restrict__ x2,
+                                                        int k2, const float* __restrict__ w, const float* __restrict__ bias,
+                                                        int act, int B, int N, float* __restrict__ y) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx, b = blockIdx.y;
+  float acc = 0.f;
+  if (n < N) {
+    for (int k = ty; k < k1; k += 8) acc = fmaf(x1[b * k1 + k], w[static_cast<size_t>(k) * N + n], acc);
+    for (int k = ty; k < k2; k += 8) acc = fmaf(x2[b * k2 + k], w[static_cast<size_t>(k1 + k) * N + n], acc);
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = bias ? bias[n] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    if (act == ICSG3D_ACT_RELU) t = fmaxf(t, 0.f);
+    y[b * N + n] = t;
+  }
 }
 // dy <- dy * relu'(y) in place when act == RELU (y = saved forward output); then
 // dx[b,k] = sum_n dy[b,n] W[k,n] for k < kx (the first kx rows of W), dW[k,n] = sum_b x[b,k] dy[b,n], db[n] = sum_b dy[b,n]
@@ -88,14 +98,17 @@ __global__ void dense_bwd_mask_kernel(float* __restrict__ dy, const float* __res
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && !(y[i] > 0.f)) dy[i] = 0.f;
 }
-__global__ void dense_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B, int N, int kx,
-                                       float* __restrict__ dx, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per (b,k): lanes stride over n (coalesced W row), fixed-order shuffle tree
+__global__ void __launch_bounds__(256) dense_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B,
+                                                              int N, int kx, float* __restrict__ dx, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (idx >= B * kx) return;
   const int b = idx / kx, k = idx % kx;
   float acc = 0.f;
-  for (int n = 0; n < N; ++n) acc = fmaf(dy[b * N + n], w[static_cast<size_t>(k) * N + n], acc);
-  dx[idx] = accumulate ? dx[idx] + acc : acc;
+  for (int n = lane; n < N; n += 32) acc = fmaf(dy[b * N + n], w[static_cast<size_t>(k) * N + n], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) dx[idx] = accumulate ? dx[idx] + acc : acc;
 }
 __global__ void dense_bwd_weight_kernel(const float* __restrict__ x1, int k1, const float* __restrict__ x2, int k2,
                                         const float* __restrict__ dy, int B, int N, float* __restrict__ dw,
@@ -367,7 +380,7 @@ extern "C" int icsg3d_bf16_rows_to_f32(const void* src, int ld, int c, int64_t r
 extern "C" int icsg3d_dense_fwd(const float* x1, int k1, const float* x2, int k2, const float* w, const float* bias,
                                 int act, int B, int N, float* y, void* stream) {
   ICSG_REQUIRE(x1 && w && y && (k2 == 0 || x2), "dense_fwd: null pointer");
-  dense_fwd_kernel<<<ceil_div(B * N, 128), 128, 0, ST>>>(x1, k1, x2, k2, w, bias, act, B, N, y);
+  dense_fwd_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, ST>>>(x1, k1, x2, k2, w, bias, act, B, N, y);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -382,7 +395,7 @@ extern "C" int icsg3d_dense_bwd(const float* x1, int k1, const float* x2, int k2
     ICSG_CHECK_LAUNCH();
   }
   if (dx1) {
-    dense_bwd_input_kernel<<<ceil_div(B * k1, 128), 128, 0, ST>>>(dy, w, B, N, k1, dx1, accumulate_dx);
+    dense_bwd_input_kernel<<<ceil_div(B * k1, 8), 256, 0, ST>>>(dy, w, B, N, k1, dx1, accumulate_dx);
     ICSG_CHECK_LAUNCH();
   }
   dense_bwd_weight_kernel<<<ceil_div((k1 + k2 + 1) * N, 128), 128, 0, ST>>>(x1, k1, x2, k2, dy, B, N, dw, db);
