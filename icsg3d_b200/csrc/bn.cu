@@ -308,6 +308,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_fwd_kernel(const BnFwdPar
 struct BnBwdParams {
   const void* dy;   // gradient w.r.t. the forward output (post domain)
   int lddy;
+  const void* dy2;  // optional second gradient w.r.t. the un-pooled BN output (U-Net skip connection), x's shape
+  int lddy2;
   const void* x;    // BN input (pre-normalisation)
   int ldx;
   const float* mean;
@@ -343,6 +345,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_kernel(const BnBwdParams p)
   constexpr int V = VecIO<T>::N;
   const T* x = static_cast<const T*>(p.x);
   const T* dy = static_cast<const T*>(p.dy);
+  const T* dy2 = static_cast<const T*>(p.dy2);
   const int cg = p.C / V;
   // Thread -> channel group is fixed for the whole kernel (grid-stride keeps idx % cg constant when the
   // stride is a multiple of cg; enforce it by striding in units of whole rows).
@@ -444,6 +447,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_kernel(const BnBwdParams p)
           VecIO<T>::load(x + r * p.ldx + g * V, xv);
 #pragma unroll
           for (int i = 0; i < V; ++i) sel[i] = bi[i] == k ? dyv[i] : 0.f;
+          if (dy2) {
+            float e[V];
+            VecIO<T>::load(dy2 + r * p.lddy2 + g * V, e);
+#pragma unroll
+            for (int i = 0; i < V; ++i) sel[i] += e[i];
+          }
           g_from<V>(xv, sel, sc, sh, p.act, p.alpha, gv);
           emit(r, xv, gv);
         }
@@ -473,6 +482,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_kernel(const BnBwdParams p)
           }
         } else {
           VecIO<T>::load(dy + r * p.lddy + g * V, dyv);
+        }
+        if (dy2) {
+          float e[V];
+          VecIO<T>::load(dy2 + r * p.lddy2 + g * V, e);
+#pragma unroll
+          for (int i = 0; i < V; ++i) dyv[i] += e[i];
         }
         g_from<V>(xv, dyv, sc, sh, p.act, p.alpha, gv);
         emit(r, xv, gv);
@@ -615,7 +630,7 @@ extern "C" int icsg3d_bn_apply_fwd(const void* x, int ldx, int x_dtype, const fl
   return ICSG3D_OK;
 }
 
-static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype, const float* mean,
                          const float* rstd, const float* scale, const float* shift, int act, float alpha, int post,
                          const uint8_t* pool_idx, int B, int D, int H, int W, int C, double* partials, int nparts,
                          const double* sums, double count, int pre_relu, const void* tap_other, int ld_other,
@@ -623,14 +638,14 @@ static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* x, in
   ICSG_REQUIRE(dy && x && mean && rstd && scale && shift, "bn_bwd: null pointer");
   ICSG_REQUIRE(bn_shape_ok(C, dtype), "bn_bwd: unsupported C=%d for dtype %d", C, dtype);
   const int V = dtype == ICSG3D_DT_BF16 ? 8 : 4;
-  ICSG_REQUIRE(ldx % V == 0 && lddy % V == 0, "bn_bwd: ld must be a multiple of %d", V);
+  ICSG_REQUIRE(ldx % V == 0 && lddy % V == 0 && (!dy2 || lddy2 % V == 0), "bn_bwd: ld must be a multiple of %d", V);
   ICSG_REQUIRE(post != ICSG3D_POST_POOL2 || pool_idx, "bn_bwd: pool needs pool_idx");
   ICSG_REQUIRE(!tap_other || dtype == ICSG3D_DT_BF16, "bn_bwd: tap gradient needs bf16 activations");
   long long rows = static_cast<long long>(B) * D * H * W;
   if (post == ICSG3D_POST_POOL2) rows /= 8;
   const int grid = bn_grid(rows, C, V);
   BnBwdParams p{};
-  p.dy = dy; p.lddy = lddy; p.x = x; p.ldx = ldx; p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
+  p.dy = dy; p.lddy = lddy; p.dy2 = dy2; p.lddy2 = lddy2; p.x = x; p.ldx = ldx; p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
   p.act = act; p.alpha = alpha; p.post = post; p.pool_idx = pool_idx; p.B = B; p.D = D; p.H = H; p.W = W; p.C = C;
   p.partials = partials; p.sums = sums; p.count = count; p.pre_relu = pre_relu;
   p.tap_other = static_cast<const __nv_bfloat16*>(tap_other); p.ld_other = ld_other; p.tap_coef = tap_coef;
@@ -663,20 +678,20 @@ extern "C" int icsg3d_bn_bwd_nparts(int B, int D, int H, int W, int C, int dtype
   return bn_grid(rows, C, dtype == ICSG3D_DT_BF16 ? 8 : 4);
 }
 
-extern "C" int icsg3d_bn_bwd_reduce(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+extern "C" int icsg3d_bn_bwd_reduce(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype, const float* mean,
                                     const float* rstd, const float* scale, const float* shift, int act, float alpha,
                                     int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C,
                                     double* partials, int nparts, void* stream) {
-  return bn_bwd_launch(false, dy, lddy, x, ldx, dtype, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D, H, W, C,
+  return bn_bwd_launch(false, dy, lddy, dy2, lddy2, x, ldx, dtype, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D, H, W, C,
                        partials, nparts, nullptr, 0.0, 0, nullptr, 0, 0.f, nullptr, 0, stream);
 }
 
-extern "C" int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+extern "C" int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype, const float* mean,
                                    const float* rstd, const float* scale, const float* shift, int act, float alpha,
                                    int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C,
                                    const double* sums, double count, int pre_relu, const void* tap_other, int ld_other,
                                    float tap_coef, void* dx, int lddx, void* stream) {
-  return bn_bwd_launch(true, dy, lddy, x, ldx, dtype, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D, H, W, C,
+  return bn_bwd_launch(true, dy, lddy, dy2, lddy2, x, ldx, dtype, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D, H, W, C,
                        nullptr, 0, sums, count, pre_relu, tap_other, ld_other, tap_coef, dx, lddx, stream);
 }
 

@@ -28,7 +28,8 @@ struct ConvIgemmParams {
   int nt;               // N tile
   int tiles_n, tiles_m;
   int ups;              // k-units per pipeline stage
-  int iters;            // 27*chunks/ups
+  int ntaps;            // 27 (3x3x3) or 1 (1x1x1)
+  int iters;            // ntaps*chunks/ups
   int stages;
   uint32_t a_unit_bytes;  // 128*kc*2
   uint32_t b_unit_bytes;  // nt*kc*2
@@ -111,9 +112,10 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint8_t* sb = sa + static_cast<size_t>(p.ups) * p.a_unit_bytes;
         if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
         for (int j = 0; j < p.ups; ++j) {
-          const int kd = tap / 9;
-          const int kh = (tap - kd * 9) / 3;
-          const int kw = tap - kd * 9 - kh * 3;
+          int kd = tap / 9;
+          int kh = (tap - kd * 9) / 3;
+          int kw = tap - kd * 9 - kh * 3;
+          if (p.ntaps == 1) kd = kh = kw = 1;  // 1x1x1: no spatial shift
           if (leader) {
             tma_load_5d(sa + static_cast<size_t>(j) * p.a_unit_bytes, &tmA, &full_bar[stage], ch * p.kc, w0 + kw - 1,
                         h0 + kh - 1, d0 + kd - 1, n0);
@@ -292,9 +294,9 @@ static int conv_impl_choice() {
 
 using namespace icsg3d;
 
-extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const float* bias, void* y,
-                                      int ldy, int y_dtype, int n_store, int B, int D, int H, int W, int cin,
-                                      int nout, int act, float leaky_alpha, void* stream) {
+static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                             int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                             float leaky_alpha, void* stream) {
   ICSG_REQUIRE(x && wpack && y, "conv3d_k3_igemm: null pointer");
   ICSG_REQUIRE(B > 0 && is_pow2(D) && is_pow2(H) && is_pow2(W) && D >= 2 && H >= 2 && W >= 2 && W <= 128,
                "conv3d_k3_igemm: D,H,W must be powers of two in [2,128] (got %d %d %d)", D, H, W);
@@ -311,7 +313,7 @@ extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack,
   {
     const int sms0 = sm_count();
     ConvHaloParams hp;
-    if (sms0 > 0 && conv_impl_choice() == 0 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp))
+    if (ntaps == 27 && sms0 > 0 && conv_impl_choice() == 0 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp))
       return launch_conv_halo(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, hp, sms0,
                               static_cast<cudaStream_t>(stream));
   }
@@ -336,8 +338,10 @@ extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack,
   ICSG_REQUIRE(nout % nt == 0, "conv3d_k3_igemm: unsupported nout %d", nout);
   p.nt = nt;
   p.tiles_n = nout / nt;
+  p.ntaps = ntaps;
   p.ups = (p.kc == 64) ? 1 : 3;
-  p.iters = 27 * p.chunks / p.ups;
+  if ((ntaps * p.chunks) % p.ups != 0) p.ups = 1;
+  p.iters = ntaps * p.chunks / p.ups;
   p.a_unit_bytes = 128u * p.kc * 2u;
   p.b_unit_bytes = static_cast<uint32_t>(nt) * p.kc * 2u;
   p.stage_bytes = (static_cast<uint32_t>(p.ups) * (p.a_unit_bytes + p.b_unit_bytes) + 1023u) & ~1023u;
@@ -364,7 +368,7 @@ extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack,
   int rc = encode_act_map(&tmA, x, ldx, B, D, H, W, cin, p.kc);
   if (rc) return rc;
   {
-    uint64_t dims[3] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(nout), 27};
+    uint64_t dims[3] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(nout), static_cast<uint64_t>(ntaps)};
     uint64_t strides[2] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(nout) * cin * 2};
     uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(nt), 1};
     rc = encode_tiled_bf16(&tmB, wpack, 3, dims, strides, box, p.kc * 2);
@@ -387,6 +391,18 @@ extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack,
   else conv3d_k3_igemm_kernel<4><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                                      int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                                      float leaky_alpha, void* stream) {
+  return conv3d_igemm_impl(27, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream);
+}
+
+extern "C" int icsg3d_conv3d_k1_igemm(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                                      int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                                      float leaky_alpha, void* stream) {
+  return conv3d_igemm_impl(1, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream);
 }
 
 // Diagnostic: which kernel and tiling the dispatcher picks for a layer shape (host only; no device needed).

@@ -20,6 +20,7 @@ struct WgradParams {
   int D, H, W;
   int tiles_m;
   int cin, cout;
+  int ntaps;                   // 27 or 1
   int kca, chunks_a, bpg;      // channels per row-block, chunks per tap, row-blocks per group
   int total_blocks, total_groups;
   int groups_per_cta;
@@ -96,9 +97,10 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const int blk = blk0 + b;
             const int tap = blk / p.chunks_a;
             const int ch = blk - tap * p.chunks_a;
-            const int kd = tap / 9;
-            const int kh = (tap - kd * 9) / 3;
-            const int kw = tap - kd * 9 - kh * 3;
+            int kd = tap / 9;
+            int kh = (tap - kd * 9) / 3;
+            int kw = tap - kd * 9 - kh * 3;
+            if (p.ntaps == 1) kd = kh = kw = 1;
             tma_load_5d(sa + static_cast<size_t>(b) * p.a_box_bytes, &tmX, &full_bar[stage], ch * p.kca, w0 + kw - 1,
                         h0 + kh - 1, d0 + kd - 1, n0);
           }
@@ -148,7 +150,7 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const int row = quarter * 32 + lane;
     mbar_wait(&done_bar, 0);
     tc_fence_after();
-    float* ws = p.ws + static_cast<size_t>(split) * 27 * p.cin * p.cout;
+    float* ws = p.ws + static_cast<size_t>(split) * p.ntaps * p.cin * p.cout;
     for (int g = g_begin; g < g_end; ++g) {
       const int blk = g * p.bpg + row / p.kca;
       const int tap = blk / p.chunks_a;
@@ -191,7 +193,8 @@ int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H
 
 static bool wg_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-static int wgrad_plan(int B, int D, int H, int W, int cin, int cout, WgradParams* p) {
+static int wgrad_plan(int ntaps, int B, int D, int H, int W, int cin, int cout, WgradParams* p) {
+  p->ntaps = ntaps;
   const long long m_total = static_cast<long long>(B) * D * H * W;
   p->m_total = static_cast<int>(m_total);
   p->D = D;
@@ -203,7 +206,7 @@ static int wgrad_plan(int B, int D, int H, int W, int cin, int cout, WgradParams
   p->kca = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
   p->chunks_a = cin / p->kca;
   p->bpg = 128 / p->kca;
-  p->total_blocks = 27 * p->chunks_a;
+  p->total_blocks = ntaps * p->chunks_a;
   p->total_groups = (p->total_blocks + p->bpg - 1) / p->bpg;
   p->kcb = (cout % 64 == 0) ? 64 : (cout % 32 == 0 ? 32 : 16);
   p->ntw = cout < 128 ? cout : 128;
@@ -244,16 +247,21 @@ static int wgrad_plan(int B, int D, int H, int W, int cin, int cout, WgradParams
 
 using namespace icsg3d;
 
-extern "C" int64_t icsg3d_conv3d_k3_wgrad_workspace(int B, int D, int H, int W, int cin, int cout) {
+static int64_t wgrad_workspace_impl(int ntaps, int B, int D, int H, int W, int cin, int cout) {
   if (B <= 0 || cin <= 0 || cout <= 0 || cin % 16 || cout % 16) return -1;
   WgradParams p{};
-  wgrad_plan(B, D, H, W, cin, cout, &p);
-  return static_cast<int64_t>(p.splits) * 27 * cin * cout * 4;
+  wgrad_plan(ntaps, B, D, H, W, cin, cout, &p);
+  return static_cast<int64_t>(p.splits) * ntaps * cin * cout * 4;
+}
+extern "C" int64_t icsg3d_conv3d_k3_wgrad_workspace(int B, int D, int H, int W, int cin, int cout) {
+  return wgrad_workspace_impl(27, B, D, H, W, cin, cout);
+}
+extern "C" int64_t icsg3d_conv3d_k1_wgrad_workspace(int B, int D, int H, int W, int cin, int cout) {
+  return wgrad_workspace_impl(1, B, D, H, W, cin, cout);
 }
 
-extern "C" int icsg3d_conv3d_k3_wgrad(const void* x, int ldx, const void* dy, int ldy, float* dw, int B, int D, int H,
-                                      int W, int cin, int cout, void* workspace, int64_t workspace_bytes,
-                                      void* stream) {
+static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy, float* dw, int B, int D, int H, int W,
+                      int cin, int cout, void* workspace, int64_t workspace_bytes, void* stream) {
   ICSG_REQUIRE(x && dy && dw && workspace, "conv3d_k3_wgrad: null pointer");
   ICSG_REQUIRE(B > 0 && wg_pow2(D) && wg_pow2(H) && wg_pow2(W) && D >= 2 && H >= 2 && W >= 2 && W <= 128,
                "conv3d_k3_wgrad: D,H,W must be powers of two in [2,128]");
@@ -261,9 +269,9 @@ extern "C" int icsg3d_conv3d_k3_wgrad(const void* x, int ldx, const void* dy, in
                "conv3d_k3_wgrad: cin/cout must be multiples of 16 (got %d/%d)", cin, cout);
   ICSG_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cin && ldy >= cout, "conv3d_k3_wgrad: bad ldx/ldy");
   WgradParams p{};
-  wgrad_plan(B, D, H, W, cin, cout, &p);
+  wgrad_plan(ntaps, B, D, H, W, cin, cout, &p);
   ICSG_REQUIRE(p.stages >= 2, "conv3d_k3_wgrad: stage too large");
-  const int64_t need = static_cast<int64_t>(p.splits) * 27 * cin * cout * 4;
+  const int64_t need = static_cast<int64_t>(p.splits) * ntaps * cin * cout * 4;
   ICSG_REQUIRE(workspace_bytes >= need, "conv3d_k3_wgrad: workspace too small (%lld < %lld)",
                static_cast<long long>(workspace_bytes), static_cast<long long>(need));
   p.ws = static_cast<float*>(workspace);
@@ -283,10 +291,22 @@ extern "C" int icsg3d_conv3d_k3_wgrad(const void* x, int ldx, const void* dy, in
   dim3 grid(p.splits, (p.total_groups + p.groups_per_cta - 1) / p.groups_per_cta, cout / p.ntw);
   conv3d_k3_wgrad_kernel<<<grid, kWgradThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmDY, p);
   ICSG_CHECK_LAUNCH();
-  const long long n = 27ll * cin * cout;
+  const long long n = static_cast<long long>(ntaps) * cin * cout;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p.ws, dw, n, p.splits);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_conv3d_k3_wgrad(const void* x, int ldx, const void* dy, int ldy, float* dw, int B, int D, int H,
+                                      int W, int cin, int cout, void* workspace, int64_t workspace_bytes,
+                                      void* stream) {
+  return wgrad_impl(27, x, ldx, dy, ldy, dw, B, D, H, W, cin, cout, workspace, workspace_bytes, stream);
+}
+
+extern "C" int icsg3d_conv3d_k1_wgrad(const void* x, int ldx, const void* dy, int ldy, float* dw, int B, int D, int H,
+                                      int W, int cin, int cout, void* workspace, int64_t workspace_bytes,
+                                      void* stream) {
+  return wgrad_impl(1, x, ldx, dy, ldy, dw, B, D, H, W, cin, cout, workspace, workspace_bytes, stream);
 }

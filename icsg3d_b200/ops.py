@@ -30,10 +30,22 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _ld(t):
+    """Channel stride (elements) of one voxel: supports channel slices of a wider NDHWC tensor (concat buffers)."""
+    return t.stride(-2) if t.dim() >= 2 else t.shape[-1]
+
+
 def _chk(t, dtype, name):
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
-    if not t.is_contiguous():
+    if t.stride(-1) != 1:
+        raise ValueError(f"{name}: channels must be contiguous")
+    if t.dim() == 5:
+        B, D, H, W, _ = t.shape
+        ld = t.stride(-2)
+        if t.stride(2) != W * ld or t.stride(1) != H * W * ld or t.stride(0) != D * H * W * ld:
+            raise ValueError(f"{name}: only channel-sliced views of a contiguous NDHWC tensor are supported")
+    elif not t.is_contiguous():
         raise ValueError(f"{name}: tensor must be contiguous")
 
 
@@ -114,7 +126,8 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
     """
     _chk(x, torch.bfloat16, "x")
     _chk(wpack, torch.bfloat16, "wpack")
-    B, D, H, W, ldx = x.shape
+    B, D, H, W, _ = x.shape
+    ldx = _ld(x)
     nout, cin_w = wpack.shape[1], wpack.shape[2]
     cin = cin or cin_w
     if cin != cin_w:
@@ -133,9 +146,10 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
         out = torch.empty((B, D, H, W, n_store), dtype=out_dtype, device=x.device)
     ydt = DT_BF16 if out.dtype == torch.bfloat16 else DT_F32
     nc, no = nominal if nominal else (cin, nout)
-    with _timed(("igemm", tag), 2.0 * B * D * H * W * 27 * nc * no):
-        _lib.call("icsg3d_conv3d_k3_igemm", _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), out.shape[-1], ydt,
-                  n_store, B, D, H, W, cin, nout, act, alpha, _stream())
+    with _timed(("igemm", tag), 2.0 * B * D * H * W * wpack.shape[0] * nc * no):
+        fn = "icsg3d_conv3d_k1_igemm" if wpack.shape[0] == 1 else "icsg3d_conv3d_k3_igemm"
+        _lib.call(fn, _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt, n_store, B, D, H, W, cin, nout,
+                  act, alpha, _stream())
     return out
 
 
@@ -191,7 +205,7 @@ def bn_nparts(rows, C, dtype):
 def bn_stats(x, C, partials):
     """x: [..., ld]; partials: float64 [nparts, 2, C]."""
     rows = x.numel() // x.shape[-1]
-    _lib.call("icsg3d_bn_stats", _ptr(x), x.shape[-1], _dt(x), ctypes.c_int64(rows), C, _ptr(partials),
+    _lib.call("icsg3d_bn_stats", _ptr(x), _ld(x), _dt(x), ctypes.c_int64(rows), C, _ptr(partials),
               partials.shape[0], _stream())
 
 
@@ -212,9 +226,9 @@ def bn_inference_coeffs(gamma, beta, moving_mean, moving_var, scale, shift, eps=
 
 
 def bn_apply_fwd(x, C, scale, shift, act, post, y=None, y32=None, pool_idx=None, alpha=LEAKY_ALPHA):
-    B, D, H, W, ldx = x.shape
-    _lib.call("icsg3d_bn_apply_fwd", _ptr(x), ldx, _dt(x), _ptr(scale), _ptr(shift), act, alpha, post, B, D, H, W, C,
-              _ptr(y), y.shape[-1] if y is not None else 0, _ptr(y32), y32.shape[-1] if y32 is not None else 0,
+    B, D, H, W, _ = x.shape
+    _lib.call("icsg3d_bn_apply_fwd", _ptr(x), _ld(x), _dt(x), _ptr(scale), _ptr(shift), act, alpha, post, B, D, H, W, C,
+              _ptr(y), _ld(y) if y is not None else 0, _ptr(y32), y32.shape[-1] if y32 is not None else 0,
               _ptr(pool_idx), _stream())
 
 
@@ -226,19 +240,21 @@ def bn_bwd_nparts(x, C, post):
     return n
 
 
-def bn_bwd_reduce(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, partials, alpha=LEAKY_ALPHA):
-    B, D, H, W, ldx = x.shape
-    _lib.call("icsg3d_bn_bwd_reduce", _ptr(dy), dy.shape[-1], _ptr(x), ldx, _dt(x), _ptr(mean), _ptr(rstd), _ptr(scale),
+def bn_bwd_reduce(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, partials, alpha=LEAKY_ALPHA, dy2=None):
+    B, D, H, W, _ = x.shape
+    ldx = _ld(x)
+    _lib.call("icsg3d_bn_bwd_reduce", _ptr(dy), _ld(dy), _ptr(dy2), _ld(dy2) if dy2 is not None else 0, _ptr(x), ldx, _dt(x), _ptr(mean), _ptr(rstd), _ptr(scale),
               _ptr(shift), act, alpha, post, _ptr(pool_idx), B, D, H, W, C, _ptr(partials), partials.shape[0], _stream())
 
 
 def bn_bwd_apply(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums, count, dx, pre_relu=False,
-                 tap_other=None, tap_coef=0.0, alpha=LEAKY_ALPHA):
-    B, D, H, W, ldx = x.shape
-    _lib.call("icsg3d_bn_bwd_apply", _ptr(dy), dy.shape[-1], _ptr(x), ldx, _dt(x), _ptr(mean), _ptr(rstd), _ptr(scale),
+                 tap_other=None, tap_coef=0.0, alpha=LEAKY_ALPHA, dy2=None):
+    B, D, H, W, _ = x.shape
+    ldx = _ld(x)
+    _lib.call("icsg3d_bn_bwd_apply", _ptr(dy), _ld(dy), _ptr(dy2), _ld(dy2) if dy2 is not None else 0, _ptr(x), ldx, _dt(x), _ptr(mean), _ptr(rstd), _ptr(scale),
               _ptr(shift), act, alpha, post, _ptr(pool_idx), B, D, H, W, C, _ptr(sums), ctypes.c_double(count),
               1 if pre_relu else 0, _ptr(tap_other), tap_other.shape[-1] if tap_other is not None else 0,
-              tap_coef, _ptr(dx), dx.shape[-1], _stream())
+              tap_coef, _ptr(dx), _ld(dx), _stream())
 
 
 def bn_param_grads(sums, dgamma, dbeta):
@@ -331,3 +347,49 @@ def adam_keras_step(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-7, gra
     _lib.call("icsg3d_adam_keras_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(state), ctypes.c_double(lr),
               ctypes.c_double(beta1), ctypes.c_double(beta2), ctypes.c_double(eps), grad_scale,
               ctypes.c_int64(p.numel()), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# U-Net heads
+# ------------------------------------------------------------------------------------------------
+def conv3d_k1_wgrad(x, dy, *, cin, cout, out):
+    """dW[1][cin][cout] of a 1x1x1 conv (tcgen05, same kernel as the 3x3x3 filter gradient)."""
+    B, D, H, W, _ = x.shape
+    need = _lib.lib().icsg3d_conv3d_k1_wgrad_workspace(B, D, H, W, cin, cout)
+    key = (x.device.index,)
+    ws = _wgrad_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(int(need), dtype=torch.uint8, device=x.device)
+        _wgrad_ws[key] = ws
+    with _timed(("wgrad", "heads.wgrad"), 2.0 * B * D * H * W * cin * cout):
+        _lib.call("icsg3d_conv3d_k1_wgrad", _ptr(x), _ld(x), _ptr(dy), _ld(dy), _ptr(out), B, D, H, W, cin, cout, _ptr(ws),
+                  ctypes.c_int64(ws.numel()), _stream())
+    return out
+
+
+def pack_heads_w(w_soft, w_sig, b_soft, b_sig, wf, wd, bias):
+    cin, c1 = w_soft.shape[-2], w_soft.shape[-1]
+    _lib.call("icsg3d_pack_heads_w", _ptr(w_soft), _ptr(w_sig), _ptr(b_soft), _ptr(b_sig), cin, c1, wf.shape[1], _ptr(wf),
+              _ptr(wd), _ptr(bias), _stream())
+
+
+def unpack_heads_grad(dwcat, colsum, c1, dw_soft, dw_sig, db_soft, db_sig):
+    cin, nout = dwcat.shape[-2], dwcat.shape[-1]
+    _lib.call("icsg3d_unpack_heads_grad", _ptr(dwcat), _ptr(colsum), cin, c1, nout, _ptr(dw_soft), _ptr(dw_sig),
+              _ptr(db_soft), _ptr(db_sig), _stream())
+
+
+def heads_loss_nparts(M):
+    return _lib.lib().icsg3d_heads_loss_nparts(ctypes.c_int64(M))
+
+
+def heads_loss(logits, c1, species, class_w, inv_count, partials, argmax_out=None, sig_prob=None, dlogits=None, probs=None):
+    M = logits.numel() // logits.shape[-1]
+    _lib.call("icsg3d_heads_loss", _ptr(logits), logits.shape[-1], c1, _ptr(species), _ptr(class_w), ctypes.c_int64(M),
+              inv_count, _ptr(argmax_out), _ptr(sig_prob), _ptr(probs), _ptr(dlogits), dlogits.shape[-1] if dlogits is not None else 0,
+              _ptr(partials), partials.shape[0], _stream())
+
+
+def heads_loss_finalize(partials, count, out, raw=None):
+    _lib.call("icsg3d_heads_loss_finalize", _ptr(partials), partials.shape[0], ctypes.c_double(count), _ptr(out), _ptr(raw),
+              _stream())

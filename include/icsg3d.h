@@ -73,6 +73,15 @@ int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const floa
  * out[0..9] = {impl (0 per-tap TMA kernel, 1 halo-reuse kernel), TD, TH, G, NT, a_bufs, b_stages, items, kc, smem} */
 int icsg3d_conv3d_k3_plan(int B, int D, int H, int W, int cin, int nout, int sms, int* out);
 
+/* Conv3D 1x1x1 (the U-Net heads `soft`/`sig`, unet.py:339-352) through the same tcgen05 kernel with a single tap:
+ * wpack bf16 [1][nout][cin]. */
+int icsg3d_conv3d_k1_igemm(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                           int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                           float leaky_alpha, void* stream);
+int64_t icsg3d_conv3d_k1_wgrad_workspace(int B, int D, int H, int W, int cin, int cout);
+int icsg3d_conv3d_k1_wgrad(const void* x, int ldx, const void* dy, int ldy, float* dw, int B, int D, int H,
+                           int W, int cin, int cout, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Conv3DBackpropFilterV2: dW[tap][ci][co] = sum_voxels x[voxel+tap, ci] * dy[voxel, co]
  * (gradient of the layers above w.r.t. their kernels).  tcgen05 GEMM with both operands MN-major,
  * the voxel range split over CTAs; partials are reduced in a fixed order (deterministic).
@@ -136,14 +145,18 @@ int icsg3d_bn_apply_fwd(const void* x, int ldx, int x_dtype, const float* scale,
                         float alpha, int post, int B, int D, int H, int W, int C, void* y, int ldy, float* y32,
                         int ldy32, uint8_t* pool_idx, void* stream);
 int icsg3d_bn_bwd_nparts(int B, int D, int H, int W, int C, int dtype, int post);
-int icsg3d_bn_bwd_reduce(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+/* dy2 (optional, may be NULL): a second gradient w.r.t. the UN-pooled BN output with x's shape — the U-Net skip
+ * connections feed both MaxPool3D and a later Concatenate (unet.py:282,332). */
+int icsg3d_bn_bwd_reduce(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype,
+                         const float* mean,
                          const float* rstd, const float* scale, const float* shift, int act, float alpha,
                          int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C, double* partials,
                          int nparts, void* stream);
 /* pre_relu: U-Net ordering Conv->ReLU->BN (unet.py:276-278): x is the ReLU output and dx is masked by x>0.
  * tap_other/tap_coef: DFC feature-loss gradient tap_coef*(x - tap_other) added before the mask
  * (lattice_vae.py:257-270).  dx is bf16 with stride lddx. */
-int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype,
+                        const float* mean,
                         const float* rstd, const float* scale, const float* shift, int act, float alpha,
                         int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C, const double* sums,
                         double count, int pre_relu, const void* tap_other, int ld_other, float tap_coef,
@@ -190,6 +203,27 @@ int icsg3d_bias_grad(const void* dy, int ld, int64_t rows, int C, float* db, voi
  * state: double[2] on the device = {t, lr_t}; advanced on the device so the step is CUDA-graph replayable. */
 int icsg3d_adam_keras_step(float* p, const float* g, float* m, float* v, double* state, double lr, double beta1,
                            double beta2, double eps, float grad_scale, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * U-Net heads (unet.py:339-352) and their losses/metrics (unet.py:159-221, 249-259).
+ * The two 1x1x1 convolutions (95-way softmax + 1 sigmoid) are ONE GEMM with nout = 96 columns
+ * (icsg3d_conv3d_k1_igemm); pack_heads_w builds its operands from the Keras kernels; heads_loss is the fused
+ * per-voxel pass over the fp32 logits [M][ld]: weighted CCE, logits-form BCE, argmax label, sigmoid
+ * probability, optional softmax probabilities (fp32 [M][c1], what model.predict returns), metric counts, and
+ * d(loss)/d(logits) (bf16 [M][ldd], already scaled by inv_count).
+ * partials: fp64 [nparts][6] = {soft loss, sig loss, tp, predicted, tp_w, possible_w} sums.
+ * ---------------------------------------------------------------------------------------------- */
+int icsg3d_pack_heads_w(const float* w_soft, const float* w_sig, const float* b_soft, const float* b_sig, int cin,
+                        int c1, int nout, void* wf, void* wd, float* bias, void* stream);
+int icsg3d_unpack_heads_grad(const float* dwcat, const double* colsum, int cin, int c1, int nout, float* dw_soft,
+                             float* dw_sig, float* db_soft, float* db_sig, void* stream);
+int icsg3d_heads_loss_nparts(int64_t M);
+int icsg3d_heads_loss(const float* logits, int ld, int c1, const uint8_t* species, const float* class_w, int64_t M,
+                      float inv_count, uint8_t* argmax_out, float* sig_prob, float* probs, void* dlogits, int ldd,
+                      double* partials, int nparts, void* stream);
+/* out = [loss, soft_loss, sig_loss, f1_m, wr_m]; raw (optional) = the six term sums (for data-parallel reduction) */
+int icsg3d_heads_loss_finalize(const double* partials, int nparts, double count, float* out, double* raw,
+                               void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Gaussian atomic-density voxeliser — utils.py:97-144 density_matrix + utils.py:88-94 coordinate_grid

@@ -1,0 +1,152 @@
+"""U-Net rows of the scope table: the fused head kernel against the oracle's loss/metric
+restatements (unet.py:159-221), one full train step (forward, weighted CCE + BCE, backward through skips /
+pools / upsamplings, Keras-Adam) and the inference path (argmax labels) against oracle/nets.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import cosine, rel_l2, synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_heads_loss_kernel_matches_oracle():
+    from icsg3d_b200 import ops
+    from oracle import nets
+    g = torch.Generator().manual_seed(0)
+    B, d, C = 2, 8, 95
+    species = torch.randint(0, C, (B, d, d, d), generator=g)
+    species[torch.rand(B, d, d, d, generator=g) < 0.6] = 0
+    logits = torch.randn(B, d, d, d, 96, generator=g) * 2.0
+    # make a third of the voxels confidently right so that the rounded metrics are non-trivial
+    sel = torch.rand(B, d, d, d, generator=g) < 0.33
+    logits[..., :C][sel] += 8.0 * torch.nn.functional.one_hot(species, C)[sel].float()
+    soft, sig = logits[..., :C].clone().requires_grad_(True), logits[..., C:].clone().requires_grad_(True)
+    w = torch.rand(C, generator=g) + 0.5
+    ls = nets.weighted_cce(soft, species, w)
+    lb = nets.sigmoid_bce(sig, species != 0)
+    (ls + lb).backward()
+    f1, wr = nets.unet_metrics(soft.detach(), species)
+
+    dev = "cuda"
+    M = B * d ** 3
+    n = ops.heads_loss_nparts(M)
+    part = torch.zeros(n, 6, dtype=torch.float64, device=dev)
+    out = torch.zeros(5, device=dev)
+    am = torch.zeros(M, dtype=torch.uint8, device=dev)
+    sp = torch.zeros(M, device=dev)
+    dl = torch.zeros(M, 96, dtype=torch.bfloat16, device=dev)
+    probs = torch.zeros(M, C, device=dev)
+    ops.heads_loss(logits.to(dev).view(M, 96), C, species.to(torch.uint8).to(dev).view(M), w.to(dev), 1.0 / M, part,
+                   argmax_out=am, sig_prob=sp, dlogits=dl, probs=probs)
+    ops.heads_loss_finalize(part, float(M), out)
+    torch.cuda.synchronize()
+    got = out.cpu().tolist()
+    want = [float(ls + lb), float(ls), float(lb), float(f1), float(wr)]
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (got, want)
+    assert torch.equal(am.cpu().view(B, d, d, d).long(), logits[..., :C].argmax(-1))
+    assert rel_l2(sp.cpu(), torch.sigmoid(logits[..., C]).flatten()) < 1e-6
+    assert rel_l2(probs.cpu(), torch.softmax(logits[..., :C], -1).reshape(M, C)) < 1e-6
+    dref = torch.cat([soft.grad, sig.grad], dim=-1).reshape(M, 96)
+    assert rel_l2(dl.float().cpu(), dref) < 1e-2
+
+
+def _unet_setup(B, d, seed=0):
+    from icsg3d_b200.unet_engine import UNetEngine
+    eng = UNetEngine(B, d=d, seed=5, lr=1e-3)
+    M, _, S = synthetic_batch(B, d=d, seed=seed)
+    eng.set_inputs(M.cuda(), S.cuda())
+    p = {k: torch.from_numpy(v) for k, v in eng.pp.to_dict().items()}
+    return eng, M, S, p
+
+
+@pytest.mark.parametrize("B,d", [(2, 16), (1, 32)])
+def test_unet_train_step_matches_oracle(B, d):
+    from oracle import nets
+    eng, M, S, p = _unet_setup(B, d)
+    names = nets.trainable_names(p)
+    leaves = {k: p[k].clone().requires_grad_(True) for k in names}
+    pp = dict(p)
+    pp.update(leaves)
+    taps = {}
+    out, soft, sig = nets.unet_loss(pp, M, S.long(), training=True, weight=95.0, taps=taps)
+    grads = dict(zip(names, torch.autograd.grad(out[0], [leaves[k] for k in names])))
+    theta0 = eng.pp.theta.clone()
+    eng.train_step()
+    torch.cuda.synchronize()
+    got = eng.metrics_host()
+    want = [float(o) for o in out]
+    report = {"metrics_cuda": got, "metrics_oracle": want, "act": {}, "grad": {}}
+    for n in ("c1", "c2", "c6", "c10", "c13", "c17", "c18"):
+        report["act"][n] = rel_l2(eng.L[n]["a"].float(), taps[n])
+    report["act"]["soft_logits"] = rel_l2(eng.logits[..., :95], taps["soft_logits"])
+    report["act"]["sig_logit"] = rel_l2(eng.logits[..., 95:96], taps["sig_logit"])
+    for k in names:
+        report["grad"][k] = {"rel_l2": rel_l2(eng.pp.g[k], grads[k]), "cos": cosine(eng.pp.g[k], grads[k])}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/unet_step_parity_B{B}_d{d}.json", "w") as f:
+        json.dump(report, f, indent=1)
+    print(json.dumps({k: report[k] for k in ("metrics_cuda", "metrics_oracle", "act")}, indent=1))
+    worst = sorted(report["grad"].items(), key=lambda kv: kv[1]["cos"])[:6]
+    print("worst grads", worst)
+    # losses: the CCE carries the reference's x95 scalar weight (unet.py:254) -> compare relatively (1e-3 of the value)
+    for a, b in zip(got[:3], want[:3]):
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (got, want)
+    assert report["act"]["c1"] < 1e-2 and report["act"]["soft_logits"] < 6e-2
+    bad = {k: v for k, v in report["grad"].items() if k.endswith("kernel") and v["cos"] < 0.9}
+    assert not bad, bad
+    assert float((eng.pp.theta - theta0).abs().max()) > 0
+
+
+def test_unet_predict_labels_agree_with_oracle():
+    """generate.py:220-225: argmax over the 95 classes and sigmoid >= 0.8.  bf16 operand mode: near-ties may flip
+     -> require >= 99 % agreement and that every mismatch is a near-tie in the oracle (top-2 margin small)."""
+    from oracle import nets
+    B, d = 2, 16
+    eng, M, S, p = _unet_setup(B, d, seed=3)
+    # larger head weights so that the argmax is not a 95-way coin flip
+    g = torch.Generator().manual_seed(1)
+    p["soft/kernel"] = torch.randn(p["soft/kernel"].shape, generator=g) * 0.3
+    eng.pp.load_dict(p)
+    with torch.no_grad():
+        soft, sig = nets.unet_forward(p, M, training=False)
+    probs = torch.empty(B, d, d, d, 95, device="cuda")
+    eng.predict(probs)
+    torch.cuda.synchronize()
+    lab = eng.argmax.cpu().long()
+    ref = soft.argmax(-1)
+    agree = float((lab == ref).float().mean())
+    top2 = soft.topk(2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1])[lab != ref]
+    print("argmax agreement", agree, "max mismatch margin", float(margin.max()) if margin.numel() else 0.0)
+    assert agree >= 0.99
+    if margin.numel():
+        assert float(margin.max()) < 0.05 * float(soft.abs().max())
+    assert rel_l2(probs.cpu(), torch.softmax(soft, -1)) < 5e-2
+    assert rel_l2(eng.sigp.cpu(), torch.sigmoid(sig[..., 0])) < 2e-2
+
+
+def test_atomunet_facade_roundtrip(tmp_path):
+    """AtomUnet API (unet.py:235-270, 357-390): predict shapes/dtypes, train_on_batch with one-hot labels, save/load."""
+    from icsg3d_b200.unet.unet import AtomUnet
+    d = 16
+    net = AtomUnet(input_shape=(d, d, d, 4), lr=1e-4, use_cuda_graph=False)
+    M, _, S = synthetic_batch(2, d=d, seed=4)
+    onehot = torch.nn.functional.one_hot(S.long(), 95).float().numpy()
+    mask = (S != 0).float().numpy()[..., None]
+    m = net.model.train_on_batch(M.numpy().astype(np.float64), [onehot, mask])
+    assert len(m) == 5 and all(np.isfinite(m))
+    soft, sig = net.model.predict(M.numpy())
+    assert soft.shape == (2, d, d, d, 95) and sig.shape == (2, d, d, d, 1) and soft.dtype == np.float32
+    np.testing.assert_allclose(soft.sum(-1), 1.0, rtol=1e-4)
+    path = str(tmp_path / "unet_weights.best.hdf5")
+    net.model.save_weights(path)
+    net2 = AtomUnet(input_shape=(d, d, d, 4), weights=path, use_cuda_graph=False)
+    soft2, _ = net2.model.predict(M.numpy())
+    np.testing.assert_array_equal(soft, soft2)
+    lab, mask8 = net2.predict_labels(M.numpy())
+    assert lab.dtype == np.uint8 and np.array_equal(lab, soft.argmax(-1).astype(np.uint8))
