@@ -96,10 +96,40 @@ def test_unet_train_step_matches_oracle(B, d):
     # losses: the CCE carries the reference's x95 scalar weight (unet.py:254) -> compare relatively (1e-3 of the value)
     for a, b in zip(got[:3], want[:3]):
         assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (got, want)
-    assert report["act"]["c1"] < 1e-2 and report["act"]["soft_logits"] < 6e-2
-    bad = {k: v for k, v in report["grad"].items() if k.endswith("kernel") and v["cos"] < 0.9}
+    # bf16 operand mode (T2/T3 of SURVEY §8c): activations drift with depth (~6e-2 after 14 conv+BN blocks) and the
+    # gradients are REPORTED — ReLU-mask / pool-argmax flips dominate (cosine falls smoothly from 0.999 at c18 to
+    # ~0.85 at c1, no jump at the skip / pool / upsample boundaries); backward<->forward consistency of the CUDA path
+    # itself is checked exactly by test_unet_directional_derivative below.
+    assert report["act"]["c1"] < 1e-2 and report["act"]["soft_logits"] < 0.1
+    bad = {k: v for k, v in report["grad"].items() if k.endswith("kernel") and v["cos"] < 0.8}
     assert not bad, bad
+    assert report["grad"]["c18/kernel"]["cos"] > 0.99 and report["grad"]["soft/kernel"]["cos"] > 0.99
     assert float((eng.pp.theta - theta0).abs().max()) > 0
+
+
+def test_unet_directional_derivative():
+    """Self-consistency of the CUDA backward with the CUDA forward: moving the weights by -h*g/|g| must lower the
+    loss by ~h*|g| (first order).  Independent of the oracle and of bf16 flip noise in it."""
+    B, d = 2, 16
+    eng, M, S, p = _unet_setup(B, d, seed=7)
+    eng.pack_weights()
+    eng.forward(True, with_grad=True)
+    eng.backward()
+    torch.cuda.synchronize()
+    L0 = float(eng.metrics[0])
+    g = eng.pp.grad[: eng.pp.n_trainable].clone()
+    gn = float(g.norm())
+    theta0 = eng.pp.theta.clone()
+    ratios = []
+    for h in (0.001, 0.003):
+        eng.pp.theta[: eng.pp.n_trainable] = theta0[: eng.pp.n_trainable] - h * g / gn
+        eng.pack_weights()
+        eng.forward(True)
+        torch.cuda.synchronize()
+        ratios.append((L0 - float(eng.metrics[0])) / (h * gn))
+    eng.pp.theta.copy_(theta0)
+    print("directional derivative ratios", ratios, "L0", L0, "|g|", gn)
+    assert 0.7 < ratios[0] < 1.3, ratios
 
 
 def test_unet_predict_labels_agree_with_oracle():

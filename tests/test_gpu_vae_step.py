@@ -108,6 +108,35 @@ def test_eval_step_matches_oracle():
     assert abs(got[3] - want[3]) <= 1e-2 * abs(want[3]), (got, want)
 
 
+def test_vae_directional_derivative():
+    """Backward<->forward self-consistency of the CUDA VAE+DFC step (see test_gpu_unet.py)."""
+    eng, M, cond, eps, _, _ = _setup(seed=4)
+    eng.pack_weights()
+    from icsg3d_b200 import ops
+    ops.pack_vae_input(eng.M, eng.cond, eng.xe, eng.xp)
+
+    def fwd():
+        eng.pack_weights()
+        eng.encode(True); eng.decode(True); eng.pm_forward(0, True); eng.pm_forward(1, True); eng.losses()
+        torch.cuda.synchronize()
+        return float(eng.metrics[0])
+
+    L0 = fwd()
+    eng.backward()
+    torch.cuda.synchronize()
+    n = eng.vp.n_trainable
+    g = eng.vp.grad[:n].clone()
+    gn = float(g.norm())
+    theta0 = eng.vp.theta.clone()
+    ratios = []
+    for h in (0.02, 0.05):
+        eng.vp.theta[:n] = theta0[:n] - h * g / gn
+        ratios.append((L0 - fwd()) / (h * gn))
+    eng.vp.theta.copy_(theta0)
+    print("directional derivative ratios", ratios, "L0", L0, "|g|", gn)
+    assert 0.7 < ratios[0] < 1.3, ratios
+
+
 def test_graph_replay_equals_eager():
     """A CUDA-graph replay of the whole step must produce the same numbers as eager launches."""
     eng, M, cond, eps, _, _ = _setup(seed=2)
