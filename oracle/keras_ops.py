@@ -28,9 +28,26 @@ def conv3d_same(x, kernel, bias=None):
     return y.permute(0, 2, 3, 4, 1)
 
 
+# Data-parallel restatement hook (tests only): when set to a differentiable all-reduce-sum, batch statistics are
+# computed from (sum x, sum x^2, count) summed over the ranks — the sync-BN scheme of SURVEY §8e — so that N ranks on
+# batch shards reproduce one rank on the full batch.
+STAT_ALLREDUCE = None
+
+
 def batchnorm(x, gamma, beta, moving_mean, moving_var, training, eps=BN_EPS):
     """keras BatchNormalization(axis=-1) on a 5-D tensor (R3): biased batch variance in training,
     moving statistics otherwise.  Returns (y, batch_mean, batch_var) (stats are None in inference)."""
+    if training and STAT_ALLREDUCE is not None:
+        dims = tuple(range(x.dim() - 1))
+        n_local = x.numel() // x.shape[-1]
+        packed = torch.cat([x.sum(dim=dims), (x * x).sum(dim=dims), torch.full((1,), float(n_local), dtype=x.dtype)])
+        packed = STAT_ALLREDUCE(packed)
+        C = x.shape[-1]
+        n = packed[-1]
+        mean = packed[:C] / n
+        var = packed[C:2 * C] / n - mean * mean
+        y = (x - mean) / torch.sqrt(var + eps) * gamma + beta
+        return y, mean, var
     if training:
         dims = tuple(range(x.dim() - 1))
         mean = x.mean(dim=dims)
