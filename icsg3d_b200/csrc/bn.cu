@@ -73,7 +73,7 @@ static constexpr int kBnThreads = 256;
 // statistics: partials[blk][0][c] = sum x, partials[blk][1][c] = sum x^2 (fp64)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, int ldx, long long M, int C,
+__global__ void __launch_bounds__(kBnThreads, 4) bn_stats_kernel(const T* __restrict__ x, int ldx, long long M, int C,
                                                              double* __restrict__ partials) {
   constexpr int V = VecIO<T>::N;
   extern __shared__ double sred[];  // [2][rows_per_iter][C] would be too big: reduce per channel group instead
@@ -81,36 +81,20 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
   const int rpi = kBnThreads / cg;  // rows per iteration handled by this block
   const int g = threadIdx.x % cg;
   const int rl = threadIdx.x / cg;
+  // per-thread partials in fp32: the grid is sized so that a thread sees at most a few dozen rows; everything
+  // downstream (block reduction, partials, final sums) is fp64
   float s[V], q[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
-  double ds[V], dq[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) ds[i] = dq[i] = 0.0;
   if (rl < rpi) {
-    int n = 0;
     for (long long r = static_cast<long long>(blockIdx.x) * rpi + rl; r < M; r += static_cast<long long>(gridDim.x) * rpi) {
       float v[V];
       VecIO<T>::load(x + r * ldx + g * V, v);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         s[i] += v[i];
-        q[i] += v[i] * v[i];
+        q[i] = fmaf(v[i], v[i], q[i]);
       }
-      if (++n == 32) {  // flush fp32 partials to fp64 regularly
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          ds[i] += s[i];
-          dq[i] += q[i];
-          s[i] = q[i] = 0.f;
-        }
-        n = 0;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      ds[i] += s[i];
-      dq[i] += q[i];
     }
   }
   // block reduction over the row lanes: smem [rpi][cg*V] doubles, two passes (sum, sumsq)
@@ -119,7 +103,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
     __syncthreads();
     if (rl < rpi) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) sred[rl * C + g * V + i] = pass == 0 ? ds[i] : dq[i];
+      for (int i = 0; i < V; ++i) sred[rl * C + g * V + i] = static_cast<double>(pass == 0 ? s[i] : q[i]);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += kBnThreads) {
@@ -183,6 +167,73 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
   }
 }
 
+// Fused single-GPU path: fixed-order reduction of the partials (as bn_reduce_partials_kernel) followed by the
+// finalisation of the same 32 channels.  mode 0: forward statistics -> mean/rstd/scale/shift (+moving averages);
+// mode 1: backward sums -> sums[2][C] (+ dgamma = sum g*xhat, dbeta = sum g).
+__global__ void __launch_bounds__(256) bn_reduce_fused_kernel(const double* __restrict__ partials, int nparts, int C,
+                                                              int mode, double count, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps,
+                                                              double* __restrict__ sums, float* __restrict__ mean_out,
+                                                              float* __restrict__ rstd_out, float* __restrict__ scale,
+                                                              float* __restrict__ shift, float* __restrict__ moving_mean,
+                                                              float* __restrict__ moving_var, float momentum,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double red[8][33];
+  __shared__ double tot[2][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int C2 = 2 * C;
+  for (int half = 0; half < 2; ++half) {
+    const int col = half * C + c;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (c < C) {
+      int p = w;
+      for (; p + 24 < nparts; p += 32) {
+        a0 += partials[static_cast<size_t>(p) * C2 + col];
+        a1 += partials[static_cast<size_t>(p + 8) * C2 + col];
+        a2 += partials[static_cast<size_t>(p + 16) * C2 + col];
+        a3 += partials[static_cast<size_t>(p + 24) * C2 + col];
+      }
+      for (; p < nparts; p += 8) a0 += partials[static_cast<size_t>(p) * C2 + col];
+    }
+    red[w][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (w == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][lane];
+      tot[half][lane] = t;
+    }
+    __syncthreads();
+  }
+  if (w != 0 || c >= C) return;
+  const double s0 = tot[0][lane], s1 = tot[1][lane];
+  if (sums) {
+    sums[c] = s0;
+    sums[C + c] = s1;
+  }
+  if (mode == 0) {
+    const double mean = s0 / count;
+    double var = s1 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const double g = gamma ? static_cast<double>(gamma[c]) : 1.0;
+    const double b = beta ? static_cast<double>(beta[c]) : 0.0;
+    mean_out[c] = static_cast<float>(mean);
+    rstd_out[c] = static_cast<float>(rstd);
+    scale[c] = static_cast<float>(g * rstd);
+    shift[c] = static_cast<float>(b - mean * g * rstd);
+    if (moving_mean) {
+      const double var_unbiased = var * (count / (count - (1.0 + static_cast<double>(eps))));
+      moving_mean[c] = static_cast<float>(moving_mean[c] - (moving_mean[c] - mean) * (1.0 - momentum));
+      moving_var[c] = static_cast<float>(moving_var[c] - (moving_var[c] - var_unbiased) * (1.0 - momentum));
+    }
+  } else {
+    if (dbeta) dbeta[c] = static_cast<float>(s0);
+    if (dgamma) dgamma[c] = static_cast<float>(s1);
+  }
+}
+
 __global__ void bn_inference_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                            const float* __restrict__ mm, const float* __restrict__ mv, float eps,
                                            float* __restrict__ scale, float* __restrict__ shift, int C) {
@@ -214,7 +265,7 @@ struct BnFwdParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) bn_apply_fwd_kernel(const BnFwdParams p) {
+__global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_kernel(const BnFwdParams p) {
   constexpr int V = VecIO<T>::N;
   const T* x = static_cast<const T*>(p.x);
   const int cg = p.C / V;
@@ -341,7 +392,7 @@ __device__ __forceinline__ void g_from(const float (&xv)[V], const float (&dyv)[
 }
 
 template <typename T, bool kApply>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_kernel(const BnBwdParams p) {
+__global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_kernel(const BnBwdParams p) {
   constexpr int V = VecIO<T>::N;
   const T* x = static_cast<const T*>(p.x);
   const T* dy = static_cast<const T*>(p.dy);
@@ -366,10 +417,6 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_kernel(const BnBwdParams p)
       k2[i] = static_cast<float>(p.sums[p.C + g * V + i] / p.count);
     }
   }
-  double d1[V], d2[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) d1[i] = d2[i] = 0.0;
-  int nacc = 0;
 
   auto emit = [&](long long r, const float (&xv)[V], const float (&gv)[V]) {
     if (kApply) {
@@ -396,16 +443,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_kernel(const BnBwdParams p)
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         s1[i] += gv[i];
-        s2[i] += gv[i] * (xv[i] - mu[i]) * rs[i];
-      }
-      if (++nacc == 32) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          d1[i] += s1[i];
-          d2[i] += s2[i];
-          s1[i] = s2[i] = 0.f;
-        }
-        nacc = 0;
+        s2[i] = fmaf(gv[i], (xv[i] - mu[i]) * rs[i], s2[i]);
       }
     }
   };
@@ -439,7 +477,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_kernel(const BnBwdParams p)
             for (int i = 0; i < 4; ++i) bi[i] = (q >> (8 * i)) & 0xff;
           }
         }
-#pragma unroll
+#pragma unroll 2
         for (int k = 0; k < 8; ++k) {
           const int dd = 2 * dz + (k >> 2), hh = 2 * ho + ((k >> 1) & 1), ww = 2 * wo + (k & 1);
           const long long r = ((static_cast<long long>(n) * p.D + dd) * p.H + hh) * p.W + ww;
@@ -496,17 +534,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_kernel(const BnBwdParams p)
   }
   if (!kApply) {
     extern __shared__ double sred[];
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      d1[i] += s1[i];
-      d2[i] += s2[i];
-    }
     double* out = p.partials + static_cast<size_t>(blockIdx.x) * 2 * p.C;
     for (int pass = 0; pass < 2; ++pass) {
       __syncthreads();
       if (rl < rpi) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) sred[rl * p.C + g * V + i] = pass == 0 ? d1[i] : d2[i];
+        for (int i = 0; i < V; ++i) sred[rl * p.C + g * V + i] = static_cast<double>(pass == 0 ? s1[i] : s2[i]);
       }
       __syncthreads();
       for (int c = threadIdx.x; c < p.C; c += kBnThreads) {
@@ -698,6 +731,29 @@ extern "C" int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* dy2, in
 extern "C" int icsg3d_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream) {
   ICSG_REQUIRE(sums, "bn_param_grads: null pointer");
   bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, dgamma, dbeta, C);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_bn_reduce_finalize(const double* partials, int nparts, double count, const float* gamma,
+                                         const float* beta, float eps, double* sums, float* mean, float* rstd, float* scale,
+                                         float* shift, float* moving_mean, float* moving_var, float momentum, int C,
+                                         void* stream) {
+  ICSG_REQUIRE(partials && nparts > 0 && mean && rstd && scale && shift && count > 0, "bn_reduce_finalize: bad arguments");
+  ICSG_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "bn_reduce_finalize: moving_mean/var must both be given");
+  bn_reduce_fused_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, nparts, C, 0, count, gamma, beta, eps, sums, mean, rstd, scale, shift, moving_mean, moving_var, momentum, nullptr,
+      nullptr);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_bn_reduce_grads(const double* partials, int nparts, int C, double* sums, float* dgamma, float* dbeta,
+                                      void* stream) {
+  ICSG_REQUIRE(partials && nparts > 0 && sums, "bn_reduce_grads: bad arguments");
+  bn_reduce_fused_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, nparts, C, 1, 1.0, nullptr, nullptr, 0.f, sums, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, dgamma,
+      dbeta);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -105,7 +105,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded spin: a descriptor/phase bug must surface as a trap (launch error), never as a hung box.
 #ifndef ICSG_MBAR_SPIN_LIMIT
-#define ICSG_MBAR_SPIN_LIMIT (1u << 26)
+#define ICSG_MBAR_SPIN_LIMIT (1u << 23)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -253,6 +253,39 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+// Column sums over the 32 rows held by the lanes of a warp, for 16 columns at once, with a transpose-reduce
+// butterfly (16 shuffles instead of 80): on return lane L holds in `v[0]` the sum over all 32 lanes of column
+// colsum16_owner(L); lanes with (L & 1) == 1 hold duplicates.
+__device__ __forceinline__ int colsum16_owner(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0;
+  float a[8], b[4], c[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = h16 ? v[i] : v[i + 8];
+    const float keep = h16 ? v[i + 8] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = h8 ? a[i] : a[i + 4];
+    const float keep = h8 ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = h4 ? b[i] : b[i + 2];
+    const float keep = h4 ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = h2 ? c[0] : c[1];
+  const float keep = h2 ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
 }
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }

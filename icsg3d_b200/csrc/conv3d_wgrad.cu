@@ -32,7 +32,11 @@ struct WgradParams {
   float* ws;                   // [splits][27*cin*cout]
 };
 
-static constexpr int kWgradThreads = 192;
+// warp 0: TMA producer | warps 1..kWgradIssuers: MMA issuers — accumulator group gl is owned by issuer gl % kWgradIssuers,
+// so every accumulator sees its MMAs from one thread in a fixed order (deterministic) while the issue latencies of
+// the issuers overlap | last 4 warps: epilogue
+static constexpr int kWgradIssuers = 3;
+static constexpr int kWgradThreads = (1 + kWgradIssuers + 4) * 32;
 static constexpr int kWgradMaxStages = 6;
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -59,9 +63,9 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     tma_prefetch_desc(&tmDY);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kWgradIssuers);
     }
-    mbar_init(&done_bar, 1);
+    mbar_init(&done_bar, kWgradIssuers);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
@@ -114,29 +118,37 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // MMA issuer: whole warp runs the loop, one elected lane issues; descriptor high words are loop invariant
+  } else if (warp <= kWgradIssuers) {
+    // MMA issuers: whole warp runs the loop, one elected lane issues; descriptor high words are loop invariant
+    const int issuer = warp - 1;
     const bool leader = elect_one();
-    int stage = 0;
-    uint32_t phase = 0;
-    int ti = 0;
+    const int g_cnt = g_end - g_begin;
     const uint32_t a_hi = umma_desc_hi(p.sbo_a, p.layout_a), b_hi = umma_desc_hi(p.sbo_b, p.layout_b);
     const uint32_t ring_lo_a = umma_desc_lo(ring_base, p.lbo_a);
     const uint32_t ring_lo_b = umma_desc_lo(ring_base + p.a_bytes, p.lbo_b);
     const uint32_t stage_lo = p.stage_bytes >> 4;
     const uint32_t ka = (2u * p.sbo_a) >> 4, kb = (2u * p.sbo_b) >> 4;
+    // Every issuer walks the WHOLE stage sequence and waits on every full barrier in order (mbarrier parity waits are
+    // only sound when a waiter observes each phase); it issues MMAs for the groups it owns and simply arrives on the
+    // empty barrier for the others, so a stage is recycled after its owner's MMAs retired and all issuers moved on.
+    int ti = 0, stage = 0;
+    uint32_t phase = 0;
     for (int tile = split; tile < p.tiles_m; tile += p.splits, ++ti) {
-      for (int g = g_begin; g < g_end; ++g) {
+      for (int gl = 0; gl < g_cnt; ++gl) {
         mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t a_lo = ring_lo_a + static_cast<uint32_t>(stage) * stage_lo;
-        const uint32_t b_lo = ring_lo_b + static_cast<uint32_t>(stage) * stage_lo;
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((g - g_begin) * p.ntw);
-        if (leader) {
+        if (gl % kWgradIssuers == issuer) {
+          tc_fence_after();
+          const uint32_t a_lo = ring_lo_a + static_cast<uint32_t>(stage) * stage_lo;
+          const uint32_t b_lo = ring_lo_b + static_cast<uint32_t>(stage) * stage_lo;
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(gl * p.ntw);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)  // 8 x 16 voxels
-            umma_bf16_lohi(d_tmem, a_lo + k * ka, a_hi, b_lo + k * kb, b_hi, p.idesc, (ti | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+            for (int k = 0; k < 8; ++k)  // 8 x 16 voxels
+              umma_bf16_lohi(d_tmem, a_lo + k * ka, a_hi, b_lo + k * kb, b_hi, p.idesc, (ti | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+          }
+        } else if (leader) {
+          mbar_arrive(&empty_bar[stage]);
         }
         if (++stage == p.stages) {
           stage = 0;

@@ -81,6 +81,11 @@ class VAEEngine:
         self.vp = vae_params or ParamStore(vae_specs(channels, ncond, d, latent, filters), dev).init(seed)
         self.pp = pm_params or ParamStore(unet_specs(channels), dev, with_grads=False, with_adam=False).init(seed + 1)
         self.ctx = _Ctx(dev)
+        # pm(x) does not depend on the encoder/decoder: it runs on a side stream (forked/joined inside the captured
+        # graph) so that its large convs overlap the small, latency-bound VAE kernels.  Own scratch per stream.
+        self.ctx2 = _Ctx(dev, max_dw=16)
+        self.overlap_pm = self.world == 1
+        self._side = None
         B = batch
         z = lambda *s, dt=BF16: torch.zeros(*s, dtype=dt, device=dev)
 
@@ -168,16 +173,18 @@ class VAEEngine:
     # ------------------------------------------------------------------------------------------
     # helpers
     # ------------------------------------------------------------------------------------------
-    def _bn_fwd(self, x, C, st: _BN, gamma, beta, mm, mv, training, act, post, y=None, y32=None, idx=None):
+    def _bn_fwd(self, x, C, st: _BN, gamma, beta, mm, mv, training, act, post, y=None, y32=None, idx=None, ctx=None):
         if training:
             rows = x.numel() // x.shape[-1]
             n = ops.bn_nparts(rows, C, x.dtype)
-            part = self.ctx.partials[: n * 2 * C].view(n, 2, C)
+            part = (ctx or self.ctx).partials[: n * 2 * C].view(n, 2, C)
             ops.bn_stats(x, C, part)
-            ops.bn_reduce_partials(part, st.sums)
             if self.world > 1:
+                ops.bn_reduce_partials(part, st.sums)
                 self.dist.all_reduce_sum(st.sums)
-            ops.bn_finalize(st.sums, float(rows * self.world), gamma, beta, st.mean, st.rstd, st.scale, st.shift, mm, mv)
+                ops.bn_finalize(st.sums, float(rows * self.world), gamma, beta, st.mean, st.rstd, st.scale, st.shift, mm, mv)
+            else:
+                ops.bn_reduce_finalize(part, float(rows), gamma, beta, st.sums, st.mean, st.rstd, st.scale, st.shift, mm, mv)
         else:
             ops.bn_inference_coeffs(gamma, beta, mm, mv, st.scale, st.shift)
         ops.bn_apply_fwd(x, C, st.scale, st.shift, act, post, y=y, y32=y32, pool_idx=idx)
@@ -187,9 +194,7 @@ class VAEEngine:
         n = ops.bn_bwd_nparts(x, C, post)
         part = self.ctx.partials[: n * 2 * C].view(n, 2, C)
         ops.bn_bwd_reduce(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, part)
-        ops.bn_reduce_partials(part, st.bsums)
-        if dgamma is not None:
-            ops.bn_param_grads(st.bsums, dgamma, dbeta)  # local sums: the gradient all-reduce adds the ranks
+        ops.bn_reduce_grads(part, st.bsums, dgamma, dbeta)  # local sums: the gradient all-reduce adds the ranks
         sums = st.bsums
         if self.world > 1:
             st.bsums_g.copy_(st.bsums)
@@ -274,7 +279,7 @@ class VAEEngine:
         self._bn_fwd(self.c5, 4, self.bn5, p["dec_bn5/gamma"], p["dec_bn5/beta"], p["dec_bn5/moving_mean"],
                      p["dec_bn5/moving_variance"], training, ACT_RELU, POST_NONE, y=self.xhat16, y32=self.xhat)
 
-    def pm_forward(self, branch, training):
+    def pm_forward(self, branch, training, ctx=None):
         """U-Net prefix c1..c10 (unet.py:276-306) on x (branch 0) or x_hat (branch 1); BN follows the learning
         phase and its moving averages are never updated from here."""
         p = self.pp.p
@@ -289,7 +294,7 @@ class VAEEngine:
             self._bn_fwd(L["a"][branch], L["cout"], L["bnst"][branch], p[bn + "/gamma"], p[bn + "/beta"],
                          p[bn + "/moving_mean"] if not training else None,
                          p[bn + "/moving_variance"] if not training else None, training, ACT_NONE,
-                         POST_POOL2 if L["pool"] else POST_NONE, y=L["y"][branch], idx=L["idx"][branch])
+                         POST_POOL2 if L["pool"] else POST_NONE, y=L["y"][branch], idx=L["idx"][branch], ctx=ctx)
             x = L["y"][branch]
 
     def _loss_meta(self):
@@ -413,10 +418,22 @@ class VAEEngine:
     def _train_body(self):
         self.pack_weights()
         ops.pack_vae_input(self.M, self.cond, self.xe, self.xp)
-        self.encode(True)
-        self.decode(True)
-        self.pm_forward(0, True)
-        self.pm_forward(1, True)
+        if self.overlap_pm:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.pm_forward(0, True, ctx=self.ctx2)
+            self.encode(True)
+            self.decode(True)
+            self.pm_forward(1, True)
+            main.wait_stream(self._side)
+        else:
+            self.encode(True)
+            self.decode(True)
+            self.pm_forward(0, True)
+            self.pm_forward(1, True)
         self.losses()
         self.backward()
         self.optimizer_step()

@@ -220,6 +220,19 @@ def bn_finalize(sums, count, gamma, beta, mean, rstd, scale, shift, moving_mean=
               _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(moving_mean), _ptr(moving_var), momentum, C, _stream())
 
 
+def bn_reduce_finalize(partials, count, gamma, beta, sums, mean, rstd, scale, shift, moving_mean=None, moving_var=None,
+                       eps=BN_EPS, momentum=BN_MOMENTUM):
+    C = mean.numel()
+    _lib.call("icsg3d_bn_reduce_finalize", _ptr(partials), partials.shape[0], ctypes.c_double(count), _ptr(gamma), _ptr(beta),
+              eps, _ptr(sums), _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(moving_mean), _ptr(moving_var),
+              momentum, C, _stream())
+
+
+def bn_reduce_grads(partials, sums, dgamma=None, dbeta=None):
+    _lib.call("icsg3d_bn_reduce_grads", _ptr(partials), partials.shape[0], partials.shape[2], _ptr(sums), _ptr(dgamma),
+              _ptr(dbeta), _stream())
+
+
 def bn_inference_coeffs(gamma, beta, moving_mean, moving_var, scale, shift, eps=BN_EPS):
     _lib.call("icsg3d_bn_inference_coeffs", _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), eps,
               _ptr(scale), _ptr(shift), scale.numel(), _stream())

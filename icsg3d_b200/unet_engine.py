@@ -138,10 +138,12 @@ class UNetEngine:
             np_ = ops.bn_nparts(rows, C, x.dtype)
             part = self.ctx.partials[: np_ * 2 * C].view(np_, 2, C)
             ops.bn_stats(x, C, part)
-            ops.bn_reduce_partials(part, st.sums)
             if self.world > 1:
+                ops.bn_reduce_partials(part, st.sums)
                 self.dist.all_reduce_sum(st.sums)
-            ops.bn_finalize(st.sums, float(rows * self.world), g, b, st.mean, st.rstd, st.scale, st.shift, mm, mv)
+                ops.bn_finalize(st.sums, float(rows * self.world), g, b, st.mean, st.rstd, st.scale, st.shift, mm, mv)
+            else:
+                ops.bn_reduce_finalize(part, float(rows), g, b, st.sums, st.mean, st.rstd, st.scale, st.shift, mm, mv)
         else:
             ops.bn_inference_coeffs(g, b, mm, mv, st.scale, st.shift)
         if "up" in L:
@@ -176,8 +178,7 @@ class UNetEngine:
         n = ops.bn_nparts(rows, C, dc.dtype)
         part = self.ctx.partials[: n * 2 * C].view(n, 2, C)
         ops.bn_stats(dc, C, part)
-        ops.bn_reduce_partials(part, self.colsum[: 2 * C])
-        ops.bn_param_grads(self.colsum[: 2 * C], None, gbias)
+        ops.bn_reduce_grads(part, self.colsum[: 2 * C], None, gbias)
 
     def _grad_wrt_output(self, L):
         """(dy, post, idx, dy2) describing the gradient reaching block L's BN output."""
@@ -217,8 +218,7 @@ class UNetEngine:
             nb = ops.bn_bwd_nparts(x, C, post)
             part = self.ctx.partials[: nb * 2 * C].view(nb, 2, C)
             ops.bn_bwd_reduce(dy, x, C, st.mean, st.rstd, st.scale, st.shift, ACT_NONE, post, idx, part, dy2=dy2)
-            ops.bn_reduce_partials(part, st.bsums)
-            ops.bn_param_grads(st.bsums, g[f"bn_{nme}/gamma"], g[f"bn_{nme}/beta"])
+            ops.bn_reduce_grads(part, st.bsums, g[f"bn_{nme}/gamma"], g[f"bn_{nme}/beta"])
             sums = st.bsums
             if self.world > 1:
                 st.bsums_g.copy_(st.bsums)

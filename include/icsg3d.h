@@ -135,6 +135,13 @@ int icsg3d_bn_reduce_partials(const double* partials, int nparts, int C, double*
 int icsg3d_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
                        float* mean, float* rstd, float* scale, float* shift, float* moving_mean,
                        float* moving_var, float momentum, int C, void* stream);
+/* Single-process fusions of the two steps above (same fixed summation order, one launch):
+ * bn_reduce_finalize = bn_reduce_partials + bn_finalize;  bn_reduce_grads = bn_reduce_partials + bn_param_grads. */
+int icsg3d_bn_reduce_finalize(const double* partials, int nparts, double count, const float* gamma, const float* beta,
+                              float eps, double* sums, float* mean, float* rstd, float* scale, float* shift,
+                              float* moving_mean, float* moving_var, float momentum, int C, void* stream);
+int icsg3d_bn_reduce_grads(const double* partials, int nparts, int C, double* sums, float* dgamma, float* dbeta,
+                           void* stream);
 /* learning phase 0 (predict / test_on_batch): scale/shift from the moving statistics */
 int icsg3d_bn_inference_coeffs(const float* gamma, const float* beta, const float* moving_mean,
                                const float* moving_var, float eps, float* scale, float* shift, int C,
