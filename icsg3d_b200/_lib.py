@@ -89,10 +89,23 @@ def last_error() -> str:
     return lib().icsg3d_last_error().decode()
 
 
+# Optional per-call device timing (tools/profile_step.py): when PROFILE is a list, every entry-point call is
+# bracketed by CUDA events on the current stream and (name, start, end) is appended.  Off on the product path.
+PROFILE = None
+
+
 def call(name: str, *args):
     """Call an int-returning entry point; raise Icsg3dError with the library's message on failure."""
     fn = getattr(lib(), name)
-    rc = fn(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.append((name, e0, e1))
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise Icsg3dError(f"{name} failed ({rc}): {last_error()}")
     return rc

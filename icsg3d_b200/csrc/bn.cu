@@ -20,6 +20,12 @@ struct VecIO;
 template <>
 struct VecIO<__nv_bfloat16> {
   static constexpr int N = 8;
+  typedef uint4 raw_t;
+  __device__ static raw_t load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ static void cvt(const raw_t& q, float (&v)[8]) {
+    float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
   __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
     const uint4 q = *reinterpret_cast<const uint4*>(p);
     float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
@@ -35,6 +41,9 @@ struct VecIO<__nv_bfloat16> {
 template <>
 struct VecIO<float> {
   static constexpr int N = 4;
+  typedef float4 raw_t;
+  __device__ static raw_t load_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ static void cvt(const raw_t& q, float (&v)[4]) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
   __device__ static void load(const float* p, float (&v)[4]) {
     const float4 q = *reinterpret_cast<const float4*>(p);
     v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
@@ -87,13 +96,24 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_stats_kernel(const T* __rest
 #pragma unroll
   for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
   if (rl < rpi) {
-    for (long long r = static_cast<long long>(blockIdx.x) * rpi + rl; r < M; r += static_cast<long long>(gridDim.x) * rpi) {
-      float v[V];
-      VecIO<T>::load(x + r * ldx + g * V, v);
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    const long long stride = static_cast<long long>(gridDim.x) * rpi;
+    for (long long r0 = static_cast<long long>(blockIdx.x) * rpi + rl; r0 < M; r0 += U * stride) {
+      typename VecIO<T>::raw_t raw[U];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        s[i] += v[i];
-        q[i] = fmaf(v[i], v[i], q[i]);
+      for (int j = 0; j < U; ++j)
+        if (r0 + j * stride < M) raw[j] = VecIO<T>::load_raw(x + (r0 + j * stride) * ldx + g * V);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (r0 + j * stride < M) {
+          float v[V];
+          VecIO<T>::cvt(raw[j], v);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            s[i] += v[i];
+            q[i] = fmaf(v[i], v[i], q[i]);
+          }
+        }
       }
     }
   }
@@ -170,44 +190,52 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 // Fused single-GPU path: fixed-order reduction of the partials (as bn_reduce_partials_kernel) followed by the
 // finalisation of the same 32 channels.  mode 0: forward statistics -> mean/rstd/scale/shift (+moving averages);
 // mode 1: backward sums -> sums[2][C] (+ dgamma = sum g*xhat, dbeta = sum g).
-__global__ void __launch_bounds__(256) bn_reduce_fused_kernel(const double* __restrict__ partials, int nparts, int C,
-                                                              int mode, double count, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, float eps,
-                                                              double* __restrict__ sums, float* __restrict__ mean_out,
-                                                              float* __restrict__ rstd_out, float* __restrict__ scale,
-                                                              float* __restrict__ shift, float* __restrict__ moving_mean,
-                                                              float* __restrict__ moving_var, float momentum,
-                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ double red[8][33];
-  __shared__ double tot[2][32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  const int C2 = 2 * C;
-  for (int half = 0; half < 2; ++half) {
-    const int col = half * C + c;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (c < C) {
-      int p = w;
-      for (; p + 24 < nparts; p += 32) {
-        a0 += partials[static_cast<size_t>(p) * C2 + col];
-        a1 += partials[static_cast<size_t>(p + 8) * C2 + col];
-        a2 += partials[static_cast<size_t>(p + 16) * C2 + col];
-        a3 += partials[static_cast<size_t>(p + 24) * C2 + col];
-      }
-      for (; p < nparts; p += 8) a0 += partials[static_cast<size_t>(p) * C2 + col];
+static constexpr int kRedCh = 8;        // channels per block of bn_reduce_fused_kernel
+static constexpr int kRedSlots = 64;    // partial-row slots per block (1024 threads = 64 slots x 16 columns)
+__global__ void __launch_bounds__(1024) bn_reduce_fused_kernel(const double* __restrict__ partials, int nparts, int C,
+                                                               int mode, double count, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps,
+                                                               double* __restrict__ sums, float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out, float* __restrict__ scale,
+                                                               float* __restrict__ shift, float* __restrict__ moving_mean,
+                                                               float* __restrict__ moving_var, float momentum,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  // The reduction is latency bound (a few hundred KB of fp64 partials): 1024 threads keep every load of a column
+  // independent and in flight at once; the order of the additions is a function of (nparts) only => deterministic.
+  __shared__ double red[kRedSlots][2 * kRedCh + 1];
+  __shared__ double tot[2 * kRedCh];
+  const int col = threadIdx.x & (2 * kRedCh - 1);   // 0..7 = sum x / sum g, 8..15 = sum x^2 / sum g*xhat
+  const int slot = threadIdx.x >> 4;
+  const int c = blockIdx.x * kRedCh + (col & (kRedCh - 1));
+  const int gcol = (col >> 3) * C + c;
+  const size_t C2 = 2 * static_cast<size_t>(C);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (c < C) {
+    int p = slot;
+    for (; p + 3 * kRedSlots < nparts; p += 4 * kRedSlots) {
+      a0 += partials[static_cast<size_t>(p) * C2 + gcol];
+      a1 += partials[static_cast<size_t>(p + kRedSlots) * C2 + gcol];
+      a2 += partials[static_cast<size_t>(p + 2 * kRedSlots) * C2 + gcol];
+      a3 += partials[static_cast<size_t>(p + 3 * kRedSlots) * C2 + gcol];
     }
-    red[w][lane] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-    if (w == 0) {
-      double t = 0.0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) t += red[i][lane];
-      tot[half][lane] = t;
-    }
-    __syncthreads();
+    for (; p < nparts; p += kRedSlots) a0 += partials[static_cast<size_t>(p) * C2 + gcol];
   }
-  if (w != 0 || c >= C) return;
-  const double s0 = tot[0][lane], s1 = tot[1][lane];
+  red[slot][col] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (threadIdx.x < 2 * kRedCh) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kRedSlots; i += 4) {
+      t0 += red[i][threadIdx.x];
+      t1 += red[i + 1][threadIdx.x];
+      t2 += red[i + 2][threadIdx.x];
+      t3 += red[i + 3][threadIdx.x];
+    }
+    tot[threadIdx.x] = (t0 + t1) + (t2 + t3);
+  }
+  __syncthreads();
+  if (threadIdx.x >= kRedCh || c >= C) return;
+  const double s0 = tot[threadIdx.x], s1 = tot[kRedCh + threadIdx.x];
   if (sums) {
     sums[c] = s0;
     sums[C + c] = s1;
@@ -321,6 +349,38 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_kernel(const BnFwd
   }
   const long long M = static_cast<long long>(p.B) * p.D * p.H * p.W;
   const long long total = M * cg;
+  if (p.post == ICSG3D_POST_NONE) {
+    // plain BN+activation: 4 independent vectors in flight per thread
+    constexpr int U = 4;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < total; i0 += U * stride) {
+      typename VecIO<T>::raw_t raw[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const long long idx = i0 + j * stride;
+        if (idx < total) raw[j] = VecIO<T>::load_raw(x + (idx / cg) * p.ldx + static_cast<int>(idx % cg) * V);
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const long long idx = i0 + j * stride;
+        if (idx < total) {
+          const int g = static_cast<int>(idx % cg);
+          const long long r = idx / cg;
+          float v[V];
+          VecIO<T>::cvt(raw[j], v);
+#pragma unroll
+          for (int i = 0; i < V; ++i) v[i] = act_fwd(fmaf(p.scale[g * V + i], v[i], p.shift[g * V + i]), p.act, p.alpha);
+          if (p.y) store_bf16_vec<V>(p.y + r * p.ldy + g * V, v);
+          if (p.y32) {
+            float* d32 = p.y32 + r * p.ldy32 + g * V;
+#pragma unroll
+            for (int i = 0; i < V; ++i) d32[i] = v[i];
+          }
+        }
+      }
+    }
+    return;
+  }
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(idx % cg);
@@ -392,47 +452,49 @@ __device__ __forceinline__ void g_from(const float (&xv)[V], const float (&dyv)[
 }
 
 template <typename T, bool kApply>
-__global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_kernel(const BnBwdParams p) {
+__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_kernel(const BnBwdParams p) {
+  // HBM-bound: every thread keeps 4 independent rows (x, dy, optional skip gradient / tap) in flight before it
+  // touches any of them (load phase, then compute phase), ~8-12 x 16 B per thread.
   constexpr int V = VecIO<T>::N;
+  constexpr int U = 4;
+  typedef typename VecIO<T>::raw_t raw_t;
   const T* x = static_cast<const T*>(p.x);
   const T* dy = static_cast<const T*>(p.dy);
   const T* dy2 = static_cast<const T*>(p.dy2);
   const int cg = p.C / V;
-  // Thread -> channel group is fixed for the whole kernel (grid-stride keeps idx % cg constant when the
-  // stride is a multiple of cg; enforce it by striding in units of whole rows).
+  // Thread -> channel group is fixed for the whole kernel (the grid strides in units of whole rows).
   const int rpi = kBnThreads / cg;
   const int g = threadIdx.x % cg;
   const int rl = threadIdx.x / cg;
-  float sc[V], sh[V], mu[V], rs[V];
-  float s1[V], s2[V], k1[V], k2[V];
+  const bool has_tap = kApply && p.tap_other != nullptr;
+  const bool has_dy2 = dy2 != nullptr;
+  // reduce: s1 = sum g, s2 = sum g*(x-mean) (rstd applied once at the end)
+  // apply : dx = scale*g + ca*x + cb  with  ca = -scale*rstd*k2,  cb = -scale*k1 - ca*mean
+  float sc[V], sh[V], mu[V], s1[V], s2[V], ca[V], cb[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     sc[i] = p.scale[g * V + i];
     sh[i] = p.shift[g * V + i];
     mu[i] = p.mean[g * V + i];
-    rs[i] = p.rstd[g * V + i];
     s1[i] = s2[i] = 0.f;
     if (kApply) {
-      k1[i] = static_cast<float>(p.sums[g * V + i] / p.count);
-      k2[i] = static_cast<float>(p.sums[p.C + g * V + i] / p.count);
+      const float k1 = static_cast<float>(p.sums[g * V + i] / p.count);
+      const float k2 = static_cast<float>(p.sums[p.C + g * V + i] / p.count);
+      ca[i] = -sc[i] * p.rstd[g * V + i] * k2;
+      cb[i] = -sc[i] * k1 - ca[i] * mu[i];
     }
   }
 
-  auto emit = [&](long long r, const float (&xv)[V], const float (&gv)[V]) {
+  auto emit = [&](long long r, const float (&xv)[V], const float (&gv)[V], const raw_t& tapraw) {
     if (kApply) {
       float o[V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float xh = (xv[i] - mu[i]) * rs[i];
-        o[i] = sc[i] * (gv[i] - k1[i] - xh * k2[i]);
-      }
-      if (p.tap_other) {
-        float ov[8];
-        const uint4 q = *reinterpret_cast<const uint4*>(p.tap_other + r * p.ld_other + g * V);
-        float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
-        ov[0] = a.x; ov[1] = a.y; ov[2] = b.x; ov[3] = b.y; ov[4] = c.x; ov[5] = c.y; ov[6] = d.x; ov[7] = d.y;
+      for (int i = 0; i < V; ++i) o[i] = fmaf(sc[i], gv[i], fmaf(ca[i], xv[i], cb[i]));
+      if (has_tap) {
+        float ov[V];
+        VecIO<T>::cvt(tapraw, ov);
 #pragma unroll
-        for (int i = 0; i < V; ++i) o[i] += p.tap_coef * (xv[i] - ov[i < 8 ? i : 0]);
+        for (int i = 0; i < V; ++i) o[i] += p.tap_coef * (xv[i] - ov[i]);
       }
       if (p.pre_relu) {
 #pragma unroll
@@ -443,10 +505,11 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_kernel(const BnBwdParams
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         s1[i] += gv[i];
-        s2[i] = fmaf(gv[i], (xv[i] - mu[i]) * rs[i], s2[i]);
+        s2[i] = fmaf(gv[i], xv[i] - mu[i], s2[i]);
       }
     }
   };
+  const T* tap = reinterpret_cast<const T*>(p.tap_other);
 
   if (rl < rpi) {
     if (p.post == ICSG3D_POST_POOL2) {
@@ -459,8 +522,7 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_kernel(const BnBwdParams
         t /= Ho;
         const int dz = static_cast<int>(t % Do);
         const int n = static_cast<int>(t / Do);
-        float dyv[V];
-        VecIO<T>::load(dy + o * p.lddy + g * V, dyv);
+        const raw_t dyr = VecIO<T>::load_raw(dy + o * p.lddy + g * V);
         int bi[V];
         {
           const uint8_t* ip = p.pool_idx + o * p.C + g * V;
@@ -477,58 +539,110 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_kernel(const BnBwdParams
             for (int i = 0; i < 4; ++i) bi[i] = (q >> (8 * i)) & 0xff;
           }
         }
-#pragma unroll 2
-        for (int k = 0; k < 8; ++k) {
-          const int dd = 2 * dz + (k >> 2), hh = 2 * ho + ((k >> 1) & 1), ww = 2 * wo + (k & 1);
-          const long long r = ((static_cast<long long>(n) * p.D + dd) * p.H + hh) * p.W + ww;
-          float xv[V], sel[V], gv[V];
-          VecIO<T>::load(x + r * p.ldx + g * V, xv);
+        float dyv[V];
+        VecIO<T>::cvt(dyr, dyv);
 #pragma unroll
-          for (int i = 0; i < V; ++i) sel[i] = bi[i] == k ? dyv[i] : 0.f;
-          if (dy2) {
-            float e[V];
-            VecIO<T>::load(dy2 + r * p.lddy2 + g * V, e);
+        for (int k0 = 0; k0 < 8; k0 += U) {
+          raw_t xr[U], er[U], tr[U];
+          long long rr[U];
 #pragma unroll
-            for (int i = 0; i < V; ++i) sel[i] += e[i];
+          for (int j = 0; j < U; ++j) {
+            const int k = k0 + j;
+            const int dd = 2 * dz + (k >> 2), hh = 2 * ho + ((k >> 1) & 1), ww = 2 * wo + (k & 1);
+            rr[j] = ((static_cast<long long>(n) * p.D + dd) * p.H + hh) * p.W + ww;
+            xr[j] = VecIO<T>::load_raw(x + rr[j] * p.ldx + g * V);
+            if (has_dy2) er[j] = VecIO<T>::load_raw(dy2 + rr[j] * p.lddy2 + g * V);
+            if (has_tap) tr[j] = VecIO<T>::load_raw(tap + rr[j] * p.ld_other + g * V);
           }
-          g_from<V>(xv, sel, sc, sh, p.act, p.alpha, gv);
-          emit(r, xv, gv);
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const int k = k0 + j;
+            float xv[V], sel[V], gv[V];
+            VecIO<T>::cvt(xr[j], xv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) sel[i] = bi[i] == k ? dyv[i] : 0.f;
+            if (has_dy2) {
+              float e[V];
+              VecIO<T>::cvt(er[j], e);
+#pragma unroll
+              for (int i = 0; i < V; ++i) sel[i] += e[i];
+            }
+            g_from<V>(xv, sel, sc, sh, p.act, p.alpha, gv);
+            emit(rr[j], xv, gv, tr[j]);
+          }
         }
       }
-    } else {
+    } else if (p.post == ICSG3D_POST_UP2) {
       const long long M = static_cast<long long>(p.B) * p.D * p.H * p.W;
       for (long long r = static_cast<long long>(blockIdx.x) * rpi + rl; r < M; r += static_cast<long long>(gridDim.x) * rpi) {
-        float xv[V], dyv[V], gv[V];
-        VecIO<T>::load(x + r * p.ldx + g * V, xv);
-        if (p.post == ICSG3D_POST_UP2) {
-          const int w = static_cast<int>(r % p.W);
-          long long t = r / p.W;
-          const int h = static_cast<int>(t % p.H);
-          t /= p.H;
-          const int d = static_cast<int>(t % p.D);
-          const int n = static_cast<int>(t / p.D);
+        const int w = static_cast<int>(r % p.W);
+        long long t = r / p.W;
+        const int h = static_cast<int>(t % p.H);
+        t /= p.H;
+        const int d = static_cast<int>(t % p.D);
+        const int n = static_cast<int>(t / p.D);
+        raw_t cr[8], er, tr;
+        const raw_t xr = VecIO<T>::load_raw(x + r * p.ldx + g * V);
 #pragma unroll
-          for (int i = 0; i < V; ++i) dyv[i] = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const long long ro = ((static_cast<long long>(n) * 2 * p.D + 2 * d + (k >> 2)) * 2 * p.H + 2 * h + ((k >> 1) & 1)) *
-                                     2 * p.W + 2 * w + (k & 1);
-            float c[V];
-            VecIO<T>::load(dy + ro * p.lddy + g * V, c);
-#pragma unroll
-            for (int i = 0; i < V; ++i) dyv[i] += c[i];
-          }
-        } else {
-          VecIO<T>::load(dy + r * p.lddy + g * V, dyv);
+        for (int k = 0; k < 8; ++k) {
+          const long long ro = ((static_cast<long long>(n) * 2 * p.D + 2 * d + (k >> 2)) * 2 * p.H + 2 * h + ((k >> 1) & 1)) *
+                                   2 * p.W + 2 * w + (k & 1);
+          cr[k] = VecIO<T>::load_raw(dy + ro * p.lddy + g * V);
         }
-        if (dy2) {
+        if (has_dy2) er = VecIO<T>::load_raw(dy2 + r * p.lddy2 + g * V);
+        if (has_tap) tr = VecIO<T>::load_raw(tap + r * p.ld_other + g * V);
+        float xv[V], dyv[V], gv[V];
+        VecIO<T>::cvt(xr, xv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) dyv[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float c[V];
+          VecIO<T>::cvt(cr[k], c);
+#pragma unroll
+          for (int i = 0; i < V; ++i) dyv[i] += c[i];
+        }
+        if (has_dy2) {
           float e[V];
-          VecIO<T>::load(dy2 + r * p.lddy2 + g * V, e);
+          VecIO<T>::cvt(er, e);
 #pragma unroll
           for (int i = 0; i < V; ++i) dyv[i] += e[i];
         }
         g_from<V>(xv, dyv, sc, sh, p.act, p.alpha, gv);
-        emit(r, xv, gv);
+        emit(r, xv, gv, tr);
+      }
+    } else {
+      const long long M = static_cast<long long>(p.B) * p.D * p.H * p.W;
+      const long long stride = static_cast<long long>(gridDim.x) * rpi;
+      for (long long r0 = static_cast<long long>(blockIdx.x) * rpi + rl; r0 < M; r0 += U * stride) {
+        raw_t xr[U], dr[U], er[U], tr[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const long long r = r0 + j * stride;
+          if (r < M) {
+            xr[j] = VecIO<T>::load_raw(x + r * p.ldx + g * V);
+            dr[j] = VecIO<T>::load_raw(dy + r * p.lddy + g * V);
+            if (has_dy2) er[j] = VecIO<T>::load_raw(dy2 + r * p.lddy2 + g * V);
+            if (has_tap) tr[j] = VecIO<T>::load_raw(tap + r * p.ld_other + g * V);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const long long r = r0 + j * stride;
+          if (r < M) {
+            float xv[V], dyv[V], gv[V];
+            VecIO<T>::cvt(xr[j], xv);
+            VecIO<T>::cvt(dr[j], dyv);
+            if (has_dy2) {
+              float e[V];
+              VecIO<T>::cvt(er[j], e);
+#pragma unroll
+              for (int i = 0; i < V; ++i) dyv[i] += e[i];
+            }
+            g_from<V>(xv, dyv, sc, sh, p.act, p.alpha, gv);
+            emit(r, xv, gv, tr[j]);
+          }
+        }
       }
     }
   }
@@ -539,7 +653,9 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_kernel(const BnBwdParams
       __syncthreads();
       if (rl < rpi) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) sred[rl * p.C + g * V + i] = static_cast<double>(pass == 0 ? s1[i] : s2[i]);
+        for (int i = 0; i < V; ++i)
+          sred[rl * p.C + g * V + i] = pass == 0 ? static_cast<double>(s1[i])
+                                                 : static_cast<double>(s2[i]) * static_cast<double>(p.rstd[g * V + i]);
       }
       __syncthreads();
       for (int c = threadIdx.x; c < p.C; c += kBnThreads) {
@@ -741,7 +857,7 @@ extern "C" int icsg3d_bn_reduce_finalize(const double* partials, int nparts, dou
                                          void* stream) {
   ICSG_REQUIRE(partials && nparts > 0 && mean && rstd && scale && shift && count > 0, "bn_reduce_finalize: bad arguments");
   ICSG_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "bn_reduce_finalize: moving_mean/var must both be given");
-  bn_reduce_fused_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_reduce_fused_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, nparts, C, 0, count, gamma, beta, eps, sums, mean, rstd, scale, shift, moving_mean, moving_var, momentum, nullptr,
       nullptr);
   ICSG_CHECK_LAUNCH();
@@ -751,7 +867,7 @@ extern "C" int icsg3d_bn_reduce_finalize(const double* partials, int nparts, dou
 extern "C" int icsg3d_bn_reduce_grads(const double* partials, int nparts, int C, double* sums, float* dgamma, float* dbeta,
                                       void* stream) {
   ICSG_REQUIRE(partials && nparts > 0 && sums, "bn_reduce_grads: bad arguments");
-  bn_reduce_fused_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_reduce_fused_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, nparts, C, 1, 1.0, nullptr, nullptr, 0.f, sums, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, dgamma,
       dbeta);
   ICSG_CHECK_LAUNCH();
