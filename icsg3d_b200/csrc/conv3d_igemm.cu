@@ -280,13 +280,16 @@ int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H
 #include <string.h>
 
 #include "conv3d_halo.cuh"
+#include "conv3d_stream.cuh"
 namespace icsg3d {
-// ICSG3D_CONV_IMPL=v1 forces the per-tap TMA kernel (A/B comparisons); default picks the halo kernel when it applies.
+// ICSG3D_CONV_IMPL=v1 forces the per-tap TMA kernel, =halo the halo kernel (A/B comparisons); the default picks the
+// plane-streaming kd-folded kernel when it applies, then the halo kernel, then the per-tap kernel.
+static int g_conv_impl = -1;
 static int conv_impl_choice() {
-  static int v = -1;
+  int& v = g_conv_impl;
   if (v < 0) {
     const char* e = getenv("ICSG3D_CONV_IMPL");
-    v = (e && strcmp(e, "v1") == 0) ? 1 : 0;
+    v = (e && strcmp(e, "v1") == 0) ? 1 : (e && strcmp(e, "halo") == 0) ? 2 : 0;
   }
   return v;
 }
@@ -312,8 +315,12 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
 
   {
     const int sms0 = sm_count();
+    ConvStreamParams sp;
+    if (ntaps == 27 && sms0 > 0 && conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms0, &sp))
+      return launch_conv_stream(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, nullptr, sp,
+                                static_cast<cudaStream_t>(stream));
     ConvHaloParams hp;
-    if (ntaps == 27 && sms0 > 0 && conv_impl_choice() == 0 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp))
+    if (ntaps == 27 && sms0 > 0 && conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp))
       return launch_conv_halo(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, hp, sms0,
                               static_cast<cudaStream_t>(stream));
   }
@@ -405,13 +412,26 @@ extern "C" int icsg3d_conv3d_k1_igemm(const void* x, int ldx, const void* wpack,
   return conv3d_igemm_impl(1, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream);
 }
 
+extern "C" int icsg3d_conv3d_set_impl(int impl) {
+  ICSG_REQUIRE(impl >= 0 && impl <= 2, "conv3d_set_impl: impl must be 0, 1 or 2");
+  g_conv_impl = impl;
+  return ICSG3D_OK;
+}
+
 // Diagnostic: which kernel and tiling the dispatcher picks for a layer shape (host only; no device needed).
 // out[0..9] = {impl (0 = per-tap TMA kernel, 1 = halo kernel), TD, TH, G, NT, a_bufs, b_stages, items, kc, smem_bytes}
 extern "C" int icsg3d_conv3d_k3_plan(int B, int D, int H, int W, int cin, int nout, int sms, int* out) {
   ICSG_REQUIRE(out && sms > 0, "conv3d_k3_plan: bad arguments");
   for (int i = 0; i < 10; ++i) out[i] = 0;
+  ConvStreamParams sp;
+  if (conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms, &sp)) {
+    out[0] = 2; out[1] = sp.R; out[2] = sp.TH; out[3] = sp.T; out[4] = sp.C; out[5] = sp.stages; out[6] = sp.issuers;
+    out[7] = conv_stream_grid(sp); out[8] = sp.kc;
+    out[9] = static_cast<int>(((sp.w_bytes + 1023u) & ~1023u) + sp.stages * sp.a_stage_bytes);
+    return ICSG3D_OK;
+  }
   ConvHaloParams hp;
-  if (conv_impl_choice() == 0 && conv_halo_plan(B, D, H, W, cin, nout, sms, &hp)) {
+  if (conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms, &hp)) {
     out[0] = 1; out[1] = hp.TD; out[2] = hp.TH; out[3] = hp.G; out[4] = hp.nt; out[5] = hp.a_bufs; out[6] = hp.b_stages;
     out[7] = hp.total_items; out[8] = hp.kc;
     out[9] = static_cast<int>(hp.a_bufs * hp.a_buf_bytes + hp.b_stages * hp.b_unit_bytes);

@@ -1,0 +1,459 @@
+// Conv3D 3x3x3 "same" — plane-streaming implicit GEMM with the kd taps folded into the MMA N dimension
+// (tcgen05 / TMEM / TMA, sm_100a).  Third-generation kernel for the narrow layers (Cout <= 64) at W >= 16,
+// which carry most of the VAE+DFC step (c1, c2, enc_conv1/2, dec_conv3/4, decoder_output and their
+// dgrads).  Replaces the same reference ops as conv3d_igemm.cu (Keras Conv3D + BiasAdd [+ReLU/LeakyReLU],
+// Conv3DBackpropInput): vae/lattice_vae.py:173,178,213,219-224; unet/unet.py:276-336.
+//
+// Why: measured on B200 (profiles/r01_mma_rate_probe.json) a tcgen05.mma (SS, bf16, K=16, M=128) costs
+// max(54.7, N/2) cycles — the 128x32 B A-operand read from shared memory is the floor — so an N = Cout <= 64
+// layer runs the tensor pipe at <= 58 %, and the tap-outer halo kernel also re-loads every input plane for each
+// of the 3 output planes it feeds.  Here:
+//   * a CTA walks a column (sample n, h-block hb) of the volume along d; every INPUT plane slab
+//     (TH+2) x (W+1) voxels x Cin is TMA-loaded ONCE into a shared-memory ring (out-of-bounds zero fill = "same"
+//     padding in h and w; the d padding planes are simply never issued);
+//   * input plane i contributes to output planes i-1, i, i+1 through kd = 2, 1, 0.  The accumulators of
+//     consecutive output planes sit side by side in TMEM columns (a ring of R slots), so ONE MMA with
+//     N = 3*Cout and the weight tile [kd=2 | kd=1 | kd=0] x Cout rows updates all three: 3x fewer MMA
+//     instructions and A-operand reads, N = 48..192 instead of 16..64;
+//   * the (kh, kw) taps are row-shifted UMMA descriptors into the same slab (as in conv3d_halo.cu);
+//   * all 27 weight tiles stay resident in shared memory (loaded once per CTA);
+//   * the first MMA that touches a fresh slot is split off with accumulate = 0; a ring wrap splits the MMA in two;
+//   * the epilogue drains output plane d (TMEM -> bias/activation -> global) while the MMAs of the following
+//     planes run; optional per-channel sum / sum-of-squares of the stored values (BatchNorm statistics).
+//   * work = B * n_hblk * D plane steps, split evenly over the CTAs (a CTA may start mid-column: it re-reads
+//     one neighbour plane on each side of the cut).
+#include "conv3d_stream.cuh"
+
+namespace icsg3d {
+
+static constexpr int kStreamMaxIssuers = 4;
+static constexpr int kStreamThreads = (1 + kStreamMaxIssuers + 4) * 32;
+static constexpr int kStreamMaxStages = 6;
+static constexpr int kStreamMaxR = 8;
+
+struct StreamOp {      // one MMA target: `n` consecutive kd blocks starting at weight block `blk` into ring slot `slot`
+  int slot, blk, n, acc;
+};
+
+// Split the output-plane range [q_lo, q_lo + cnt) (ring positions q % R) at the ring wrap.
+__device__ __forceinline__ int stream_ops(int q_lo, int cnt, int blk0, int acc, int R, StreamOp* ops, int nops) {
+  if (cnt <= 0) return nops;
+  const int s = q_lo % R;
+  const int first = cnt < R - s ? cnt : R - s;
+  ops[nops++] = StreamOp{s, blk0, first, acc};
+  if (cnt > first) ops[nops++] = StreamOp{0, blk0 + first, cnt - first, acc};
+  return nops;
+}
+
+template <int KSTEPS>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const ConvStreamParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kStreamMaxStages], a_empty[kStreamMaxStages];
+  __shared__ __align__(8) uint64_t slot_full[kStreamMaxR], slot_empty[kStreamMaxR];
+  __shared__ __align__(8) uint64_t w_full;
+  __shared__ float s_bias[64];
+  __shared__ double s_stats[2][64];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_off = (p.w_bytes + 1023u) & ~1023u;  // weights first, then the plane ring
+
+  // zero the guard row behind every plane slab chunk: it is the w = W pad of the slab's last row
+  {
+    const int words = p.row_bytes / 4;
+    const int slab_rows = p.HP * p.WP;
+    for (int i = threadIdx.x; i < p.stages * p.chunks * words; i += blockDim.x) {
+      const int st = i / (p.chunks * words);
+      const int ch = (i / words) % p.chunks;
+      const int w = i % words;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sm + a_off + static_cast<size_t>(st) * p.a_stage_bytes +
+                                                  static_cast<size_t>(ch) * p.a_chunk_bytes +
+                                                  static_cast<size_t>(slab_rows) * p.row_bytes);
+      dst[w] = 0u;
+    }
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], p.issuers);
+    }
+    for (int i = 0; i < p.R; ++i) {
+      mbar_init(&slot_full[i], p.issuers);
+      mbar_init(&slot_empty[i], 4);
+    }
+    mbar_init(&w_full, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.C) ? p.bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < 128) s_stats[threadIdx.x >> 6][threadIdx.x & 63] = 0.0;
+  if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int s_begin = blockIdx.x * p.steps_per_cta;
+  const int s_end = min(p.total_steps, s_begin + p.steps_per_cta);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const bool leader = elect_one();
+    if (leader) {  // all 27 * chunks weight tiles, laid out [kh*3+kw][chunk][kd = 2, 1, 0][C rows]
+      mbar_expect_tx(&w_full, p.w_bytes);
+      for (int khw = 0; khw < 9; ++khw)
+        for (int ch = 0; ch < p.chunks; ++ch)
+          for (int blk = 0; blk < 3; ++blk)
+            tma_load_3d(sm + static_cast<size_t>((khw * p.chunks + ch) * 3 + blk) * p.blk_bytes, &tmB, &w_full, ch * p.kc, 0,
+                        (2 - blk) * 9 + khw);
+    }
+    int astep = 0;
+    for (int s = s_begin; s < s_end;) {
+      const int col = s / p.D, db = s - col * p.D;
+      const int de = min(p.D, db + (s_end - s));
+      const int n = col / p.n_hblk, hb = col - n * p.n_hblk;
+      const int i_lo = max(0, db - 1), i_hi = min(p.D - 1, de);
+      for (int i = i_lo; i <= i_hi; ++i, ++astep) {
+        const int stage = astep % p.stages;
+        mbar_wait(&a_empty[stage], (static_cast<uint32_t>(astep / p.stages) & 1u) ^ 1u);
+        if (leader) {
+          mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
+          for (int ch = 0; ch < p.chunks; ++ch)
+            tma_load_5d(sm + a_off + static_cast<size_t>(stage) * p.a_stage_bytes + static_cast<size_t>(ch) * p.a_chunk_bytes,
+                        &tmA, &a_full[stage], ch * p.kc, -1, hb * p.TH - 1, i, n);
+        }
+      }
+      s += de - db;
+    }
+  } else if (warp <= kStreamMaxIssuers) {
+    // ===================== MMA issuers (tile t is owned by issuer t % issuers) =====================
+    const int issuer = warp - 1;
+    if (issuer < p.issuers) {
+      const bool leader = elect_one();
+      const uint32_t desc_hi = umma_desc_hi(p.sbo, p.layout);
+      const uint32_t w_lo = umma_desc_lo(base, 16u);
+      const uint32_t blk_lo = p.blk_bytes >> 4;
+      const uint32_t a_ring_lo = umma_desc_lo(base + a_off, 16u);
+      const uint32_t tile_lo = (128u * static_cast<uint32_t>(p.row_bytes)) >> 4;
+      mbar_wait(&w_full, 0);
+      int astep = 0, qbase = 0;
+      for (int s = s_begin; s < s_end;) {
+        const int col = s / p.D, db = s - col * p.D;
+        const int de = min(p.D, db + (s_end - s));
+        const int hb = col % p.n_hblk;
+        const int th_valid = min(p.TH, p.H - hb * p.TH);
+        const int t_valid = (th_valid * p.WP + 127) >> 7;  // tiles that hold at least one real output row
+        const int i_lo = max(0, db - 1), i_hi = min(p.D - 1, de);
+        for (int i = i_lo; i <= i_hi; ++i, ++astep) {
+          const int o_lo = max(db, i - 1), o_hi = min(de - 1, i + 1);
+          const int o_f = (i == 0) ? o_lo : min(i + 1, o_hi + 1);  // outputs [o_f, o_hi] are touched for the first time
+          for (int o = o_f; o <= o_hi; ++o) {
+            const int q = qbase + o - db;
+            mbar_wait(&slot_empty[q % p.R], (static_cast<uint32_t>(q / p.R) & 1u) ^ 1u);
+          }
+          const int stage = astep % p.stages;
+          mbar_wait(&a_full[stage], static_cast<uint32_t>(astep / p.stages) & 1u);
+          tc_fence_after();
+          StreamOp ops_first[4], ops_rest[2];
+          int n_first = stream_ops(qbase + o_lo - db, o_f - o_lo, o_lo - (i - 1), 1, p.R, ops_first, 0);
+          n_first = stream_ops(qbase + o_f - db, o_hi - o_f + 1, o_f - (i - 1), 0, p.R, ops_first, n_first);
+          const int n_rest = stream_ops(qbase + o_lo - db, o_hi - o_lo + 1, o_lo - (i - 1), 1, p.R, ops_rest, 0);
+          const uint32_t a_stage_lo = a_ring_lo + static_cast<uint32_t>(stage) * (p.a_stage_bytes >> 4);
+          int unit = 0;
+          for (int kh = 0; kh < 3; ++kh) {
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t shift_lo = (static_cast<uint32_t>(kh * p.WP + kw) * static_cast<uint32_t>(p.row_bytes)) >> 4;
+              for (int ch = 0; ch < p.chunks; ++ch, ++unit) {
+                const uint32_t b_unit_lo = w_lo + static_cast<uint32_t>(unit * 3) * blk_lo;
+                const uint32_t a_unit_lo = a_stage_lo + static_cast<uint32_t>(ch) * (p.a_chunk_bytes >> 4) + shift_lo;
+                for (int t = issuer; t < t_valid; t += p.issuers) {
+                  const uint32_t a_lo = a_unit_lo + static_cast<uint32_t>(t) * tile_lo;
+                  const uint32_t d_tile = tmem_base + static_cast<uint32_t>(t * p.R * p.C);
+                  if (unit == 0) {
+                    for (int j = 0; j < n_first; ++j) {
+                      const StreamOp op = ops_first[j];
+                      if (leader)
+                        umma_bf16_lohi(d_tile + static_cast<uint32_t>(op.slot * p.C), a_lo, desc_hi,
+                                       b_unit_lo + static_cast<uint32_t>(op.blk) * blk_lo, desc_hi, p.idesc[op.n - 1],
+                                       static_cast<uint32_t>(op.acc));
+                    }
+                    if (KSTEPS > 1) {
+                      for (int j = 0; j < n_rest; ++j) {
+                        const StreamOp op = ops_rest[j];
+                        if (leader) {
+#pragma unroll
+                          for (int k = 1; k < KSTEPS; ++k)
+                            umma_bf16_lohi(d_tile + static_cast<uint32_t>(op.slot * p.C), a_lo + 2u * k, desc_hi,
+                                           b_unit_lo + static_cast<uint32_t>(op.blk) * blk_lo + 2u * k, desc_hi,
+                                           p.idesc[op.n - 1], 1u);
+                        }
+                      }
+                    }
+                  } else {
+                    for (int j = 0; j < n_rest; ++j) {
+                      const StreamOp op = ops_rest[j];
+                      if (leader) {
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; ++k)
+                          umma_bf16_lohi(d_tile + static_cast<uint32_t>(op.slot * p.C), a_lo + 2u * k, desc_hi,
+                                         b_unit_lo + static_cast<uint32_t>(op.blk) * blk_lo + 2u * k, desc_hi,
+                                         p.idesc[op.n - 1], 1u);
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          }
+          if (leader) {
+            umma_commit(&a_empty[stage]);
+            if (i - 1 >= db) umma_commit(&slot_full[(qbase + i - 1 - db) % p.R]);            // output plane i-1 is complete
+            if (i == p.D - 1 && de == p.D) umma_commit(&slot_full[(qbase + i - db) % p.R]);  // and the last plane of the column
+          }
+          __syncwarp();
+        }
+        qbase += de - db;
+        s += de - db;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;
+    int q = 0;
+    for (int s = s_begin; s < s_end;) {
+      const int col = s / p.D, db = s - col * p.D;
+      const int de = min(p.D, db + (s_end - s));
+      const int n = col / p.n_hblk, hb = col - n * p.n_hblk;
+      const int th_valid = min(p.TH, p.H - hb * p.TH);
+      const int t_valid = (th_valid * p.WP + 127) >> 7;
+      for (int o = db; o < de; ++o, ++q) {
+        const int slot = q % p.R;
+        mbar_wait(&slot_full[slot], static_cast<uint32_t>(q / p.R) & 1u);
+        tc_fence_after();
+        for (int t = 0; t < t_valid; ++t) {
+          const int f = t * 128 + quarter * 32 + lane;
+          const int hl = f / p.WP;
+          const int wl = f - hl * p.WP;
+          const bool ok = hl < th_valid && wl < p.W;
+          const long long pixel = ((static_cast<long long>(n) * p.D + o) * p.H + hb * p.TH + hl) * p.W + wl;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>((t * p.R + slot) * p.C);
+          for (int c0 = 0; c0 < p.C; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
+            tmem_ld_wait();
+            if (c0 >= p.n_store) continue;
+            float fv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x = __uint_as_float(v[i]) + s_bias[c0 + i];
+              if (p.act == ICSG3D_ACT_RELU) x = fmaxf(x, 0.f);
+              else if (p.act == ICSG3D_ACT_LEAKY) x = x > 0.f ? x : p.alpha * x;
+              fv[i] = x;
+            }
+            const int nvalid = min(16, p.n_store - c0);
+            if (p.y_dtype == ICSG3D_DT_BF16) {
+              uint4 q0, q1;
+              q0.x = pack_bf16x2(fv[0], fv[1]);
+              q0.y = pack_bf16x2(fv[2], fv[3]);
+              q0.z = pack_bf16x2(fv[4], fv[5]);
+              q0.w = pack_bf16x2(fv[6], fv[7]);
+              q1.x = pack_bf16x2(fv[8], fv[9]);
+              q1.y = pack_bf16x2(fv[10], fv[11]);
+              q1.z = pack_bf16x2(fv[12], fv[13]);
+              q1.w = pack_bf16x2(fv[14], fv[15]);
+              if (ok) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + c0;
+                if (nvalid == 16 && (p.ldy & 7) == 0) {
+                  reinterpret_cast<uint4*>(dst)[0] = q0;
+                  reinterpret_cast<uint4*>(dst)[1] = q1;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (i < nvalid) dst[i] = f2bf(fv[i]);
+                }
+              }
+              if (p.stats) {  // statistics of the values as stored (bf16-rounded)
+                float2 u;
+                u = unpack_bf16x2(q0.x); fv[0] = u.x; fv[1] = u.y;
+                u = unpack_bf16x2(q0.y); fv[2] = u.x; fv[3] = u.y;
+                u = unpack_bf16x2(q0.z); fv[4] = u.x; fv[5] = u.y;
+                u = unpack_bf16x2(q0.w); fv[6] = u.x; fv[7] = u.y;
+                u = unpack_bf16x2(q1.x); fv[8] = u.x; fv[9] = u.y;
+                u = unpack_bf16x2(q1.y); fv[10] = u.x; fv[11] = u.y;
+                u = unpack_bf16x2(q1.z); fv[12] = u.x; fv[13] = u.y;
+                u = unpack_bf16x2(q1.w); fv[14] = u.x; fv[15] = u.y;
+              }
+            } else if (ok) {
+              float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + c0;
+              if (nvalid == 16 && (p.ldy & 3) == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  reinterpret_cast<float4*>(dst)[i] = make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
+              } else if (nvalid == 4 && (p.ldy & 3) == 0) {
+                reinterpret_cast<float4*>(dst)[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < nvalid) dst[i] = fv[i];
+              }
+            }
+            if (p.stats) {
+              float sq[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                fv[i] = ok ? fv[i] : 0.f;
+                sq[i] = fv[i] * fv[i];
+              }
+              const float s1 = warp_colsum16(fv, lane);
+              const float s2 = warp_colsum16(sq, lane);
+              if ((lane & 1) == 0) {
+                const int c = c0 + colsum16_owner(lane);
+                atomicAdd(&s_stats[0][c], static_cast<double>(s1));
+                atomicAdd(&s_stats[1][c], static_cast<double>(s2));
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_empty[slot]);
+      }
+      s += de - db;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.stats && threadIdx.x < 2 * p.C) {
+    const int half = threadIdx.x / p.C, c = threadIdx.x - half * p.C;
+    p.stats[static_cast<size_t>(blockIdx.x) * 2 * p.C + half * p.C + c] = s_stats[half][c];
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static bool stream_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvStreamParams* out) {
+  if (nout != 16 && nout != 32 && nout != 64) return false;
+  if (W < 16 || W > 64 || !stream_pow2(W) || !stream_pow2(H) || !stream_pow2(D) || D < 4) return false;
+  if (cin % 16 != 0 || cin > 256) return false;
+  const int C = nout;
+  const int kc = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+  const int chunks = cin / kc;
+  const int row_bytes = kc * 2;
+  const int WP = W + 1;
+  const uint32_t budget = 222u * 1024u;
+  const uint32_t w_bytes = 27u * static_cast<uint32_t>(cin) * C * 2u;
+  const uint32_t w_alloc = (w_bytes + 1023u) & ~1023u;
+  if (w_alloc + 2048u >= budget) return false;
+  int Tmax = 512 / (4 * C);
+  if (Tmax > 8) Tmax = 8;
+  double best = -1.0;
+  ConvStreamParams bp{};
+  for (int nb = 1; nb <= H; ++nb) {  // balanced h-blocks only: every plane step of the layer costs about the same
+    const int TH = (H + nb - 1) / nb;
+    if ((H + TH - 1) / TH != nb) continue;
+    const int T = (TH * WP + 127) / 128;
+    if (T > Tmax) continue;
+    const int HP = TH + 2;
+    const int n_hblk = nb;
+    const int rows_alloc = (HP * WP + 1 > T * 128 + 2 * WP + 3) ? HP * WP + 1 : T * 128 + 2 * WP + 3;
+    const uint32_t a_chunk = (static_cast<uint32_t>(rows_alloc) * row_bytes + 1023u) & ~1023u;
+    const uint32_t a_stage = a_chunk * chunks;
+    int stages = static_cast<int>((budget - w_alloc) / a_stage);
+    if (stages > kStreamMaxStages) stages = kStreamMaxStages;
+    if (stages < 2) continue;
+    // tiles actually issued per column plane (the partial last block skips empty tiles)
+    int tiles = 0;
+    for (int hb = 0; hb < n_hblk; ++hb) {
+      const int thv = (H - hb * TH) < TH ? (H - hb * TH) : TH;
+      tiles += (thv * WP + 127) / 128;
+    }
+    double eff = static_cast<double>(H) * W / (tiles * 128.0);
+    if (stages < 3) eff *= 0.9;
+    eff -= 0.002 * HP / TH;  // tie-break: less h-halo re-read
+    if (eff > best) {
+      best = eff;
+      bp = ConvStreamParams{};
+      bp.B = B; bp.D = D; bp.H = H; bp.W = W;
+      bp.TH = TH; bp.HP = HP; bp.WP = WP; bp.n_hblk = n_hblk;
+      bp.T = T; bp.C = C;
+      int R = 512 / (T * C);
+      if (R > kStreamMaxR) R = kStreamMaxR;
+      bp.R = R;
+      bp.kc = kc; bp.chunks = chunks; bp.row_bytes = row_bytes;
+      bp.stages = stages;
+      bp.issuers = T < kStreamMaxIssuers ? T : kStreamMaxIssuers;
+      bp.a_chunk_bytes = a_chunk; bp.a_stage_bytes = a_stage;
+      bp.a_tx_bytes = static_cast<uint32_t>(HP * WP) * row_bytes * chunks;
+      bp.w_bytes = w_bytes; bp.blk_bytes = static_cast<uint32_t>(C) * row_bytes;
+    }
+  }
+  if (best < 0.0) return false;
+  bp.total_steps = B * bp.n_hblk * D;
+  int grid = sms;
+  if (grid > bp.total_steps / 4) grid = bp.total_steps / 4;  // at least ~4 planes per CTA (each cut costs 2 extra plane passes)
+  if (grid < 1) grid = 1;
+  bp.steps_per_cta = (bp.total_steps + grid - 1) / grid;
+  bp.sbo = 8u * bp.row_bytes;
+  bp.layout = umma_layout_for_swizzle(bp.row_bytes);
+  for (int n = 1; n <= 3; ++n) bp.idesc[n - 1] = umma_idesc_bf16(n * C, 0, 0);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(bp.R * bp.T * C)) cols <<= 1;
+  bp.tmem_cols = cols;
+  *out = bp;
+  return true;
+}
+
+int conv_stream_grid(const ConvStreamParams& p) { return (p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta; }
+
+int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
+                       int n_store, int cin, int nout, int act, float alpha, double* stats, ConvStreamParams p,
+                       cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
+                        static_cast<uint64_t>(p.D), static_cast<uint64_t>(p.B)};
+    uint64_t strides[4] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(p.W) * ldx * 2,
+                           static_cast<uint64_t>(p.H) * p.W * ldx * 2, static_cast<uint64_t>(p.D) * p.H * p.W * ldx * 2};
+    uint32_t box[5] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.WP), static_cast<uint32_t>(p.HP), 1, 1};
+    int rc = encode_tiled_bf16(&tmA, x, 5, dims, strides, box, p.row_bytes);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(nout), 27};
+    uint64_t strides[2] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(nout) * cin * 2};
+    uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.C), 1};
+    int rc = encode_tiled_bf16(&tmB, wpack, 3, dims, strides, box, p.row_bytes);
+    if (rc) return rc;
+  }
+  p.y = y; p.ldy = ldy; p.y_dtype = y_dtype; p.n_store = n_store; p.bias = bias; p.act = act; p.alpha = alpha;
+  p.stats = stats;
+  static bool configured = false;
+  if (!configured) {
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    configured = true;
+  }
+  const size_t smem = ((p.w_bytes + 1023u) & ~1023u) + static_cast<size_t>(p.stages) * p.a_stage_bytes + 1024;
+  const int grid = conv_stream_grid(p);
+  if (p.kc == 16) conv3d_k3_stream_kernel<1><<<grid, kStreamThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.kc == 32) conv3d_k3_stream_kernel<2><<<grid, kStreamThreads, smem, st>>>(tmA, tmB, p);
+  else conv3d_k3_stream_kernel<4><<<grid, kStreamThreads, smem, st>>>(tmA, tmB, p);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+}  // namespace icsg3d

@@ -1,0 +1,34 @@
+// Shared declarations of the plane-streaming, kd-folded Conv3D kernel (conv3d_stream.cu), used by the dispatcher
+// in conv3d_igemm.cu.
+#pragma once
+#include "common.cuh"
+
+namespace icsg3d {
+
+struct ConvStreamParams {
+  int B, D, H, W;
+  int TH, HP, WP, n_hblk;
+  int T, R, C;           // M tiles per plane slab, accumulator ring slots (output planes), channels per kd block (= nout)
+  int kc, chunks, row_bytes;
+  int stages;            // input-plane ring depth in shared memory
+  int issuers;           // MMA issuer warps in use (tiles are dealt round-robin)
+  int total_steps, steps_per_cta;
+  uint32_t a_chunk_bytes, a_stage_bytes, a_tx_bytes;
+  uint32_t w_bytes, blk_bytes;
+  uint32_t sbo, layout, idesc[3], tmem_cols;
+  void* y;
+  int ldy, y_dtype, n_store;
+  const float* bias;
+  int act;
+  float alpha;
+  double* stats;         // optional per-CTA BatchNorm partials [grid][2][C] (sum, sum of squares of the stored values)
+};
+
+// false when the layer shape does not fit the streaming scheme (the dispatcher then falls back to the other kernels).
+bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvStreamParams* out);
+int conv_stream_grid(const ConvStreamParams& p);
+int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
+                       int n_store, int cin, int nout, int act, float alpha, double* stats, ConvStreamParams p,
+                       cudaStream_t st);
+
+}  // namespace icsg3d

@@ -70,8 +70,13 @@ int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const floa
                            float leaky_alpha, void* stream);
 
 /* Diagnostic (host only): kernel/tiling choice of the dispatcher for a layer shape.
- * out[0..9] = {impl (0 per-tap TMA kernel, 1 halo-reuse kernel), TD, TH, G, NT, a_bufs, b_stages, items, kc, smem} */
+ * out[0] = impl: 0 per-tap TMA kernel; 1 halo-reuse kernel {1, TD, TH, G, NT, a_bufs, b_stages, items, kc, smem};
+ * 2 plane-streaming kd-folded kernel {2, R, TH, T, C, stages, issuers, grid, kc, smem}. */
 int icsg3d_conv3d_k3_plan(int B, int D, int H, int W, int cin, int nout, int sms, int* out);
+
+/* Diagnostic: restrict the dispatcher (A/B timing of the kernel generations).  impl = 0 automatic (default),
+ * 1 per-tap TMA kernel only, 2 halo-reuse kernel (no plane-streaming kernel).  Same as env ICSG3D_CONV_IMPL=v1|halo. */
+int icsg3d_conv3d_set_impl(int impl);
 
 /* Conv3D 1x1x1 (the U-Net heads `soft`/`sig`, unet.py:339-352) through the same tcgen05 kernel with a single tap:
  * wpack bf16 [1][nout][cin]. */

@@ -12,6 +12,8 @@ pytestmark = pytest.mark.gpu
 SHAPES = [  # (B, D, cin, cout) — the layer shapes of SURVEY §8a at reduced batch
     (2, 32, 16, 16), (2, 32, 32, 64), (1, 32, 64, 32), (2, 16, 64, 128), (2, 8, 128, 256), (4, 4, 256, 512),
     (8, 2, 128, 16), (1, 2, 16, 16),
+    # plane-streaming kd-folded kernel (conv3d_stream.cu): narrow layers at W >= 16, incl. odd batch / mid-column cuts
+    (3, 32, 16, 32), (2, 16, 16, 32), (1, 16, 64, 32), (5, 16, 32, 16), (1, 32, 32, 16),
 ]
 
 
@@ -40,7 +42,7 @@ def test_fprop_matches_oracle(B, D, cin, cout):
     assert rel_l2(y.float(), ref) < 1e-2
 
 
-@pytest.mark.parametrize("B,D,cin,cout", SHAPES[:6])
+@pytest.mark.parametrize("B,D,cin,cout", SHAPES[:6] + SHAPES[8:])
 def test_dgrad_matches_oracle(B, D, cin, cout):
     """Conv3DBackpropInput = the same kernel on mirrored/transposed weights."""
     from icsg3d_b200 import ops
@@ -100,3 +102,20 @@ def test_condition_fold_equals_tiled_concat():
     K.conv3d_same(fr, wr).backward(dy.float())
     torch.cuda.synchronize()
     assert rel_l2(dw, wr.grad) < 2e-5
+
+
+@pytest.mark.parametrize("B,D,cin,cout", [(32, 32, 32, 64), (32, 32, 64, 32), (32, 32, 16, 16), (32, 16, 64, 32)])
+def test_stream_kernel_full_batch_matches_cuda_core_reference(B, D, cin, cout):
+    """Full BASELINE batch: the tcgen05 path (plane-streaming kernel for these shapes) against the CUDA-core
+    cross-check kernel on the device (fp32 outputs; same operands, different accumulation order)."""
+    from icsg3d_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(B, D, D, D, cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(3, 3, 3, cin, cout, device="cuda", generator=g) / (27 * cin) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g)
+    wp = ops.pack_conv_w_fprop(w)
+    y = ops.conv3d_k3(x, wp, b, act=ops.ACT_LEAKY, out_dtype=torch.float32)
+    yr = ops.conv3d_k3(x, wp, b, act=ops.ACT_LEAKY, ref=True)
+    torch.cuda.synchronize()
+    assert rel_l2(y, yr) < 2e-5
+    assert float((y - yr).abs().max()) < 1e-3
