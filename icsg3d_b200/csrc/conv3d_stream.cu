@@ -27,23 +27,10 @@
 namespace icsg3d {
 
 static constexpr int kStreamMaxIssuers = 4;
-static constexpr int kStreamThreads = (1 + kStreamMaxIssuers + 4) * 32;
+static constexpr int kStreamEpiWarps = 8;
+static constexpr int kStreamThreads = (1 + kStreamMaxIssuers + kStreamEpiWarps) * 32;
 static constexpr int kStreamMaxStages = 6;
 static constexpr int kStreamMaxR = 8;
-
-struct StreamOp {      // one MMA target: `n` consecutive kd blocks starting at weight block `blk` into ring slot `slot`
-  int slot, blk, n, acc;
-};
-
-// Split the output-plane range [q_lo, q_lo + cnt) (ring positions q % R) at the ring wrap.
-__device__ __forceinline__ int stream_ops(int q_lo, int cnt, int blk0, int acc, int R, StreamOp* ops, int nops) {
-  if (cnt <= 0) return nops;
-  const int s = q_lo % R;
-  const int first = cnt < R - s ? cnt : R - s;
-  ops[nops++] = StreamOp{s, blk0, first, acc};
-  if (cnt > first) ops[nops++] = StreamOp{0, blk0 + first, cnt - first, acc};
-  return nops;
-}
 
 template <int KSTEPS>
 __global__ void __launch_bounds__(kStreamThreads, 1)
@@ -53,11 +40,13 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __shared__ __align__(8) uint64_t a_full[kStreamMaxStages], a_empty[kStreamMaxStages];
   __shared__ __align__(8) uint64_t slot_full[kStreamMaxR], slot_empty[kStreamMaxR];
   __shared__ __align__(8) uint64_t w_full;
-  __shared__ float s_bias[64];
+  __shared__ __align__(16) float s_bias[64];
   __shared__ double s_stats[2][64];
   __shared__ uint32_t tmem_base_slot;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so that everything derived from it (MMA
+  // descriptors, TMEM addresses) stays in uniform registers — the MMA issue loop is instruction bound otherwise
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -87,7 +76,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
     for (int i = 0; i < p.R; ++i) {
       mbar_init(&slot_full[i], p.issuers);
-      mbar_init(&slot_empty[i], 4);
+      mbar_init(&slot_empty[i], kStreamEpiWarps);
     }
     mbar_init(&w_full, 1);
     fence_mbar_init();
@@ -140,8 +129,12 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t desc_hi = umma_desc_hi(p.sbo, p.layout);
       const uint32_t w_lo = umma_desc_lo(base, 16u);
       const uint32_t blk_lo = p.blk_bytes >> 4;
+      const uint32_t unit_lo = 3u * blk_lo;
+      const uint32_t chunk_lo = p.a_chunk_bytes >> 4;
+      const uint32_t row_lo = static_cast<uint32_t>(p.row_bytes) >> 4;
       const uint32_t a_ring_lo = umma_desc_lo(base + a_off, 16u);
-      const uint32_t tile_lo = (128u * static_cast<uint32_t>(p.row_bytes)) >> 4;
+      const uint32_t tile_lo = 128u * row_lo;
+      const uint32_t idesc_c = p.idesc[0];
       mbar_wait(&w_full, 0);
       int astep = 0, qbase = 0;
       for (int s = s_begin; s < s_end;) {
@@ -161,58 +154,46 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           const int stage = astep % p.stages;
           mbar_wait(&a_full[stage], static_cast<uint32_t>(astep / p.stages) & 1u);
           tc_fence_after();
-          StreamOp ops_first[4], ops_rest[2];
-          int n_first = stream_ops(qbase + o_lo - db, o_f - o_lo, o_lo - (i - 1), 1, p.R, ops_first, 0);
-          n_first = stream_ops(qbase + o_f - db, o_hi - o_f + 1, o_f - (i - 1), 0, p.R, ops_first, n_first);
-          const int n_rest = stream_ops(qbase + o_lo - db, o_hi - o_lo + 1, o_lo - (i - 1), 1, p.R, ops_rest, 0);
+          // outputs o_lo..o_hi = consecutive ring positions; split once at the ring wrap: op0 (n0 blocks), op1 (n1 blocks)
+          const int q_lo = qbase + o_lo - db;
+          const int cnt = o_hi - o_lo + 1;
+          const int s0 = q_lo % p.R;
+          const int n0 = cnt < p.R - s0 ? cnt : p.R - s0;
+          const int n1 = cnt - n0;
+          const int blk0 = o_lo - (i - 1);
+          const uint32_t d0 = static_cast<uint32_t>(s0 * p.C);
+          const uint32_t b0 = static_cast<uint32_t>(blk0) * blk_lo;
+          const uint32_t b1 = static_cast<uint32_t>(blk0 + n0) * blk_lo;
+          const uint32_t idesc0 = p.idesc[n0 - 1];
+          const uint32_t idesc1 = p.idesc[n1 > 0 ? n1 - 1 : 0];
           const uint32_t a_stage_lo = a_ring_lo + static_cast<uint32_t>(stage) * (p.a_stage_bytes >> 4);
-          int unit = 0;
-          for (int kh = 0; kh < 3; ++kh) {
-            for (int kw = 0; kw < 3; ++kw) {
-              const uint32_t shift_lo = (static_cast<uint32_t>(kh * p.WP + kw) * static_cast<uint32_t>(p.row_bytes)) >> 4;
-              for (int ch = 0; ch < p.chunks; ++ch, ++unit) {
-                const uint32_t b_unit_lo = w_lo + static_cast<uint32_t>(unit * 3) * blk_lo;
-                const uint32_t a_unit_lo = a_stage_lo + static_cast<uint32_t>(ch) * (p.a_chunk_bytes >> 4) + shift_lo;
-                for (int t = issuer; t < t_valid; t += p.issuers) {
-                  const uint32_t a_lo = a_unit_lo + static_cast<uint32_t>(t) * tile_lo;
-                  const uint32_t d_tile = tmem_base + static_cast<uint32_t>(t * p.R * p.C);
-                  if (unit == 0) {
-                    for (int j = 0; j < n_first; ++j) {
-                      const StreamOp op = ops_first[j];
-                      if (leader)
-                        umma_bf16_lohi(d_tile + static_cast<uint32_t>(op.slot * p.C), a_lo, desc_hi,
-                                       b_unit_lo + static_cast<uint32_t>(op.blk) * blk_lo, desc_hi, p.idesc[op.n - 1],
-                                       static_cast<uint32_t>(op.acc));
-                    }
-                    if (KSTEPS > 1) {
-                      for (int j = 0; j < n_rest; ++j) {
-                        const StreamOp op = ops_rest[j];
-                        if (leader) {
+          if (leader) {
+            for (int t = issuer; t < t_valid; t += p.issuers) {
+              const uint32_t a_t = a_stage_lo + static_cast<uint32_t>(t) * tile_lo;
+              const uint32_t d_t = tmem_base + static_cast<uint32_t>(t * p.R * p.C);
+              // very first K step of the plane: one MMA per output plane, accumulate only into the planes already begun
+              for (int o = o_lo; o <= o_hi; ++o)
+                umma_bf16_lohi(d_t + static_cast<uint32_t>(((qbase + o - db) % p.R) * p.C), a_t, desc_hi,
+                               w_lo + static_cast<uint32_t>(o - (i - 1)) * blk_lo, desc_hi, idesc_c, o < o_f ? 1u : 0u);
+              uint32_t b_u = w_lo;
+              for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-                          for (int k = 1; k < KSTEPS; ++k)
-                            umma_bf16_lohi(d_tile + static_cast<uint32_t>(op.slot * p.C), a_lo + 2u * k, desc_hi,
-                                           b_unit_lo + static_cast<uint32_t>(op.blk) * blk_lo + 2u * k, desc_hi,
-                                           p.idesc[op.n - 1], 1u);
-                        }
-                      }
-                    }
-                  } else {
-                    for (int j = 0; j < n_rest; ++j) {
-                      const StreamOp op = ops_rest[j];
-                      if (leader) {
+                for (int kw = 0; kw < 3; ++kw) {
+                  uint32_t a_u = a_t + static_cast<uint32_t>(kh * p.WP + kw) * row_lo;
+                  for (int ch = 0; ch < p.chunks; ++ch, a_u += chunk_lo, b_u += unit_lo) {
+                    const int k_first = (kh | kw | ch) == 0 ? 1 : 0;
 #pragma unroll
-                        for (int k = 0; k < KSTEPS; ++k)
-                          umma_bf16_lohi(d_tile + static_cast<uint32_t>(op.slot * p.C), a_lo + 2u * k, desc_hi,
-                                         b_unit_lo + static_cast<uint32_t>(op.blk) * blk_lo + 2u * k, desc_hi,
-                                         p.idesc[op.n - 1], 1u);
-                      }
+                    for (int k = 0; k < KSTEPS; ++k)
+                      if (k >= k_first) umma_bf16_lohi(d_t + d0, a_u + 2u * k, desc_hi, b_u + b0 + 2u * k, desc_hi, idesc0, 1u);
+                    if (n1 > 0) {
+#pragma unroll
+                      for (int k = 0; k < KSTEPS; ++k)
+                        if (k >= k_first) umma_bf16_lohi(d_t, a_u + 2u * k, desc_hi, b_u + b1 + 2u * k, desc_hi, idesc1, 1u);
                     }
                   }
                 }
               }
             }
-          }
-          if (leader) {
             umma_commit(&a_empty[stage]);
             if (i - 1 >= db) umma_commit(&slot_full[(qbase + i - 1 - db) % p.R]);            // output plane i-1 is complete
             if (i == p.D - 1 && de == p.D) umma_commit(&slot_full[(qbase + i - db) % p.R]);  // and the last plane of the column
@@ -224,8 +205,13 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue warps: 2 per TMEM lane quarter, (tile, 16-column group) items dealt alternately ======
     const int quarter = warp & 3;
+    const int half = (warp - 1 - kStreamMaxIssuers) >> 2;
+    const int groups = (min(p.n_store, p.C) + 15) >> 4;
+    const float inv_wp = 1.0f / static_cast<float>(p.WP);
+    // LeakyReLU / ReLU / identity as max(x, slope * x)
+    const float slope = p.act == ICSG3D_ACT_RELU ? 0.f : (p.act == ICSG3D_ACT_LEAKY ? p.alpha : 1.f);
     int q = 0;
     for (int s = s_begin; s < s_end;) {
       const int col = s / p.D, db = s - col * p.D;
@@ -233,92 +219,96 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int n = col / p.n_hblk, hb = col - n * p.n_hblk;
       const int th_valid = min(p.TH, p.H - hb * p.TH);
       const int t_valid = (th_valid * p.WP + 127) >> 7;
+      const int items = t_valid * groups;
       for (int o = db; o < de; ++o, ++q) {
         const int slot = q % p.R;
+        const long long plane0 = ((static_cast<long long>(n) * p.D + o) * p.H + hb * p.TH) * p.W;
         mbar_wait(&slot_full[slot], static_cast<uint32_t>(q / p.R) & 1u);
         tc_fence_after();
-        for (int t = 0; t < t_valid; ++t) {
+        for (int item = half; item < items; item += 2) {
+          const int t = item / groups;
+          const int c0 = (item - t * groups) << 4;
           const int f = t * 128 + quarter * 32 + lane;
-          const int hl = f / p.WP;
+          const int hl = static_cast<int>((static_cast<float>(f) + 0.5f) * inv_wp);
           const int wl = f - hl * p.WP;
           const bool ok = hl < th_valid && wl < p.W;
-          const long long pixel = ((static_cast<long long>(n) * p.D + o) * p.H + hb * p.TH + hl) * p.W + wl;
+          const long long pixel = plane0 + hl * p.W + wl;
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                 static_cast<uint32_t>((t * p.R + slot) * p.C);
-          for (int c0 = 0; c0 < p.C; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
-            tmem_ld_wait();
-            if (c0 >= p.n_store) continue;
-            float fv[16];
+                                 static_cast<uint32_t>((t * p.R + slot) * p.C + c0);
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+          float fv[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x = __uint_as_float(v[i]) + s_bias[c0 + i];
-              if (p.act == ICSG3D_ACT_RELU) x = fmaxf(x, 0.f);
-              else if (p.act == ICSG3D_ACT_LEAKY) x = x > 0.f ? x : p.alpha * x;
-              fv[i] = x;
-            }
-            const int nvalid = min(16, p.n_store - c0);
-            if (p.y_dtype == ICSG3D_DT_BF16) {
-              uint4 q0, q1;
-              q0.x = pack_bf16x2(fv[0], fv[1]);
-              q0.y = pack_bf16x2(fv[2], fv[3]);
-              q0.z = pack_bf16x2(fv[4], fv[5]);
-              q0.w = pack_bf16x2(fv[6], fv[7]);
-              q1.x = pack_bf16x2(fv[8], fv[9]);
-              q1.y = pack_bf16x2(fv[10], fv[11]);
-              q1.z = pack_bf16x2(fv[12], fv[13]);
-              q1.w = pack_bf16x2(fv[14], fv[15]);
-              if (ok) {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + c0;
-                if (nvalid == 16 && (p.ldy & 7) == 0) {
-                  reinterpret_cast<uint4*>(dst)[0] = q0;
-                  reinterpret_cast<uint4*>(dst)[1] = q1;
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    if (i < nvalid) dst[i] = f2bf(fv[i]);
-                }
-              }
-              if (p.stats) {  // statistics of the values as stored (bf16-rounded)
-                float2 u;
-                u = unpack_bf16x2(q0.x); fv[0] = u.x; fv[1] = u.y;
-                u = unpack_bf16x2(q0.y); fv[2] = u.x; fv[3] = u.y;
-                u = unpack_bf16x2(q0.z); fv[4] = u.x; fv[5] = u.y;
-                u = unpack_bf16x2(q0.w); fv[6] = u.x; fv[7] = u.y;
-                u = unpack_bf16x2(q1.x); fv[8] = u.x; fv[9] = u.y;
-                u = unpack_bf16x2(q1.y); fv[10] = u.x; fv[11] = u.y;
-                u = unpack_bf16x2(q1.z); fv[12] = u.x; fv[13] = u.y;
-                u = unpack_bf16x2(q1.w); fv[14] = u.x; fv[15] = u.y;
-              }
-            } else if (ok) {
-              float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + c0;
-              if (nvalid == 16 && (p.ldy & 3) == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  reinterpret_cast<float4*>(dst)[i] = make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
-              } else if (nvalid == 4 && (p.ldy & 3) == 0) {
-                reinterpret_cast<float4*>(dst)[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + i]);
+            const float x0 = __uint_as_float(v[i]) + b4.x, x1 = __uint_as_float(v[i + 1]) + b4.y;
+            const float x2 = __uint_as_float(v[i + 2]) + b4.z, x3 = __uint_as_float(v[i + 3]) + b4.w;
+            fv[i] = fmaxf(x0, slope * x0);
+            fv[i + 1] = fmaxf(x1, slope * x1);
+            fv[i + 2] = fmaxf(x2, slope * x2);
+            fv[i + 3] = fmaxf(x3, slope * x3);
+          }
+          const int nvalid = min(16, p.n_store - c0);
+          if (p.y_dtype == ICSG3D_DT_BF16) {
+            uint4 q0, q1;
+            q0.x = pack_bf16x2(fv[0], fv[1]);
+            q0.y = pack_bf16x2(fv[2], fv[3]);
+            q0.z = pack_bf16x2(fv[4], fv[5]);
+            q0.w = pack_bf16x2(fv[6], fv[7]);
+            q1.x = pack_bf16x2(fv[8], fv[9]);
+            q1.y = pack_bf16x2(fv[10], fv[11]);
+            q1.z = pack_bf16x2(fv[12], fv[13]);
+            q1.w = pack_bf16x2(fv[14], fv[15]);
+            if (ok) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + c0;
+              if (nvalid == 16 && (p.ldy & 7) == 0) {
+                reinterpret_cast<uint4*>(dst)[0] = q0;
+                reinterpret_cast<uint4*>(dst)[1] = q1;
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                  if (i < nvalid) dst[i] = fv[i];
+                  if (i < nvalid) dst[i] = f2bf(fv[i]);
               }
             }
-            if (p.stats) {
-              float sq[16];
+            if (p.stats) {  // statistics of the values as stored (bf16-rounded)
+              float2 u;
+              u = unpack_bf16x2(q0.x); fv[0] = u.x; fv[1] = u.y;
+              u = unpack_bf16x2(q0.y); fv[2] = u.x; fv[3] = u.y;
+              u = unpack_bf16x2(q0.z); fv[4] = u.x; fv[5] = u.y;
+              u = unpack_bf16x2(q0.w); fv[6] = u.x; fv[7] = u.y;
+              u = unpack_bf16x2(q1.x); fv[8] = u.x; fv[9] = u.y;
+              u = unpack_bf16x2(q1.y); fv[10] = u.x; fv[11] = u.y;
+              u = unpack_bf16x2(q1.z); fv[12] = u.x; fv[13] = u.y;
+              u = unpack_bf16x2(q1.w); fv[14] = u.x; fv[15] = u.y;
+            }
+          } else if (ok) {
+            float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + c0;
+            if (nvalid == 16 && (p.ldy & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                fv[i] = ok ? fv[i] : 0.f;
-                sq[i] = fv[i] * fv[i];
-              }
-              const float s1 = warp_colsum16(fv, lane);
-              const float s2 = warp_colsum16(sq, lane);
-              if ((lane & 1) == 0) {
-                const int c = c0 + colsum16_owner(lane);
-                atomicAdd(&s_stats[0][c], static_cast<double>(s1));
-                atomicAdd(&s_stats[1][c], static_cast<double>(s2));
-              }
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(dst)[i] = make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
+            } else if (nvalid == 4 && (p.ldy & 3) == 0) {
+              reinterpret_cast<float4*>(dst)[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) dst[i] = fv[i];
+            }
+          }
+          if (p.stats) {
+            float sq[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              fv[i] = ok ? fv[i] : 0.f;
+              sq[i] = fv[i] * fv[i];
+            }
+            const float s1 = warp_colsum16(fv, lane);
+            const float s2 = warp_colsum16(sq, lane);
+            if ((lane & 1) == 0) {
+              const int c = c0 + colsum16_owner(lane);
+              atomicAdd(&s_stats[0][c], static_cast<double>(s1));
+              atomicAdd(&s_stats[1][c], static_cast<double>(s2));
             }
           }
         }
