@@ -284,6 +284,7 @@ int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H
 namespace icsg3d {
 // ICSG3D_CONV_IMPL=v1 forces the per-tap TMA kernel, =halo the halo kernel (A/B comparisons); the default picks the
 // plane-streaming kd-folded kernel when it applies, then the halo kernel, then the per-tap kernel.
+extern int g_wgrad_impl;  // conv3d_wgrad.cu
 static int g_conv_impl = -1;
 static int conv_impl_choice() {
   int& v = g_conv_impl;
@@ -415,6 +416,7 @@ extern "C" int icsg3d_conv3d_k1_igemm(const void* x, int ldx, const void* wpack,
 extern "C" int icsg3d_conv3d_set_impl(int impl) {
   ICSG_REQUIRE(impl >= 0 && impl <= 2, "conv3d_set_impl: impl must be 0, 1 or 2");
   g_conv_impl = impl;
+  g_wgrad_impl = impl == 0 ? 0 : 1;
   return ICSG3D_OK;
 }
 

@@ -11,6 +11,9 @@
 // Every group owns NT TMEM columns; a CTA keeps up to 512/NT groups resident for its whole voxel range,
 // then dumps fp32 partials to the workspace; a second kernel reduces the voxel splits in a fixed order
 // (deterministic: needed for the 1-rank vs N-rank data-parallel equivalence test).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace icsg3d {
@@ -192,16 +195,32 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int splits) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[static_cast<long long>(s) * n + i];
-    dw[i] = acc;
+// dw[i] = sum over splits of ws[s][i], in a FIXED order (deterministic): 4 interleaved split lanes per element keep the
+// loads of a column independent and in flight, then the 4 lane sums are added in lane order.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n,
+                                                           int splits) {
+  __shared__ float red[4][64];
+  const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const long long i = static_cast<long long>(blockIdx.x) * 64 + e;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < n) {
+    int s = sl;
+    for (; s + 4 < splits; s += 8) {
+      a0 += ws[static_cast<long long>(s) * n + i];
+      a1 += ws[static_cast<long long>(s + 4) * n + i];
+    }
+    if (s < splits) a0 += ws[static_cast<long long>(s) * n + i];
   }
+  red[sl][e] = a0 + a1;
+  __syncthreads();
+  if (sl == 0 && i < n) dw[i] = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
 }
 
 int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H, int W, int c_extent, int kc);
+// conv3d_wgrad_stream.cu: plane-streaming variant for the narrow W >= 16 layers (returns < 0 when the shape does not fit)
+int64_t wgrad_stream_workspace_bytes(int B, int D, int H, int W, int cin, int cout, int sms);
+int wgrad_stream_run(const void* x, int ldx, const void* dy, int ldy, int B, int D, int H, int W, int cin, int cout, int sms,
+                     float* ws, int64_t ws_bytes, int* splits_out, cudaStream_t st);
 
 static bool wg_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -263,13 +282,32 @@ static int64_t wgrad_workspace_impl(int ntaps, int B, int D, int H, int W, int c
   if (B <= 0 || cin <= 0 || cout <= 0 || cin % 16 || cout % 16) return -1;
   WgradParams p{};
   wgrad_plan(ntaps, B, D, H, W, cin, cout, &p);
-  return static_cast<int64_t>(p.splits) * ntaps * cin * cout * 4;
+  int64_t need = static_cast<int64_t>(p.splits) * ntaps * cin * cout * 4;
+  if (ntaps == 27) {
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    const int64_t alt = wgrad_stream_workspace_bytes(B, D, H, W, cin, cout, sms);
+    if (alt > need) need = alt;
+  }
+  return need;
 }
 extern "C" int64_t icsg3d_conv3d_k3_wgrad_workspace(int B, int D, int H, int W, int cin, int cout) {
   return wgrad_workspace_impl(27, B, D, H, W, cin, cout);
 }
 extern "C" int64_t icsg3d_conv3d_k1_wgrad_workspace(int B, int D, int H, int W, int cin, int cout) {
   return wgrad_workspace_impl(1, B, D, H, W, cin, cout);
+}
+
+// ICSG3D_WGRAD_IMPL=v1 forces the per-tap kernel (A/B comparisons); icsg3d_conv3d_set_impl(1|2) does the same at run time.
+namespace icsg3d {
+int g_wgrad_impl = -1;
+}
+static int wgrad_impl_choice() {
+  if (g_wgrad_impl < 0) {
+    const char* e = getenv("ICSG3D_WGRAD_IMPL");
+    g_wgrad_impl = (e && strcmp(e, "v1") == 0) ? 1 : 0;
+  }
+  return g_wgrad_impl;
 }
 
 static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy, float* dw, int B, int D, int H, int W,
@@ -280,6 +318,21 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
   ICSG_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && cin >= 16 && cout >= 16,
                "conv3d_k3_wgrad: cin/cout must be multiples of 16 (got %d/%d)", cin, cout);
   ICSG_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cin && ldy >= cout, "conv3d_k3_wgrad: bad ldx/ldy");
+  const long long n_dw = static_cast<long long>(ntaps) * cin * cout;
+  if (ntaps == 27 && wgrad_impl_choice() == 0) {
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    int splits = 0;
+    const int rc = wgrad_stream_run(x, ldx, dy, ldy, B, D, H, W, cin, cout, sms, static_cast<float*>(workspace), workspace_bytes,
+                                    &splits, static_cast<cudaStream_t>(stream));
+    if (rc == ICSG3D_OK) {
+      wgrad_reduce_kernel<<<static_cast<int>((n_dw + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<const float*>(workspace), dw, n_dw, splits);
+      ICSG_CHECK_LAUNCH();
+      return ICSG3D_OK;
+    }
+    if (rc != 1) return rc;  // 1 = shape not eligible: fall through to the per-tap kernel
+  }
   WgradParams p{};
   wgrad_plan(ntaps, B, D, H, W, cin, cout, &p);
   ICSG_REQUIRE(p.stages >= 2, "conv3d_k3_wgrad: stage too large");
@@ -303,10 +356,7 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
   dim3 grid(p.splits, (p.total_groups + p.groups_per_cta - 1) / p.groups_per_cta, cout / p.ntw);
   conv3d_k3_wgrad_kernel<<<grid, kWgradThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmDY, p);
   ICSG_CHECK_LAUNCH();
-  const long long n = static_cast<long long>(ntaps) * cin * cout;
-  long long blocks = (n + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p.ws, dw, n, p.splits);
+  wgrad_reduce_kernel<<<static_cast<int>((n_dw + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(p.ws, dw, n_dw, p.splits);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

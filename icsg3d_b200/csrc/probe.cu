@@ -267,3 +267,104 @@ extern "C" int icsg3d_probe_halo_pattern(int64_t* out, int G, int nt, int plane_
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Probe 4: MN-major swizzled operands whose MN blocks OVERLAP (leading byte offset = a few rows instead of a whole
+// atom-aligned slab).  Decides whether the filter-gradient GEMM can fold taps into M (x shifted by kw rows per
+// channel block) and into N (dy shifted by kh*WP rows per channel block) straight from one resident halo slab:
+//   out[j*ca + ci][l*cb + co] = sum_{r < 16*ksteps} X[r + j*a_shift][ci] * Y[r + l*b_shift][co]
+// X: [rows][ca], Y: [rows][cb] bf16 row-major, TMA-loaded with swizzle = row bytes (the production layout).
+// ------------------------------------------------------------------------------------------------
+namespace icsg3d {
+__global__ void __launch_bounds__(128, 1)
+probe_mn_fold_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, float* out, int rows,
+                     int ca, int cb, int a_shift, int nblk_b, int b_shift, int ksteps) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t load_bar;
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sX = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t x_bytes = static_cast<uint32_t>(rows) * ca * 2u;
+  const uint32_t x_bytes_al = (x_bytes + 1023u) & ~1023u;
+  const uint32_t y_bytes = static_cast<uint32_t>(rows) * cb * 2u;
+  uint8_t* sY = sX + x_bytes_al;
+  if (threadIdx.x == 0) {
+    mbar_init(&load_bar, 1);
+    mbar_init(&mma_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&load_bar, x_bytes + y_bytes);
+    tma_load_2d(sX, &tmX, &load_bar, 0, 0);
+    tma_load_2d(sY, &tmY, &load_bar, 0, 0);
+  }
+  mbar_wait(&load_bar, 0);
+  tc_fence_after();
+  const int n = nblk_b * cb;
+  if (threadIdx.x == 0) {
+    const uint32_t rba = ca * 2u, rbb = cb * 2u;
+    const uint32_t idesc = umma_idesc_bf16(n, 1, 1);
+    for (int s = 0; s < ksteps; ++s) {
+      const uint64_t adesc = umma_smem_desc(base + static_cast<uint32_t>(s) * 16u * rba, static_cast<uint32_t>(a_shift) * rba,
+                                            8u * rba, umma_layout_for_swizzle(rba));
+      const uint64_t bdesc = umma_smem_desc(base + x_bytes_al + static_cast<uint32_t>(s) * 16u * rbb,
+                                            static_cast<uint32_t>(b_shift) * rbb, 8u * rbb, umma_layout_for_swizzle(rbb));
+      umma_bf16(tmem, adesc, bdesc, idesc, s != 0);
+    }
+    umma_commit(&mma_bar);
+  }
+  mbar_wait(&mma_bar, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[static_cast<size_t>(row) * n + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+}  // namespace icsg3d
+
+extern "C" int icsg3d_probe_mn_fold(const void* x, const void* y, float* out, int rows, int ca, int cb, int a_shift,
+                                    int nblk_b, int b_shift, int ksteps, void* stream) {
+  ICSG_REQUIRE(x && y && out, "probe_mn_fold: null pointer");
+  ICSG_REQUIRE((ca == 16 || ca == 32 || ca == 64) && (cb == 16 || cb == 32 || cb == 64) && nblk_b >= 1 && nblk_b * cb <= 256 &&
+                   rows <= 256 && ksteps >= 1,
+               "probe_mn_fold: bad shape");
+  ICSG_REQUIRE(16 * ksteps + (128 / ca - 1) * a_shift <= rows && 16 * ksteps + (nblk_b - 1) * b_shift <= rows,
+               "probe_mn_fold: not enough rows");
+  CUtensorMap tmX, tmY;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(ca), static_cast<uint64_t>(rows)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ca) * 2};
+    uint32_t box[2] = {static_cast<uint32_t>(ca), static_cast<uint32_t>(rows)};
+    int rc = encode_tiled_bf16(&tmX, x, 2, dims, strides, box, ca * 2);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(cb), static_cast<uint64_t>(rows)};
+    uint64_t strides[1] = {static_cast<uint64_t>(cb) * 2};
+    uint32_t box[2] = {static_cast<uint32_t>(cb), static_cast<uint32_t>(rows)};
+    int rc = encode_tiled_bf16(&tmY, y, 2, dims, strides, box, cb * 2);
+    if (rc) return rc;
+  }
+  const size_t smem = static_cast<size_t>(rows) * (ca + cb) * 2 + 3072;
+  ICSG_CUDA(cudaFuncSetAttribute(probe_mn_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  probe_mn_fold_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmY, out, rows, ca, cb, a_shift, nblk_b,
+                                                                           b_shift, ksteps);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}

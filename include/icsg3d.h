@@ -259,6 +259,11 @@ int icsg3d_synth_perovskite_sites(uint64_t seed, int ncells, int max_sites, doub
 int icsg3d_probe_shifted_desc(const void* a, const void* b, float* out, int rows, int kc, int n, int nshift,
                               void* stream);
 
+/* Hardware probe: MN-major swizzled operands with overlapping MN blocks (leading byte offset = a_shift / b_shift rows):
+ * out fp32 [128][nblk_b*cb]; see csrc/probe.cu "Probe 4". */
+int icsg3d_probe_mn_fold(const void* x, const void* y, float* out, int rows, int ca, int cb, int a_shift, int nblk_b,
+                         int b_shift, int ksteps, void* stream);
+
 /* Hardware probe: cycles for `reps` back-to-back tcgen05.mma (SS, bf16, K=16) of shape (m,n); out[0] = issue
  * cycles, out[1] = cycles until the commit barrier fires. */
 int icsg3d_probe_mma_rate(int64_t* out, int m, int n, int reps, int nacc, int swizzle_bytes, int a_step, int b_step,

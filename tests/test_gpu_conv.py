@@ -59,7 +59,8 @@ def test_dgrad_matches_oracle(B, D, cin, cout):
 
 
 @pytest.mark.parametrize("B,D,cin,cout", [(2, 32, 16, 16), (1, 32, 32, 16), (2, 16, 64, 32), (2, 8, 128, 64),
-                                          (4, 4, 64, 128), (8, 2, 128, 16), (4, 4, 16, 128), (2, 8, 256, 256)])
+                                          (4, 4, 64, 128), (8, 2, 128, 16), (4, 4, 16, 128), (2, 8, 256, 256),
+                                          (3, 16, 16, 32), (1, 32, 64, 32), (5, 16, 32, 16), (1, 64, 16, 16)])
 def test_wgrad_matches_oracle(B, D, cin, cout):
     from icsg3d_b200 import ops
     from oracle import keras_ops as K
@@ -119,3 +120,23 @@ def test_stream_kernel_full_batch_matches_cuda_core_reference(B, D, cin, cout):
     torch.cuda.synchronize()
     assert rel_l2(y, yr) < 2e-5
     assert float((y - yr).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("B,D,cin,cout", [(32, 32, 32, 16), (32, 32, 16, 16), (32, 16, 64, 32)])
+def test_wgrad_stream_kernel_full_batch_matches_per_tap_kernel(B, D, cin, cout):
+    """Full BASELINE batch: the plane-streaming filter-gradient kernel (kh folded into M, kw into N) against the
+    per-tap im2col kernel (independent operand path); both accumulate in fp32 on the tensor cores."""
+    from icsg3d_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(B, D, D, D, cin, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(B, D, D, D, cout, device="cuda", generator=g).to(torch.bfloat16)
+    try:
+        _lib.call("icsg3d_conv3d_set_impl", 1)
+        ref = ops.conv3d_k3_wgrad(x, dy).clone()
+    finally:
+        _lib.call("icsg3d_conv3d_set_impl", 0)
+    got = ops.conv3d_k3_wgrad(x, dy)
+    got2 = ops.conv3d_k3_wgrad(x, dy)
+    torch.cuda.synchronize()
+    assert rel_l2(got, ref) < 1e-5
+    assert torch.equal(got, got2)
