@@ -300,7 +300,7 @@ using namespace icsg3d;
 
 static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                              int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
-                             float leaky_alpha, void* stream) {
+                             float leaky_alpha, void* stream, double* stats = nullptr, int stats_parts = 0) {
   ICSG_REQUIRE(x && wpack && y, "conv3d_k3_igemm: null pointer");
   ICSG_REQUIRE(B > 0 && is_pow2(D) && is_pow2(H) && is_pow2(W) && D >= 2 && H >= 2 && W >= 2 && W <= 128,
                "conv3d_k3_igemm: D,H,W must be powers of two in [2,128] (got %d %d %d)", D, H, W);
@@ -317,9 +317,13 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   {
     const int sms0 = sm_count();
     ConvStreamParams sp;
-    if (ntaps == 27 && sms0 > 0 && conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms0, &sp))
-      return launch_conv_stream(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, nullptr, sp,
+    if (ntaps == 27 && sms0 > 0 && conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms0, &sp)) {
+      ICSG_REQUIRE(!stats || stats_parts == conv_stream_grid(sp), "conv3d_k3_igemm_stats: stats_parts %d != %d", stats_parts,
+                   conv_stream_grid(sp));
+      return launch_conv_stream(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, stats, sp,
                                 static_cast<cudaStream_t>(stream));
+    }
+    ICSG_REQUIRE(!stats, "conv3d_k3_igemm_stats: this layer shape has no fused-statistics path (stats_parts() == 0)");
     ConvHaloParams hp;
     if (ntaps == 27 && sms0 > 0 && conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp))
       return launch_conv_halo(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, hp, sms0,
@@ -405,6 +409,21 @@ extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack,
                                       int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                                       float leaky_alpha, void* stream) {
   return conv3d_igemm_impl(27, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream);
+}
+
+extern "C" int icsg3d_conv3d_k3_stats_parts(int B, int D, int H, int W, int cin, int nout) {
+  const int sms = sm_count();
+  ConvStreamParams sp;
+  if (sms <= 0 || conv_impl_choice() != 0 || !conv_stream_plan(B, D, H, W, cin, nout, sms, &sp)) return 0;
+  return conv_stream_grid(sp);
+}
+
+extern "C" int icsg3d_conv3d_k3_igemm_stats(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                                            int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                                            float leaky_alpha, double* stats, int stats_parts, void* stream) {
+  ICSG_REQUIRE(stats && stats_parts > 0, "conv3d_k3_igemm_stats: stats buffer required");
+  return conv3d_igemm_impl(27, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream,
+                           stats, stats_parts);
 }
 
 extern "C" int icsg3d_conv3d_k1_igemm(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,

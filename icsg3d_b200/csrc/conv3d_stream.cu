@@ -212,6 +212,11 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const float inv_wp = 1.0f / static_cast<float>(p.WP);
     // LeakyReLU / ReLU / identity as max(x, slope * x)
     const float slope = p.act == ICSG3D_ACT_RELU ? 0.f : (p.act == ICSG3D_ACT_LEAKY ? p.alpha : 1.f);
+    // BatchNorm statistics of the stored values: per-thread fp32 running sums for the (at most two) 16-column groups
+    // this warp ever sees (item parity = warp half), reduced across lanes once at the end of the kernel.
+    float sA[16], qA[16], sB[16], qB[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sA[i] = qA[i] = sB[i] = qB[i] = 0.f;
     int q = 0;
     for (int s = s_begin; s < s_end;) {
       const int col = s / p.D, db = s - col * p.D;
@@ -296,19 +301,19 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 if (i < nvalid) dst[i] = fv[i];
             }
           }
-          if (p.stats) {
-            float sq[16];
+          if (p.stats && ok) {
+            if (c0 < 32) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              fv[i] = ok ? fv[i] : 0.f;
-              sq[i] = fv[i] * fv[i];
-            }
-            const float s1 = warp_colsum16(fv, lane);
-            const float s2 = warp_colsum16(sq, lane);
-            if ((lane & 1) == 0) {
-              const int c = c0 + colsum16_owner(lane);
-              atomicAdd(&s_stats[0][c], static_cast<double>(s1));
-              atomicAdd(&s_stats[1][c], static_cast<double>(s2));
+              for (int i = 0; i < 16; ++i) {
+                sA[i] += fv[i];
+                qA[i] = fmaf(fv[i], fv[i], qA[i]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                sB[i] += fv[i];
+                qB[i] = fmaf(fv[i], fv[i], qB[i]);
+              }
             }
           }
         }
@@ -317,6 +322,26 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (lane == 0) mbar_arrive(&slot_empty[slot]);
       }
       s += de - db;
+    }
+    if (p.stats) {
+      // groups == 1: both halves saw group 0; groups == 2: half h saw group h; groups == 4: half h saw groups h and h+2
+      const int gA = groups >= 2 ? half : 0;
+      {
+        const float s1 = warp_colsum16(sA, lane), s2 = warp_colsum16(qA, lane);
+        if ((lane & 1) == 0) {
+          const int c = gA * 16 + colsum16_owner(lane);
+          atomicAdd(&s_stats[0][c], static_cast<double>(s1));
+          atomicAdd(&s_stats[1][c], static_cast<double>(s2));
+        }
+      }
+      if (groups == 4) {
+        const float s1 = warp_colsum16(sB, lane), s2 = warp_colsum16(qB, lane);
+        if ((lane & 1) == 0) {
+          const int c = (half + 2) * 16 + colsum16_owner(lane);
+          atomicAdd(&s_stats[0][c], static_cast<double>(s1));
+          atomicAdd(&s_stats[1][c], static_cast<double>(s2));
+        }
+      }
     }
   }
 

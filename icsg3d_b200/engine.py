@@ -169,16 +169,30 @@ class VAEEngine:
         self._loss_meta_ready = False
         self._graph = None
         self.use_graph = False
+        self.fuse_stats = True  # BatchNorm statistics from the conv epilogue where the streaming kernel serves the layer
 
     # ------------------------------------------------------------------------------------------
     # helpers
     # ------------------------------------------------------------------------------------------
-    def _bn_fwd(self, x, C, st: _BN, gamma, beta, mm, mv, training, act, post, y=None, y32=None, idx=None, ctx=None):
+    def _conv_bn(self, x, wf, bias, out, C, training, ctx=None, **kw):
+        """Conv3D whose output feeds a BatchNorm: when the layer is served by the plane-streaming kernel the batch
+        statistics come out of the conv epilogue (no separate read pass).  Returns the partials view or None."""
+        part = None
+        if training and self.fuse_stats and out.dtype == BF16 and out.shape[-1] == C:
+            n = ops.conv3d_k3_stats_parts(x, wf)
+            if n > 0:
+                part = (ctx or self.ctx).partials[: n * 2 * C].view(n, 2, C)
+        ops.conv3d_k3(x, wf, bias, out=out, stats=part, **kw)
+        return part
+
+    def _bn_fwd(self, x, C, st: _BN, gamma, beta, mm, mv, training, act, post, y=None, y32=None, idx=None, ctx=None,
+                part=None):
         if training:
             rows = x.numel() // x.shape[-1]
-            n = ops.bn_nparts(rows, C, x.dtype)
-            part = (ctx or self.ctx).partials[: n * 2 * C].view(n, 2, C)
-            ops.bn_stats(x, C, part)
+            if part is None:
+                n = ops.bn_nparts(rows, C, x.dtype)
+                part = (ctx or self.ctx).partials[: n * 2 * C].view(n, 2, C)
+                ops.bn_stats(x, C, part)
             if self.world > 1:
                 ops.bn_reduce_partials(part, st.sums)
                 self.dist.all_reduce_sum(st.sums)
@@ -247,12 +261,12 @@ class VAEEngine:
         p = self.vp.p
         x = self.xe
         for L in self.enc:
-            ops.conv3d_k3(x, L["wf"], p[L["name"] + "/bias"], out=L["c"], tag=L["name"] + ".fprop",
-                          nominal=(4 + 4 * self.ncond, L["cout"]) if L is self.enc[0] else None)
+            part = self._conv_bn(x, L["wf"], p[L["name"] + "/bias"], L["c"], L["cout"], training, tag=L["name"] + ".fprop",
+                                 nominal=(4 + 4 * self.ncond, L["cout"]) if L is self.enc[0] else None)
             bn = L["bn"]
             self._bn_fwd(L["c"], L["cout"], L["bns"], p[bn + "/gamma"], p[bn + "/beta"],
                          p[bn + "/moving_mean"], p[bn + "/moving_variance"], training, ACT_LEAKY, POST_POOL2, y=L["y"],
-                         idx=L["idx"])
+                         idx=L["idx"], part=part)
             x = L["y"]
         ops.conv3d_k3(x, self.e5_wf, p["enc_conv5/bias"], out=self.e5, n_store=4, act=ACT_LEAKY, tag="enc_conv5.fprop",
                       nominal=(self.filters[-1], 4))
@@ -268,11 +282,12 @@ class VAEEngine:
         ops.f32_to_bf16_rows(self.dd, 4, self.d0)
         x = self.d0
         for L in self.dec:
-            ops.conv3d_k3(x, L["wf"], p[L["name"] + "/bias"], out=L["c"], tag=L["name"] + ".fprop",
-                          nominal=(4, L["cout"]) if L is self.dec[0] else None)
+            part = self._conv_bn(x, L["wf"], p[L["name"] + "/bias"], L["c"], L["cout"], training, tag=L["name"] + ".fprop",
+                                 nominal=(4, L["cout"]) if L is self.dec[0] else None)
             bn = L["bn"]
             self._bn_fwd(L["c"], L["cout"], L["bns"], p[bn + "/gamma"], p[bn + "/beta"], p[bn + "/moving_mean"],
-                         p[bn + "/moving_variance"], training, ACT_LEAKY, POST_UP2 if L["up"] else POST_NONE, y=L["u"])
+                         p[bn + "/moving_variance"], training, ACT_LEAKY, POST_UP2 if L["up"] else POST_NONE, y=L["u"],
+                         part=part)
             x = L["u"]
         ops.conv3d_k3(x, self.out_wf, p["decoder_output/bias"], out=self.c5, n_store=4, tag="decoder_output.fprop",
                       nominal=(self.filters[0], 4))
@@ -286,15 +301,16 @@ class VAEEngine:
         x = self.xp if branch == 0 else self.xhat16
         for L in self.pm:
             n = L["name"]
-            ops.conv3d_k3(x, L["wf"], p[n + "/bias"], out=L["a"][branch], act=ACT_RELU, tag=f"pm{branch}.{n}.fprop",
-                          nominal=(4, L["cout"]) if n == "c1" else None)
+            kw = dict(act=ACT_RELU, tag=f"pm{branch}.{n}.fprop", nominal=(4, L["cout"]) if n == "c1" else None)
             if not L["has_bn"]:
+                ops.conv3d_k3(x, L["wf"], p[n + "/bias"], out=L["a"][branch], **kw)
                 break
+            part = self._conv_bn(x, L["wf"], p[n + "/bias"], L["a"][branch], L["cout"], training, ctx=ctx, **kw)
             bn = "bn_" + n
             self._bn_fwd(L["a"][branch], L["cout"], L["bnst"][branch], p[bn + "/gamma"], p[bn + "/beta"],
                          p[bn + "/moving_mean"] if not training else None,
                          p[bn + "/moving_variance"] if not training else None, training, ACT_NONE,
-                         POST_POOL2 if L["pool"] else POST_NONE, y=L["y"][branch], idx=L["idx"][branch], ctx=ctx)
+                         POST_POOL2 if L["pool"] else POST_NONE, y=L["y"][branch], idx=L["idx"][branch], ctx=ctx, part=part)
             x = L["y"][branch]
 
     def _loss_meta(self):

@@ -118,11 +118,19 @@ def _timed(tag, flops):
     return _T()
 
 
+def conv3d_k3_stats_parts(x, wpack):
+    """Rows of BatchNorm partials the fused conv+statistics path writes for this layer shape (0 = not available)."""
+    B, D, H, W, _ = x.shape
+    return int(_lib.lib().icsg3d_conv3d_k3_stats_parts(B, D, H, W, wpack.shape[2], wpack.shape[1]))
+
+
 def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alpha=LEAKY_ALPHA, out=None,
-              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv"):
+              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv", stats=None):
     """x: bf16 [B,D,H,W,ldx]; wpack: bf16 [27][nout][cin]; returns y [B,D,H,W,n_store].
 
     `ref=True` runs the CUDA-core cross-check kernel (fp32 output) instead of the tcgen05 kernel.
+    `stats`: fp64 [parts, 2, nout] with parts = conv3d_k3_stats_parts(x, wpack) > 0 — the kernel also writes the
+    per-CTA BatchNorm partials (sum, sum of squares) of the stored output.
     """
     _chk(x, torch.bfloat16, "x")
     _chk(wpack, torch.bfloat16, "wpack")
@@ -147,9 +155,16 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
     ydt = DT_BF16 if out.dtype == torch.bfloat16 else DT_F32
     nc, no = nominal if nominal else (cin, nout)
     with _timed(("igemm", tag), 2.0 * B * D * H * W * wpack.shape[0] * nc * no):
-        fn = "icsg3d_conv3d_k1_igemm" if wpack.shape[0] == 1 else "icsg3d_conv3d_k3_igemm"
-        _lib.call(fn, _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt, n_store, B, D, H, W, cin, nout,
-                  act, alpha, _stream())
+        if stats is not None:
+            _chk(stats, torch.float64, "stats")
+            if stats.dim() != 3 or stats.shape[1] != 2 or stats.shape[2] != nout or not stats.is_contiguous():
+                raise ValueError("conv3d_k3: stats must be a contiguous [parts, 2, nout] fp64 tensor")
+            _lib.call("icsg3d_conv3d_k3_igemm_stats", _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt,
+                      n_store, B, D, H, W, cin, nout, act, alpha, _ptr(stats), stats.shape[0], _stream())
+        else:
+            fn = "icsg3d_conv3d_k1_igemm" if wpack.shape[0] == 1 else "icsg3d_conv3d_k3_igemm"
+            _lib.call(fn, _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt, n_store, B, D, H, W, cin, nout,
+                      act, alpha, _stream())
     return out
 
 

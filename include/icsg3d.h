@@ -69,6 +69,16 @@ int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const floa
                            int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                            float leaky_alpha, void* stream);
 
+/* Conv3D + BiasAdd(+activation) that also emits the BatchNorm statistics of its own (stored, bf16-rounded) output from the
+ * epilogue — replaces a separate icsg3d_bn_stats read pass for the BatchNormalization() that follows the conv
+ * (lattice_vae.py:174,214; unet.py:278).  stats: fp64 [parts][2][nout] (sum, sum of squares per channel), the layout of
+ * icsg3d_bn_stats partials; parts = icsg3d_conv3d_k3_stats_parts(...) for the same shape (0 = not served by the fused
+ * path on this device/shape: use icsg3d_conv3d_k3_igemm + icsg3d_bn_stats). */
+int icsg3d_conv3d_k3_stats_parts(int B, int D, int H, int W, int cin, int nout);
+int icsg3d_conv3d_k3_igemm_stats(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                                 int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                                 float leaky_alpha, double* stats, int stats_parts, void* stream);
+
 /* Diagnostic (host only): kernel/tiling choice of the dispatcher for a layer shape.
  * out[0] = impl: 0 per-tap TMA kernel; 1 halo-reuse kernel {1, TD, TH, G, NT, a_bufs, b_stages, items, kc, smem};
  * 2 plane-streaming kd-folded kernel {2, R, TH, T, C, stages, issuers, grid, kc, smem}. */

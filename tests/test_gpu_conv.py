@@ -140,3 +140,24 @@ def test_wgrad_stream_kernel_full_batch_matches_per_tap_kernel(B, D, cin, cout):
     torch.cuda.synchronize()
     assert rel_l2(got, ref) < 1e-5
     assert torch.equal(got, got2)
+
+
+@pytest.mark.parametrize("B,D,cin,cout,act", [(3, 32, 32, 64, 1), (2, 32, 16, 16, 0), (5, 16, 64, 32, 2), (2, 32, 16, 32, 1)])
+def test_fused_conv_bn_statistics_match_stored_output(B, D, cin, cout, act):
+    """conv epilogue statistics (icsg3d_conv3d_k3_igemm_stats) == per-channel sum / sum of squares of the stored
+    bf16 output, i.e. what a separate icsg3d_bn_stats pass over the same tensor measures."""
+    from icsg3d_b200 import ops
+    x, w, b = _mk(B, D, cin, cout, seed=21)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    wp = ops.pack_conv_w_fprop(wd)
+    n = ops.conv3d_k3_stats_parts(xd, wp)
+    assert n > 0, "this shape must be served by the plane-streaming kernel"
+    part = torch.full((n, 2, cout), float("nan"), dtype=torch.float64, device="cuda")
+    y = ops.conv3d_k3(xd, wp, bd, act=act, stats=part)
+    y_plain = ops.conv3d_k3(xd, wp, bd, act=act)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_plain)
+    yd = y.double().view(-1, cout)
+    got = part.sum(0)
+    assert torch.allclose(got[0], yd.sum(0), rtol=1e-5, atol=1e-3 * yd.abs().sum(0).max().item() * 1e-3)
+    assert torch.allclose(got[1], (yd * yd).sum(0), rtol=1e-5)
