@@ -226,6 +226,7 @@ def run_cuda(args):
     # ---- roofline pass: per-launch CUDA-event timing of the conv kernels (eager, same stream) ----
     # (every rank executes the pass — the step contains collectives — rank 0 keeps the timings)
     roof, per_layer = None, None
+    eng.overlap_pm = eng.overlap_wgrad = False  # one stream: every launch is timed alone
     for _ in range(2):
         eng._train_body()
     torch.cuda.synchronize()

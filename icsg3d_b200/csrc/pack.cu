@@ -56,6 +56,44 @@ __global__ void unpack_dw_kernel(const float* __restrict__ dwp, float* __restric
   }
 }
 
+// All weight packs of a model in ONE launch: jobs[j] = {w, wp, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode}
+// (int64 each; mode 0 = fprop layout, 1 = dgrad layout); blockIdx.y = job.
+__global__ void pack_w_batch_kernel(const long long* __restrict__ jobs) {
+  const long long* jb = jobs + static_cast<size_t>(blockIdx.y) * 10;
+  const float* w = reinterpret_cast<const float*>(jb[0]);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(jb[1]);
+  const int cin = static_cast<int>(jb[2]), cout = static_cast<int>(jb[3]);
+  const int cin_pad = static_cast<int>(jb[4]), cout_pad = static_cast<int>(jb[5]);
+  const int cin_lead = static_cast<int>(jb[6]), fold = static_cast<int>(jb[7]), fold_c = static_cast<int>(jb[8]);
+  const int mode = static_cast<int>(jb[9]);
+  const long long total = 27ll * cout_pad * cin_pad;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = 0.f;
+    if (mode == 0) {
+      const int ci = static_cast<int>(idx % cin_pad);
+      const int co = static_cast<int>((idx / cin_pad) % cout_pad);
+      const int tap = static_cast<int>(idx / (static_cast<long long>(cin_pad) * cout_pad));
+      if (co < cout) {
+        const float* wt = w + static_cast<long long>(tap) * cin * cout;
+        if (fold <= 1) {
+          if (ci < cin) v = wt[static_cast<long long>(ci) * cout + co];
+        } else if (ci < cin_lead) {
+          v = wt[static_cast<long long>(ci) * cout + co];
+        } else if (ci < cin_lead + fold_c) {
+          for (int r = 0; r < fold; ++r) v += wt[static_cast<long long>(cin_lead + r * fold_c + (ci - cin_lead)) * cout + co];
+        }
+      }
+    } else {
+      const int co = static_cast<int>(idx % cout_pad);
+      const int ci = static_cast<int>((idx / cout_pad) % cin_pad);
+      const int tap = static_cast<int>(idx / (static_cast<long long>(cin_pad) * cout_pad));
+      if (ci < cin && co < cout) v = w[(static_cast<long long>(26 - tap) * cin + ci) * cout + co];
+    }
+    wp[idx] = f2bf(v);
+  }
+}
+
 static int grid_for(long long total) {
   long long b = (total + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
@@ -99,6 +137,15 @@ extern "C" int icsg3d_unpack_conv_dw(const float* dw_pad, float* dw, int cin, in
   ICSG_REQUIRE(dw_pad && dw, "unpack_conv_dw: null pointer");
   unpack_dw_kernel<<<grid_for(27ll * cin * cout), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       dw_pad, dw, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+
+extern "C" int icsg3d_pack_conv_w_batch(const int64_t* jobs, int njobs, int max_blocks, void* stream) {
+  ICSG_REQUIRE(jobs && njobs > 0 && njobs <= 65535 && max_blocks > 0, "pack_conv_w_batch: bad arguments");
+  pack_w_batch_kernel<<<dim3(max_blocks, njobs), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(jobs));
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

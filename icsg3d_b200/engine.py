@@ -169,6 +169,9 @@ class VAEEngine:
         self._loss_meta_ready = False
         self._graph = None
         self.use_graph = False
+        self._pack_table = None
+        self._wg_side = None
+        self.overlap_wgrad = True  # filter gradients on a side stream, under the BN-backward / dgrad chain
         self.fuse_stats = True  # BatchNorm statistics from the conv epilogue where the streaming kernel serves the layer
 
     # ------------------------------------------------------------------------------------------
@@ -219,7 +222,24 @@ class VAEEngine:
                          pre_relu=pre_relu, tap_other=tap_other, tap_coef=tap_coef)
 
     def _wgrad(self, x, dy, name, cin, cout, cin_pad, cout_pad, fold=None):
-        """dW of conv `name` into the flat gradient buffer (Keras layout)."""
+        """dW of conv `name` into the flat gradient buffer (Keras layout).  Off the critical path (only Adam needs it):
+        launched on a side stream that forks here and joins before the optimiser step."""
+        if not self.overlap_wgrad:
+            return self._wgrad_now(x, dy, name, cin, cout, cin_pad, cout_pad, fold)
+        main = torch.cuda.current_stream()
+        if self._wg_side is None:
+            self._wg_side = torch.cuda.Stream()
+        self._wg_side.wait_stream(main)
+        with torch.cuda.stream(self._wg_side):
+            self._wgrad_now(x, dy, name, cin, cout, cin_pad, cout_pad, fold)
+        self._wg_pending = True
+
+    def _wgrad_join(self):
+        if self.overlap_wgrad and getattr(self, "_wg_pending", False):
+            torch.cuda.current_stream().wait_stream(self._wg_side)
+            self._wg_pending = False
+
+    def _wgrad_now(self, x, dy, name, cin, cout, cin_pad, cout_pad, fold=None):
         g = self.vp.g[name + "/kernel"]
         if cin == cin_pad and cout == cout_pad and fold is None:
             ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=g.view(27, cin, cout), tag=name + ".wgrad")
@@ -232,21 +252,25 @@ class VAEEngine:
             ops.unpack_conv_dw(scratch, cin, cout, cin_lead=fold[0], fold=fold[1], fold_c=fold[2], out=g)
 
     def pack_weights(self):
-        """fp32 master weights -> bf16 GEMM operand layouts (after every optimiser step)."""
-        p = self.vp.p
-        for i, L in enumerate(self.enc):
-            if i == 0:
-                ops.pack_conv_w_fprop(p[L["name"] + "/kernel"], cin_pad=16, cin_lead=4, fold=4, fold_c=self.ncond, out=L["wf"])
-            else:
-                ops.pack_conv_w_fprop(p[L["name"] + "/kernel"], out=L["wf"])
-                ops.pack_conv_w_dgrad(p[L["name"] + "/kernel"], out=L["wd"])
-        ops.pack_conv_w_fprop(p["enc_conv5/kernel"], out=self.e5_wf)
-        ops.pack_conv_w_dgrad(p["enc_conv5/kernel"], out=self.e5_wd)
-        for L in self.dec:
-            ops.pack_conv_w_fprop(p[L["name"] + "/kernel"], out=L["wf"])
-            ops.pack_conv_w_dgrad(p[L["name"] + "/kernel"], out=L["wd"])
-        ops.pack_conv_w_fprop(p["decoder_output/kernel"], out=self.out_wf)
-        ops.pack_conv_w_dgrad(p["decoder_output/kernel"], out=self.out_wd)
+        """fp32 master weights -> bf16 GEMM operand layouts (after every optimiser step): one launch for all 19 packs."""
+        if self._pack_table is None:
+            p = self.vp.p
+            jobs = []
+            for i, L in enumerate(self.enc):
+                if i == 0:
+                    jobs.append((p[L["name"] + "/kernel"], L["wf"], 0, 4, 4, self.ncond))
+                else:
+                    jobs.append((p[L["name"] + "/kernel"], L["wf"], 0, 0, 1, 0))
+                    jobs.append((p[L["name"] + "/kernel"], L["wd"], 1, 0, 1, 0))
+            jobs.append((p["enc_conv5/kernel"], self.e5_wf, 0, 0, 1, 0))
+            jobs.append((p["enc_conv5/kernel"], self.e5_wd, 1, 0, 1, 0))
+            for L in self.dec:
+                jobs.append((p[L["name"] + "/kernel"], L["wf"], 0, 0, 1, 0))
+                jobs.append((p[L["name"] + "/kernel"], L["wd"], 1, 0, 1, 0))
+            jobs.append((p["decoder_output/kernel"], self.out_wf, 0, 0, 1, 0))
+            jobs.append((p["decoder_output/kernel"], self.out_wd, 1, 0, 1, 0))
+            self._pack_table = ops.pack_jobs_table(jobs, self.dev)
+        ops.pack_conv_w_batch(self._pack_table)
 
     def repack_pm(self):
         for L in self.pm:
@@ -414,8 +438,10 @@ class VAEEngine:
                 ops.conv3d_k3(L["dc"], L["wd"], None, out=self.enc[li - 1]["dy"], tag=L["name"] + ".dgrad")
             else:
                 self._wgrad(self.xe, L["dc"], L["name"], 4 + 4 * self.ncond, L["cout"], 16, L["cout"], fold=(4, 4, self.ncond))
+        self._wgrad_join()
 
     def optimizer_step(self):
+        self._wgrad_join()
         if self.world > 1:
             self.dist.all_reduce_sum(self.vp.grad)
         ops.adam_keras_step(self.vp.theta, self.vp.grad, self.vp.adam_m, self.vp.adam_v, self.vp.adam_state, self.lr)

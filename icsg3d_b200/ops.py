@@ -87,6 +87,22 @@ def pack_conv_w_dgrad(w, cin_pad=None, cout_pad=None, out=None):
     return out
 
 
+def pack_jobs_table(jobs, device):
+    """jobs: list of (w fp32 (3,3,3,Cin,Cout), wpack bf16, mode 0|1, cin_lead, fold, fold_c) -> device int64 table."""
+    rows = []
+    for w, wp, mode, cin_lead, fold, fold_c in jobs:
+        _chk(w, torch.float32, "w")
+        _chk(wp, torch.bfloat16, "wpack")
+        cin, cout = w.shape[3], w.shape[4]
+        cout_pad, cin_pad = (wp.shape[1], wp.shape[2]) if mode == 0 else (wp.shape[2], wp.shape[1])
+        rows.append([w.data_ptr(), wp.data_ptr(), cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode])
+    return torch.tensor(rows, dtype=torch.int64).to(device)
+
+
+def pack_conv_w_batch(table, max_blocks=32):
+    _lib.call("icsg3d_pack_conv_w_batch", _ptr(table), table.shape[0], max_blocks, _stream())
+
+
 def unpack_conv_dw(dw_pad, cin, cout, cin_lead=0, fold=1, fold_c=0, out=None):
     _chk(dw_pad, torch.float32, "dw_pad")
     cin_pad, cout_pad = dw_pad.shape[1], dw_pad.shape[2]

@@ -126,6 +126,11 @@ int icsg3d_pack_conv_w_fprop(const float* w, void* wpack, int cin, int cout, int
                              int cin_lead, int fold, int fold_c, void* stream);
 int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, int cout, int cin_pad, int cout_pad,
                              void* stream);
+
+/* All weight packs of a model in one launch.  jobs: DEVICE array [njobs][10] of int64
+ * {w ptr, wpack ptr, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode (0 = fprop layout, 1 = dgrad layout)};
+ * max_blocks = grid.x (each job strides over its own element count). */
+int icsg3d_pack_conv_w_batch(const int64_t* jobs, int njobs, int max_blocks, void* stream);
 /* dW (padded, from wgrad) -> gradient in Keras layout, undoing padding and the condition fold. */
 int icsg3d_unpack_conv_dw(const float* dw_pad, float* dw, int cin, int cout, int cin_pad, int cout_pad,
                           int cin_lead, int fold, int fold_c, void* stream);

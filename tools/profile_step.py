@@ -16,6 +16,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 tag = sys.argv[3] if len(sys.argv) > 3 else "step"
 eng = VAEEngine(B, d=32, seed=1)
 eng.overlap_pm = False
+eng.overlap_wgrad = False
 M, cond, _ = utils.synthetic_batch(B, d=32, seed=1000)
 eng.set_inputs(M, cond, torch.randn(B, 256, device="cuda"))
 for _ in range(3):
