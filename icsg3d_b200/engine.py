@@ -84,7 +84,7 @@ class VAEEngine:
         # pm(x) does not depend on the encoder/decoder: it runs on a side stream (forked/joined inside the captured
         # graph) so that its large convs overlap the small, latency-bound VAE kernels.  Own scratch per stream.
         self.ctx2 = _Ctx(dev, max_dw=16)
-        self.overlap_pm = self.world == 1
+        self.overlap_pm = self.world == 1  # (data parallel: one stream, so that collectives can split the captured graph)
         self._side = None
         B = batch
         z = lambda *s, dt=BF16: torch.zeros(*s, dtype=dt, device=dev)
@@ -168,10 +168,11 @@ class VAEEngine:
         self.metrics = torch.zeros(4, dtype=F32, device=dev)
         self._loss_meta_ready = False
         self._graph = None
+        self._segments = None
         self.use_graph = False
         self._pack_table = None
         self._wg_side = None
-        self.overlap_wgrad = True  # filter gradients on a side stream, under the BN-backward / dgrad chain
+        self.overlap_wgrad = self.world == 1  # filter gradients on a side stream, under the BN-backward / dgrad chain
         self.fuse_stats = True  # BatchNorm statistics from the conv epilogue where the streaming kernel serves the layer
 
     # ------------------------------------------------------------------------------------------
@@ -487,7 +488,14 @@ class VAEEngine:
                 self._train_body()  # warm-up: attribute setup, lazy allocations
                 torch.cuda.synchronize()
                 raise RuntimeError("call capture_train_graph() before train_step() with use_graph")
-            self._graph.replay()
+            if self._segments is not None:
+                for kind, obj in self._segments:
+                    if kind == "g":
+                        obj.replay()
+                    else:
+                        self.dist.dist.all_reduce(obj, op=self.dist.dist.ReduceOp.SUM, group=self.dist.group)
+            else:
+                self._graph.replay()
         else:
             self._train_body()
         return self.metrics
@@ -505,9 +513,47 @@ class VAEEngine:
                 self._train_body()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._train_body()
+        self._segments = None
+        if self.world > 1:
+            # Data parallel: NCCL stays OUTSIDE the graphs.  Every all-reduce of the step (BatchNorm statistic sums,
+            # the flat gradient) ends one captured segment and starts the next; a step = replaying ~50 small graphs
+            # with the eager collectives in between (CPU cost ~1 ms/step, hidden behind the GPU).
+            segs, pool, cap = [], torch.cuda.graph_pool_handle(), torch.cuda.Stream()
+            cur = {}
+
+            def begin():
+                cur["g"] = torch.cuda.CUDAGraph()
+                cur["ctx"] = torch.cuda.graph(cur["g"], pool=pool, stream=cap)
+                cur["ctx"].__enter__()
+
+            def end():
+                cur["ctx"].__exit__(None, None, None)
+                segs.append(("g", cur["g"]))
+
+            # the eager collective issued between two segments also keeps the ranks in lock step during capture
+            dist_obj = self.dist
+            real = dist_obj.dist.all_reduce
+
+            def hooked_all_reduce_sum(t):
+                end()
+                segs.append(("ar", t))
+                real(t, op=dist_obj.dist.ReduceOp.SUM, group=dist_obj.group)
+                begin()
+
+            orig = dist_obj.all_reduce_sum
+            dist_obj.all_reduce_sum = hooked_all_reduce_sum
+            try:
+                begin()
+                self._train_body()
+                end()
+            finally:
+                dist_obj.all_reduce_sum = orig
+            g = segs
+            self._segments = segs
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._train_body()
         torch.cuda.synchronize()
         if saved is not None:
             for t, sv in zip((self.vp.theta, self.vp.state, self.vp.adam_m, self.vp.adam_v, self.vp.adam_state), saved):

@@ -26,6 +26,14 @@ def _to_dev(a, dev, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(a)).to(device=dev, dtype=dtype, non_blocking=True)
 
 
+def _as_f32(a):
+    """numpy / torch (host or device) -> fp32 torch tensor without touching the device (Keras casts float64 batches)."""
+    if torch.is_tensor(a):
+        return a if a.dtype == torch.float32 else a.float()
+    a = np.ascontiguousarray(a)
+    return torch.from_numpy(a if a.dtype == np.float32 else a.astype(np.float32))
+
+
 class _Facade:
     def __init__(self, owner):
         self._o = owner
@@ -199,7 +207,8 @@ class LatticeDFCVAE:
     def _step(self, M, cond, train):
         B = len(M)
         eng = self.engine(B)
-        eng.set_inputs(_to_dev(M, self.device), _to_dev(cond, self.device))
+        # host batches go straight into the engine's static input buffers (one H2D DMA, no staging allocation)
+        eng.set_inputs(_as_f32(M), _as_f32(cond))
         if train:
             if self.use_cuda_graph and not eng.use_graph:
                 eng.capture_train_graph()

@@ -56,6 +56,24 @@ def main():
         ok = dm < 1e-3 and cos > 0.995
         print(json.dumps({"world": world, "metrics_dp": m_dp, "metrics_1rank": m_1, "grad_rel_l2": rel, "grad_cos": cos,
                           "ok": ok}))
+    # ---- segmented CUDA-graph replay of the DP step == eager DP step (same kernels, same collectives) ----
+    engA = VAEEngine(Bl, d=32, seed=3, device=dev, dist=Dist())
+    engB = VAEEngine(Bl, d=32, seed=3, device=dev, dist=Dist())
+    for e in (engA, engB):
+        e.set_inputs(M[sl], cond[sl], eps[sl])
+    engA.capture_train_graph()
+    nseg = len(engA._segments)
+    for _ in range(3):
+        engA.train_step()
+        engB.train_step()
+    torch.cuda.synchronize()
+    dtheta = float((engA.vp.theta - engB.vp.theta).abs().max())
+    mA, mB = engA.metrics_host(), engB.metrics_host()
+    ok_graph = dtheta == 0.0 and mA == mB
+    if rank == 0:
+        print(json.dumps({"world": world, "graph_segments": nseg, "theta_max_abs_diff_graph_vs_eager": dtheta,
+                          "metrics_graph": mA, "metrics_eager": mB, "ok": bool(ok and ok_graph)}))
+    ok = ok and ok_graph
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
