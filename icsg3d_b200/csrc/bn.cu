@@ -262,6 +262,144 @@ __global__ void __launch_bounds__(1024) bn_reduce_fused_kernel(const double* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Data-parallel fusion: partial reduction + ALL-REDUCE over NVLink peer memory + finalisation in ONE kernel.
+// Replaces bn_reduce_partials -> NCCL all-reduce (2C doubles, pure latency) -> bn_finalize / the backward-sum
+// exchange.  Every rank owns one symmetric buffer (torch symmetric memory; all peers' buffers are mapped into this
+// process):   flags  uint64 [nslots][2][world][64]          (byte offset 0)
+//             data   double [nslots][2][world][2*cmax]      (byte offset nslots*2*world*64*8)
+// Protocol per call site (slot) and step (epoch, read from device memory so that a CUDA graph can be replayed):
+//   1. block b reduces the local partials of its 8 channels (fixed order);
+//   2. it PUSHES the 16 sums into data[slot][epoch&1][my_rank] of EVERY rank (remote stores), fences system-wide,
+//      then writes flags[slot][epoch&1][my_rank][b] = epoch on every rank;
+//   3. it polls its LOCAL flags of all source ranks, then adds the LOCAL copies in rank order: every rank computes
+//      bit-identical global sums (deterministic, no atomics); parity double-buffering + the step's other exchanges keep
+//      a fast rank from overwriting a slot a slow rank still reads.
+// Spins are bounded (trap after ~4 s) so a mismatched launch sequence surfaces as an error, never as a hung GPU.
+// ------------------------------------------------------------------------------------------------
+struct BnPeerParams {
+  const unsigned long long* peers;  // device array [world]: base address of every rank's symmetric buffer
+  int world, rank, slot, nslots, cmax;
+  const long long* epoch;           // device scalar, >= 1, incremented once per step
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(1024) bn_reduce_allreduce_kernel(const double* __restrict__ partials, int nparts, int C,
+                                                                   int mode, double count, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, float eps,
+                                                                   double* __restrict__ sums, float* __restrict__ mean_out,
+                                                                   float* __restrict__ rstd_out, float* __restrict__ scale,
+                                                                   float* __restrict__ shift, float* __restrict__ moving_mean,
+                                                                   float* __restrict__ moving_var, float momentum,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                   const BnPeerParams pp) {
+  __shared__ double red[kRedSlots][2 * kRedCh + 1];
+  __shared__ double tot[2 * kRedCh];
+  const int col = threadIdx.x & (2 * kRedCh - 1);
+  const int slot_r = threadIdx.x >> 4;
+  const int c = blockIdx.x * kRedCh + (col & (kRedCh - 1));
+  const int gcol = (col >> 3) * C + c;
+  const size_t C2 = 2 * static_cast<size_t>(C);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (c < C) {
+    int p = slot_r;
+    for (; p + 3 * kRedSlots < nparts; p += 4 * kRedSlots) {
+      a0 += partials[static_cast<size_t>(p) * C2 + gcol];
+      a1 += partials[static_cast<size_t>(p + kRedSlots) * C2 + gcol];
+      a2 += partials[static_cast<size_t>(p + 2 * kRedSlots) * C2 + gcol];
+      a3 += partials[static_cast<size_t>(p + 3 * kRedSlots) * C2 + gcol];
+    }
+    for (; p < nparts; p += kRedSlots) a0 += partials[static_cast<size_t>(p) * C2 + gcol];
+  }
+  red[slot_r][col] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  const unsigned long long epoch = static_cast<unsigned long long>(*pp.epoch);
+  const int par = static_cast<int>(epoch & 1ull);
+  const size_t flags_bytes = static_cast<size_t>(pp.nslots) * 2 * pp.world * 64 * sizeof(unsigned long long);
+  const size_t slot_idx = static_cast<size_t>(pp.slot) * 2 + par;
+  if (threadIdx.x < 2 * kRedCh) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kRedSlots; i += 4) {
+      t0 += red[i][threadIdx.x];
+      t1 += red[i + 1][threadIdx.x];
+      t2 += red[i + 2][threadIdx.x];
+      t3 += red[i + 3][threadIdx.x];
+    }
+    const double local = (t0 + t1) + (t2 + t3);
+    tot[threadIdx.x] = local;  // local sums (dgamma / dbeta in backward mode: the gradient all-reduce adds the ranks)
+    if (c < C) {
+      for (int r = 0; r < pp.world; ++r) {  // push into every rank's copy (own included)
+        double* data = reinterpret_cast<double*>(pp.peers[r] + flags_bytes) +
+                       (slot_idx * pp.world + pp.rank) * (2 * static_cast<size_t>(pp.cmax));
+        data[(threadIdx.x >> 3) * pp.cmax + c] = local;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x < pp.world) {
+    const int r = threadIdx.x;
+    // publish: my contribution for block b is complete on rank r
+    unsigned long long* rflag = reinterpret_cast<unsigned long long*>(pp.peers[r]) +
+                                (slot_idx * pp.world + pp.rank) * 64 + blockIdx.x;
+    st_release_sys_u64(rflag, epoch);
+    // wait: rank r's contribution has arrived in MY buffer
+    const unsigned long long* lflag = reinterpret_cast<const unsigned long long*>(pp.peers[pp.rank]) +
+                                      (slot_idx * pp.world + r) * 64 + blockIdx.x;
+    const long long t_start = clock64();
+    while (ld_acquire_sys_u64(lflag) != epoch) {
+      if (clock64() - t_start > 8000000000ll) {
+        printf("icsg3d: bn all-reduce timeout rank %d slot %d block %d waiting for rank %d (epoch %llu)\n", pp.rank, pp.slot,
+               blockIdx.x, r, epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= kRedCh || c >= C) return;
+  const double* mine = reinterpret_cast<const double*>(pp.peers[pp.rank] + flags_bytes) +
+                       slot_idx * pp.world * (2 * static_cast<size_t>(pp.cmax));
+  double s0 = 0.0, s1 = 0.0;
+  for (int r = 0; r < pp.world; ++r) {  // rank order: identical on every rank
+    const volatile double* d = mine + static_cast<size_t>(r) * 2 * pp.cmax;
+    s0 += d[c];
+    s1 += d[pp.cmax + c];
+  }
+  if (sums) {
+    sums[c] = s0;
+    sums[C + c] = s1;
+  }
+  if (mode == 0) {
+    const double mean = s0 / count;
+    double var = s1 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const double g = gamma ? static_cast<double>(gamma[c]) : 1.0;
+    const double b = beta ? static_cast<double>(beta[c]) : 0.0;
+    mean_out[c] = static_cast<float>(mean);
+    rstd_out[c] = static_cast<float>(rstd);
+    scale[c] = static_cast<float>(g * rstd);
+    shift[c] = static_cast<float>(b - mean * g * rstd);
+    if (moving_mean) {
+      const double var_unbiased = var * (count / (count - (1.0 + static_cast<double>(eps))));
+      moving_mean[c] = static_cast<float>(moving_mean[c] - (moving_mean[c] - mean) * (1.0 - momentum));
+      moving_var[c] = static_cast<float>(moving_var[c] - (moving_var[c] - var_unbiased) * (1.0 - momentum));
+    }
+  } else {
+    if (dbeta) dbeta[c] = static_cast<float>(tot[threadIdx.x]);
+    if (dgamma) dgamma[c] = static_cast<float>(tot[kRedCh + threadIdx.x]);
+  }
+}
+
 __global__ void bn_inference_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                            const float* __restrict__ mm, const float* __restrict__ mv, float eps,
                                            float* __restrict__ scale, float* __restrict__ shift, int C) {
@@ -870,6 +1008,51 @@ extern "C" int icsg3d_bn_reduce_grads(const double* partials, int nparts, int C,
   bn_reduce_fused_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, nparts, C, 1, 1.0, nullptr, nullptr, 0.f, sums, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, dgamma,
       dbeta);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+
+static int bn_peer_check(const uint64_t* peers, int world, int rank, int slot, int nslots, int cmax, const int64_t* epoch, int C) {
+  ICSG_REQUIRE(peers && epoch, "bn all-reduce: null peer table / epoch");
+  ICSG_REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world, "bn all-reduce: bad world/rank %d/%d", world, rank);
+  ICSG_REQUIRE(slot >= 0 && slot < nslots && cmax >= C && ceil_div(C, kRedCh) <= 64, "bn all-reduce: bad slot/cmax (C=%d)", C);
+  return ICSG3D_OK;
+}
+
+extern "C" int64_t icsg3d_bn_allreduce_buffer_bytes(int world, int nslots, int cmax) {
+  if (world < 1 || nslots < 1 || cmax < 1) return -1;
+  return static_cast<int64_t>(nslots) * 2 * world * (64 * 8 + 2 * static_cast<int64_t>(cmax) * 8);
+}
+
+extern "C" int icsg3d_bn_reduce_allreduce_finalize(const double* partials, int nparts, double count_global, const float* gamma,
+                                                   const float* beta, float eps, double* sums, float* mean, float* rstd,
+                                                   float* scale, float* shift, float* moving_mean, float* moving_var,
+                                                   float momentum, int C, const uint64_t* peers, int world, int rank, int slot,
+                                                   int nslots, int cmax, const int64_t* epoch, void* stream) {
+  ICSG_REQUIRE(partials && nparts > 0 && mean && rstd && scale && shift && count_global > 0, "bn_reduce_allreduce_finalize: bad arguments");
+  int rc = bn_peer_check(peers, world, rank, slot, nslots, cmax, epoch, C);
+  if (rc) return rc;
+  BnPeerParams pp{reinterpret_cast<const unsigned long long*>(peers), world, rank, slot, nslots, cmax,
+                  reinterpret_cast<const long long*>(epoch)};
+  bn_reduce_allreduce_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, nparts, C, 0, count_global, gamma, beta, eps, sums, mean, rstd, scale, shift, moving_mean, moving_var, momentum,
+      nullptr, nullptr, pp);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_bn_reduce_allreduce_grads(const double* partials, int nparts, int C, double* sums_global, float* dgamma,
+                                                float* dbeta, const uint64_t* peers, int world, int rank, int slot, int nslots,
+                                                int cmax, const int64_t* epoch, void* stream) {
+  ICSG_REQUIRE(partials && nparts > 0 && sums_global, "bn_reduce_allreduce_grads: bad arguments");
+  int rc = bn_peer_check(peers, world, rank, slot, nslots, cmax, epoch, C);
+  if (rc) return rc;
+  BnPeerParams pp{reinterpret_cast<const unsigned long long*>(peers), world, rank, slot, nslots, cmax,
+                  reinterpret_cast<const long long*>(epoch)};
+  bn_reduce_allreduce_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, nparts, C, 1, 1.0, nullptr, nullptr, 0.f, sums_global, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f,
+      dgamma, dbeta, pp);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -11,6 +11,8 @@ and the flat gradient buffer are summed with NCCL all-reduce; nothing else is ex
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -41,6 +43,39 @@ class Dist:
     def all_reduce_sum(self, t):
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class PeerBN:
+    """Symmetric (NVLink peer-mapped) buffer + step epoch for the in-kernel BatchNorm-statistics all-reduce
+    (csrc/bn.cu::bn_reduce_allreduce_kernel).  One per engine and process group."""
+
+    NSLOTS, CMAX = 64, 512
+
+    def __init__(self, dist: "Dist", dev):
+        import torch.distributed as td
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.world, dist.rank
+        nbytes = ops.bn_allreduce_buffer_bytes(self.world, self.NSLOTS, self.CMAX)
+        self.buf = symm.empty(nbytes // 8, dtype=torch.int64, device=dev)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, dist.group if dist.group is not None else td.group.WORLD)
+        self.peers = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._slots = {}
+        torch.cuda.synchronize()
+        td.barrier(group=dist.group)  # every rank's buffer is zeroed before anybody pushes into it
+
+    def slot(self, key):
+        s = self._slots.setdefault(key, len(self._slots))
+        assert s < self.NSLOTS, "PeerBN: out of all-reduce slots"
+        return s
+
+    def tick(self):
+        self.epoch.add_(1)
+
+    def args(self, key):
+        return dict(peers=self.peers, world=self.world, rank=self.rank, slot=self.slot(key), nslots=self.NSLOTS,
+                    cmax=self.CMAX, epoch=self.epoch)
 
 
 class _BN:
@@ -84,7 +119,17 @@ class VAEEngine:
         # pm(x) does not depend on the encoder/decoder: it runs on a side stream (forked/joined inside the captured
         # graph) so that its large convs overlap the small, latency-bound VAE kernels.  Own scratch per stream.
         self.ctx2 = _Ctx(dev, max_dw=16)
-        self.overlap_pm = self.world == 1  # (data parallel: one stream, so that collectives can split the captured graph)
+        # Data parallel: BatchNorm statistic sums are exchanged INSIDE the finalize kernels over NVLink peer memory
+        # (PeerBN); only the flat gradient goes through NCCL.  ICSG3D_DP_PEER=0 (or no symmetric memory) falls back to
+        # NCCL all-reduces of the sums, which also forces a single stream (collectives split the captured graph).
+        self.peer = None
+        if self.world > 1 and os.environ.get("ICSG3D_DP_PEER", "1") != "0":
+            try:
+                self.peer = PeerBN(dist, self.dev)
+            except Exception as e:  # noqa: BLE001
+                import warnings
+                warnings.warn(f"icsg3d: symmetric-memory BatchNorm all-reduce unavailable ({e!r}); using NCCL")
+        self.overlap_pm = self.world == 1 or self.peer is not None
         self._side = None
         B = batch
         z = lambda *s, dt=BF16: torch.zeros(*s, dtype=dt, device=dev)
@@ -172,7 +217,7 @@ class VAEEngine:
         self.use_graph = False
         self._pack_table = None
         self._wg_side = None
-        self.overlap_wgrad = self.world == 1  # filter gradients on a side stream, under the BN-backward / dgrad chain
+        self.overlap_wgrad = self.world == 1 or self.peer is not None  # filter gradients on a side stream, under the BN-backward / dgrad chain
         self.fuse_stats = True  # BatchNorm statistics from the conv epilogue where the streaming kernel serves the layer
 
     # ------------------------------------------------------------------------------------------
@@ -197,7 +242,11 @@ class VAEEngine:
                 n = ops.bn_nparts(rows, C, x.dtype)
                 part = (ctx or self.ctx).partials[: n * 2 * C].view(n, 2, C)
                 ops.bn_stats(x, C, part)
-            if self.world > 1:
+            if self.peer is not None:
+                ops.bn_reduce_allreduce_finalize(part, float(rows * self.world), gamma, beta, st.sums, st.mean, st.rstd,
+                                                 st.scale, st.shift, moving_mean=mm, moving_var=mv,
+                                                 **self.peer.args((id(st), "fwd")))
+            elif self.world > 1:
                 ops.bn_reduce_partials(part, st.sums)
                 self.dist.all_reduce_sum(st.sums)
                 ops.bn_finalize(st.sums, float(rows * self.world), gamma, beta, st.mean, st.rstd, st.scale, st.shift, mm, mv)
@@ -212,6 +261,12 @@ class VAEEngine:
         n = ops.bn_bwd_nparts(x, C, post)
         part = self.ctx.partials[: n * 2 * C].view(n, 2, C)
         ops.bn_bwd_reduce(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, part)
+        if self.peer is not None:
+            ops.bn_reduce_allreduce_grads(part, st.bsums_g, dgamma=dgamma, dbeta=dbeta, **self.peer.args((id(st), "bwd")))
+            rows = x.numel() // x.shape[-1]
+            ops.bn_bwd_apply(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, st.bsums_g,
+                             float(rows * self.world), dx, pre_relu=pre_relu, tap_other=tap_other, tap_coef=tap_coef)
+            return
         ops.bn_reduce_grads(part, st.bsums, dgamma, dbeta)  # local sums: the gradient all-reduce adds the ranks
         sums = st.bsums
         if self.world > 1:
@@ -459,6 +514,8 @@ class VAEEngine:
             self.eps.normal_()
 
     def _train_body(self):
+        if self.peer is not None:
+            self.peer.tick()
         self.pack_weights()
         ops.pack_vae_input(self.M, self.cond, self.xe, self.xp)
         if self.overlap_pm:

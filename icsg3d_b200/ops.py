@@ -264,6 +264,25 @@ def bn_reduce_grads(partials, sums, dgamma=None, dbeta=None):
               _ptr(dbeta), _stream())
 
 
+def bn_allreduce_buffer_bytes(world, nslots, cmax):
+    return int(_lib.lib().icsg3d_bn_allreduce_buffer_bytes(world, nslots, cmax))
+
+
+def bn_reduce_allreduce_finalize(partials, count_global, gamma, beta, sums, mean, rstd, scale, shift, peers, world, rank, slot,
+                                 nslots, cmax, epoch, moving_mean=None, moving_var=None, eps=BN_EPS, momentum=BN_MOMENTUM):
+    """bn_reduce_finalize with the 2C sums all-reduced over NVLink peer memory inside the kernel (data parallel)."""
+    _lib.call("icsg3d_bn_reduce_allreduce_finalize", _ptr(partials), partials.shape[0], ctypes.c_double(count_global),
+              _ptr(gamma), _ptr(beta), eps, _ptr(sums), _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), _ptr(moving_mean),
+              _ptr(moving_var), momentum, partials.shape[2], _ptr(peers), world, rank, slot, nslots, cmax, _ptr(epoch),
+              _stream())
+
+
+def bn_reduce_allreduce_grads(partials, sums_global, peers, world, rank, slot, nslots, cmax, epoch, dgamma=None, dbeta=None):
+    """bn_reduce_grads with the backward sums all-reduced over peer memory; dgamma/dbeta stay LOCAL sums."""
+    _lib.call("icsg3d_bn_reduce_allreduce_grads", _ptr(partials), partials.shape[0], partials.shape[2], _ptr(sums_global),
+              _ptr(dgamma), _ptr(dbeta), _ptr(peers), world, rank, slot, nslots, cmax, _ptr(epoch), _stream())
+
+
 def bn_inference_coeffs(gamma, beta, moving_mean, moving_var, scale, shift, eps=BN_EPS):
     _lib.call("icsg3d_bn_inference_coeffs", _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), eps,
               _ptr(scale), _ptr(shift), scale.numel(), _stream())

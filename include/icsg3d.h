@@ -162,6 +162,24 @@ int icsg3d_bn_reduce_finalize(const double* partials, int nparts, double count, 
                               float* moving_mean, float* moving_var, float momentum, int C, void* stream);
 int icsg3d_bn_reduce_grads(const double* partials, int nparts, int C, double* sums, float* dgamma, float* dbeta,
                            void* stream);
+/* Data-parallel fusions (sync-BN statistics): partial reduction + all-reduce of the 2C sums over NVLink
+ * PEER MEMORY + finalisation in one kernel, instead of bn_reduce_partials -> NCCL all-reduce -> bn_finalize.
+ * `peers`: DEVICE array [world] with the base address of every rank's symmetric buffer as mapped into this process
+ * (torch symmetric memory), each icsg3d_bn_allreduce_buffer_bytes(world, nslots, cmax) bytes, zeroed once;
+ * `slot`: a distinct id per call site (layer x forward/backward), the same on every rank; `epoch`: DEVICE int64 >= 1 that
+ * the caller increments once per step (read on the device, so the launch is CUDA-graph replayable); count_global = rows
+ * summed over all ranks.  _finalize writes mean/rstd/scale/shift (+moving averages) from the GLOBAL statistics; _grads
+ * writes the global sums (sum g, sum g*xhat) and the LOCAL dbeta/dgamma (the gradient all-reduce adds the ranks).
+ * Deterministic: every rank adds the per-rank sums in rank order.  Every rank must launch the same sequence. */
+int64_t icsg3d_bn_allreduce_buffer_bytes(int world, int nslots, int cmax);
+int icsg3d_bn_reduce_allreduce_finalize(const double* partials, int nparts, double count_global, const float* gamma,
+                                        const float* beta, float eps, double* sums, float* mean, float* rstd, float* scale,
+                                        float* shift, float* moving_mean, float* moving_var, float momentum, int C,
+                                        const uint64_t* peers, int world, int rank, int slot, int nslots, int cmax,
+                                        const int64_t* epoch, void* stream);
+int icsg3d_bn_reduce_allreduce_grads(const double* partials, int nparts, int C, double* sums_global, float* dgamma,
+                                     float* dbeta, const uint64_t* peers, int world, int rank, int slot, int nslots, int cmax,
+                                     const int64_t* epoch, void* stream);
 /* learning phase 0 (predict / test_on_batch): scale/shift from the moving statistics */
 int icsg3d_bn_inference_coeffs(const float* gamma, const float* beta, const float* moving_mean,
                                const float* moving_var, float eps, float* scale, float* shift, int C,

@@ -123,3 +123,58 @@ def test_bn_fp32_c4():
     assert rel_l2(y32, y_ref) < 1e-5
     assert rel_l2(y16[..., :4].float(), y_ref) < 1e-2 and float(y16[..., 4:].abs().max()) == 0.0
     assert rel_l2(dx[..., :4].float(), dx_ref) < 1e-2
+
+
+def test_peer_memory_allreduce_kernel_two_emulated_ranks():
+    """csrc/bn.cu::bn_reduce_allreduce_kernel (sync-BN statistics over NVLink peer memory, SURVEY 8e) with two "ranks"
+    emulated on ONE device: two buffers in the same address space, the two launches on different streams (they spin on
+    each other's flags, so they must run concurrently).  Checks the protocol (push, flags, parity double buffering across
+    epochs), that both ranks get bit-identical global sums, and the finalisation against torch."""
+    from icsg3d_b200 import ops
+    dev = torch.device("cuda")
+    world, nslots, cmax, C = 2, 4, 128, 64
+    nbytes = ops.bn_allreduce_buffer_bytes(world, nslots, cmax)
+    bufs = [torch.zeros(nbytes // 8, dtype=torch.int64, device=dev) for _ in range(world)]
+    peers = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(3):
+        epoch.add_(1)
+        parts = [torch.randn(37 + 5 * r, 2, C, dtype=torch.float64, device=dev, generator=g).abs() * 100 for r in range(world)]
+        outs = []
+        torch.cuda.synchronize()
+        for r in range(world):
+            o = dict(sums=torch.zeros(2 * C, dtype=torch.float64, device=dev),
+                     **{k: torch.zeros(C, device=dev) for k in ("mean", "rstd", "scale", "shift")})
+            with torch.cuda.stream(streams[r]):
+                ops.bn_reduce_allreduce_finalize(parts[r], 1000.0, None, None, o["sums"], o["mean"], o["rstd"], o["scale"],
+                                                 o["shift"], peers, world, r, slot=step % nslots, nslots=nslots, cmax=cmax,
+                                                 epoch=epoch)
+            outs.append(o)
+        torch.cuda.synchronize()
+        want = sum(p.sum(0) for p in parts).reshape(-1)
+        assert torch.equal(outs[0]["sums"], outs[1]["sums"]), "ranks must agree bit for bit"
+        assert torch.allclose(outs[0]["sums"], want, rtol=1e-12)
+        mean = want[:C] / 1000.0
+        var = (want[C:] / 1000.0 - mean * mean).clamp_min(0)
+        assert torch.allclose(outs[1]["mean"].double(), mean, rtol=1e-6)
+        assert torch.allclose(outs[1]["rstd"].double(), 1.0 / torch.sqrt(var + 1e-3), rtol=1e-6)
+    # backward flavour: global sums + LOCAL dgamma/dbeta
+    epoch.add_(1)
+    parts = [torch.randn(19, 2, C, dtype=torch.float64, device=dev, generator=g) for _ in range(world)]
+    res = []
+    for r in range(world):
+        sg = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        with torch.cuda.stream(streams[r]):
+            ops.bn_reduce_allreduce_grads(parts[r], sg, peers, world, r, slot=3, nslots=nslots, cmax=cmax, epoch=epoch,
+                                          dgamma=dg, dbeta=db)
+        res.append((sg, dg, db))
+    torch.cuda.synchronize()
+    want = sum(p.sum(0) for p in parts).reshape(-1)
+    assert torch.equal(res[0][0], res[1][0]) and torch.allclose(res[0][0], want, rtol=1e-12, atol=1e-12)
+    for r in range(world):
+        loc = parts[r].sum(0)
+        assert torch.allclose(res[r][2].double(), loc[0], rtol=1e-6, atol=1e-6)  # dbeta = local sum g
+        assert torch.allclose(res[r][1].double(), loc[1], rtol=1e-6, atol=1e-6)  # dgamma = local sum g*xhat

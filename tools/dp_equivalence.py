@@ -32,6 +32,8 @@ def main():
     eng = VAEEngine(Bl, d=32, seed=3, device=dev, dist=Dist())
     sl = slice(rank * Bl, (rank + 1) * Bl)
     eng.set_inputs(M[sl], cond[sl], eps[sl])
+    if eng.peer is not None:
+        eng.peer.tick()  # the in-kernel BatchNorm all-reduce needs an epoch >= 1 (normally advanced by _train_body)
     eng.pack_weights()
     from icsg3d_b200 import ops
     ops.pack_vae_input(eng.M, eng.cond, eng.xe, eng.xp)
@@ -71,7 +73,7 @@ def main():
     mA, mB = engA.metrics_host(), engB.metrics_host()
     ok_graph = dtheta == 0.0 and mA == mB
     if rank == 0:
-        print(json.dumps({"world": world, "graph_segments": nseg, "theta_max_abs_diff_graph_vs_eager": dtheta,
+        print(json.dumps({"world": world, "graph_segments": nseg, "bn_allreduce": "peer-memory kernel" if engA.peer is not None else "nccl", "theta_max_abs_diff_graph_vs_eager": dtheta,
                           "metrics_graph": mA, "metrics_eager": mB, "ok": bool(ok and ok_graph)}))
     ok = ok and ok_graph
     dist.barrier()
