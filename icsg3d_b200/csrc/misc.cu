@@ -347,6 +347,77 @@ __global__ void adam_update_kernel(float* __restrict__ p, const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Data parallel: gradient ALL-REDUCE over NVLink peer memory fused with the Keras-Adam update (replaces
+// NCCL all-reduce of the 3.36 MB flat gradient + adam_update).  Symmetric buffer per rank:
+//   flags uint64 [2][world][nchunks]   data float [2][world][nchunks*kAdamChunk]   (parity = epoch & 1)
+// Block b pushes its chunk of the LOCAL gradient into every rank's data[par][my_rank], publishes flag b on every rank,
+// waits for flag b of every rank in its own buffer, then adds the copies in rank order (bit-identical on every rank),
+// writes the global gradient back to g and applies Adam to the chunk.  Chunks pipeline independently.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kAdamChunk = 4096;
+
+__global__ void __launch_bounds__(256) adam_allreduce_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                             float* __restrict__ v, const double* __restrict__ state, float b1,
+                                                             float b2, float eps, float grad_scale, long long n,
+                                                             const unsigned long long* __restrict__ peers, int world, int rank,
+                                                             int nchunks, size_t data_off, const long long* __restrict__ epoch_p) {
+  const unsigned long long epoch = static_cast<unsigned long long>(*epoch_p);
+  const int par = static_cast<int>(epoch & 1ull);
+  const long long i0 = static_cast<long long>(blockIdx.x) * kAdamChunk;
+  const size_t slice = static_cast<size_t>(nchunks) * kAdamChunk;  // floats per (parity, rank)
+  // 1. push (float4; the flat buffers are padded to a multiple of the chunk by the caller's layout, guard the tail)
+  for (int r = 0; r < world; ++r) {
+    float* dst = reinterpret_cast<float*>(peers[r] + data_off) + (static_cast<size_t>(par) * world + rank) * slice + i0;
+    for (int j = threadIdx.x * 4; j < kAdamChunk; j += 256 * 4) {
+      const long long i = i0 + j;
+      if (i + 3 < n) {
+        *reinterpret_cast<float4*>(dst + j) = *reinterpret_cast<const float4*>(g + i);
+      } else {
+        for (int k = 0; k < 4; ++k)
+          if (i + k < n) dst[j + k] = g[i + k];
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const int r = threadIdx.x;
+    unsigned long long* rflag = reinterpret_cast<unsigned long long*>(peers[r]) +
+                                (static_cast<size_t>(par) * world + rank) * nchunks + blockIdx.x;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(rflag), "l"(epoch) : "memory");
+    const unsigned long long* lflag = reinterpret_cast<const unsigned long long*>(peers[rank]) +
+                                      (static_cast<size_t>(par) * world + r) * nchunks + blockIdx.x;
+    const long long t_start = clock64();
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(lflag) : "memory");
+      if (seen != epoch && clock64() - t_start > 8000000000ll) {
+        printf("icsg3d: gradient all-reduce timeout rank %d chunk %d waiting for rank %d (epoch %llu)\n", rank, blockIdx.x, r,
+               epoch);
+        __trap();
+      }
+    } while (seen != epoch);
+  }
+  __syncthreads();
+  // 2. rank-ordered sum + Adam
+  const float lr_t = static_cast<float>(state[1]);
+  const float* mine = reinterpret_cast<const float*>(peers[rank] + data_off) + static_cast<size_t>(par) * world * slice + i0;
+  for (int j = threadIdx.x; j < kAdamChunk; j += 256) {
+    const long long i = i0 + j;
+    if (i >= n) break;
+    float gs = 0.f;
+    for (int r = 0; r < world; ++r) gs += __ldcv(mine + static_cast<size_t>(r) * slice + j);
+    g[i] = gs;
+    const float gi = gs * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
 }  // namespace icsg3d
 
 using namespace icsg3d;
@@ -486,6 +557,32 @@ extern "C" int icsg3d_adam_keras_step(float* p, const float* g, float* m, float*
   ICSG_CHECK_LAUNCH();
   adam_update_kernel<<<grid1d(n), 256, 0, ST>>>(p, g, m, v, state, static_cast<float>(beta1), static_cast<float>(beta2),
                                                static_cast<float>(eps), grad_scale, n);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+
+extern "C" int64_t icsg3d_adam_allreduce_buffer_bytes(int world, int64_t n) {
+  if (world < 1 || n < 1) return -1;
+  const int64_t nchunks = (n + kAdamChunk - 1) / kAdamChunk;
+  const int64_t flags = ((2 * world * nchunks * 8 + 255) / 256) * 256;
+  return flags + 2 * world * nchunks * kAdamChunk * 4;
+}
+
+extern "C" int icsg3d_adam_keras_allreduce_step(float* p, float* g, float* m, float* v, double* state, double lr, double beta1,
+                                                double beta2, double eps, float grad_scale, int64_t n, const uint64_t* peers,
+                                                int world, int rank, const int64_t* epoch, void* stream) {
+  ICSG_REQUIRE(p && g && m && v && state && peers && epoch, "adam_keras_allreduce_step: null pointer");
+  ICSG_REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world && n > 0, "adam_keras_allreduce_step: bad world/rank/n");
+  ICSG_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "adam_keras_allreduce_step: g must be 16-byte aligned");
+  const int64_t nchunks = (n + kAdamChunk - 1) / kAdamChunk;
+  const size_t data_off = static_cast<size_t>(((2 * world * nchunks * 8 + 255) / 256) * 256);
+  adam_tick_kernel<<<1, 1, 0, ST>>>(state, lr, beta1, beta2);
+  ICSG_CHECK_LAUNCH();
+  adam_allreduce_kernel<<<static_cast<int>(nchunks), 256, 0, ST>>>(
+      p, g, m, v, state, static_cast<float>(beta1), static_cast<float>(beta2), static_cast<float>(eps), grad_scale, n,
+      reinterpret_cast<const unsigned long long*>(peers), world, rank, static_cast<int>(nchunks), data_off,
+      reinterpret_cast<const long long*>(epoch));
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -51,15 +51,24 @@ class PeerBN:
 
     NSLOTS, CMAX = 64, 512
 
-    def __init__(self, dist: "Dist", dev):
+    def __init__(self, dist: "Dist", dev, n_grad=0):
         import torch.distributed as td
         import torch.distributed._symmetric_memory as symm
         self.world, self.rank = dist.world, dist.rank
+        grp = dist.group if dist.group is not None else td.group.WORLD
         nbytes = ops.bn_allreduce_buffer_bytes(self.world, self.NSLOTS, self.CMAX)
         self.buf = symm.empty(nbytes // 8, dtype=torch.int64, device=dev)
         self.buf.zero_()
-        self.hdl = symm.rendezvous(self.buf, dist.group if dist.group is not None else td.group.WORLD)
+        self.hdl = symm.rendezvous(self.buf, grp)
         self.peers = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        # second symmetric buffer: the flat gradient of every rank (all-reduce fused into the Adam kernel)
+        self.grad_peers = None
+        if n_grad > 0:
+            gbytes = ops.adam_allreduce_buffer_bytes(self.world, n_grad)
+            self.gbuf = symm.empty((gbytes + 7) // 8, dtype=torch.int64, device=dev)
+            self.gbuf.zero_()
+            self.ghdl = symm.rendezvous(self.gbuf, grp)
+            self.grad_peers = torch.tensor([int(p) for p in self.ghdl.buffer_ptrs], dtype=torch.int64, device=dev)
         self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
         self._slots = {}
         torch.cuda.synchronize()
@@ -125,7 +134,7 @@ class VAEEngine:
         self.peer = None
         if self.world > 1 and os.environ.get("ICSG3D_DP_PEER", "1") != "0":
             try:
-                self.peer = PeerBN(dist, self.dev)
+                self.peer = PeerBN(dist, self.dev, n_grad=self._vp_numel())
             except Exception as e:  # noqa: BLE001
                 import warnings
                 warnings.warn(f"icsg3d: symmetric-memory BatchNorm all-reduce unavailable ({e!r}); using NCCL")
@@ -496,8 +505,15 @@ class VAEEngine:
                 self._wgrad(self.xe, L["dc"], L["name"], 4 + 4 * self.ncond, L["cout"], 16, L["cout"], fold=(4, 4, self.ncond))
         self._wgrad_join()
 
+    def _vp_numel(self):
+        return int(self.vp.theta.numel())
+
     def optimizer_step(self):
         self._wgrad_join()
+        if self.peer is not None and self.peer.grad_peers is not None:
+            ops.adam_keras_allreduce_step(self.vp.theta, self.vp.grad, self.vp.adam_m, self.vp.adam_v, self.vp.adam_state,
+                                          self.lr, self.peer.grad_peers, self.world, self.dist.rank, self.peer.epoch)
+            return
         if self.world > 1:
             self.dist.all_reduce_sum(self.vp.grad)
         ops.adam_keras_step(self.vp.theta, self.vp.grad, self.vp.adam_m, self.vp.adam_v, self.vp.adam_state, self.lr)

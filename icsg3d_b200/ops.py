@@ -412,6 +412,18 @@ def adam_keras_step(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-7, gra
               ctypes.c_int64(p.numel()), _stream())
 
 
+def adam_allreduce_buffer_bytes(world, n):
+    return int(_lib.lib().icsg3d_adam_allreduce_buffer_bytes(world, ctypes.c_int64(n)))
+
+
+def adam_keras_allreduce_step(p, g, m, v, state, lr, peers, world, rank, epoch, beta1=0.9, beta2=0.999, eps=1e-7,
+                              grad_scale=1.0):
+    """Gradient all-reduce over NVLink peer memory fused with Keras-Adam (data parallel); g becomes the global sum."""
+    _lib.call("icsg3d_adam_keras_allreduce_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(state), ctypes.c_double(lr),
+              ctypes.c_double(beta1), ctypes.c_double(beta2), ctypes.c_double(eps), grad_scale, ctypes.c_int64(p.numel()),
+              _ptr(peers), world, rank, _ptr(epoch), _stream())
+
+
 # ------------------------------------------------------------------------------------------------
 # U-Net heads
 # ------------------------------------------------------------------------------------------------

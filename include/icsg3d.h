@@ -249,6 +249,16 @@ int icsg3d_bias_grad(const void* dy, int ld, int64_t rows, int C, float* db, voi
 int icsg3d_adam_keras_step(float* p, const float* g, float* m, float* v, double* state, double lr, double beta1,
                            double beta2, double eps, float grad_scale, int64_t n, void* stream);
 
+/* Data parallel: all-reduce of the flat gradient over NVLink PEER MEMORY fused with the Adam update — one
+ * kernel instead of NCCL all-reduce + icsg3d_adam_keras_step.  `peers`: DEVICE array [world] of every rank's symmetric
+ * buffer (icsg3d_adam_allreduce_buffer_bytes(world, n) bytes each, zeroed once); `epoch`: DEVICE int64 >= 1, incremented by
+ * the caller once per step.  On return (stream order) g holds the GLOBAL (rank-ordered, bit-identical on all ranks)
+ * gradient sum and p/m/v are updated with it.  Every rank must launch it once per step. */
+int64_t icsg3d_adam_allreduce_buffer_bytes(int world, int64_t n);
+int icsg3d_adam_keras_allreduce_step(float* p, float* g, float* m, float* v, double* state, double lr, double beta1,
+                                     double beta2, double eps, float grad_scale, int64_t n, const uint64_t* peers, int world,
+                                     int rank, const int64_t* epoch, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * U-Net heads (unet.py:339-352) and their losses/metrics (unet.py:159-221, 249-259).
  * The two 1x1x1 convolutions (95-way softmax + 1 sigmoid) are ONE GEMM with nout = 96 columns

@@ -178,3 +178,37 @@ def test_peer_memory_allreduce_kernel_two_emulated_ranks():
         loc = parts[r].sum(0)
         assert torch.allclose(res[r][2].double(), loc[0], rtol=1e-6, atol=1e-6)  # dbeta = local sum g
         assert torch.allclose(res[r][1].double(), loc[1], rtol=1e-6, atol=1e-6)  # dgamma = local sum g*xhat
+
+
+def test_peer_memory_gradient_allreduce_adam_two_emulated_ranks():
+    """csrc/misc.cu::adam_allreduce_kernel: gradient all-reduce over peer memory fused with Keras-Adam, two ranks emulated
+    on one device (two streams).  Both ranks must end with bit-identical parameters == plain adam_keras_step on g0+g1."""
+    from icsg3d_b200 import ops
+    dev = torch.device("cuda")
+    world, n = 2, 3 * 4096 + 1234
+    gbytes = ops.adam_allreduce_buffer_bytes(world, n)
+    bufs = [torch.zeros((gbytes + 7) // 8, dtype=torch.int64, device=dev) for _ in range(world)]
+    peers = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    p0 = torch.randn(n, device=dev, generator=gen)
+    st = [dict(p=p0.clone(), m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev),
+               state=torch.zeros(2, dtype=torch.float64, device=dev)) for _ in range(world + 1)]
+    for step in range(3):
+        epoch.add_(1)
+        gs = [torch.randn(n, device=dev, generator=gen) * 1e-2 for _ in range(world)]
+        gsum = gs[0] + gs[1]
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                ops.adam_keras_allreduce_step(st[r]["p"], gs[r], st[r]["m"], st[r]["v"], st[r]["state"], 5e-4, peers, world, r,
+                                              epoch)
+        ref = st[world]
+        ops.adam_keras_step(ref["p"], gsum.clone(), ref["m"], ref["v"], ref["state"], 5e-4)
+        torch.cuda.synchronize()
+        assert torch.equal(gs[0], gsum) and torch.equal(gs[1], gsum), "g must hold the global sum on every rank"
+        assert torch.equal(st[0]["p"], st[1]["p"]) and torch.equal(st[0]["v"], st[1]["v"]), "ranks must agree bit for bit"
+        # vs the single-process kernel: same formula, separately compiled (FMA contraction may differ in the last bit)
+        assert torch.allclose(st[0]["p"], ref["p"], rtol=1e-6, atol=1e-7), float((st[0]["p"] - ref["p"]).abs().max())
+        assert torch.allclose(st[0]["v"], ref["v"], rtol=1e-5, atol=1e-12)
