@@ -170,7 +170,12 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
         out = torch.empty((B, D, H, W, n_store), dtype=out_dtype, device=x.device)
     ydt = DT_BF16 if out.dtype == torch.bfloat16 else DT_F32
     nc, no = nominal if nominal else (cin, nout)
-    with _timed(("igemm", tag), 2.0 * B * D * H * W * wpack.shape[0] * nc * no):
+    kind = "igemm"
+    if TIMING is not None and wpack.shape[0] == 27:
+        plan = (ctypes.c_int * 10)()
+        _lib.lib().icsg3d_conv3d_k3_plan(B, D, H, W, cin, nout, 148, plan)
+        kind = ("pertap", "halo", "stream")[plan[0]]
+    with _timed((kind, tag), 2.0 * B * D * H * W * wpack.shape[0] * nc * no):
         if stats is not None:
             _chk(stats, torch.float64, "stats")
             if stats.dim() != 3 or stats.shape[1] != 2 or stats.shape[2] != nout or not stats.is_contiguous():
