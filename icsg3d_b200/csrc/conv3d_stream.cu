@@ -26,11 +26,85 @@
 
 namespace icsg3d {
 
-static constexpr int kStreamMaxIssuers = 4;
+static constexpr int kStreamMaxIssuers = 3;  // 1 + 3 + 8 = 12 warps = 3 per SM sub-partition: up to 168 registers per thread
 static constexpr int kStreamEpiWarps = 8;
 static constexpr int kStreamThreads = (1 + kStreamMaxIssuers + kStreamEpiWarps) * 32;
 static constexpr int kStreamMaxStages = 6;
 static constexpr int kStreamMaxR = 8;
+
+// One epilogue item: NC accumulator columns of 32 rows (TMEM -> bias/activation -> global, + BatchNorm running sums).
+// NC = 32 gives the warp two independent 16-column chains per TMEM round trip (the epilogue is latency bound).
+template <int NC>
+__device__ __forceinline__ void stream_epi_item(const ConvStreamParams& p, uint32_t taddr, int c0, bool ok, long long pixel,
+                                                const float* s_bias, float slope, float (&sacc)[32], float (&qacc)[32]) {
+  uint32_t v[NC];
+  if constexpr (NC == 32) tmem_ld32(taddr, v);
+  else tmem_ld16(taddr, v);
+  tmem_ld_wait();
+  float fv[NC];
+#pragma unroll
+  for (int i = 0; i < NC; i += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + i]);
+    const float x0 = __uint_as_float(v[i]) + b4.x, x1 = __uint_as_float(v[i + 1]) + b4.y;
+    const float x2 = __uint_as_float(v[i + 2]) + b4.z, x3 = __uint_as_float(v[i + 3]) + b4.w;
+    fv[i] = fmaxf(x0, slope * x0);
+    fv[i + 1] = fmaxf(x1, slope * x1);
+    fv[i + 2] = fmaxf(x2, slope * x2);
+    fv[i + 3] = fmaxf(x3, slope * x3);
+  }
+  const int nvalid = min(NC, p.n_store - c0);
+  if (p.y_dtype == ICSG3D_DT_BF16) {
+    uint4 qv[NC / 8];
+#pragma unroll
+    for (int j = 0; j < NC / 8; ++j) {
+      qv[j].x = pack_bf16x2(fv[8 * j], fv[8 * j + 1]);
+      qv[j].y = pack_bf16x2(fv[8 * j + 2], fv[8 * j + 3]);
+      qv[j].z = pack_bf16x2(fv[8 * j + 4], fv[8 * j + 5]);
+      qv[j].w = pack_bf16x2(fv[8 * j + 6], fv[8 * j + 7]);
+    }
+    if (ok) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + c0;
+      if (nvalid == NC && (p.ldy & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = qv[j];
+      } else {
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+          if (i < nvalid) dst[i] = f2bf(fv[i]);
+      }
+    }
+    if (p.stats) {  // statistics of the values as stored (bf16-rounded)
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) {
+        float2 u;
+        u = unpack_bf16x2(qv[j].x); fv[8 * j] = u.x; fv[8 * j + 1] = u.y;
+        u = unpack_bf16x2(qv[j].y); fv[8 * j + 2] = u.x; fv[8 * j + 3] = u.y;
+        u = unpack_bf16x2(qv[j].z); fv[8 * j + 4] = u.x; fv[8 * j + 5] = u.y;
+        u = unpack_bf16x2(qv[j].w); fv[8 * j + 6] = u.x; fv[8 * j + 7] = u.y;
+      }
+    }
+  } else if (ok) {
+    float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + c0;
+    if (nvalid == NC && (p.ldy & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i)
+        reinterpret_cast<float4*>(dst)[i] = make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
+    } else if (nvalid == 4 && (p.ldy & 3) == 0) {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (i < nvalid) dst[i] = fv[i];
+    }
+  }
+  if (p.stats && ok) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      sacc[i] += fv[i];
+      qacc[i] = fmaf(fv[i], fv[i], qacc[i]);
+    }
+  }
+}
 
 template <int KSTEPS>
 __global__ void __launch_bounds__(kStreamThreads, 1)
@@ -110,8 +184,8 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int n = col / p.n_hblk, hb = col - n * p.n_hblk;
       const int i_lo = max(0, db - 1), i_hi = min(p.D - 1, de);
       for (int i = i_lo; i <= i_hi; ++i, ++astep) {
-        const int stage = astep % p.stages;
-        mbar_wait(&a_empty[stage], (static_cast<uint32_t>(astep / p.stages) & 1u) ^ 1u);
+        const int stage = astep & (p.stages - 1);
+        mbar_wait(&a_empty[stage], (static_cast<uint32_t>(astep >> p.st_log2) & 1u) ^ 1u);
         if (leader) {
           mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
           for (int ch = 0; ch < p.chunks; ++ch)
@@ -147,17 +221,18 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         for (int i = i_lo; i <= i_hi; ++i, ++astep) {
           const int o_lo = max(db, i - 1), o_hi = min(de - 1, i + 1);
           const int o_f = (i == 0) ? o_lo : min(i + 1, o_hi + 1);  // outputs [o_f, o_hi] are touched for the first time
+          const int rmask = p.R - 1;
           for (int o = o_f; o <= o_hi; ++o) {
             const int q = qbase + o - db;
-            mbar_wait(&slot_empty[q % p.R], (static_cast<uint32_t>(q / p.R) & 1u) ^ 1u);
+            mbar_wait(&slot_empty[q & rmask], (static_cast<uint32_t>(q >> p.r_log2) & 1u) ^ 1u);
           }
-          const int stage = astep % p.stages;
-          mbar_wait(&a_full[stage], static_cast<uint32_t>(astep / p.stages) & 1u);
+          const int stage = astep & (p.stages - 1);
+          mbar_wait(&a_full[stage], static_cast<uint32_t>(astep >> p.st_log2) & 1u);
           tc_fence_after();
           // outputs o_lo..o_hi = consecutive ring positions; split once at the ring wrap: op0 (n0 blocks), op1 (n1 blocks)
           const int q_lo = qbase + o_lo - db;
           const int cnt = o_hi - o_lo + 1;
-          const int s0 = q_lo % p.R;
+          const int s0 = q_lo & rmask;
           const int n0 = cnt < p.R - s0 ? cnt : p.R - s0;
           const int n1 = cnt - n0;
           const int blk0 = o_lo - (i - 1);
@@ -167,36 +242,60 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           const uint32_t idesc0 = p.idesc[n0 - 1];
           const uint32_t idesc1 = p.idesc[n1 > 0 ? n1 - 1 : 0];
           const uint32_t a_stage_lo = a_ring_lo + static_cast<uint32_t>(stage) * (p.a_stage_bytes >> 4);
+          const uint32_t wp_lo = static_cast<uint32_t>(p.WP) * row_lo;
           if (leader) {
             for (int t = issuer; t < t_valid; t += p.issuers) {
               const uint32_t a_t = a_stage_lo + static_cast<uint32_t>(t) * tile_lo;
               const uint32_t d_t = tmem_base + static_cast<uint32_t>(t * p.R * p.C);
               // very first K step of the plane: one MMA per output plane, accumulate only into the planes already begun
               for (int o = o_lo; o <= o_hi; ++o)
-                umma_bf16_lohi(d_t + static_cast<uint32_t>(((qbase + o - db) % p.R) * p.C), a_t, desc_hi,
+                umma_bf16_lohi(d_t + static_cast<uint32_t>(((qbase + o - db) & rmask) * p.C), a_t, desc_hi,
                                w_lo + static_cast<uint32_t>(o - (i - 1)) * blk_lo, desc_hi, idesc_c, o < o_f ? 1u : 0u);
-              uint32_t b_u = w_lo;
-              for (int kh = 0; kh < 3; ++kh) {
+              const uint32_t da = d_t + d0;
+              const uint32_t wa = w_lo + b0, wb = w_lo + b1;
+              // rest of unit (kh, kw, chunk) = (0, 0, 0)
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                  uint32_t a_u = a_t + static_cast<uint32_t>(kh * p.WP + kw) * row_lo;
-                  for (int ch = 0; ch < p.chunks; ++ch, a_u += chunk_lo, b_u += unit_lo) {
-                    const int k_first = (kh | kw | ch) == 0 ? 1 : 0;
+              for (int k = 1; k < KSTEPS; ++k) {
+                umma_bf16_lohi(da, a_t + 2u * k, desc_hi, wa + 2u * k, desc_hi, idesc0, 1u);
+                if (n1 > 0) umma_bf16_lohi(d_t, a_t + 2u * k, desc_hi, wb + 2u * k, desc_hi, idesc1, 1u);
+              }
+              if (p.chunks == 1) {
+                // single channel chunk (Cin <= 64): the other 8 taps as one flat unrolled sequence
+#pragma unroll
+                for (int tap = 1; tap < 9; ++tap) {
+                  const uint32_t a_u = a_t + static_cast<uint32_t>(tap / 3) * wp_lo + static_cast<uint32_t>(tap % 3) * row_lo;
+                  const uint32_t bo = static_cast<uint32_t>(tap) * unit_lo;
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) umma_bf16_lohi(da, a_u + 2u * k, desc_hi, wa + bo + 2u * k, desc_hi, idesc0, 1u);
+                  if (n1 > 0) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k)
-                      if (k >= k_first) umma_bf16_lohi(d_t + d0, a_u + 2u * k, desc_hi, b_u + b0 + 2u * k, desc_hi, idesc0, 1u);
-                    if (n1 > 0) {
+                      umma_bf16_lohi(d_t, a_u + 2u * k, desc_hi, wb + bo + 2u * k, desc_hi, idesc1, 1u);
+                  }
+                }
+              } else {
+                uint32_t bo = 0;
+                for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-                      for (int k = 0; k < KSTEPS; ++k)
-                        if (k >= k_first) umma_bf16_lohi(d_t, a_u + 2u * k, desc_hi, b_u + b1 + 2u * k, desc_hi, idesc1, 1u);
+                  for (int kw = 0; kw < 3; ++kw) {
+                    uint32_t a_u = a_t + static_cast<uint32_t>(kh) * wp_lo + static_cast<uint32_t>(kw) * row_lo;
+                    for (int ch = 0; ch < p.chunks; ++ch, a_u += chunk_lo, bo += unit_lo) {
+                      if ((kh | kw | ch) == 0) continue;  // done above
+#pragma unroll
+                      for (int k = 0; k < KSTEPS; ++k) umma_bf16_lohi(da, a_u + 2u * k, desc_hi, wa + bo + 2u * k, desc_hi, idesc0, 1u);
+                      if (n1 > 0) {
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; ++k)
+                          umma_bf16_lohi(d_t, a_u + 2u * k, desc_hi, wb + bo + 2u * k, desc_hi, idesc1, 1u);
+                      }
                     }
                   }
                 }
               }
             }
             umma_commit(&a_empty[stage]);
-            if (i - 1 >= db) umma_commit(&slot_full[(qbase + i - 1 - db) % p.R]);            // output plane i-1 is complete
-            if (i == p.D - 1 && de == p.D) umma_commit(&slot_full[(qbase + i - db) % p.R]);  // and the last plane of the column
+            if (i - 1 >= db) umma_commit(&slot_full[(qbase + i - 1 - db) & rmask]);            // output plane i-1 is complete
+            if (i == p.D - 1 && de == p.D) umma_commit(&slot_full[(qbase + i - db) & rmask]);  // and the last plane of the column
           }
           __syncwarp();
         }
@@ -205,18 +304,22 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
   } else {
-    // ===================== epilogue warps: 2 per TMEM lane quarter, (tile, 16-column group) items dealt alternately ======
+    // ===================== epilogue warps: 2 per TMEM lane quarter =====================
+    // C = 64: warp half h owns columns [32h, 32h+32) of every tile; C <= 32: the halves take alternate tiles.
     const int quarter = warp & 3;
     const int half = (warp - 1 - kStreamMaxIssuers) >> 2;
-    const int groups = (min(p.n_store, p.C) + 15) >> 4;
+    const bool split_cols = p.C == 64;
+    const int c0 = split_cols ? 32 * half : 0;
+    const int t_first = split_cols ? 0 : half, t_step = split_cols ? 1 : 2;
+    const bool active = c0 < p.n_store;
     const float inv_wp = 1.0f / static_cast<float>(p.WP);
     // LeakyReLU / ReLU / identity as max(x, slope * x)
     const float slope = p.act == ICSG3D_ACT_RELU ? 0.f : (p.act == ICSG3D_ACT_LEAKY ? p.alpha : 1.f);
-    // BatchNorm statistics of the stored values: per-thread fp32 running sums for the (at most two) 16-column groups
-    // this warp ever sees (item parity = warp half), reduced across lanes once at the end of the kernel.
-    float sA[16], qA[16], sB[16], qB[16];
+    // BatchNorm statistics of the stored values: per-thread fp32 running sums for this warp's (at most 32) columns,
+    // reduced across lanes once at the end of the kernel
+    float sacc[32], qacc[32];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sA[i] = qA[i] = sB[i] = qB[i] = 0.f;
+    for (int i = 0; i < 32; ++i) sacc[i] = qacc[i] = 0.f;
     int q = 0;
     for (int s = s_begin; s < s_end;) {
       const int col = s / p.D, db = s - col * p.D;
@@ -224,97 +327,22 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int n = col / p.n_hblk, hb = col - n * p.n_hblk;
       const int th_valid = min(p.TH, p.H - hb * p.TH);
       const int t_valid = (th_valid * p.WP + 127) >> 7;
-      const int items = t_valid * groups;
       for (int o = db; o < de; ++o, ++q) {
-        const int slot = q % p.R;
+        const int slot = q & (p.R - 1);
         const long long plane0 = ((static_cast<long long>(n) * p.D + o) * p.H + hb * p.TH) * p.W;
-        mbar_wait(&slot_full[slot], static_cast<uint32_t>(q / p.R) & 1u);
+        mbar_wait(&slot_full[slot], static_cast<uint32_t>(q >> p.r_log2) & 1u);
         tc_fence_after();
-        for (int item = half; item < items; item += 2) {
-          const int t = item / groups;
-          const int c0 = (item - t * groups) << 4;
-          const int f = t * 128 + quarter * 32 + lane;
-          const int hl = static_cast<int>((static_cast<float>(f) + 0.5f) * inv_wp);
-          const int wl = f - hl * p.WP;
-          const bool ok = hl < th_valid && wl < p.W;
-          const long long pixel = plane0 + hl * p.W + wl;
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                 static_cast<uint32_t>((t * p.R + slot) * p.C + c0);
-          uint32_t v[16];
-          tmem_ld16(taddr, v);
-          tmem_ld_wait();
-          float fv[16];
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + i]);
-            const float x0 = __uint_as_float(v[i]) + b4.x, x1 = __uint_as_float(v[i + 1]) + b4.y;
-            const float x2 = __uint_as_float(v[i + 2]) + b4.z, x3 = __uint_as_float(v[i + 3]) + b4.w;
-            fv[i] = fmaxf(x0, slope * x0);
-            fv[i + 1] = fmaxf(x1, slope * x1);
-            fv[i + 2] = fmaxf(x2, slope * x2);
-            fv[i + 3] = fmaxf(x3, slope * x3);
-          }
-          const int nvalid = min(16, p.n_store - c0);
-          if (p.y_dtype == ICSG3D_DT_BF16) {
-            uint4 q0, q1;
-            q0.x = pack_bf16x2(fv[0], fv[1]);
-            q0.y = pack_bf16x2(fv[2], fv[3]);
-            q0.z = pack_bf16x2(fv[4], fv[5]);
-            q0.w = pack_bf16x2(fv[6], fv[7]);
-            q1.x = pack_bf16x2(fv[8], fv[9]);
-            q1.y = pack_bf16x2(fv[10], fv[11]);
-            q1.z = pack_bf16x2(fv[12], fv[13]);
-            q1.w = pack_bf16x2(fv[14], fv[15]);
-            if (ok) {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + c0;
-              if (nvalid == 16 && (p.ldy & 7) == 0) {
-                reinterpret_cast<uint4*>(dst)[0] = q0;
-                reinterpret_cast<uint4*>(dst)[1] = q1;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (i < nvalid) dst[i] = f2bf(fv[i]);
-              }
-            }
-            if (p.stats) {  // statistics of the values as stored (bf16-rounded)
-              float2 u;
-              u = unpack_bf16x2(q0.x); fv[0] = u.x; fv[1] = u.y;
-              u = unpack_bf16x2(q0.y); fv[2] = u.x; fv[3] = u.y;
-              u = unpack_bf16x2(q0.z); fv[4] = u.x; fv[5] = u.y;
-              u = unpack_bf16x2(q0.w); fv[6] = u.x; fv[7] = u.y;
-              u = unpack_bf16x2(q1.x); fv[8] = u.x; fv[9] = u.y;
-              u = unpack_bf16x2(q1.y); fv[10] = u.x; fv[11] = u.y;
-              u = unpack_bf16x2(q1.z); fv[12] = u.x; fv[13] = u.y;
-              u = unpack_bf16x2(q1.w); fv[14] = u.x; fv[15] = u.y;
-            }
-          } else if (ok) {
-            float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + c0;
-            if (nvalid == 16 && (p.ldy & 3) == 0) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                reinterpret_cast<float4*>(dst)[i] = make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
-            } else if (nvalid == 4 && (p.ldy & 3) == 0) {
-              reinterpret_cast<float4*>(dst)[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) dst[i] = fv[i];
-            }
-          }
-          if (p.stats && ok) {
-            if (c0 < 32) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                sA[i] += fv[i];
-                qA[i] = fmaf(fv[i], fv[i], qA[i]);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                sB[i] += fv[i];
-                qB[i] = fmaf(fv[i], fv[i], qB[i]);
-              }
-            }
+        if (active) {
+          for (int t = t_first; t < t_valid; t += t_step) {
+            const int f = t * 128 + quarter * 32 + lane;
+            const int hl = static_cast<int>((static_cast<float>(f) + 0.5f) * inv_wp);
+            const int wl = f - hl * p.WP;
+            const bool ok = hl < th_valid && wl < p.W;
+            const long long pixel = plane0 + hl * p.W + wl;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>((t * p.R + slot) * p.C + c0);
+            if (p.C >= 32) stream_epi_item<32>(p, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
+            else stream_epi_item<16>(p, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
           }
         }
         tc_fence_before();
@@ -323,21 +351,18 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
       s += de - db;
     }
-    if (p.stats) {
-      // groups == 1: both halves saw group 0; groups == 2: half h saw group h; groups == 4: half h saw groups h and h+2
-      const int gA = groups >= 2 ? half : 0;
-      {
-        const float s1 = warp_colsum16(sA, lane), s2 = warp_colsum16(qA, lane);
-        if ((lane & 1) == 0) {
-          const int c = gA * 16 + colsum16_owner(lane);
-          atomicAdd(&s_stats[0][c], static_cast<double>(s1));
-          atomicAdd(&s_stats[1][c], static_cast<double>(s2));
+    if (p.stats && active) {
+      const int ncol = p.C >= 32 ? 32 : 16;
+      for (int j = 0; j < ncol; j += 16) {
+        float a[16], b[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          a[i] = j == 0 ? sacc[i] : sacc[16 + i];
+          b[i] = j == 0 ? qacc[i] : qacc[16 + i];
         }
-      }
-      if (groups == 4) {
-        const float s1 = warp_colsum16(sB, lane), s2 = warp_colsum16(qB, lane);
+        const float s1 = warp_colsum16(a, lane), s2 = warp_colsum16(b, lane);
         if ((lane & 1) == 0) {
-          const int c = (half + 2) * 16 + colsum16_owner(lane);
+          const int c = c0 + j + colsum16_owner(lane);
           atomicAdd(&s_stats[0][c], static_cast<double>(s1));
           atomicAdd(&s_stats[1][c], static_cast<double>(s2));
         }
@@ -387,8 +412,8 @@ bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, Co
     const uint32_t a_chunk = (static_cast<uint32_t>(rows_alloc) * row_bytes + 1023u) & ~1023u;
     const uint32_t a_stage = a_chunk * chunks;
     int stages = static_cast<int>((budget - w_alloc) / a_stage);
-    if (stages > kStreamMaxStages) stages = kStreamMaxStages;
     if (stages < 2) continue;
+    stages = stages >= 4 ? 4 : 2;  // power of two (ring arithmetic by mask)
     // tiles actually issued per column plane (the partial last block skips empty tiles)
     int tiles = 0;
     for (int hb = 0; hb < n_hblk; ++hb) {
@@ -396,7 +421,7 @@ bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, Co
       tiles += (thv * WP + 127) / 128;
     }
     double eff = static_cast<double>(H) * W / (tiles * 128.0);
-    if (stages < 3) eff *= 0.9;
+    if (stages < 4) eff *= 0.9;
     eff -= 0.002 * HP / TH;  // tie-break: less h-halo re-read
     if (eff > best) {
       best = eff;
@@ -404,9 +429,10 @@ bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, Co
       bp.B = B; bp.D = D; bp.H = H; bp.W = W;
       bp.TH = TH; bp.HP = HP; bp.WP = WP; bp.n_hblk = n_hblk;
       bp.T = T; bp.C = C;
-      int R = 512 / (T * C);
-      if (R > kStreamMaxR) R = kStreamMaxR;
+      const int R = 512 / (T * C) >= 8 ? 8 : 4;  // power of two, >= 4 by the choice of Tmax
       bp.R = R;
+      bp.r_log2 = R == 8 ? 3 : 2;
+      bp.st_log2 = stages == 4 ? 2 : 1;
       bp.kc = kc; bp.chunks = chunks; bp.row_bytes = row_bytes;
       bp.stages = stages;
       bp.issuers = T < kStreamMaxIssuers ? T : kStreamMaxIssuers;

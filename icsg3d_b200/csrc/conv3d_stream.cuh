@@ -8,9 +8,10 @@ namespace icsg3d {
 struct ConvStreamParams {
   int B, D, H, W;
   int TH, HP, WP, n_hblk;
-  int T, R, C;           // M tiles per plane slab, accumulator ring slots (output planes), channels per kd block (= nout)
+  int T, R, C;           // M tiles per plane slab, accumulator ring slots (output planes, power of two), channels per kd block (= nout)
+  int r_log2, st_log2;   // log2(R), log2(stages): ring arithmetic is masks and shifts in the issue loop
   int kc, chunks, row_bytes;
-  int stages;            // input-plane ring depth in shared memory
+  int stages;            // input-plane ring depth in shared memory (power of two)
   int issuers;           // MMA issuer warps in use (tiles are dealt round-robin)
   int total_steps, steps_per_cta;
   uint32_t a_chunk_bytes, a_stage_bytes, a_tx_bytes;
