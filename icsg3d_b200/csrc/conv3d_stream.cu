@@ -208,7 +208,6 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t row_lo = static_cast<uint32_t>(p.row_bytes) >> 4;
       const uint32_t a_ring_lo = umma_desc_lo(base + a_off, 16u);
       const uint32_t tile_lo = 128u * row_lo;
-      const uint32_t idesc_c = p.idesc[0];
       mbar_wait(&w_full, 0);
       int astep = 0, qbase = 0;
       for (int s = s_begin; s < s_end;) {
@@ -224,7 +223,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           const int rmask = p.R - 1;
           for (int o = o_f; o <= o_hi; ++o) {
             const int q = qbase + o - db;
-            mbar_wait(&slot_empty[q & rmask], (static_cast<uint32_t>(q >> p.r_log2) & 1u) ^ 1u);
+            mbar_wait(&slot_empty[q & rmask], static_cast<uint32_t>(q >> p.r_log2) & 1u);  // zeroed by the epilogue
           }
           const int stage = astep & (p.stages - 1);
           mbar_wait(&a_full[stage], static_cast<uint32_t>(astep >> p.st_log2) & 1u);
@@ -247,15 +246,11 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int t = issuer; t < t_valid; t += p.issuers) {
               const uint32_t a_t = a_stage_lo + static_cast<uint32_t>(t) * tile_lo;
               const uint32_t d_t = tmem_base + static_cast<uint32_t>(t * p.R * p.C);
-              // very first K step of the plane: one MMA per output plane, accumulate only into the planes already begun
-              for (int o = o_lo; o <= o_hi; ++o)
-                umma_bf16_lohi(d_t + static_cast<uint32_t>(((qbase + o - db) & rmask) * p.C), a_t, desc_hi,
-                               w_lo + static_cast<uint32_t>(o - (i - 1)) * blk_lo, desc_hi, idesc_c, o < o_f ? 1u : 0u);
               const uint32_t da = d_t + d0;
               const uint32_t wa = w_lo + b0, wb = w_lo + b1;
-              // rest of unit (kh, kw, chunk) = (0, 0, 0)
+              // every slot was zeroed by the epilogue when it was drained: all MMAs accumulate.  Unit (0, 0, 0):
 #pragma unroll
-              for (int k = 1; k < KSTEPS; ++k) {
+              for (int k = 0; k < KSTEPS; ++k) {
                 umma_bf16_lohi(da, a_t + 2u * k, desc_hi, wa + 2u * k, desc_hi, idesc0, 1u);
                 if (n1 > 0) umma_bf16_lohi(d_t, a_t + 2u * k, desc_hi, wb + 2u * k, desc_hi, idesc1, 1u);
               }
@@ -320,6 +315,15 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     float sacc[32], qacc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) sacc[i] = qacc[i] = 0.f;
+    // The accumulator slots are kept ZERO between uses (so every MMA accumulates and the first K step of a plane needs no
+    // overwrite split): zero the whole allocation once, then every drained item is zeroed right after it was read.
+    for (uint32_t cz = static_cast<uint32_t>(half) * 32u; cz < p.tmem_cols; cz += 64u)
+      tmem_st_zero<32>(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + cz);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int i = 0; i < p.R; ++i) mbar_arrive(&slot_empty[i]);
     int q = 0;
     for (int s = s_begin; s < s_end;) {
       const int col = s / p.D, db = s - col * p.D;
@@ -332,7 +336,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const long long plane0 = ((static_cast<long long>(n) * p.D + o) * p.H + hb * p.TH) * p.W;
         mbar_wait(&slot_full[slot], static_cast<uint32_t>(q >> p.r_log2) & 1u);
         tc_fence_after();
-        if (active) {
+        {
           for (int t = t_first; t < t_valid; t += t_step) {
             const int f = t * 128 + quarter * 32 + lane;
             const int hl = static_cast<int>((static_cast<float>(f) + 0.5f) * inv_wp);
@@ -341,10 +345,16 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const long long pixel = plane0 + hl * p.W + wl;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>((t * p.R + slot) * p.C + c0);
-            if (p.C >= 32) stream_epi_item<32>(p, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
-            else stream_epi_item<16>(p, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
+            if (p.C >= 32) {
+              if (active) stream_epi_item<32>(p, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
+              tmem_st_zero<32>(taddr);
+            } else {
+              if (active) stream_epi_item<16>(p, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
+              tmem_st_zero<16>(taddr);
+            }
           }
         }
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_empty[slot]);
