@@ -30,6 +30,8 @@ struct ConvIgemmParams {
   int ups;              // k-units per pipeline stage
   int ntaps;            // 27 (3x3x3) or 1 (1x1x1)
   int iters;            // ntaps*chunks/ups
+  int ksplit, ips;      // split-K: number of K slices and pipeline iterations per slice (ksplit == 1: no split)
+  float* ws;            // split-K partials fp32 [ksplit][m_total][tiles_n*nt]
   int stages;
   uint32_t a_unit_bytes;  // 128*kc*2
   uint32_t b_unit_bytes;  // nt*kc*2
@@ -87,7 +89,7 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.ksplit;  // tile index = (tm * tiles_n + tn) * ksplit + ks
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
@@ -96,8 +98,10 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint32_t phase = 0;
     const uint32_t tx_bytes = static_cast<uint32_t>(p.ups) * (p.a_unit_bytes + p.b_unit_bytes);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int tm = tile / p.tiles_n;
-      const int tn = tile - tm * p.tiles_n;
+      const int ks = tile % p.ksplit;
+      const int tmn = tile / p.ksplit;
+      const int tm = tmn / p.tiles_n;
+      const int tn = tmn - tm * p.tiles_n;
       int pix = tm * 128;
       const int w0 = pix % p.W;
       pix /= p.W;
@@ -105,8 +109,10 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       pix /= p.H;
       const int d0 = pix % p.D;
       const int n0 = pix / p.D;
-      int tap = 0, ch = 0;
-      for (int it = 0; it < p.iters; ++it) {
+      const int it0 = ks * p.ips, it1 = min(p.iters, it0 + p.ips);
+      const int unit0 = it0 * p.ups;
+      int tap = unit0 / p.chunks, ch = unit0 - tap * p.chunks;
+      for (int it = it0; it < it1; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
         uint8_t* sb = sa + static_cast<size_t>(p.ups) * p.a_unit_bytes;
@@ -147,7 +153,9 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.nt);
-      for (int it = 0; it < p.iters; ++it) {
+      const int ks = tile % p.ksplit;
+      const int it0 = ks * p.ips, it1 = min(p.iters, it0 + p.ips);
+      for (int it = it0; it < it1; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         uint32_t a_lo = ring_lo + static_cast<uint32_t>(stage) * stage_lo;
@@ -156,7 +164,7 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (leader) {
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k)
-              umma_bf16_lohi(d_tmem, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, p.idesc, (it | j | k) != 0 ? 1u : 0u);
+              umma_bf16_lohi(d_tmem, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, p.idesc, ((it - it0) | j | k) != 0 ? 1u : 0u);
           }
           a_lo += a_unit_lo;
           b_lo += b_unit_lo;
@@ -177,8 +185,10 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = static_cast<uint32_t>(local >> 1) & 1u;
-      const int tm = tile / p.tiles_n;
-      const int tn = tile - tm * p.tiles_n;
+      const int ks = tile % p.ksplit;
+      const int tmn = tile / p.ksplit;
+      const int tm = tmn / p.tiles_n;
+      const int tn = tmn - tm * p.tiles_n;
       const long long pixel = static_cast<long long>(tm) * 128 + row;
       const bool row_ok = pixel < p.m_total;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -189,6 +199,16 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
         tmem_ld_wait();
         const int col0 = tn * p.nt + c0;
+        if (p.ksplit > 1) {  // raw fp32 partial of this K slice; bias/activation/conversion happen in the reduce kernel
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(ks) * p.m_total + pixel) * (p.tiles_n * p.nt) + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                   __uint_as_float(v[4 * i + 3]));
+          }
+          continue;
+        }
         if (!row_ok || col0 >= p.n_store) continue;
         float f[16];
 #pragma unroll
@@ -247,6 +267,52 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+// y[pixel][c] = act(sum over K slices of ws[ks][pixel][c] + bias[c]), fixed slice order (deterministic)
+__global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, long long m_total,
+                                                                 int ncols, const float* __restrict__ bias, int act, float alpha,
+                                                                 void* __restrict__ y, int ldy, int y_dtype, int n_store) {
+  const int c4 = ncols >> 2;
+  const long long total = m_total * c4;
+  const size_t slice = static_cast<size_t>(m_total) * ncols;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pixel = idx / c4;
+    const int c = static_cast<int>(idx - pixel * c4) << 2;
+    if (c >= n_store) continue;
+    const float* src = ws + static_cast<size_t>(pixel) * ncols + c;
+    float4 a = *reinterpret_cast<const float4*>(src);
+    for (int k = 1; k < ksplit; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(src + k * slice);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float o[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x = o[i] + (bias ? bias[c + i] : 0.f);
+      if (act == ICSG3D_ACT_RELU) x = fmaxf(x, 0.f);
+      else if (act == ICSG3D_ACT_LEAKY) x = x > 0.f ? x : alpha * x;
+      o[i] = x;
+    }
+    const int nv = min(4, n_store - c);
+    if (y_dtype == ICSG3D_DT_BF16) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + pixel * ldy + c;
+      if (nv == 4 && (ldy & 3) == 0) {
+        uint2 q;
+        q.x = pack_bf16x2(o[0], o[1]);
+        q.y = pack_bf16x2(o[2], o[3]);
+        *reinterpret_cast<uint2*>(dst) = q;
+      } else {
+        for (int i = 0; i < nv; ++i) dst[i] = f2bf(o[i]);
+      }
+    } else {
+      float* dst = reinterpret_cast<float*>(y) + pixel * ldy + c;
+      if (nv == 4 && (ldy & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      else
+        for (int i = 0; i < nv; ++i) dst[i] = o[i];
+    }
+  }
+}
+
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // Decompose a 128-voxel tile into a TMA box over (W, H, D, B).
@@ -298,9 +364,34 @@ static int conv_impl_choice() {
 
 using namespace icsg3d;
 
+// N tile and K split of the per-tap kernel.  Without a workspace: the widest N tile that still yields about one tile per
+// SM (never below 64 unless the layer is narrower).  With a workspace and too few tiles to fill the machine (the 4^3 / 2^3
+// layers: M = B*64 voxels but K up to 13,824): the WIDEST N tile (least operand re-fetch through L2) and the K range
+// (taps x channel chunks) split over ~sms/tiles CTAs, fp32 partials reduced in a fixed order.
+static void igemm_tiling(int tiles_m, int nout, int iters, int sms, bool allow_split, int* nt_out, int* ksplit_out) {
+  int wide = nout < 256 ? nout : 256;
+  while (wide > 16 && nout % wide != 0) wide -= 16;
+  *ksplit_out = 1;
+  if (allow_split) {
+    const long long tiles = static_cast<long long>(tiles_m) * (nout / wide);
+    long long ks = sms / tiles;
+    if (ks > iters / 4) ks = iters / 4;
+    if (ks >= 2) {
+      *nt_out = wide;
+      *ksplit_out = static_cast<int>(ks);
+      return;
+    }
+  }
+  int nt = wide;
+  while (nt > 64 && nout % nt != 0) nt -= 16;
+  while (nt > 64 && (nt % 2 == 0) && nout % (nt / 2) == 0 && static_cast<long long>(tiles_m) * (nout / nt) < sms) nt /= 2;
+  *nt_out = nt;
+}
+
 static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                              int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
-                             float leaky_alpha, void* stream, double* stats = nullptr, int stats_parts = 0) {
+                             float leaky_alpha, void* stream, double* stats = nullptr, int stats_parts = 0,
+                             void* ws = nullptr, int64_t ws_bytes = 0) {
   ICSG_REQUIRE(x && wpack && y, "conv3d_k3_igemm: null pointer");
   ICSG_REQUIRE(B > 0 && is_pow2(D) && is_pow2(H) && is_pow2(W) && D >= 2 && H >= 2 && W >= 2 && W <= 128,
                "conv3d_k3_igemm: D,H,W must be powers of two in [2,128] (got %d %d %d)", D, H, W);
@@ -340,20 +431,21 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   p.tiles_m = static_cast<int>((m_total + 127) / 128);
   const int sms = sm_count();
   if (sms <= 0) return cuda_fail(cudaGetLastError(), "sm_count", __FILE__, __LINE__);
-  // N tile: the widest tile (best operand reuse) that still yields at least one tile per SM; never
-  // below 64 unless the layer itself is narrower.
-  int nt = nout < 256 ? nout : 256;
-  while (nt > 64 && nout % nt != 0) nt -= 16;
-  while (nt > 64 && (nt % 2 == 0) && nout % (nt / 2) == 0 &&
-         static_cast<long long>(p.tiles_m) * (nout / nt) < sms)
-    nt /= 2;
-  ICSG_REQUIRE(nout % nt == 0, "conv3d_k3_igemm: unsupported nout %d", nout);
-  p.nt = nt;
-  p.tiles_n = nout / nt;
   p.ntaps = ntaps;
   p.ups = (p.kc == 64) ? 1 : 3;
   if ((ntaps * p.chunks) % p.ups != 0) p.ups = 1;
   p.iters = ntaps * p.chunks / p.ups;
+  int nt = 0, ksplit = 1;
+  igemm_tiling(p.tiles_m, nout, p.iters, sms, ws != nullptr, &nt, &ksplit);
+  if (ksplit > 1 && ws_bytes < static_cast<int64_t>(ksplit) * m_total * nout * 4) {
+    igemm_tiling(p.tiles_m, nout, p.iters, sms, false, &nt, &ksplit);  // workspace too small: no split
+  }
+  ICSG_REQUIRE(nt > 0 && nout % nt == 0, "conv3d_k3_igemm: unsupported nout %d", nout);
+  p.nt = nt;
+  p.tiles_n = nout / nt;
+  p.ips = (p.iters + ksplit - 1) / ksplit;
+  p.ksplit = (p.iters + p.ips - 1) / p.ips;
+  p.ws = static_cast<float*>(ws);
   p.a_unit_bytes = 128u * p.kc * 2u;
   p.b_unit_bytes = static_cast<uint32_t>(nt) * p.kc * 2u;
   p.stage_bytes = (static_cast<uint32_t>(p.ups) * (p.a_unit_bytes + p.b_unit_bytes) + 1023u) & ~1023u;
@@ -395,13 +487,21 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
     ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     configured = true;
   }
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.ksplit;
   const int grid = total_tiles < sms ? total_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p.kc == 16) conv3d_k3_igemm_kernel<1><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
   else if (p.kc == 32) conv3d_k3_igemm_kernel<2><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
   else conv3d_k3_igemm_kernel<4><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
   ICSG_CHECK_LAUNCH();
+  if (p.ksplit > 1) {
+    const long long items = m_total * (nout / 4);
+    long long blocks = (items + 255) / 256;
+    if (blocks > sms * 8) blocks = sms * 8;
+    conv_splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(p.ws, p.ksplit, m_total, nout, bias, act, leaky_alpha, y,
+                                                                      ldy, y_dtype, n_store);
+    ICSG_CHECK_LAUNCH();
+  }
   return ICSG3D_OK;
 }
 
@@ -409,6 +509,31 @@ extern "C" int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack,
                                       int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                                       float leaky_alpha, void* stream) {
   return conv3d_igemm_impl(27, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream);
+}
+
+// Workspace (bytes) with which icsg3d_conv3d_k3_igemm_ws splits the K range of this layer; 0 = the layer is not split.
+extern "C" int64_t icsg3d_conv3d_k3_workspace_bytes(int B, int D, int H, int W, int cin, int nout) {
+  const int sms = sm_count();
+  if (sms <= 0 || cin < 16 || cin % 16 || nout < 16 || nout % 16) return 0;
+  ConvStreamParams sp;
+  ConvHaloParams hp;
+  if (conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms, &sp)) return 0;
+  if (conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms, &hp)) return 0;
+  const long long m_total = static_cast<long long>(B) * D * H * W;
+  const int kc = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+  const int chunks = cin / kc;
+  int ups = (kc == 64) ? 1 : 3;
+  if ((27 * chunks) % ups != 0) ups = 1;
+  int nt = 0, ksplit = 1;
+  igemm_tiling(static_cast<int>((m_total + 127) / 128), nout, 27 * chunks / ups, sms, true, &nt, &ksplit);
+  return ksplit > 1 ? static_cast<int64_t>(ksplit) * m_total * nout * 4 : 0;
+}
+
+extern "C" int icsg3d_conv3d_k3_igemm_ws(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                                         int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                                         float leaky_alpha, void* ws, int64_t ws_bytes, void* stream) {
+  return conv3d_igemm_impl(27, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream,
+                           nullptr, 0, ws, ws_bytes);
 }
 
 extern "C" int icsg3d_conv3d_k3_stats_parts(int B, int D, int H, int W, int cin, int nout) {

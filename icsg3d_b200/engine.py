@@ -104,9 +104,11 @@ class _BN:
 class _Ctx:
     """Scratch shared by the launches of one stream."""
 
-    def __init__(self, dev, max_partials=148 * 4 * 2 * 1024, max_dw=27 * 512 * 512):
+    def __init__(self, dev, max_partials=148 * 4 * 2 * 1024, max_dw=27 * 512 * 512, conv_ws_bytes=0):
         self.partials = torch.zeros(max_partials, dtype=F64, device=dev)
         self.dw_pad = torch.zeros(max_dw, dtype=F32, device=dev)
+        # split-K partials of the per-tap conv kernel (4^3 / 2^3 layers); one buffer per stream
+        self.conv_ws = torch.empty(max(conv_ws_bytes, 16), dtype=torch.uint8, device=dev)
 
 
 class VAEEngine:
@@ -124,10 +126,11 @@ class VAEEngine:
         dev = self.dev
         self.vp = vae_params or ParamStore(vae_specs(channels, ncond, d, latent, filters), dev).init(seed)
         self.pp = pm_params or ParamStore(unet_specs(channels), dev, with_grads=False, with_adam=False).init(seed + 1)
-        self.ctx = _Ctx(dev)
+        ws_bytes = self._conv_ws_bytes(batch, d, filters)
+        self.ctx = _Ctx(dev, conv_ws_bytes=ws_bytes)
         # pm(x) does not depend on the encoder/decoder: it runs on a side stream (forked/joined inside the captured
         # graph) so that its large convs overlap the small, latency-bound VAE kernels.  Own scratch per stream.
-        self.ctx2 = _Ctx(dev, max_dw=16)
+        self.ctx2 = _Ctx(dev, max_dw=16, conv_ws_bytes=ws_bytes)
         # Data parallel: BatchNorm statistic sums are exchanged INSIDE the finalize kernels over NVLink peer memory
         # (PeerBN); only the flat gradient goes through NCCL.  ICSG3D_DP_PEER=0 (or no symmetric memory) falls back to
         # NCCL all-reduces of the sums, which also forces a single stream (collectives split the captured graph).
@@ -232,6 +235,31 @@ class VAEEngine:
     # ------------------------------------------------------------------------------------------
     # helpers
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _conv_ws_bytes(B, d, filters):
+        """Largest split-K workspace any conv of the step asks for (fprop and dgrad operand shapes)."""
+        shapes = [(d >> lvl, pad16(cin), cout) for _, cin, cout, lvl, _, _ in PM_BLOCKS]
+        f = list(filters)
+        D = d
+        cin = 16
+        for c in f:
+            shapes.append((D, cin, c))
+            cin, D = c, D // 2
+        shapes.append((D, f[-1], 16))
+        S = d // 8
+        cin = 16
+        for i, c in enumerate(f[::-1]):
+            shapes.append((S, cin, c))
+            cin, S = c, (S * 2 if i < len(f) - 1 else S)
+        need = 0
+        for D_, ci, co in shapes:
+            need = max(need, ops.conv3d_k3_workspace_bytes(B, D_, ci, co), ops.conv3d_k3_workspace_bytes(B, D_, co, ci))
+        return need
+
+    def _conv(self, x, w, bias, ctx=None, **kw):
+        """Conv3D through the dispatcher with this stream's split-K workspace (used by the 4^3 / 2^3 layers)."""
+        return ops.conv3d_k3(x, w, bias, ws=(ctx or self.ctx).conv_ws, **kw)
+
     def _conv_bn(self, x, wf, bias, out, C, training, ctx=None, **kw):
         """Conv3D whose output feeds a BatchNorm: when the layer is served by the plane-streaming kernel the batch
         statistics come out of the conv epilogue (no separate read pass).  Returns the partials view or None."""
@@ -240,7 +268,7 @@ class VAEEngine:
             n = ops.conv3d_k3_stats_parts(x, wf)
             if n > 0:
                 part = (ctx or self.ctx).partials[: n * 2 * C].view(n, 2, C)
-        ops.conv3d_k3(x, wf, bias, out=out, stats=part, **kw)
+        self._conv(x, wf, bias, ctx=ctx, out=out, stats=part, **kw)
         return part
 
     def _bn_fwd(self, x, C, st: _BN, gamma, beta, mm, mv, training, act, post, y=None, y32=None, idx=None, ctx=None,
@@ -357,7 +385,7 @@ class VAEEngine:
                          p[bn + "/moving_mean"], p[bn + "/moving_variance"], training, ACT_LEAKY, POST_POOL2, y=L["y"],
                          idx=L["idx"], part=part)
             x = L["y"]
-        ops.conv3d_k3(x, self.e5_wf, p["enc_conv5/bias"], out=self.e5, n_store=4, act=ACT_LEAKY, tag="enc_conv5.fprop",
+        self._conv(x, self.e5_wf, p["enc_conv5/bias"], out=self.e5, n_store=4, act=ACT_LEAKY, tag="enc_conv5.fprop",
                       nominal=(self.filters[-1], 4))
         ops.dense_fwd(self.e5.view(self.B, -1), p["enc_dense/kernel"], p["enc_dense/bias"], self.h, act=ACT_RELU)
         ops.dense_fwd(self.h, p["z_mean/kernel"], p["z_mean/bias"], self.mu)
@@ -378,7 +406,7 @@ class VAEEngine:
                          p[bn + "/moving_variance"], training, ACT_LEAKY, POST_UP2 if L["up"] else POST_NONE, y=L["u"],
                          part=part)
             x = L["u"]
-        ops.conv3d_k3(x, self.out_wf, p["decoder_output/bias"], out=self.c5, n_store=4, tag="decoder_output.fprop",
+        self._conv(x, self.out_wf, p["decoder_output/bias"], out=self.c5, n_store=4, tag="decoder_output.fprop",
                       nominal=(self.filters[0], 4))
         self._bn_fwd(self.c5, 4, self.bn5, p["dec_bn5/gamma"], p["dec_bn5/beta"], p["dec_bn5/moving_mean"],
                      p["dec_bn5/moving_variance"], training, ACT_RELU, POST_NONE, y=self.xhat16, y32=self.xhat)
@@ -392,7 +420,7 @@ class VAEEngine:
             n = L["name"]
             kw = dict(act=ACT_RELU, tag=f"pm{branch}.{n}.fprop", nominal=(4, L["cout"]) if n == "c1" else None)
             if not L["has_bn"]:
-                ops.conv3d_k3(x, L["wf"], p[n + "/bias"], out=L["a"][branch], **kw)
+                self._conv(x, L["wf"], p[n + "/bias"], ctx=ctx, out=L["a"][branch], **kw)
                 break
             part = self._conv_bn(x, L["wf"], p[n + "/bias"], L["a"][branch], L["cout"], training, ctx=ctx, **kw)
             bn = "bn_" + n
@@ -449,7 +477,7 @@ class VAEEngine:
         last = self.pm[-1]
         ops.tap_grad_relu(last["a"][1], last["a"][0], coef[last["name"]], last["dc"])
         dy = self.pm[-2]["dy"]
-        ops.conv3d_k3(last["dc"], last["wd"], None, out=dy, tag="pm1.c10.dgrad")
+        self._conv(last["dc"], last["wd"], None, out=dy, tag="pm1.c10.dgrad")
         for li in range(len(self.pm) - 2, -1, -1):
             L = self.pm[li]
             self._bn_bwd(dy, L["a"][1], L["cout"], L["bnst"][1], ACT_NONE, POST_POOL2 if L["pool"] else POST_NONE,
@@ -457,16 +485,16 @@ class VAEEngine:
                          tap_coef=coef.get(L["name"], 0.0))
             if li > 0:
                 dy = self.pm[li - 1]["dy"]
-                ops.conv3d_k3(L["dc"], L["wd"], None, out=dy, tag=f"pm1.{L['name']}.dgrad")
+                self._conv(L["dc"], L["wd"], None, out=dy, tag=f"pm1.{L['name']}.dgrad")
             else:
-                ops.conv3d_k3(L["dc"], L["wd"], None, out=self.dxh16, tag="pm1.c1.dgrad", nominal=(L["cout"], 4))
+                self._conv(L["dc"], L["wd"], None, out=self.dxh16, tag="pm1.c1.dgrad", nominal=(L["cout"], 4))
         # ---- decoder ----
         ops.xhat_grad(self.M, self.xhat, 2.0 / (self.M.numel() // self.B * Bg), self.dxh16, self.dxhat)
         self._bn_bwd(self.dxhat, self.c5, 4, self.bn5, ACT_RELU, POST_NONE, None, self.dc5, dgamma=g["dec_bn5/gamma"],
                      dbeta=g["dec_bn5/beta"])
         lastd = self.dec[-1]
         self._wgrad(lastd["u"], self.dc5, "decoder_output", lastd["cout"], 4, lastd["cout"], 16)
-        ops.conv3d_k3(self.dc5, self.out_wd, None, out=lastd["du"], tag="decoder_output.dgrad", nominal=(4, lastd["cout"]))
+        self._conv(self.dc5, self.out_wd, None, out=lastd["du"], tag="decoder_output.dgrad", nominal=(4, lastd["cout"]))
         for li in range(len(self.dec) - 1, -1, -1):
             L = self.dec[li]
             bn = L["bn"]
@@ -475,7 +503,7 @@ class VAEEngine:
             xin = self.dec[li - 1]["u"] if li > 0 else self.d0
             cin = self.dec[li - 1]["cout"] if li > 0 else 4
             self._wgrad(xin, L["dc"], L["name"], cin, L["cout"], L["cin_pad"], L["cout"])
-            ops.conv3d_k3(L["dc"], L["wd"], None, out=self.dec[li - 1]["du"] if li > 0 else self.dy_d0,
+            self._conv(L["dc"], L["wd"], None, out=self.dec[li - 1]["du"] if li > 0 else self.dy_d0,
                           tag=L["name"] + ".dgrad", nominal=(L["cout"], 4) if li == 0 else None)
         # ---- bottleneck ----
         ops.bf16_rows_to_f32(self.dy_d0, 4, self.ddd)
@@ -492,7 +520,7 @@ class VAEEngine:
         e4 = self.enc[-1]
         ops.bias_grad(self.dc_e5, 4, g["enc_conv5/bias"])
         self._wgrad(e4["y"], self.dc_e5, "enc_conv5", e4["cout"], 4, e4["cout"], 16)
-        ops.conv3d_k3(self.dc_e5, self.e5_wd, None, out=e4["dy"], tag="enc_conv5.dgrad", nominal=(4, e4["cout"]))
+        self._conv(self.dc_e5, self.e5_wd, None, out=e4["dy"], tag="enc_conv5.dgrad", nominal=(4, e4["cout"]))
         for li in range(len(self.enc) - 1, -1, -1):
             L = self.enc[li]
             bn = L["bn"]
@@ -500,7 +528,7 @@ class VAEEngine:
                          dgamma=g[bn + "/gamma"], dbeta=g[bn + "/beta"])
             if li > 0:
                 self._wgrad(self.enc[li - 1]["y"], L["dc"], L["name"], L["cin_pad"], L["cout"], L["cin_pad"], L["cout"])
-                ops.conv3d_k3(L["dc"], L["wd"], None, out=self.enc[li - 1]["dy"], tag=L["name"] + ".dgrad")
+                self._conv(L["dc"], L["wd"], None, out=self.enc[li - 1]["dy"], tag=L["name"] + ".dgrad")
             else:
                 self._wgrad(self.xe, L["dc"], L["name"], 4 + 4 * self.ncond, L["cout"], 16, L["cout"], fold=(4, 4, self.ncond))
         self._wgrad_join()

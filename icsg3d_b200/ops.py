@@ -134,6 +134,10 @@ def _timed(tag, flops):
     return _T()
 
 
+def conv3d_k3_workspace_bytes(B, D, cin, nout):
+    return int(_lib.lib().icsg3d_conv3d_k3_workspace_bytes(B, D, D, D, cin, nout))
+
+
 def conv3d_k3_stats_parts(x, wpack):
     """Rows of BatchNorm partials the fused conv+statistics path writes for this layer shape (0 = not available)."""
     B, D, H, W, _ = x.shape
@@ -141,12 +145,13 @@ def conv3d_k3_stats_parts(x, wpack):
 
 
 def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alpha=LEAKY_ALPHA, out=None,
-              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv", stats=None):
+              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv", stats=None, ws=None):
     """x: bf16 [B,D,H,W,ldx]; wpack: bf16 [27][nout][cin]; returns y [B,D,H,W,n_store].
 
     `ref=True` runs the CUDA-core cross-check kernel (fp32 output) instead of the tcgen05 kernel.
     `stats`: fp64 [parts, 2, nout] with parts = conv3d_k3_stats_parts(x, wpack) > 0 — the kernel also writes the
     per-CTA BatchNorm partials (sum, sum of squares) of the stored output.
+    `ws`: optional scratch tensor (any dtype, one per stream): layers with too few tiles (4^3 / 2^3 grids) split K over it.
     """
     _chk(x, torch.bfloat16, "x")
     _chk(wpack, torch.bfloat16, "wpack")
@@ -182,6 +187,9 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
                 raise ValueError("conv3d_k3: stats must be a contiguous [parts, 2, nout] fp64 tensor")
             _lib.call("icsg3d_conv3d_k3_igemm_stats", _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt,
                       n_store, B, D, H, W, cin, nout, act, alpha, _ptr(stats), stats.shape[0], _stream())
+        elif ws is not None and wpack.shape[0] == 27:
+            _lib.call("icsg3d_conv3d_k3_igemm_ws", _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt, n_store,
+                      B, D, H, W, cin, nout, act, alpha, _ptr(ws), ctypes.c_int64(ws.numel() * ws.element_size()), _stream())
         else:
             fn = "icsg3d_conv3d_k1_igemm" if wpack.shape[0] == 1 else "icsg3d_conv3d_k3_igemm"
             _lib.call(fn, _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt, n_store, B, D, H, W, cin, nout,

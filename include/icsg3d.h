@@ -69,6 +69,14 @@ int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const floa
                            int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                            float leaky_alpha, void* stream);
 
+/* Same conv with a caller-owned fp32 workspace: layers with too few output tiles to fill the GPU (4^3 / 2^3 grids with a
+ * deep K = 27*Cin) run with the K range split over several CTAs and a fixed-order reduction (deterministic).
+ * icsg3d_conv3d_k3_workspace_bytes() = bytes needed for this shape (0: the layer is not split; ws may then be NULL). */
+int64_t icsg3d_conv3d_k3_workspace_bytes(int B, int D, int H, int W, int cin, int nout);
+int icsg3d_conv3d_k3_igemm_ws(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                              int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                              float leaky_alpha, void* ws, int64_t ws_bytes, void* stream);
+
 /* Conv3D + BiasAdd(+activation) that also emits the BatchNorm statistics of its own (stored, bf16-rounded) output from the
  * epilogue — replaces a separate icsg3d_bn_stats read pass for the BatchNormalization() that follows the conv
  * (lattice_vae.py:174,214; unet.py:278).  stats: fp64 [parts][2][nout] (sum, sum of squares per channel), the layout of

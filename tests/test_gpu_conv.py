@@ -161,3 +161,26 @@ def test_fused_conv_bn_statistics_match_stored_output(B, D, cin, cout, act):
     got = part.sum(0)
     assert torch.allclose(got[0], yd.sum(0), rtol=1e-5, atol=1e-3 * yd.abs().sum(0).max().item() * 1e-3)
     assert torch.allclose(got[1], (yd * yd).sum(0), rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,D,cin,cout,act", [(4, 4, 256, 512, 1), (8, 2, 128, 16, 2), (32, 4, 512, 512, 1), (32, 4, 64, 128, 0),
+                                              (3, 4, 16, 128, 0)])
+def test_split_k_per_tap_kernel_matches_unsplit(B, D, cin, cout, act):
+    """icsg3d_conv3d_k3_igemm_ws: the 4^3 / 2^3 layers with the K range (taps x channel chunks) split over several CTAs
+    and a fixed-order fp32 reduction == the unsplit kernel (fp32 output: accumulation order only) and deterministic."""
+    from icsg3d_b200 import ops
+    x, w, b = _mk(B, D, cin, cout, seed=31)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    wp = ops.pack_conv_w_fprop(wd)
+    need = ops.conv3d_k3_workspace_bytes(B, D, cin, cout)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+    y0 = ops.conv3d_k3(xd, wp, bd, act=act, out_dtype=torch.float32)
+    y1 = ops.conv3d_k3(xd, wp, bd, act=act, out_dtype=torch.float32, ws=ws)
+    y2 = ops.conv3d_k3(xd, wp, bd, act=act, out_dtype=torch.float32, ws=ws)
+    yb = ops.conv3d_k3(xd, wp, bd, act=act, ws=ws)
+    torch.cuda.synchronize()
+    assert rel_l2(y1, y0) < 2e-5
+    assert torch.equal(y1, y2)
+    assert rel_l2(yb.float(), y0) < 1e-2
+    if (B, D) == (32, 4):
+        assert need > 0, "the 4^3 layers at batch 32 must be split"

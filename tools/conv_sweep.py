@@ -15,7 +15,8 @@ SHAPES = [("c1.f", 32, 32, 16, 32), ("c1.d", 32, 32, 32, 16), ("c2.f", 32, 32, 3
           ("enc1.f/out", 32, 32, 16, 16), ("dec4.f", 32, 32, 32, 16), ("c3", 32, 16, 64, 64), ("c4.f", 32, 16, 64, 128),
           ("c4.d", 32, 16, 128, 64), ("dec3.f", 32, 16, 64, 32), ("dec3.d", 32, 16, 32, 64), ("enc2.f", 32, 16, 16, 32),
           ("c5", 32, 8, 128, 128), ("c6.f", 32, 8, 128, 256), ("c6.d", 32, 8, 256, 128), ("c9.f", 32, 4, 256, 512),
-          ("c9.d", 32, 4, 512, 256), ("c10", 32, 4, 512, 512)]
+          ("c9.d", 32, 4, 512, 256), ("c10", 32, 4, 512, 512), ("enc4.f", 32, 4, 64, 128), ("enc4.d", 32, 4, 128, 64),
+          ("enc5.f", 32, 2, 128, 16), ("dec1.f", 32, 4, 16, 128), ("dec2.f", 32, 8, 128, 64)]
 res = []
 for name, B, D, cin, cout in SHAPES:
     x = torch.randn(B, D, D, D, cin, device="cuda").to(torch.bfloat16)
@@ -23,16 +24,17 @@ for name, B, D, cin, cout in SHAPES:
     wp = ops.pack_conv_w_fprop(w)
     bias = torch.zeros(cout, device="cuda")
     y = torch.empty(B, D, D, D, cout, dtype=torch.bfloat16, device="cuda")
+    ws = torch.empty(max(ops.conv3d_k3_workspace_bytes(B, D, cin, cout), 16), dtype=torch.uint8, device="cuda")
     row = {"layer": name, "B": B, "D": D, "cin": cin, "cout": cout}
     for impl in impls:
         _lib.call("icsg3d_conv3d_set_impl", impl)
         for _ in range(2):
-            ops.conv3d_k3(x, wp, bias, act=ops.ACT_RELU, out=y)
+            ops.conv3d_k3(x, wp, bias, act=ops.ACT_RELU, out=y, ws=ws)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
-            ops.conv3d_k3(x, wp, bias, act=ops.ACT_RELU, out=y)
+            ops.conv3d_k3(x, wp, bias, act=ops.ACT_RELU, out=y, ws=ws)
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / iters * 1e3

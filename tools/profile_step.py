@@ -26,6 +26,7 @@ _lib.PROFILE = []
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
+    torch.cuda._sleep(40_000_000)  # queue the whole (CPU-launch-bound) eager step behind a spin: events bracket kernels only
     eng._train_body()
 e1.record()
 torch.cuda.synchronize()
