@@ -31,7 +31,8 @@ namespace icsg3d {
 // measured: one issuing thread sustains only ~100-150 cycles per tcgen05.mma because of its own uniform-register
 // dependency chains, vs a 55-cycle tensor floor at N <= 64 — profiles/r01_halo_pattern_probe.json) | last 4 warps: epilogue
 static constexpr int kHaloIssuers = 3;
-static constexpr int kHaloThreads = (1 + kHaloIssuers + 4) * 32;
+static constexpr int kHaloEpiWarps = 8;  // 2 per TMEM lane quarter: the epilogue is latency bound (TMEM round trips)
+static constexpr int kHaloThreads = (1 + kHaloIssuers + kHaloEpiWarps) * 32;
 static constexpr int kHaloMaxG = 32;
 static constexpr int kHaloMaxBStages = 8;
 
@@ -47,7 +48,8 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __shared__ float s_bias[512];
   __shared__ uint32_t tmem_base_slot;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: warp-uniform for the compiler, keeps the MMA descriptors in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -80,7 +82,7 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], kHaloIssuers);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], kHaloEpiWarps);
     }
     mbar_init(&b_all_full, 1);
     fence_mbar_init();
@@ -207,8 +209,11 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps: 2 per TMEM lane quarter, the (tile g, 32-column group) items alternate =====
     const int quarter = warp & 3;
+    const int half = (warp - 1 - kHaloIssuers) >> 2;
+    const int ngrp = (p.nt + 31) >> 5;  // 32-column groups per tile (the last one may be 16 wide)
+    const float slope = p.act == ICSG3D_ACT_RELU ? 0.f : (p.act == ICSG3D_ACT_LEAKY ? p.alpha : 1.f);
     int it = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
       int t = item;
@@ -221,7 +226,10 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int set = it & 1;
       mbar_wait(&acc_full[set], static_cast<uint32_t>(it >> 1) & 1u);
       tc_fence_after();
-      for (int g = 0; g < p.G; ++g) {
+      const int nwork = p.G * ngrp;
+      for (int wk = half; wk < nwork; wk += 2) {
+        const int g = wk / ngrp;
+        const int c0 = (wk - g * ngrp) << 5;
         const int f = g * 128 + quarter * 32 + lane;
         const int dl = f / p.plane_rows;
         const int rem = f - dl * p.plane_rows;
@@ -231,54 +239,59 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const bool ok = dl < p.TD && hl < p.TH && wl < p.W && d < p.D;
         const long long pixel = ((static_cast<long long>(n) * p.D + d) * p.H + hb * p.TH + hl) * p.W + wl;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>((set * p.G + g) * p.nt);
-        for (int c0 = 0; c0 < p.nt; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
-          tmem_ld_wait();
-          const int col0 = tn * p.nt + c0;
-          if (!ok || col0 >= p.n_store) continue;
-          float fv[16];
+                               static_cast<uint32_t>((set * p.G + g) * p.nt + c0);
+        const int ncol = min(32, p.nt - c0);
+        uint32_t v[32];
+        if (ncol == 32) {
+          tmem_ld32(taddr, v);
+        } else {
+          uint32_t v16[16];
+          tmem_ld16(taddr, v16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(v[i]) + s_bias[col0 + i];
-            if (p.act == ICSG3D_ACT_RELU) x = fmaxf(x, 0.f);
-            else if (p.act == ICSG3D_ACT_LEAKY) x = x > 0.f ? x : p.alpha * x;
-            fv[i] = x;
-          }
-          const int nvalid = min(16, p.n_store - col0);
-          if (p.y_dtype == ICSG3D_DT_BF16) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + col0;
-            if (nvalid == 16 && (p.ldy & 7) == 0) {
-              uint4 q0, q1;
-              q0.x = pack_bf16x2(fv[0], fv[1]);
-              q0.y = pack_bf16x2(fv[2], fv[3]);
-              q0.z = pack_bf16x2(fv[4], fv[5]);
-              q0.w = pack_bf16x2(fv[6], fv[7]);
-              q1.x = pack_bf16x2(fv[8], fv[9]);
-              q1.y = pack_bf16x2(fv[10], fv[11]);
-              q1.z = pack_bf16x2(fv[12], fv[13]);
-              q1.w = pack_bf16x2(fv[14], fv[15]);
-              reinterpret_cast<uint4*>(dst)[0] = q0;
-              reinterpret_cast<uint4*>(dst)[1] = q1;
-            } else {
+          for (int i = 0; i < 16; ++i) v[i] = v16[i];
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) dst[i] = f2bf(fv[i]);
+          for (int i = 16; i < 32; ++i) v[i] = 0u;
+        }
+        tmem_ld_wait();
+        const int col0 = tn * p.nt + c0;
+        if (!ok || col0 >= p.n_store) continue;
+        float fv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = __uint_as_float(v[i]) + s_bias[(col0 + i) & 511];
+          fv[i] = fmaxf(x, slope * x);
+        }
+        const int nvalid = min(ncol, p.n_store - col0);
+        if (p.y_dtype == ICSG3D_DT_BF16) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + col0;
+          if ((p.ldy & 7) == 0 && (nvalid & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (8 * j < nvalid) {
+                uint4 qv;
+                qv.x = pack_bf16x2(fv[8 * j], fv[8 * j + 1]);
+                qv.y = pack_bf16x2(fv[8 * j + 2], fv[8 * j + 3]);
+                qv.z = pack_bf16x2(fv[8 * j + 4], fv[8 * j + 5]);
+                qv.w = pack_bf16x2(fv[8 * j + 6], fv[8 * j + 7]);
+                reinterpret_cast<uint4*>(dst)[j] = qv;
+              }
             }
           } else {
-            float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + col0;
-            if (nvalid == 16 && (p.ldy & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                reinterpret_cast<float4*>(dst)[i] = make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
-            } else if (nvalid == 4 && (p.ldy & 3) == 0) {
-              reinterpret_cast<float4*>(dst)[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
-            } else {
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) dst[i] = f2bf(fv[i]);
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + col0;
+          if ((p.ldy & 3) == 0 && (nvalid & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) dst[i] = fv[i];
-            }
+            for (int j = 0; j < 8; ++j)
+              if (4 * j < nvalid)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(fv[4 * j], fv[4 * j + 1], fv[4 * j + 2], fv[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) dst[i] = fv[i];
           }
         }
       }
