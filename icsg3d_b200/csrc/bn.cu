@@ -11,6 +11,8 @@
 // Layouts: x, dy are [B,D,H,W,ld] channels-last with C used channels; T = bf16 (C % 8 == 0) or
 // fp32 (C % 4 == 0).  "post" describes what follows BN+activation in the forward graph:
 //   NONE : y has the shape of x;  POOL2 : y is [B,D/2,H/2,W/2,C] (+ uint8 argmax);  UP2 : y is [B,2D,2H,2W,C].
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace icsg3d {
@@ -590,7 +592,7 @@ __device__ __forceinline__ void g_from(const float (&xv)[V], const float (&dyv)[
 }
 
 template <typename T, bool kApply>
-__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_kernel(const BnBwdParams p) {
+__device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p) {
   // HBM-bound: every thread keeps 4 independent rows (x, dy, optional skip gradient / tap) in flight before it
   // touches any of them (load phase, then compute phase), ~8-12 x 16 B per thread.
   constexpr int V = VecIO<T>::N;
@@ -803,6 +805,136 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_kernel(const BnBwdParams
       }
     }
   }
+}
+
+template <typename T, bool kApply>
+__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_kernel(const BnBwdParams p) {
+  bn_bwd_body<T, kApply>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole BatchNorm backward of one layer in ONE cooperative launch (grid = co-resident blocks):
+//   phase A  sum g, sum g*xhat partials per block        (reads dy, x)
+//   grid sync
+//   phase B  blocks 0..C/8-1 reduce the partials of 8 channels each in a fixed order, [data parallel: exchange the 16
+//            sums with the other ranks over NVLink peer memory, as bn_reduce_allreduce_kernel], write the sums and the
+//            LOCAL dgamma / dbeta
+//   grid sync
+//   phase C  dx                                          (re-reads dy, x: from L2 when the layer fits)
+// Replaces bn_bwd_reduce + bn_reduce_grads (or bn_reduce_allreduce_grads) + bn_bwd_apply: two launches fewer per layer and
+// the second read of the <= 100 MB layers comes out of the 126 MB L2 instead of HBM.
+// ------------------------------------------------------------------------------------------------
+struct BnFusedExtra {
+  double* sums;   // [2][C] global sums (written in phase B, read in phase C)
+  float* dgamma;
+  float* dbeta;
+  BnPeerParams pp;  // world == 1: no exchange
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams p, const BnFusedExtra e) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  bn_bwd_body<T, false>(p);
+  __threadfence();
+  grid.sync();
+  {
+    __shared__ double red[16][17];
+    __shared__ double tot[16];
+    const int nblk = (p.C + kRedCh - 1) / kRedCh;
+    if (static_cast<int>(blockIdx.x) < nblk) {
+      const int col = threadIdx.x & 15;  // 0..7 sum g, 8..15 sum g*xhat
+      const int slot = threadIdx.x >> 4;  // 16 slots
+      const int c = blockIdx.x * kRedCh + (col & 7);
+      const int gcol = (col >> 3) * p.C + c;
+      const size_t C2 = 2 * static_cast<size_t>(p.C);
+      const int nparts = gridDim.x;
+      double a0 = 0.0, a1 = 0.0;
+      if (c < p.C) {
+        int q = slot;
+        for (; q + 16 < nparts; q += 32) {
+          a0 += p.partials[static_cast<size_t>(q) * C2 + gcol];
+          a1 += p.partials[static_cast<size_t>(q + 16) * C2 + gcol];
+        }
+        if (q < nparts) a0 += p.partials[static_cast<size_t>(q) * C2 + gcol];
+      }
+      red[slot][col] = a0 + a1;
+      __syncthreads();
+      if (threadIdx.x < 16) {
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          t0 += red[i][threadIdx.x];
+          t1 += red[i + 1][threadIdx.x];
+        }
+        tot[threadIdx.x] = t0 + t1;
+      }
+      __syncthreads();
+      const BnPeerParams& pp = e.pp;
+      if (pp.world > 1) {
+        const unsigned long long epoch = static_cast<unsigned long long>(*pp.epoch);
+        const int par = static_cast<int>(epoch & 1ull);
+        const size_t flags_bytes = static_cast<size_t>(pp.nslots) * 2 * pp.world * 64 * sizeof(unsigned long long);
+        const size_t slot_idx = static_cast<size_t>(pp.slot) * 2 + par;
+        if (threadIdx.x < 16) {
+          const int cc = blockIdx.x * kRedCh + (threadIdx.x & 7);
+          if (cc < p.C) {
+            for (int r = 0; r < pp.world; ++r) {
+              double* data = reinterpret_cast<double*>(pp.peers[r] + flags_bytes) +
+                             (slot_idx * pp.world + pp.rank) * (2 * static_cast<size_t>(pp.cmax));
+              data[(threadIdx.x >> 3) * pp.cmax + cc] = tot[threadIdx.x];
+            }
+          }
+          __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x < pp.world) {
+          const int r = threadIdx.x;
+          unsigned long long* rflag = reinterpret_cast<unsigned long long*>(pp.peers[r]) +
+                                      (slot_idx * pp.world + pp.rank) * 64 + blockIdx.x;
+          st_release_sys_u64(rflag, epoch);
+          const unsigned long long* lflag = reinterpret_cast<const unsigned long long*>(pp.peers[pp.rank]) +
+                                            (slot_idx * pp.world + r) * 64 + blockIdx.x;
+          const long long t_start = clock64();
+          while (ld_acquire_sys_u64(lflag) != epoch) {
+            if (clock64() - t_start > 8000000000ll) {
+              printf("icsg3d: bn backward all-reduce timeout rank %d slot %d block %d waiting for rank %d\n", pp.rank, pp.slot,
+                     blockIdx.x, r);
+              __trap();
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x < kRedCh) {
+        const int cc = blockIdx.x * kRedCh + threadIdx.x;
+        if (cc < p.C) {
+          double s0 = tot[threadIdx.x], s1 = tot[kRedCh + threadIdx.x];
+          if (e.dbeta) e.dbeta[cc] = static_cast<float>(s0);
+          if (e.dgamma) e.dgamma[cc] = static_cast<float>(s1);
+          if (pp.world > 1) {
+            const size_t flags_bytes = static_cast<size_t>(pp.nslots) * 2 * pp.world * 64 * sizeof(unsigned long long);
+            const unsigned long long epoch = static_cast<unsigned long long>(*pp.epoch);
+            const size_t slot_idx = static_cast<size_t>(pp.slot) * 2 + (epoch & 1ull);
+            const double* mine = reinterpret_cast<const double*>(pp.peers[pp.rank] + flags_bytes) +
+                                 slot_idx * pp.world * (2 * static_cast<size_t>(pp.cmax));
+            s0 = 0.0;
+            s1 = 0.0;
+            for (int r = 0; r < pp.world; ++r) {
+              const volatile double* d = mine + static_cast<size_t>(r) * 2 * pp.cmax;
+              s0 += d[cc];
+              s1 += d[pp.cmax + cc];
+            }
+          }
+          e.sums[cc] = s0;
+          e.sums[p.C + cc] = s1;
+        }
+      }
+    }
+  }
+  __threadfence();
+  grid.sync();
+  p.sums = e.sums;
+  bn_bwd_body<T, true>(p);
 }
 
 // dgamma = sum g*xhat, dbeta = sum g  (fp64 sums -> fp32 gradient slots)
@@ -1054,5 +1186,65 @@ extern "C" int icsg3d_bn_reduce_allreduce_grads(const double* partials, int npar
       partials, nparts, C, 1, 1.0, nullptr, nullptr, 0.f, sums_global, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f,
       dgamma, dbeta, pp);
   ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+
+// Whole BatchNorm backward in one cooperative launch (see bn_bwd_fused_kernel).  partials: scratch for at least
+// icsg3d_bn_bwd_fused_nparts() x 2C doubles.  peers == NULL (world 1): single device.
+extern "C" int icsg3d_bn_bwd_fused_nparts(int C, int dtype) {
+  if (!bn_shape_ok(C, dtype)) return -1;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  return 2 * sms;  // upper bound of the co-resident grid (2 blocks of 256 threads per SM)
+}
+
+extern "C" int icsg3d_bn_bwd_fused(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype,
+                                   const float* mean, const float* rstd, const float* scale, const float* shift, int act,
+                                   float alpha, int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C,
+                                   double* partials, double* sums, double count_global, float* dgamma, float* dbeta, int pre_relu,
+                                   const void* tap_other, int ld_other, float tap_coef, void* dx, int lddx,
+                                   const uint64_t* peers, int world, int rank, int slot, int nslots, int cmax,
+                                   const int64_t* epoch, void* stream) {
+  ICSG_REQUIRE(dy && x && mean && rstd && scale && shift && partials && sums && dx && count_global > 0, "bn_bwd_fused: null pointer");
+  ICSG_REQUIRE(bn_shape_ok(C, dtype), "bn_bwd_fused: unsupported C=%d for dtype %d", C, dtype);
+  const int V = dtype == ICSG3D_DT_BF16 ? 8 : 4;
+  ICSG_REQUIRE(ldx % V == 0 && lddy % V == 0 && (!dy2 || lddy2 % V == 0) && lddx % 4 == 0, "bn_bwd_fused: bad leading dimension");
+  ICSG_REQUIRE(post != ICSG3D_POST_POOL2 || pool_idx, "bn_bwd_fused: pool needs pool_idx");
+  ICSG_REQUIRE(!tap_other || dtype == ICSG3D_DT_BF16, "bn_bwd_fused: tap gradient needs bf16 activations");
+  BnBwdParams p{};
+  p.dy = dy; p.lddy = lddy; p.dy2 = dy2; p.lddy2 = lddy2; p.x = x; p.ldx = ldx; p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
+  p.act = act; p.alpha = alpha; p.post = post; p.pool_idx = pool_idx; p.B = B; p.D = D; p.H = H; p.W = W; p.C = C;
+  p.partials = partials; p.sums = sums; p.count = count_global; p.pre_relu = pre_relu;
+  p.tap_other = static_cast<const __nv_bfloat16*>(tap_other); p.ld_other = ld_other; p.tap_coef = tap_coef;
+  p.dx = static_cast<__nv_bfloat16*>(dx); p.lddx = lddx;
+  BnFusedExtra e{};
+  e.sums = sums; e.dgamma = dgamma; e.dbeta = dbeta;
+  e.pp = BnPeerParams{reinterpret_cast<const unsigned long long*>(peers), peers ? world : 1, rank, slot, nslots, cmax,
+                      reinterpret_cast<const long long*>(epoch)};
+  if (peers) {
+    int rc = bn_peer_check(peers, world, rank, slot, nslots, cmax, epoch, C);
+    if (rc) return rc;
+  }
+  const size_t smem = bn_red_smem(C, V);
+  const void* fn = dtype == ICSG3D_DT_BF16 ? reinterpret_cast<const void*>(bn_bwd_fused_kernel<__nv_bfloat16>)
+                                           : reinterpret_cast<const void*>(bn_bwd_fused_kernel<float>);
+  if (smem > 48 * 1024) ICSG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  int occ = 0;
+  ICSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBnThreads, smem));
+  ICSG_REQUIRE(occ >= 1, "bn_bwd_fused: kernel does not fit an SM");
+  if (occ > 2) occ = 2;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  long long rows = static_cast<long long>(B) * D * H * W;
+  if (post == ICSG3D_POST_POOL2) rows /= 8;
+  int grid = bn_grid(rows, C, V);
+  if (grid > occ * sms) grid = occ * sms;
+  const int nblk = ceil_div(C, kRedCh);
+  if (grid < nblk) grid = nblk;  // phase B needs one block per 8 channels
+  ICSG_REQUIRE(grid <= occ * sms, "bn_bwd_fused: C=%d needs more reduction blocks than can be co-resident", C);
+  void* args[] = {&p, &e};
+  ICSG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBnThreads), args, smem, static_cast<cudaStream_t>(stream)));
+  ++g_launches;
   return ICSG3D_OK;
 }

@@ -230,6 +230,10 @@ class VAEEngine:
         self._pack_table = None
         self._wg_side = None
         self.overlap_wgrad = self.world == 1 or self.peer is not None  # filter gradients on a side stream, under the BN-backward / dgrad chain
+        # whole BatchNorm backward per layer in one cooperative launch (needs the peer-memory path when data parallel).
+        # Measured slower inside the step (3.59 vs 3.35 ms: the co-resident grid is half as wide and the cooperative launch
+        # does not overlap with the filter-gradient side stream), so it is opt-in: ICSG3D_FUSE_BN_BWD=1.
+        self.fuse_bn_bwd = os.environ.get("ICSG3D_FUSE_BN_BWD", "0") == "1" and (self.world == 1 or self.peer is not None)
         self.fuse_stats = True  # BatchNorm statistics from the conv epilogue where the streaming kernel serves the layer
 
     # ------------------------------------------------------------------------------------------
@@ -295,12 +299,22 @@ class VAEEngine:
 
     def _bn_bwd(self, dy, x, C, st: _BN, act, post, idx, dx, pre_relu=False, tap_other=None, tap_coef=0.0, dgamma=None,
                 dbeta=None):
+        rows = x.numel() // x.shape[-1]
+        if self.fuse_bn_bwd:
+            # one cooperative launch: partial sums -> grid barrier -> fixed-order reduction (+ peer-memory all-reduce in
+            # data-parallel mode) -> grid barrier -> dx; the second read of dy / x comes from L2 where the layer fits
+            n = ops.bn_bwd_fused_nparts(C, x.dtype)
+            part = self.ctx.partials[: n * 2 * C].view(n, 2, C)
+            kw = self.peer.args((id(st), "bwd")) if self.peer is not None else {}
+            ops.bn_bwd_fused(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, part, st.bsums_g,
+                             float(rows * self.world), dx, dgamma=dgamma, dbeta=dbeta, pre_relu=pre_relu, tap_other=tap_other,
+                             tap_coef=tap_coef, **kw)
+            return
         n = ops.bn_bwd_nparts(x, C, post)
         part = self.ctx.partials[: n * 2 * C].view(n, 2, C)
         ops.bn_bwd_reduce(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, part)
         if self.peer is not None:
             ops.bn_reduce_allreduce_grads(part, st.bsums_g, dgamma=dgamma, dbeta=dbeta, **self.peer.args((id(st), "bwd")))
-            rows = x.numel() // x.shape[-1]
             ops.bn_bwd_apply(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, st.bsums_g,
                              float(rows * self.world), dx, pre_relu=pre_relu, tap_other=tap_other, tap_coef=tap_coef)
             return
@@ -310,7 +324,6 @@ class VAEEngine:
             st.bsums_g.copy_(st.bsums)
             self.dist.all_reduce_sum(st.bsums_g)
             sums = st.bsums_g
-        rows = x.numel() // x.shape[-1]
         ops.bn_bwd_apply(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, sums, float(rows * self.world), dx,
                          pre_relu=pre_relu, tap_other=tap_other, tap_coef=tap_coef)
 

@@ -333,6 +333,25 @@ def bn_bwd_apply(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums, 
               tap_coef, _ptr(dx), _ld(dx), _stream())
 
 
+def bn_bwd_fused_nparts(C, dtype):
+    n = _lib.lib().icsg3d_bn_bwd_fused_nparts(C, DT_BF16 if dtype == torch.bfloat16 else DT_F32)
+    if n <= 0:
+        raise _lib.Icsg3dError("bn_bwd_fused_nparts: unsupported shape")
+    return n
+
+
+def bn_bwd_fused(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, partials, sums, count_global, dx, dgamma=None,
+                 dbeta=None, pre_relu=False, tap_other=None, tap_coef=0.0, alpha=LEAKY_ALPHA, dy2=None, peers=None, world=1,
+                 rank=0, slot=0, nslots=1, cmax=0, epoch=None):
+    """Whole BatchNorm backward of one layer in one cooperative launch (reduce -> [peer all-reduce] -> apply)."""
+    B, D, H, W, _ = x.shape
+    _lib.call("icsg3d_bn_bwd_fused", _ptr(dy), _ld(dy), _ptr(dy2), _ld(dy2) if dy2 is not None else 0, _ptr(x), _ld(x), _dt(x),
+              _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), act, alpha, post, _ptr(pool_idx), B, D, H, W, C, _ptr(partials),
+              _ptr(sums), ctypes.c_double(count_global), _ptr(dgamma), _ptr(dbeta), 1 if pre_relu else 0, _ptr(tap_other),
+              tap_other.shape[-1] if tap_other is not None else 0, tap_coef, _ptr(dx), _ld(dx), _ptr(peers), world, rank, slot,
+              nslots, cmax, _ptr(epoch), _stream())
+
+
 def bn_param_grads(sums, dgamma, dbeta):
     C = sums.numel() // 2
     _lib.call("icsg3d_bn_param_grads", _ptr(sums), _ptr(dgamma), _ptr(dbeta), C, _stream())

@@ -188,6 +188,18 @@ int icsg3d_bn_reduce_allreduce_finalize(const double* partials, int nparts, doub
 int icsg3d_bn_reduce_allreduce_grads(const double* partials, int nparts, int C, double* sums_global, float* dgamma,
                                      float* dbeta, const uint64_t* peers, int world, int rank, int slot, int nslots, int cmax,
                                      const int64_t* epoch, void* stream);
+/* The whole BatchNorm backward of one layer (bn_bwd_reduce + bn_reduce_grads / bn_reduce_allreduce_grads + bn_bwd_apply)
+ * in ONE cooperative launch with two grid-wide barriers: two launches fewer and the second read of dy / x comes from L2
+ * for the layers that fit.  partials: scratch of icsg3d_bn_bwd_fused_nparts() x 2C doubles; sums [2][C] receives the
+ * (global) sums; dgamma/dbeta the LOCAL sums.  peers == NULL: single device; otherwise the peer-memory exchange described
+ * above runs between the two barriers (count_global = rows of all ranks). */
+int icsg3d_bn_bwd_fused_nparts(int C, int dtype);
+int icsg3d_bn_bwd_fused(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype,
+                        const float* mean, const float* rstd, const float* scale, const float* shift, int act, float alpha,
+                        int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C, double* partials, double* sums,
+                        double count_global, float* dgamma, float* dbeta, int pre_relu, const void* tap_other, int ld_other,
+                        float tap_coef, void* dx, int lddx, const uint64_t* peers, int world, int rank, int slot, int nslots,
+                        int cmax, const int64_t* epoch, void* stream);
 /* learning phase 0 (predict / test_on_batch): scale/shift from the moving statistics */
 int icsg3d_bn_inference_coeffs(const float* gamma, const float* beta, const float* moving_mean,
                                const float* moving_var, float eps, float* scale, float* shift, int C,

@@ -88,6 +88,20 @@ def test_bn_fwd_bwd(B, D, C, act, post, order):
                      tap_other=tap_other.to(dev) if tap_other is not None else None, tap_coef=tap_coef)
     torch.cuda.synchronize()
     assert rel_l2(dx.float(), dx_ref) < 1e-2
+    # the same backward in ONE cooperative launch (reduce -> grid barrier -> fixed-order sums -> grid barrier -> apply)
+    nf = ops.bn_bwd_fused_nparts(C, torch.bfloat16)
+    fpart = torch.zeros(nf, 2, C, dtype=torch.float64, device=dev)
+    fsums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    dx2 = torch.zeros_like(dx)
+    ops.bn_bwd_fused(dyd, xd, C, mean, rstd, scale, shift, A, P, idx, fpart, fsums, float(rows), dx2, dgamma=dg, dbeta=db,
+                     pre_relu=(order == "unet"), tap_other=tap_other.to(dev) if tap_other is not None else None,
+                     tap_coef=tap_coef)
+    torch.cuda.synchronize()
+    assert rel_l2(dx2.float(), dx_ref) < 1e-2
+    assert torch.allclose(fsums, bsums, rtol=1e-9, atol=1e-9)
+    assert rel_l2(dx2.float(), dx.float()) < 1e-3
+    assert torch.allclose(db.double(), bsums[:C], rtol=1e-5, atol=1e-5) and torch.allclose(dg.double(), bsums[C:], rtol=1e-5, atol=1e-5)
 
 
 def test_bn_fp32_c4():
@@ -123,6 +137,13 @@ def test_bn_fp32_c4():
     assert rel_l2(y32, y_ref) < 1e-5
     assert rel_l2(y16[..., :4].float(), y_ref) < 1e-2 and float(y16[..., 4:].abs().max()) == 0.0
     assert rel_l2(dx[..., :4].float(), dx_ref) < 1e-2
+    nf = ops.bn_bwd_fused_nparts(C, torch.float32)
+    fpart = torch.zeros(nf, 2, C, dtype=torch.float64, device=dev)
+    fsums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    dx2 = torch.zeros_like(dx)
+    ops.bn_bwd_fused(dyd, xd, C, mean, rstd, scale, shift, ops.ACT_RELU, ops.POST_NONE, None, fpart, fsums, float(rows), dx2)
+    torch.cuda.synchronize()
+    assert rel_l2(dx2[..., :4].float(), dx_ref) < 1e-2 and torch.allclose(fsums, bsums, rtol=1e-9, atol=1e-9)
 
 
 def test_peer_memory_allreduce_kernel_two_emulated_ranks():
