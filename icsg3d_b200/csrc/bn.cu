@@ -12,6 +12,7 @@
 // fp32 (C % 4 == 0).  "post" describes what follows BN+activation in the forward graph:
 //   NONE : y has the shape of x;  POOL2 : y is [B,D/2,H/2,W/2,C] (+ uint8 argmax);  UP2 : y is [B,2D,2H,2W,C].
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -430,7 +431,41 @@ struct BnFwdParams {
   float* y32;
   int ldy32;
   uint8_t* pool_idx;  // [B*D/2*H/2*W/2][C]
+  int split_ctot;     // > 0: y is the fp32-class split tensor [rows][3*split_ctot] = [hi | lo | hi] (split3.cu) and this
+  int split_coff;     //      layer's channels start at split_coff inside every part (U-Net skip concatenations)
+  int split_fmt;      // 0: bf16 pairs, 1: IEEE fp16 pairs (raw 2-byte values in the same buffer)
 };
+
+// BN output vector -> y: plain bf16, or the [hi | lo | hi] split of the fp32 value
+template <int V>
+__device__ __forceinline__ void bn_store_out(const BnFwdParams& p, long long row, int c, const float (&v)[V]) {
+  if (p.split_ctot == 0) {
+    store_bf16_vec<V>(p.y + row * p.ldy + c, v);
+    return;
+  }
+  __nv_bfloat16* d = p.y + row * p.ldy + p.split_coff + c;
+  if (p.split_fmt == 0) {
+    float hi[V], lo[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      hi[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+      lo[i] = v[i] - hi[i];
+    }
+    store_bf16_vec<V>(d, hi);
+    store_bf16_vec<V>(d + p.split_ctot, lo);
+    store_bf16_vec<V>(d + 2 * p.split_ctot, hi);
+  } else {
+    unsigned short* u = reinterpret_cast<unsigned short*>(d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const __half h = __float2half_rn(v[i]);
+      const __half l = __float2half_rn(v[i] - __half2float(h));
+      u[i] = __half_as_ushort(h);
+      u[p.split_ctot + i] = __half_as_ushort(l);
+      u[2 * p.split_ctot + i] = __half_as_ushort(h);
+    }
+  }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_kernel(const BnFwdParams p) {
@@ -472,7 +507,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_kernel(const BnFwd
           }
         }
       }
-      store_bf16_vec<V>(p.y + o * p.ldy + g * V, best);
+      bn_store_out<V>(p, o, g * V, best);
       if (p.pool_idx) {
         uint8_t* ip = p.pool_idx + o * p.C + g * V;
         if constexpr (V == 8) {
@@ -510,7 +545,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_kernel(const BnFwd
           VecIO<T>::cvt(raw[j], v);
 #pragma unroll
           for (int i = 0; i < V; ++i) v[i] = act_fwd(fmaf(p.scale[g * V + i], v[i], p.shift[g * V + i]), p.act, p.alpha);
-          if (p.y) store_bf16_vec<V>(p.y + r * p.ldy + g * V, v);
+          if (p.y) bn_store_out<V>(p, r, g * V, v);
           if (p.y32) {
             float* d32 = p.y32 + r * p.ldy32 + g * V;
 #pragma unroll
@@ -540,10 +575,10 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_kernel(const BnFwd
       for (int k = 0; k < 8; ++k) {
         const long long ro = ((static_cast<long long>(n) * 2 * p.D + 2 * d + (k >> 2)) * 2 * p.H + 2 * h + ((k >> 1) & 1)) *
                                  2 * p.W + 2 * w + (k & 1);
-        store_bf16_vec<V>(p.y + ro * p.ldy + g * V, v);
+        bn_store_out<V>(p, ro, g * V, v);
       }
     } else {
-      if (p.y) store_bf16_vec<V>(p.y + r * p.ldy + g * V, v);
+      if (p.y) bn_store_out<V>(p, r, g * V, v);
       if (p.y32) {
         float* d32 = p.y32 + r * p.ldy32 + g * V;
 #pragma unroll
@@ -1025,16 +1060,21 @@ extern "C" int icsg3d_bn_inference_coeffs(const float* gamma, const float* beta,
   return ICSG3D_OK;
 }
 
-extern "C" int icsg3d_bn_apply_fwd(const void* x, int ldx, int x_dtype, const float* scale, const float* shift, int act,
-                                   float alpha, int post, int B, int D, int H, int W, int C, void* y, int ldy,
-                                   float* y32, int ldy32, uint8_t* pool_idx, void* stream) {
+static int bn_apply_fwd_impl(const void* x, int ldx, int x_dtype, const float* scale, const float* shift, int act,
+                             float alpha, int post, int B, int D, int H, int W, int C, void* y, int ldy,
+                             float* y32, int ldy32, uint8_t* pool_idx, int split_ctot, int split_coff, int split_fmt,
+                             void* stream) {
   ICSG_REQUIRE(x && scale && shift && (y || y32), "bn_apply_fwd: null pointer");
   ICSG_REQUIRE(bn_shape_ok(C, x_dtype), "bn_apply_fwd: unsupported C=%d for dtype %d", C, x_dtype);
   const int V = x_dtype == ICSG3D_DT_BF16 ? 8 : 4;
   ICSG_REQUIRE(ldx % V == 0 && (!y || ldy % V == 0), "bn_apply_fwd: ld must be a multiple of the vector width %d", V);
   ICSG_REQUIRE(post == ICSG3D_POST_NONE || y, "bn_apply_fwd: pool/upsample need the bf16 output");
   ICSG_REQUIRE(post != ICSG3D_POST_POOL2 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "bn_apply_fwd: odd extent for pool");
-  BnFwdParams p{x, ldx, scale, shift, act, alpha, post, B, D, H, W, C, static_cast<__nv_bfloat16*>(y), ldy, y32, ldy32, pool_idx};
+  ICSG_REQUIRE(split_ctot == 0 || (y && split_coff >= 0 && split_coff + C <= split_ctot && ldy >= 3 * split_ctot &&
+                                   split_ctot % V == 0 && split_coff % V == 0),
+               "bn_apply_fwd: bad split3 layout (ctot %d, coff %d, C %d, ldy %d)", split_ctot, split_coff, C, ldy);
+  BnFwdParams p{x, ldx, scale, shift, act, alpha, post, B, D, H, W, C, static_cast<__nv_bfloat16*>(y), ldy, y32, ldy32, pool_idx,
+                split_ctot, split_coff, split_fmt};
   long long items = static_cast<long long>(B) * D * H * W * (C / V);
   if (post == ICSG3D_POST_POOL2) items /= 8;
   long long blocks = (items + kBnThreads - 1) / kBnThreads;
@@ -1047,6 +1087,21 @@ extern "C" int icsg3d_bn_apply_fwd(const void* x, int ldx, int x_dtype, const fl
   else bn_apply_fwd_kernel<float><<<static_cast<int>(blocks), kBnThreads, 0, st>>>(p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_bn_apply_fwd(const void* x, int ldx, int x_dtype, const float* scale, const float* shift, int act,
+                                   float alpha, int post, int B, int D, int H, int W, int C, void* y, int ldy,
+                                   float* y32, int ldy32, uint8_t* pool_idx, void* stream) {
+  return bn_apply_fwd_impl(x, ldx, x_dtype, scale, shift, act, alpha, post, B, D, H, W, C, y, ldy, y32, ldy32, pool_idx, 0, 0, 0,
+                           stream);
+}
+
+extern "C" int icsg3d_bn_apply_fwd_split3(const void* x, int ldx, int x_dtype, const float* scale, const float* shift, int act,
+                                          float alpha, int post, int B, int D, int H, int W, int C, void* y, int ldy,
+                                          uint8_t* pool_idx, int ctot, int coff, int fmt, void* stream) {
+  ICSG_REQUIRE(ctot > 0 && (fmt == 0 || fmt == 1), "bn_apply_fwd_split3: bad ctot / fmt");
+  return bn_apply_fwd_impl(x, ldx, x_dtype, scale, shift, act, alpha, post, B, D, H, W, C, y, ldy, nullptr, 0, pool_idx, ctot,
+                           coff, fmt, stream);
 }
 
 static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype, const float* mean,

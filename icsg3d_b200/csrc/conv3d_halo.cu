@@ -258,7 +258,7 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         float fv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float x = __uint_as_float(v[i]) + s_bias[(col0 + i) & 511];
+          const float x = fmaf(__uint_as_float(v[i]), p.oscale, s_bias[(col0 + i) & 511]);
           fv[i] = fmaxf(x, slope * x);
         }
         const int nvalid = min(ncol, p.n_store - col0);
@@ -394,7 +394,8 @@ bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, Conv
 }
 
 int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
-                     int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st) {
+                     int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st,
+                     float oscale) {
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
@@ -414,6 +415,7 @@ int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bia
     if (rc) return rc;
   }
   p.y = y; p.ldy = ldy; p.y_dtype = y_dtype; p.n_store = n_store; p.bias = bias; p.act = act; p.alpha = alpha;
+  p.oscale = oscale;
   static bool configured = false;
   if (!configured) {
     ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

@@ -20,11 +20,13 @@ struct ConvHaloParams {
   const float* bias;
   int act;
   float alpha;
+  float oscale;  // output = accumulator * oscale + bias (1 unless the weights were pre-scaled: fp16 split mode)
 };
 
 // Pick (TD, TH, NT) from a simple cycle model; false when the layer shape does not fit the halo scheme.
 bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvHaloParams* out);
 int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
-                     int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st);
+                     int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st,
+                     float oscale = 1.0f);
 
 }  // namespace icsg3d

@@ -48,6 +48,7 @@ struct ConvIgemmParams {
   const float* bias;
   int act;
   float alpha;
+  float oscale;  // output = accumulator * oscale + bias (1 unless the weights were pre-scaled: fp16 split mode)
 };
 
 static constexpr int kConvThreads = 192;
@@ -213,7 +214,7 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float x = __uint_as_float(v[i]);
+          float x = __uint_as_float(v[i]) * p.oscale;
           if (p.bias != nullptr) x += __ldg(p.bias + col0 + i);
           if (p.act == ICSG3D_ACT_RELU) {
             x = fmaxf(x, 0.f);
@@ -270,7 +271,8 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 // y[pixel][c] = act(sum over K slices of ws[ks][pixel][c] + bias[c]), fixed slice order (deterministic)
 __global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, long long m_total,
                                                                  int ncols, const float* __restrict__ bias, int act, float alpha,
-                                                                 void* __restrict__ y, int ldy, int y_dtype, int n_store) {
+                                                                 void* __restrict__ y, int ldy, int y_dtype, int n_store,
+                                                                 float oscale) {
   const int c4 = ncols >> 2;
   const long long total = m_total * c4;
   const size_t slice = static_cast<size_t>(m_total) * ncols;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const float* __
     float o[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float x = o[i] + (bias ? bias[c + i] : 0.f);
+      float x = o[i] * oscale + (bias ? bias[c + i] : 0.f);
       if (act == ICSG3D_ACT_RELU) x = fmaxf(x, 0.f);
       else if (act == ICSG3D_ACT_LEAKY) x = x > 0.f ? x : alpha * x;
       o[i] = x;
@@ -391,7 +393,10 @@ static void igemm_tiling(int tiles_m, int nout, int iters, int sms, bool allow_s
 static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                              int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                              float leaky_alpha, void* stream, double* stats = nullptr, int stats_parts = 0,
-                             void* ws = nullptr, int64_t ws_bytes = 0) {
+                             void* ws = nullptr, int64_t ws_bytes = 0, bool op_f16 = false, float oscale = 1.0f) {
+  // op_f16: the 2-byte operands are IEEE fp16 instead of bf16 (fp32-class split mode): same kernels and layouts, only
+  // the a/b format fields (bits 7..9 / 10..12) of the tcgen05 instruction descriptor change from BF16 (1) to F16 (0)
+  const uint32_t fmt_mask = op_f16 ? ~((7u << 7) | (7u << 10)) : ~0u;
   ICSG_REQUIRE(x && wpack && y, "conv3d_k3_igemm: null pointer");
   ICSG_REQUIRE(B > 0 && is_pow2(D) && is_pow2(H) && is_pow2(W) && D >= 2 && H >= 2 && W >= 2 && W <= 128,
                "conv3d_k3_igemm: D,H,W must be powers of two in [2,128] (got %d %d %d)", D, H, W);
@@ -411,14 +416,17 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
     if (ntaps == 27 && sms0 > 0 && conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms0, &sp)) {
       ICSG_REQUIRE(!stats || stats_parts == conv_stream_grid(sp), "conv3d_k3_igemm_stats: stats_parts %d != %d", stats_parts,
                    conv_stream_grid(sp));
+      for (int i = 0; i < 3; ++i) sp.idesc[i] &= fmt_mask;
       return launch_conv_stream(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, stats, sp,
-                                static_cast<cudaStream_t>(stream));
+                                static_cast<cudaStream_t>(stream), oscale);
     }
     ICSG_REQUIRE(!stats, "conv3d_k3_igemm_stats: this layer shape has no fused-statistics path (stats_parts() == 0)");
     ConvHaloParams hp;
-    if (ntaps == 27 && sms0 > 0 && conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp))
+    if (ntaps == 27 && sms0 > 0 && conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp)) {
+      hp.idesc &= fmt_mask;
       return launch_conv_halo(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, hp, sms0,
-                              static_cast<cudaStream_t>(stream));
+                              static_cast<cudaStream_t>(stream), oscale);
+    }
   }
   ConvIgemmParams p{};
   p.m_total = static_cast<int>(m_total);
@@ -456,7 +464,7 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   p.stages = stages;
   p.sbo = 8u * p.kc * 2u;
   p.layout = umma_layout_for_swizzle(p.kc * 2);
-  p.idesc = umma_idesc_bf16(nt, 0, 0);
+  p.idesc = umma_idesc_bf16(nt, 0, 0) & fmt_mask;
   uint32_t cols = 32;
   while (cols < 2u * nt) cols <<= 1;
   p.tmem_cols = cols;
@@ -467,6 +475,7 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   p.bias = bias;
   p.act = act;
   p.alpha = leaky_alpha;
+  p.oscale = oscale;
 
   CUtensorMap tmA, tmB;
   int rc = encode_act_map(&tmA, x, ldx, B, D, H, W, cin, p.kc);
@@ -499,7 +508,7 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
     long long blocks = (items + 255) / 256;
     if (blocks > sms * 8) blocks = sms * 8;
     conv_splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(p.ws, p.ksplit, m_total, nout, bias, act, leaky_alpha, y,
-                                                                      ldy, y_dtype, n_store);
+                                                                      ldy, y_dtype, n_store, oscale);
     ICSG_CHECK_LAUNCH();
   }
   return ICSG3D_OK;
@@ -534,6 +543,21 @@ extern "C" int icsg3d_conv3d_k3_igemm_ws(const void* x, int ldx, const void* wpa
                                          float leaky_alpha, void* ws, int64_t ws_bytes, void* stream) {
   return conv3d_igemm_impl(27, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream,
                            nullptr, 0, ws, ws_bytes);
+}
+
+// fp16 operands (the fp32-class split mode of csrc/split3.cu); same dispatcher, kernels and layouts
+extern "C" int icsg3d_conv3d_k3_igemm_f16(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                                          int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                                          float leaky_alpha, float out_scale, void* stream) {
+  return conv3d_igemm_impl(27, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream,
+                           nullptr, 0, nullptr, 0, true, out_scale);
+}
+
+extern "C" int icsg3d_conv3d_k1_igemm_f16(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                                          int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                                          float leaky_alpha, float out_scale, void* stream) {
+  return conv3d_igemm_impl(1, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream,
+                           nullptr, 0, nullptr, 0, true, out_scale);
 }
 
 extern "C" int icsg3d_conv3d_k3_stats_parts(int B, int D, int H, int W, int cin, int nout) {

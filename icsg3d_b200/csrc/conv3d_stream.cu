@@ -45,8 +45,8 @@ __device__ __forceinline__ void stream_epi_item(const ConvStreamParams& p, uint3
 #pragma unroll
   for (int i = 0; i < NC; i += 4) {
     const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + i]);
-    const float x0 = __uint_as_float(v[i]) + b4.x, x1 = __uint_as_float(v[i + 1]) + b4.y;
-    const float x2 = __uint_as_float(v[i + 2]) + b4.z, x3 = __uint_as_float(v[i + 3]) + b4.w;
+    const float x0 = fmaf(__uint_as_float(v[i]), p.oscale, b4.x), x1 = fmaf(__uint_as_float(v[i + 1]), p.oscale, b4.y);
+    const float x2 = fmaf(__uint_as_float(v[i + 2]), p.oscale, b4.z), x3 = fmaf(__uint_as_float(v[i + 3]), p.oscale, b4.w);
     fv[i] = fmaxf(x0, slope * x0);
     fv[i + 1] = fmaxf(x1, slope * x1);
     fv[i + 2] = fmaxf(x2, slope * x2);
@@ -471,7 +471,7 @@ int conv_stream_grid(const ConvStreamParams& p) { return (p.total_steps + p.step
 
 int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                        int n_store, int cin, int nout, int act, float alpha, double* stats, ConvStreamParams p,
-                       cudaStream_t st) {
+                       cudaStream_t st, float oscale) {
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
@@ -491,6 +491,7 @@ int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* b
   }
   p.y = y; p.ldy = ldy; p.y_dtype = y_dtype; p.n_store = n_store; p.bias = bias; p.act = act; p.alpha = alpha;
   p.stats = stats;
+  p.oscale = oscale;
   static bool configured = false;
   if (!configured) {
     ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));

@@ -22,6 +22,7 @@ struct ConvStreamParams {
   const float* bias;
   int act;
   float alpha;
+  float oscale;  // output = accumulator * oscale + bias (1 unless the weights were pre-scaled: fp16 split mode)
   double* stats;         // optional per-CTA BatchNorm partials [grid][2][C] (sum, sum of squares of the stored values)
 };
 
@@ -30,6 +31,6 @@ bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, Co
 int conv_stream_grid(const ConvStreamParams& p);
 int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                        int n_store, int cin, int nout, int act, float alpha, double* stats, ConvStreamParams p,
-                       cudaStream_t st);
+                       cudaStream_t st, float oscale = 1.0f);
 
 }  // namespace icsg3d

@@ -145,12 +145,13 @@ def conv3d_k3_stats_parts(x, wpack):
 
 
 def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alpha=LEAKY_ALPHA, out=None,
-              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv", stats=None, ws=None):
+              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv", stats=None, ws=None, split=False):
     """x: bf16 [B,D,H,W,ldx]; wpack: bf16 [27][nout][cin]; returns y [B,D,H,W,n_store].
 
     `ref=True` runs the CUDA-core cross-check kernel (fp32 output) instead of the tcgen05 kernel.
     `stats`: fp64 [parts, 2, nout] with parts = conv3d_k3_stats_parts(x, wpack) > 0 — the kernel also writes the
     per-CTA BatchNorm partials (sum, sum of squares) of the stored output.
+    `split=True`: x / wpack are fp32-class split operands (pack_conv_w_fprop_x3 etc.) in the format ops.SPLIT_FMT.
     `ws`: optional scratch tensor (any dtype, one per stream): layers with too few tiles (4^3 / 2^3 grids) split K over it.
     """
     _chk(x, torch.bfloat16, "x")
@@ -181,7 +182,11 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
         _lib.lib().icsg3d_conv3d_k3_plan(B, D, H, W, cin, nout, 148, plan)
         kind = ("pertap", "halo", "stream")[plan[0]]
     with _timed((kind, tag), 2.0 * B * D * H * W * wpack.shape[0] * nc * no):
-        if stats is not None:
+        if split and SPLIT_FMT == 1:
+            fn = "icsg3d_conv3d_k1_igemm_f16" if wpack.shape[0] == 1 else "icsg3d_conv3d_k3_igemm_f16"
+            _lib.call(fn, _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt, n_store, B, D, H, W, cin, nout,
+                      act, alpha, 1.0 / SPLIT_WSCALE, _stream())
+        elif stats is not None:
             _chk(stats, torch.float64, "stats")
             if stats.dim() != 3 or stats.shape[1] != 2 or stats.shape[2] != nout or not stats.is_contiguous():
                 raise ValueError("conv3d_k3: stats must be a contiguous [parts, 2, nout] fp64 tensor")
@@ -306,6 +311,47 @@ def bn_apply_fwd(x, C, scale, shift, act, post, y=None, y32=None, pool_idx=None,
     _lib.call("icsg3d_bn_apply_fwd", _ptr(x), _ld(x), _dt(x), _ptr(scale), _ptr(shift), act, alpha, post, B, D, H, W, C,
               _ptr(y), _ld(y) if y is not None else 0, _ptr(y32), y32.shape[-1] if y32 is not None else 0,
               _ptr(pool_idx), _stream())
+
+
+# ---- fp32-class split operands (csrc/split3.cu) ----
+SPLIT_FMT = 1  # fp32-class split operands: 0 = bf16 pairs, 1 = IEEE fp16 pairs (default: 22 significant bits)
+SPLIT_WSCALE = 1024.0  # fp16 pairs: weights are packed x 2^10 (their lo parts stay normal numbers), the conv output x 2^-10
+
+
+def f32_to_split3(src, c, dst, ctot, coff=0):
+    """src fp32 [..., ld] (first c channels) -> dst bf16 [..., 3*ctot] parts [hi | lo | hi] at channel offset coff."""
+    rows = src.numel() // src.shape[-1]
+    _lib.call("icsg3d_f32_to_split3", _ptr(src), src.shape[-1], c, ctypes.c_int64(rows), _ptr(dst), ctot, coff, SPLIT_FMT,
+              _stream())
+
+
+def pack_vae_input_split3(m, cond, xe, xp):
+    B = m.shape[0]
+    vox = m.numel() // (B * 4)
+    _lib.call("icsg3d_pack_vae_input_split3", _ptr(m), _ptr(cond), cond.shape[1] if cond is not None else 0, B,
+              ctypes.c_int64(vox), _ptr(xe), _ptr(xp), SPLIT_FMT, _stream())
+
+
+def pack_conv_w_fprop_x3(w, cin_pad=None, cout_pad=None, cin_lead=0, fold=1, fold_c=0, out=None):
+    """w fp32 (kd,kh,kw,Cin,Cout) (or (1,1,1,Cin,Cout)) -> bf16 [taps][cout_pad][3*cin_pad] = [w_hi | w_hi | w_lo]."""
+    _chk(w, torch.float32, "w")
+    ntaps = w.shape[0] * w.shape[1] * w.shape[2]
+    cin, cout = w.shape[3], w.shape[4]
+    if cin_pad is None:
+        cin_pad = pad16(cin if fold <= 1 else cin_lead + fold_c)
+    if cout_pad is None:
+        cout_pad = pad16(cout)
+    if out is None:
+        out = torch.empty((ntaps, cout_pad, 3 * cin_pad), dtype=torch.bfloat16, device=w.device)
+    _lib.call("icsg3d_pack_conv_w_fprop_x3", _ptr(w), _ptr(out), ntaps, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c,
+              SPLIT_FMT, SPLIT_WSCALE if SPLIT_FMT == 1 else 1.0, _stream())
+    return out
+
+
+def bn_apply_fwd_split3(x, C, scale, shift, act, post, y, ctot, coff=0, pool_idx=None, alpha=LEAKY_ALPHA):
+    B, D, H, W, _ = x.shape
+    _lib.call("icsg3d_bn_apply_fwd_split3", _ptr(x), _ld(x), _dt(x), _ptr(scale), _ptr(shift), act, alpha, post, B, D, H, W, C,
+              _ptr(y), _ld(y), _ptr(pool_idx), ctot, coff, SPLIT_FMT, _stream())
 
 
 def bn_bwd_nparts(x, C, post):

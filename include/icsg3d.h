@@ -200,6 +200,31 @@ int icsg3d_bn_bwd_fused(const void* dy, int lddy, const void* dy2, int lddy2, co
                         double count_global, float* dgamma, float* dbeta, int pre_relu, const void* tap_other, int ld_other,
                         float tap_coef, void* dx, int lddx, const uint64_t* peers, int world, int rank, int slot, int nslots,
                         int cmax, const int64_t* epoch, void* stream);
+/* ---- "fp32-class" operand mode (north_star: activations 1e-4, bit-exact argmax) ---------------------------------------
+ * Conv operands are carried as bf16 pairs hi = bf16(v), lo = bf16(v - hi); the ordinary bf16 conv kernels (fp32 output)
+ * compute x_hi*w_hi + x_lo*w_hi + x_hi*w_lo when the activation tensor stores [hi | lo | hi] (3x channels) and the
+ * packed weights [w_hi | w_hi | w_lo] along Cin.  Producers of the split layouts (csrc/split3.cu, bn.cu): */
+/* fmt: 0 = bf16 pairs (16 significant bits), 1 = IEEE fp16 pairs (22 bits: fp32 class; the 2-byte values live in the
+ * same buffers and the conv is told through icsg3d_conv3d_k3_igemm_f16 / _k1_igemm_f16 below). */
+int icsg3d_f32_to_split3(const float* src, int ld_src, int c, int64_t rows, void* dst, int ctot, int coff, int fmt,
+                         void* stream);
+int icsg3d_pack_vae_input_split3(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe, void* xp,
+                                 int fmt, void* stream);
+int icsg3d_pack_conv_w_fprop_x3(const float* w, void* wpack, int ntaps, int cin, int cout, int cin_pad, int cout_pad,
+                                int cin_lead, int fold, int fold_c, int fmt, float wscale, void* stream);
+/* The conv dispatcher on fp16 operands (same kernels and layouts; only the tcgen05 operand-format fields differ).
+ * y = accumulator * out_scale + bias: weights packed with wscale = 2^k (lo parts stay normal fp16) use out_scale = 2^-k. */
+int icsg3d_conv3d_k3_igemm_f16(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                               int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                               float leaky_alpha, float out_scale, void* stream);
+int icsg3d_conv3d_k1_igemm_f16(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
+                               int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                               float leaky_alpha, float out_scale, void* stream);
+/* BatchNorm apply (+activation, +pool/upsample) of an fp32 conv output straight into the split tensor y bf16
+ * [rows][3*ctot]; this layer's C channels start at `coff` inside every part (skip concatenations write side by side). */
+int icsg3d_bn_apply_fwd_split3(const void* x, int ldx, int x_dtype, const float* scale, const float* shift, int act,
+                               float alpha, int post, int B, int D, int H, int W, int C, void* y, int ldy,
+                               uint8_t* pool_idx, int ctot, int coff, int fmt, void* stream);
 /* learning phase 0 (predict / test_on_batch): scale/shift from the moving statistics */
 int icsg3d_bn_inference_coeffs(const float* gamma, const float* beta, const float* moving_mean,
                                const float* moving_var, float eps, float* scale, float* shift, int C,
