@@ -414,8 +414,8 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
     const int sms0 = sm_count();
     ConvStreamParams sp;
     if (ntaps == 27 && sms0 > 0 && conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms0, &sp)) {
-      ICSG_REQUIRE(!stats || stats_parts == conv_stream_grid(sp), "conv3d_k3_igemm_stats: stats_parts %d != %d", stats_parts,
-                   conv_stream_grid(sp));
+      ICSG_REQUIRE(!stats || (sp.tiles_n == 1 && stats_parts == conv_stream_grid(sp)),
+                   "conv3d_k3_igemm_stats: stats_parts %d does not match this layer's plan", stats_parts);
       for (int i = 0; i < 3; ++i) sp.idesc[i] &= fmt_mask;
       return launch_conv_stream(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, stats, sp,
                                 static_cast<cudaStream_t>(stream), oscale);
@@ -564,7 +564,7 @@ extern "C" int icsg3d_conv3d_k3_stats_parts(int B, int D, int H, int W, int cin,
   const int sms = sm_count();
   ConvStreamParams sp;
   if (sms <= 0 || conv_impl_choice() != 0 || !conv_stream_plan(B, D, H, W, cin, nout, sms, &sp)) return 0;
-  return conv_stream_grid(sp);
+  return sp.tiles_n == 1 ? conv_stream_grid(sp) : 0;  // fused statistics only for un-split layers
 }
 
 extern "C" int icsg3d_conv3d_k3_igemm_stats(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,

@@ -155,7 +155,8 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     mbar_init(&w_full, 1);
     fence_mbar_init();
   }
-  if (threadIdx.x < 64) s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.C) ? p.bias[threadIdx.x] : 0.f;
+  const int n_off = static_cast<int>(blockIdx.y) * p.C;  // N split: this CTA's slice of the output channels
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.C) ? p.bias[n_off + threadIdx.x] : 0.f;
   if (threadIdx.x < 128) s_stats[threadIdx.x >> 6][threadIdx.x & 63] = 0.0;
   if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
   tc_fence_before();
@@ -174,7 +175,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       for (int khw = 0; khw < 9; ++khw)
         for (int ch = 0; ch < p.chunks; ++ch)
           for (int blk = 0; blk < 3; ++blk)
-            tma_load_3d(sm + static_cast<size_t>((khw * p.chunks + ch) * 3 + blk) * p.blk_bytes, &tmB, &w_full, ch * p.kc, 0,
+            tma_load_3d(sm + static_cast<size_t>((khw * p.chunks + ch) * 3 + blk) * p.blk_bytes, &tmB, &w_full, ch * p.kc, n_off,
                         (2 - blk) * 9 + khw);
     }
     int astep = 0;
@@ -306,7 +307,11 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const bool split_cols = p.C == 64;
     const int c0 = split_cols ? 32 * half : 0;
     const int t_first = split_cols ? 0 : half, t_step = split_cols ? 1 : 2;
-    const bool active = c0 < p.n_store;
+    ConvStreamParams q_ = p;  // this CTA's view of the output: channels [n_off, n_off + C)
+    q_.n_store = p.n_store - n_off;
+    q_.y = static_cast<char*>(p.y) + static_cast<size_t>(n_off) * (p.y_dtype == ICSG3D_DT_BF16 ? 2 : 4);
+    const ConvStreamParams& pe = q_;
+    const bool active = c0 < pe.n_store;
     const float inv_wp = 1.0f / static_cast<float>(p.WP);
     // LeakyReLU / ReLU / identity as max(x, slope * x)
     const float slope = p.act == ICSG3D_ACT_RELU ? 0.f : (p.act == ICSG3D_ACT_LEAKY ? p.alpha : 1.f);
@@ -346,10 +351,10 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>((t * p.R + slot) * p.C + c0);
             if (p.C >= 32) {
-              if (active) stream_epi_item<32>(p, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
+              if (active) stream_epi_item<32>(pe, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
               tmem_st_zero<32>(taddr);
             } else {
-              if (active) stream_epi_item<16>(p, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
+              if (active) stream_epi_item<16>(pe, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
               tmem_st_zero<16>(taddr);
             }
           }
@@ -395,10 +400,15 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 static bool stream_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvStreamParams* out) {
-  if (nout != 16 && nout != 32 && nout != 64) return false;
   if (W < 16 || W > 64 || !stream_pow2(W) || !stream_pow2(H) || !stream_pow2(D) || D < 4) return false;
   if (cin % 16 != 0 || cin > 256) return false;
-  const int C = nout;
+  // channels per CTA (= per kd block): the whole layer when its 27 weight tiles fit in shared memory, else 32-channel
+  // slices (N split over blockIdx.y: the input is streamed once per slice, N = 96 per MMA)
+  int C = 0;
+  if ((nout == 16 || nout == 32 || nout == 64) && 27u * cin * nout * 2u + 64u * 1024u <= 222u * 1024u) C = nout;
+  else if (nout == 64 && cin <= 64 && 27u * cin * 32u * 2u + 64u * 1024u <= 222u * 1024u) C = 32;  // c3; measured: 4 slices
+  // of a 128-wide layer (c4 fprop: 91 us) lose to the halo kernel (81 us), so wider layers stay there
+  if (C == 0) return false;
   const int kc = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
   const int chunks = cin / kc;
   const int row_bytes = kc * 2;
@@ -406,7 +416,6 @@ bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, Co
   const uint32_t budget = 222u * 1024u;
   const uint32_t w_bytes = 27u * static_cast<uint32_t>(cin) * C * 2u;
   const uint32_t w_alloc = (w_bytes + 1023u) & ~1023u;
-  if (w_alloc + 2048u >= budget) return false;
   int Tmax = 512 / (4 * C);
   if (Tmax > 8) Tmax = 8;
   double best = -1.0;
@@ -452,8 +461,9 @@ bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, Co
     }
   }
   if (best < 0.0) return false;
+  bp.tiles_n = nout / C;
   bp.total_steps = B * bp.n_hblk * D;
-  int grid = sms;
+  int grid = sms / bp.tiles_n;
   if (grid > bp.total_steps / 4) grid = bp.total_steps / 4;  // at least ~4 planes per CTA (each cut costs 2 extra plane passes)
   if (grid < 1) grid = 1;
   bp.steps_per_cta = (bp.total_steps + grid - 1) / grid;
@@ -500,7 +510,7 @@ int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* b
     configured = true;
   }
   const size_t smem = ((p.w_bytes + 1023u) & ~1023u) + static_cast<size_t>(p.stages) * p.a_stage_bytes + 1024;
-  const int grid = conv_stream_grid(p);
+  const dim3 grid(conv_stream_grid(p), p.tiles_n);
   if (p.kc == 16) conv3d_k3_stream_kernel<1><<<grid, kStreamThreads, smem, st>>>(tmA, tmB, p);
   else if (p.kc == 32) conv3d_k3_stream_kernel<2><<<grid, kStreamThreads, smem, st>>>(tmA, tmB, p);
   else conv3d_k3_stream_kernel<4><<<grid, kStreamThreads, smem, st>>>(tmA, tmB, p);

@@ -9,6 +9,7 @@ struct ConvStreamParams {
   int B, D, H, W;
   int TH, HP, WP, n_hblk;
   int T, R, C;           // M tiles per plane slab, accumulator ring slots (output planes, power of two), channels per kd block (= nout)
+  int tiles_n;           // N split: blockIdx.y owns output channels [y*C, (y+1)*C) with its own resident weight slice
   int r_log2, st_log2;   // log2(R), log2(stages): ring arithmetic is masks and shifts in the issue loop
   int kc, chunks, row_bytes;
   int stages;            // input-plane ring depth in shared memory (power of two)

@@ -27,9 +27,12 @@ def test_conv_plan_diagnostic_runs_without_gpu():
     impl, R, TH, T, C, stages = out[0], out[1], out[2], out[3], out[4], out[5]
     # c2 (32->64 @32^3): plane-streaming kd-folded kernel; ring slots x tiles x Cout columns must fit TMEM
     assert impl == 2 and C == 64 and R >= 4 and R * T * C <= 512 and T * 128 >= TH * 33 and stages >= 2
-    # a wide layer (64->128 @16^3) stays on the halo-reuse kernel
-    assert _lib.lib().icsg3d_conv3d_k3_plan(32, 16, 16, 16, 64, 128, 148, out) == 0
-    assert out[0] == 1 and out[4] == 128 and 2 * out[3] * out[4] <= 512
+    # 64->64 @16^3 (weights too large to stay resident): the streaming kernel with two 32-channel slices over blockIdx.y
+    assert _lib.lib().icsg3d_conv3d_k3_plan(32, 16, 16, 16, 64, 64, 148, out) == 0
+    assert out[0] == 2 and out[4] == 32
+    # a deep-K layer (128->64 @16^3) stays on the halo-reuse kernel
+    assert _lib.lib().icsg3d_conv3d_k3_plan(32, 16, 16, 16, 128, 64, 148, out) == 0
+    assert out[0] == 1 and out[4] == 64 and 2 * out[3] * out[4] <= 512
     # invalid arguments are reported through the error string, not a crash
     assert _lib.lib().icsg3d_conv3d_k3_plan(32, 32, 32, 32, 32, 64, 0, out) != 0
     assert "plan" in _lib.last_error()
