@@ -158,3 +158,31 @@ def test_graph_replay_equals_eager():
     torch.cuda.synchronize()
     assert torch.allclose(eng.metrics, m_eager, rtol=1e-5, atol=1e-6)
     assert torch.allclose(eng.vp.theta, theta_eager, rtol=1e-4, atol=1e-6)
+
+
+def test_training_curve_tracks_oracle():
+    """Functional check of SURVEY 8c T3: N consecutive train_on_batch steps (forward, backward, Keras-Adam, BatchNorm
+    moving averages) on the CUDA path against the oracle with the same weights, data and eps stream.  Adam normalises the
+    update (|dtheta| ~ lr whatever the gradient scale), so bf16 gradient noise moves the trajectories apart slowly: the loss
+    curves must stay within 1 % over the first steps and the loss must go down."""
+    from oracle import nets
+    eng, M, cond, _, pv, pu = _setup(seed=4)
+    opt = nets.KerasAdam(5e-4)
+    gen = torch.Generator().manual_seed(123)
+    steps = 6
+    got, want = [], []
+    for k in range(steps):
+        eps = torch.randn(M.shape[0], 256, generator=gen)
+        eng.set_inputs(M.cuda(), cond.cuda(), eps.cuda())
+        eng.train_step()
+        got.append(eng.metrics_host())
+        want.append(nets.vae_train_step(pv, pu, opt, M, cond, eps)[0])
+    print("loss curve cuda  ", [round(g[0], 4) for g in got])
+    print("loss curve oracle", [round(w[0], 4) for w in want])
+    for g, w in zip(got, want):
+        assert abs(g[0] - w[0]) <= 1e-2 * abs(w[0]), (got, want)
+        assert abs(g[2] - w[2]) <= 1e-2 * abs(w[2]), (got, want)
+    assert got[-1][0] < got[0][0] and want[-1][0] < want[0][0]
+    # the moving averages of the VAE's BatchNorm layers follow Keras' update (R3) on both sides
+    mm = eng.vp.p["enc_bn1/moving_mean"].cpu()
+    assert rel_l2(mm, pv["enc_bn1/moving_mean"]) < 5e-2  # 6 steps of slowly diverging bf16/fp32 trajectories (measured 2.4e-2)
