@@ -112,3 +112,28 @@ def test_generators_keep_reference_contract(tmp_path):
     X, (y, b) = u[0]
     assert X.shape == (2, d, d, d, 4) and y.shape == (2, d, d, d, 95) and b.shape == (2, d, d, d, 1)
     assert np.array_equal(b[..., 0], (y.argmax(-1) != 0).astype(np.float32))
+
+
+def test_conv_dispatch_plans_respect_hardware_limits():
+    """Host-only sweep of the conv dispatcher's planner (icsg3d_conv3d_k3_plan) over the layer shapes of both networks
+    at several batch sizes / grid edges: every plan must fit TMEM (512 columns), shared memory (227 KB) and the SM count."""
+    from icsg3d_b200 import _lib
+    L = _lib.lib()
+    out = (ctypes.c_int * 10)()
+    shapes = [(16, 16), (16, 32), (32, 16), (32, 64), (64, 32), (64, 64), (64, 128), (128, 64), (128, 128), (128, 256),
+              (256, 128), (256, 512), (512, 512), (48, 16), (96, 64), (192, 128), (768, 512), (384, 256)]
+    seen = set()
+    for B in (1, 2, 8, 32, 128):
+        for D in (4, 8, 16, 32, 64):
+            for cin, cout in shapes:
+                assert L.icsg3d_conv3d_k3_plan(B, D, D, D, cin, cout, 148, out) == 0, _lib.last_error()
+                impl = out[0]
+                seen.add(impl)
+                if impl == 2:  # plane-streaming: {2, R, TH, T, C, stages, issuers, grid, kc, smem}
+                    R, TH, T, C, stages, issuers, grid, kc, smem = (out[i] for i in range(1, 10))
+                    assert R in (4, 8) and R * T * C <= 512 and T * 128 >= TH * (D + 1) and 1 <= issuers <= 3
+                    assert stages in (2, 4) and 1 <= grid <= 148 and smem <= 225 * 1024 and D >= 16 and C in (16, 32, 64)
+                elif impl == 1:  # halo reuse: {1, TD, TH, G, NT, a_bufs, b_stages, items, kc, smem}
+                    TD, TH, G, NT, a_bufs, b_stages, items, kc, smem = (out[i] for i in range(1, 10))
+                    assert 2 * G * NT <= 512 and smem <= 225 * 1024 and D % TH == 0 and items >= 1 and D >= 8
+    assert seen == {0, 1, 2}
