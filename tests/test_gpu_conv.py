@@ -105,7 +105,8 @@ def test_condition_fold_equals_tiled_concat():
     assert rel_l2(dw, wr.grad) < 2e-5
 
 
-@pytest.mark.parametrize("B,D,cin,cout", [(32, 32, 32, 64), (32, 32, 64, 32), (32, 32, 16, 16), (32, 16, 64, 32)])
+@pytest.mark.parametrize("B,D,cin,cout", [(32, 32, 32, 64), (32, 32, 64, 32), (32, 32, 16, 16), (32, 16, 64, 32),
+                                          (32, 16, 64, 64), (2, 64, 32, 64), (1, 64, 16, 32), (16, 64, 16, 16)])
 def test_stream_kernel_full_batch_matches_cuda_core_reference(B, D, cin, cout):
     """Full BASELINE batch: the tcgen05 path (plane-streaming kernel for these shapes) against the CUDA-core
     cross-check kernel on the device (fp32 outputs; same operands, different accumulation order)."""
@@ -122,7 +123,7 @@ def test_stream_kernel_full_batch_matches_cuda_core_reference(B, D, cin, cout):
     assert float((y - yr).abs().max()) < 1e-3
 
 
-@pytest.mark.parametrize("B,D,cin,cout", [(32, 32, 32, 16), (32, 32, 16, 16), (32, 16, 64, 32)])
+@pytest.mark.parametrize("B,D,cin,cout", [(32, 32, 32, 16), (32, 32, 16, 16), (32, 16, 64, 32), (2, 64, 32, 16), (1, 64, 16, 32)])
 def test_wgrad_stream_kernel_full_batch_matches_per_tap_kernel(B, D, cin, cout):
     """Full BASELINE batch: the plane-streaming filter-gradient kernel (kh folded into M, kw into N) against the
     per-tap im2col kernel (independent operand path); both accumulate in fp32 on the tensor cores."""
