@@ -229,7 +229,7 @@ def run_cuda(args):
 
     # ---- roofline pass: per-launch CUDA-event timing of the conv kernels (eager, same stream) ----
     # (every rank executes the pass — the step contains collectives — rank 0 keeps the timings)
-    roof, per_layer = None, None
+    roof, per_layer, roof_hbm = None, None, None
     eng.overlap_pm = eng.overlap_wgrad = False  # one stream: every launch is timed alone
     for _ in range(2):
         eng._train_body()
@@ -263,9 +263,22 @@ def run_cuda(args):
                 by_kernel[kind] = {"kernel": names[kind], "tflops": f / (ms * 1e-3) / 1e12,
                                    "frac_of_peak": f / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
                                    "launches_per_step": n // reps, "ms_per_step": ms / reps, "gflop_per_step": f / reps / 1e9}
-        tot_f = sum(v[0] for v in agg.values())
-        tot_ms = sum(v[1] for v in agg.values())
-        n_all = sum(v[2] for v in agg.values())
+        conv = {k: v for k, v in agg.items() if k[0] in names}
+        tot_f = sum(v[0] for v in conv.values())
+        tot_ms = sum(v[1] for v in conv.values())
+        n_all = sum(v[2] for v in conv.values())
+        # the HBM-bound family: BatchNorm(+activation, +pool/upsample) passes, algorithmic bytes = tensors read + written
+        bn = {k: v for k, v in agg.items() if k[0] == "bn"}
+        bn_b, bn_ms, bn_n = (sum(v[i] for v in bn.values()) for i in range(3))
+        roof_hbm = None
+        if bn_n:
+            gbs = bn_b / (bn_ms * 1e-3) / 1e9
+            roof_hbm = {"bound": "hbm", "kernel": "BatchNorm passes (bn_stats, bn_apply_fwd, bn_bwd reduce/apply) of the step",
+                        "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                        "launches_per_step": bn_n // reps, "kernel_ms_per_step": bn_ms / reps,
+                        "algorithmic_mb_per_step": bn_b / reps / 1e6,
+                        "by_pass": {t: {"GBps": v[0] / (v[1] * 1e-3) / 1e9, "ms_per_step": v[1] / reps, "launches": v[2] // reps}
+                                    for (_, t), v in sorted(bn.items())}}
         achieved = tot_f / (tot_ms * 1e-3) / 1e12
         dom = max(by_kernel, key=lambda k: by_kernel[k]["ms_per_step"])
         roof = {"bound": "tensor",
@@ -277,7 +290,7 @@ def run_cuda(args):
                 "launches_per_step": n_all // reps, "kernel_ms_per_step": tot_ms / reps, "by_kernel": by_kernel,
                 "profile": "profiles/ (ncu --set full of the dominant kernel on c2 32->64 @32^3: dram bytes, tensor-pipe activity)"}
         per_layer = {f"{k}:{t}": {"gflop": v[0] / v[2] / 1e9, "ms": v[1] / v[2], "tflops": v[0] / (v[1] * 1e-3) / 1e12}
-                     for (k, t), v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+                     for (k, t), v in sorted(conv.items(), key=lambda kv: -kv[1][1])}
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "bench_per_layer.json"), "w") as f:
             json.dump({"ms_per_step_graph": ms_step, "per_layer": per_layer}, f, indent=1)
@@ -303,7 +316,7 @@ def run_cuda(args):
             "conv_tflops_whole_step": GFLOP_PER_SAMPLE * value / 1e3,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step * args.steps),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu,
             "loss": {"loss": metrics[0], "pm": metrics[1], "mse": metrics[2], "kld": metrics[3]},
         }
         print(json.dumps(line))

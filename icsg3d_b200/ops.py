@@ -134,6 +134,10 @@ def _timed(tag, flops):
     return _T()
 
 
+def _nbytes(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
 def conv3d_k3_workspace_bytes(B, D, cin, nout):
     return int(_lib.lib().icsg3d_conv3d_k3_workspace_bytes(B, D, D, D, cin, nout))
 
@@ -252,6 +256,11 @@ def bn_nparts(rows, C, dtype):
 
 
 def bn_stats(x, C, partials):
+    with _timed(("bn", "stats"), _nbytes(x)):
+        return _bn_stats(x, C, partials)
+
+
+def _bn_stats(x, C, partials):
     """x: [..., ld]; partials: float64 [nparts, 2, C]."""
     rows = x.numel() // x.shape[-1]
     _lib.call("icsg3d_bn_stats", _ptr(x), _ld(x), _dt(x), ctypes.c_int64(rows), C, _ptr(partials),
@@ -307,6 +316,11 @@ def bn_inference_coeffs(gamma, beta, moving_mean, moving_var, scale, shift, eps=
 
 
 def bn_apply_fwd(x, C, scale, shift, act, post, y=None, y32=None, pool_idx=None, alpha=LEAKY_ALPHA):
+    with _timed(("bn", "apply_fwd"), _nbytes(x, y, y32, pool_idx)):
+        return _bn_apply_fwd(x, C, scale, shift, act, post, y, y32, pool_idx, alpha)
+
+
+def _bn_apply_fwd(x, C, scale, shift, act, post, y=None, y32=None, pool_idx=None, alpha=LEAKY_ALPHA):
     B, D, H, W, _ = x.shape
     _lib.call("icsg3d_bn_apply_fwd", _ptr(x), _ld(x), _dt(x), _ptr(scale), _ptr(shift), act, alpha, post, B, D, H, W, C,
               _ptr(y), _ld(y) if y is not None else 0, _ptr(y32), y32.shape[-1] if y32 is not None else 0,
@@ -363,6 +377,11 @@ def bn_bwd_nparts(x, C, post):
 
 
 def bn_bwd_reduce(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, partials, alpha=LEAKY_ALPHA, dy2=None):
+    with _timed(("bn", "bwd_reduce"), _nbytes(dy, x, pool_idx, dy2)):
+        return _bn_bwd_reduce(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, partials, alpha, dy2)
+
+
+def _bn_bwd_reduce(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, partials, alpha=LEAKY_ALPHA, dy2=None):
     B, D, H, W, _ = x.shape
     ldx = _ld(x)
     _lib.call("icsg3d_bn_bwd_reduce", _ptr(dy), _ld(dy), _ptr(dy2), _ld(dy2) if dy2 is not None else 0, _ptr(x), ldx, _dt(x), _ptr(mean), _ptr(rstd), _ptr(scale),
@@ -371,6 +390,13 @@ def bn_bwd_reduce(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, parti
 
 def bn_bwd_apply(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums, count, dx, pre_relu=False,
                  tap_other=None, tap_coef=0.0, alpha=LEAKY_ALPHA, dy2=None):
+    with _timed(("bn", "bwd_apply"), _nbytes(dy, x, pool_idx, dy2, dx, tap_other)):
+        return _bn_bwd_apply(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums, count, dx, pre_relu, tap_other,
+                             tap_coef, alpha, dy2)
+
+
+def _bn_bwd_apply(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums, count, dx, pre_relu=False,
+                  tap_other=None, tap_coef=0.0, alpha=LEAKY_ALPHA, dy2=None):
     B, D, H, W, _ = x.shape
     ldx = _ld(x)
     _lib.call("icsg3d_bn_bwd_apply", _ptr(dy), _ld(dy), _ptr(dy2), _ld(dy2) if dy2 is not None else 0, _ptr(x), ldx, _dt(x), _ptr(mean), _ptr(rstd), _ptr(scale),
