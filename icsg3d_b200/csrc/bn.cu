@@ -14,6 +14,8 @@
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace icsg3d {
@@ -588,6 +590,69 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_kernel(const BnFwd
   }
 }
 
+// Lean bf16 BN + activation + MaxPool3D(2) forward (plain bf16 output): thread = (window, 8-channel group) with the
+// group fixed per thread (scale / shift live in registers), window coordinates in 32-bit arithmetic, the 8 rows of the
+// window fetched in one batch from one base pointer, activation fixed at compile time.
+template <int kAct>
+__global__ void __launch_bounds__(kBnThreads, 3) bn_apply_fwd_pool_lean_kernel(const BnFwdParams p) {
+  constexpr int V = 8;
+  typedef __nv_bfloat16 T;
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const int cg = p.C / V;
+  const int rpi = kBnThreads / cg;
+  const int g = threadIdx.x % cg;
+  const int rl = threadIdx.x / cg;
+  if (rl >= rpi) return;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sc[i] = p.scale[g * V + i];
+    sh[i] = p.shift[g * V + i];
+  }
+  const float alpha = p.alpha;
+  const uint32_t Do = p.D / 2, Ho = p.H / 2, Wo = p.W / 2;
+  const uint32_t Mo = static_cast<uint32_t>(p.B) * Do * Ho * Wo;
+  const uint32_t stride = gridDim.x * rpi;
+  const long long oW = p.ldx, oH = static_cast<long long>(p.W) * p.ldx, oD = static_cast<long long>(p.H) * p.W * p.ldx;
+  for (uint32_t o = blockIdx.x * rpi + rl; o < Mo; o += stride) {
+    const uint32_t t0 = o / Wo, wo = o - t0 * Wo;
+    const uint32_t t1 = t0 / Ho, ho = t0 - t1 * Ho;
+    const uint32_t n = t1 / Do, dz = t1 - n * Do;
+    const long long rbase = ((static_cast<long long>(n) * p.D + 2 * dz) * p.H + 2 * ho) * p.W + 2 * wo;
+    const T* xb = x + rbase * p.ldx + g * V;
+    uint4 xr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xr[k] = *reinterpret_cast<const uint4*>(xb + (k >> 2) * oD + ((k >> 1) & 1) * oH + (k & 1) * oW);
+    float best[V];
+    uint32_t bi[V];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v[V];
+      VecIO<T>::cvt(xr[k], v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float z = fmaf(sc[i], v[i], sh[i]);
+        if (kAct == ICSG3D_ACT_RELU) z = z > 0.f ? z : 0.f;
+        if (kAct == ICSG3D_ACT_LEAKY) z = z > 0.f ? z : alpha * z;
+        if (k == 0) {
+          best[i] = z;
+          bi[i] = 0;
+        } else if (z > best[i]) {  // strict '>' keeps the FIRST maximum in (d,h,w) scan order
+          best[i] = z;
+          bi[i] = k;
+        }
+      }
+    }
+    VecIO<T>::store(p.y + static_cast<long long>(o) * p.ldy + g * V, best);
+    if (p.pool_idx) {
+      uint2 q;
+      q.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      q.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(p.pool_idx + static_cast<size_t>(o) * p.C + g * V) = q;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
@@ -626,8 +691,10 @@ __device__ __forceinline__ void g_from(const float (&xv)[V], const float (&dyv)[
   for (int i = 0; i < V; ++i) g[i] = dyv[i] * act_grad(fmaf(sc[i], xv[i], sh[i]), act, alpha);
 }
 
-template <typename T, bool kApply>
+template <typename T, bool kApply, int kPost = -1>
 __device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p) {
+  // kPost >= 0 fixes the post-op at compile time (registers are then sized for that path alone), -1 reads p.post
+  const int post = kPost >= 0 ? kPost : p.post;
   // HBM-bound: every thread keeps 4 independent rows (x, dy, optional skip gradient / tap) in flight before it
   // touches any of them (load phase, then compute phase), ~8-12 x 16 B per thread.
   constexpr int V = VecIO<T>::N;
@@ -687,7 +754,7 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p) {
   const T* tap = reinterpret_cast<const T*>(p.tap_other);
 
   if (rl < rpi) {
-    if (p.post == ICSG3D_POST_POOL2) {
+    if (post == ICSG3D_POST_POOL2) {
       const int Do = p.D / 2, Ho = p.H / 2, Wo = p.W / 2;
       const long long Mo = static_cast<long long>(p.B) * Do * Ho * Wo;
       for (long long o = static_cast<long long>(blockIdx.x) * rpi + rl; o < Mo; o += static_cast<long long>(gridDim.x) * rpi) {
@@ -747,7 +814,7 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p) {
           }
         }
       }
-    } else if (p.post == ICSG3D_POST_UP2) {
+    } else if (post == ICSG3D_POST_UP2) {
       const long long M = static_cast<long long>(p.B) * p.D * p.H * p.W;
       for (long long r = static_cast<long long>(blockIdx.x) * rpi + rl; r < M; r += static_cast<long long>(gridDim.x) * rpi) {
         const int w = static_cast<int>(r % p.W);
@@ -842,9 +909,224 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p) {
   }
 }
 
-template <typename T, bool kApply>
-__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_kernel(const BnBwdParams p) {
-  bn_bwd_body<T, kApply>(p);
+template <bool kApply, int kPost>
+constexpr int kBnBwdMinBlocks() { return 2; }
+
+template <typename T, bool kApply, int kPost, int kMinBlocks>
+__global__ void __launch_bounds__(kBnThreads, kMinBlocks) bn_bwd_kernel(const BnBwdParams p) {
+  bn_bwd_body<T, kApply, kPost>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lean bf16 backward passes for the layers that carry the step's BatchNorm traffic (no skip gradient; post = none or
+// MaxPool3D(2)).  Same arithmetic as bn_bwd_body, restructured for the memory system:
+//   * one instantiation per (pass, post, activation) so that each keeps only the per-channel state it needs
+//     (24-40 registers instead of 56) and every load of an iteration is issued before the first use;
+//   * pool: the 8 rows of a window are fetched in one batch from one base pointer; only the arg-max row of a channel
+//     carries gradient, so the reduce pass picks that element with a 3-level select on the argmax bits (13
+//     instructions per channel and WINDOW instead of 5 per channel and ROW) and the apply pass adds scale*g to the
+//     one matching row;
+//   * window coordinates in 32-bit arithmetic, row pointers advanced by a constant stride.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ uint32_t word_of(const uint4& q, int j) { return j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.w; }
+__device__ __forceinline__ void cvt8(const uint4& q, float (&v)[8]) { VecIO<__nv_bfloat16>::cvt(q, v); }
+
+template <bool kApply, int kPost, bool kHasAct, int kU = 4>
+__global__ void __launch_bounds__(kBnThreads, (kApply || kU == 8) ? 2 : 3)
+bn_bwd_lean_kernel(const BnBwdParams p) {
+  constexpr int V = 8;
+  typedef __nv_bfloat16 T;
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const T* __restrict__ dy = static_cast<const T*>(p.dy);
+  const T* __restrict__ tap = p.tap_other;
+  const int cg = p.C / V;
+  const int rpi = kBnThreads / cg;
+  const int g = threadIdx.x % cg;
+  const int rl = threadIdx.x / cg;
+  const bool has_tap = kApply && tap != nullptr;
+  const bool pre_relu = p.pre_relu != 0;
+  const float tap_coef = p.tap_coef;
+  const float slope = p.act == ICSG3D_ACT_RELU ? 0.f : p.alpha;  // act'(z) = z > 0 ? 1 : slope
+  float sc[V], sh[V], mu[V], s1[V], s2[V], ca[V], cb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sc[i] = p.scale[g * V + i];
+    sh[i] = p.shift[g * V + i];
+    mu[i] = p.mean[g * V + i];
+    s1[i] = s2[i] = 0.f;
+    if (kApply) {
+      const float k1 = static_cast<float>(p.sums[g * V + i] / p.count);
+      const float k2 = static_cast<float>(p.sums[p.C + g * V + i] / p.count);
+      ca[i] = -sc[i] * p.rstd[g * V + i] * k2;
+      cb[i] = -sc[i] * k1 - ca[i] * mu[i];
+    }
+  }
+  // dx row from x row, g row (apply) -- or the running sums (reduce)
+  auto finish = [&](const float (&xv)[V], float (&o)[V], const uint4& tq, T* out) {
+    if (has_tap) {
+      float ov[V];
+      cvt8(tq, ov);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] += tap_coef * (xv[i] - ov[i]);
+    }
+    if (pre_relu) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = xv[i] > 0.f ? o[i] : 0.f;
+    }
+    VecIO<T>::store(out, o);
+  };
+
+  if (rl < rpi) {
+    if constexpr (kPost == ICSG3D_POST_NONE) {
+      constexpr int U = kU;
+      const long long M = static_cast<long long>(p.B) * p.D * p.H * p.W;
+      const long long stride = static_cast<long long>(gridDim.x) * rpi;
+      long long r = static_cast<long long>(blockIdx.x) * rpi + rl;
+      const T* px = x + r * p.ldx + g * V;
+      const T* pd = dy + r * p.lddy + g * V;
+      const T* pt = has_tap ? tap + r * p.ld_other + g * V : nullptr;
+      T* po = kApply ? p.dx + r * p.lddx + g * V : nullptr;
+      const long long sx = stride * p.ldx, sd = stride * p.lddy, st = stride * p.ld_other, so = stride * p.lddx;
+      auto row = [&](const uint4& xq, const uint4& dq, const uint4& tq, T* out) {
+        float xv[V], gv[V];
+        cvt8(xq, xv);
+        cvt8(dq, gv);
+        if constexpr (kHasAct) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) gv[i] *= fmaf(sc[i], xv[i], sh[i]) > 0.f ? 1.f : slope;
+        }
+        if constexpr (kApply) {
+          float o[V];
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] = fmaf(sc[i], gv[i], fmaf(ca[i], xv[i], cb[i]));
+          finish(xv, o, tq, out);
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            s1[i] += gv[i];
+            s2[i] = fmaf(gv[i], xv[i] - mu[i], s2[i]);
+          }
+        }
+      };
+      for (; r + (U - 1) * stride < M; r += U * stride) {
+        uint4 xr[U], dr[U], tr[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          xr[j] = ldg16(px + j * sx);
+          dr[j] = ldg16(pd + j * sd);
+          if (has_tap) tr[j] = ldg16(pt + j * st);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) row(xr[j], dr[j], tr[j], kApply ? po + j * so : nullptr);
+        px += U * sx;
+        pd += U * sd;
+        if (has_tap) pt += U * st;
+        if (kApply) po += U * so;
+      }
+      for (; r < M; r += stride) {
+        uint4 tq = make_uint4(0, 0, 0, 0);
+        if (has_tap) tq = ldg16(pt);
+        row(ldg16(px), ldg16(pd), tq, po);
+        px += sx;
+        pd += sd;
+        if (has_tap) pt += st;
+        if (kApply) po += so;
+      }
+    } else {  // MaxPool3D(2)
+      const uint32_t Do = p.D / 2, Ho = p.H / 2, Wo = p.W / 2;
+      const uint32_t Mo = static_cast<uint32_t>(p.B) * Do * Ho * Wo;
+      const uint32_t stride = gridDim.x * rpi;
+      const long long oW = p.ldx, oH = static_cast<long long>(p.W) * p.ldx, oD = static_cast<long long>(p.H) * p.W * p.ldx;
+      for (uint32_t o = blockIdx.x * rpi + rl; o < Mo; o += stride) {
+        const uint32_t t0 = o / Wo, wo = o - t0 * Wo;
+        const uint32_t t1 = t0 / Ho, ho = t0 - t1 * Ho;
+        const uint32_t n = t1 / Do, dz = t1 - n * Do;
+        const long long rbase = ((static_cast<long long>(n) * p.D + 2 * dz) * p.H + 2 * ho) * p.W + 2 * wo;
+        const T* xb = x + rbase * p.ldx + g * V;
+        uint4 xr[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xr[k] = ldg16(xb + (k >> 2) * oD + ((k >> 1) & 1) * oH + (k & 1) * oW);
+        const uint4 dyr = ldg16(dy + static_cast<long long>(o) * p.lddy + g * V);
+        const uint2 q = *reinterpret_cast<const uint2*>(p.pool_idx + static_cast<size_t>(o) * p.C + g * V);
+        float gw[V];
+        cvt8(dyr, gw);
+        if constexpr (kHasAct || !kApply) {
+          // x of the arg-max row per channel: 3-level select on the bits of the window index (k = kd*4 + kh*2 + kw)
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const uint32_t qq = i < 4 ? q.x : q.y;
+            const int b = 8 * (i & 3);
+            const bool b0 = (qq & (1u << b)) != 0, b1 = (qq & (2u << b)) != 0, b2 = (qq & (4u << b)) != 0;
+            const int j = i >> 1;
+            const uint32_t a0 = b0 ? word_of(xr[1], j) : word_of(xr[0], j), a1 = b0 ? word_of(xr[3], j) : word_of(xr[2], j);
+            const uint32_t a2 = b0 ? word_of(xr[5], j) : word_of(xr[4], j), a3 = b0 ? word_of(xr[7], j) : word_of(xr[6], j);
+            const uint32_t c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2;
+            const uint32_t e = b2 ? c1 : c0;
+            const float xs = __uint_as_float((i & 1) ? (e & 0xffff0000u) : (e << 16));
+            if constexpr (kHasAct) gw[i] *= fmaf(sc[i], xs, sh[i]) > 0.f ? 1.f : slope;
+            if constexpr (!kApply) {
+              s1[i] += gw[i];
+              s2[i] = fmaf(gw[i], xs - mu[i], s2[i]);
+            }
+          }
+        }
+        if constexpr (kApply) {
+          const T* tb = has_tap ? tap + rbase * p.ld_other + g * V : nullptr;
+          T* ob = p.dx + rbase * p.lddx + g * V;
+          const long long tW = p.ld_other, tH = static_cast<long long>(p.W) * p.ld_other,
+                          tD = static_cast<long long>(p.H) * p.W * p.ld_other;
+          const long long dW = p.lddx, dH = static_cast<long long>(p.W) * p.lddx, dD = static_cast<long long>(p.H) * p.W * p.lddx;
+          float dsc[V];
+#pragma unroll
+          for (int i = 0; i < V; ++i) dsc[i] = sc[i] * gw[i];
+#pragma unroll
+          for (int k0 = 0; k0 < 8; k0 += 4) {
+            uint4 tr[4];
+            if (has_tap) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int k = k0 + j;
+                tr[j] = ldg16(tb + (k >> 2) * tD + ((k >> 1) & 1) * tH + (k & 1) * tW);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = k0 + j;
+              float xv[V], ov[V];
+              cvt8(xr[k], xv);
+#pragma unroll
+              for (int i = 0; i < V; ++i) {
+                const uint32_t qq = i < 4 ? q.x : q.y;
+                const bool hit = ((qq >> (8 * (i & 3))) & 0xffu) == static_cast<uint32_t>(k);
+                ov[i] = fmaf(ca[i], xv[i], cb[i]) + (hit ? dsc[i] : 0.f);
+              }
+              finish(xv, ov, tr[j], ob + (k >> 2) * dD + ((k >> 1) & 1) * dH + (k & 1) * dW);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!kApply) {
+    extern __shared__ double sred[];
+    double* out = p.partials + static_cast<size_t>(blockIdx.x) * 2 * p.C;
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+      if (rl < rpi) {
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          sred[rl * p.C + g * V + i] = pass == 0 ? static_cast<double>(s1[i])
+                                                 : static_cast<double>(s2[i]) * static_cast<double>(p.rstd[g * V + i]);
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < p.C; c += kBnThreads) {
+        double a = 0.0;
+        for (int r = 0; r < rpi; ++r) a += sred[r * p.C + c];
+        out[pass * p.C + c] = a;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -981,13 +1263,13 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, float* __
   if (dgamma) dgamma[c] = static_cast<float>(sums[C + c]);
 }
 
-static int bn_grid(long long rows, int C, int V) {
+static int bn_grid(long long rows, int C, int V, int per_sm = 4) {
   const int cg = C / V;
   const int rpi = kBnThreads / cg;
   long long blocks = (rows + rpi - 1) / rpi;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  const long long cap = static_cast<long long>(sms) * 4;
+  const long long cap = static_cast<long long>(sms) * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
@@ -1083,6 +1365,21 @@ static int bn_apply_fwd_impl(const void* x, int ldx, int x_dtype, const float* s
   if (blocks > static_cast<long long>(sms) * 8) blocks = static_cast<long long>(sms) * 8;
   if (blocks < 1) blocks = 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool lean = [] { const char* e = getenv("ICSG3D_BN_FWD_LEAN"); return e ? atoi(e) != 0 : true; }();
+  if (lean && x_dtype == ICSG3D_DT_BF16 && post == ICSG3D_POST_POOL2 && split_ctot == 0 && y &&
+      static_cast<long long>(B) * D * H * W / 8 < (1ll << 31)) {
+    const int rpi = kBnThreads / (C / V);
+    const long long windows = static_cast<long long>(B) * D * H * W / 8;
+    long long lb = (windows + rpi - 1) / rpi;
+    if (lb > static_cast<long long>(sms) * 3) lb = static_cast<long long>(sms) * 3;
+    if (lb < 1) lb = 1;
+    const int g = static_cast<int>(lb);
+    if (act == ICSG3D_ACT_NONE) bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_NONE><<<g, kBnThreads, 0, st>>>(p);
+    else if (act == ICSG3D_ACT_RELU) bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_RELU><<<g, kBnThreads, 0, st>>>(p);
+    else bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_LEAKY><<<g, kBnThreads, 0, st>>>(p);
+    ICSG_CHECK_LAUNCH();
+    return ICSG3D_OK;
+  }
   if (x_dtype == ICSG3D_DT_BF16) bn_apply_fwd_kernel<__nv_bfloat16><<<static_cast<int>(blocks), kBnThreads, 0, st>>>(p);
   else bn_apply_fwd_kernel<float><<<static_cast<int>(blocks), kBnThreads, 0, st>>>(p);
   ICSG_CHECK_LAUNCH();
@@ -1104,6 +1401,88 @@ extern "C" int icsg3d_bn_apply_fwd_split3(const void* x, int ldx, int x_dtype, c
                            coff, fmt, stream);
 }
 
+// Backward grids are ONE wave of co-resident blocks (grid-stride loops): the lean bf16 kernels keep 3 blocks per SM in
+// the reduce pass and 2 in the apply pass; the generic kernel (fp32, skip gradient, upsample) keeps the 4-per-SM cap.
+static int g_bn_plain_u8 = -1;  // ICSG3D_BN_BWD_PLAIN_U8=1: plain reduce with 8 rows in flight, 2 blocks per SM
+static bool bn_plain_u8() {
+  if (g_bn_plain_u8 < 0) {
+    const char* e = getenv("ICSG3D_BN_BWD_PLAIN_U8");
+    g_bn_plain_u8 = e ? atoi(e) : 0;
+  }
+  return g_bn_plain_u8 != 0;
+}
+static int bn_bwd_grid(long long rows, int C, int dtype, int post, bool apply) {
+  const int V = dtype == ICSG3D_DT_BF16 ? 8 : 4;
+  if (dtype != ICSG3D_DT_BF16 || post == ICSG3D_POST_UP2) {
+    const int g = bn_grid(rows, C, V);
+    return apply && g * 2 < 148 * 8 ? g * 2 : g;
+  }
+  if (apply) return bn_grid(rows, C, V, 2);
+  return bn_grid(rows, C, V, post == ICSG3D_POST_NONE && bn_plain_u8() ? 2 : 3);
+}
+
+// Launch the instantiation compiled for this post-op (each path gets its own register budget / occupancy).
+static int g_bn_bwd_minb = -1;  // tuning knob: ICSG3D_BN_BWD_MINB = 2 | 3 | 4 resident blocks per SM
+template <typename T, bool kApply, int kPost, int kMinB>
+static void bn_bwd_launch_one(const BnBwdParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto* k = bn_bwd_kernel<T, kApply, kPost, kMinB>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  k<<<grid, kBnThreads, smem, st>>>(p);
+}
+template <typename T, bool kApply, int kPost>
+static void bn_bwd_dispatch_minb(const BnBwdParams& p, int grid, size_t smem, cudaStream_t st) {
+  if (g_bn_bwd_minb < 0) {
+    const char* e = getenv("ICSG3D_BN_BWD_MINB");
+    g_bn_bwd_minb = e ? atoi(e) : 0;
+  }
+  const int def = kBnBwdMinBlocks<kApply, kPost>();
+  const int mb = g_bn_bwd_minb >= 2 && g_bn_bwd_minb <= 4 ? g_bn_bwd_minb : def;
+  if (mb == 2) bn_bwd_launch_one<T, kApply, kPost, 2>(p, grid, smem, st);
+  else if (mb == 3) bn_bwd_launch_one<T, kApply, kPost, 3>(p, grid, smem, st);
+  else bn_bwd_launch_one<T, kApply, kPost, 4>(p, grid, smem, st);
+}
+static bool bn_plain_u8();
+static int g_bn_bwd_lean = -1;  // ICSG3D_BN_BWD_LEAN=0 keeps the generic kernel (A/B measurements)
+template <bool kApply, int kPost, bool kHasAct, int kU = 4>
+static void bn_bwd_lean_launch(const BnBwdParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto* k = bn_bwd_lean_kernel<kApply, kPost, kHasAct, kU>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  k<<<grid, kBnThreads, smem, st>>>(p);
+}
+template <bool kApply>
+static bool bn_bwd_try_lean(const BnBwdParams& p, int grid, size_t smem, cudaStream_t st) {
+  if (g_bn_bwd_lean < 0) {
+    const char* e = getenv("ICSG3D_BN_BWD_LEAN");
+    g_bn_bwd_lean = e ? atoi(e) : 1;
+  }
+  if (!g_bn_bwd_lean || p.dy2 || p.post == ICSG3D_POST_UP2) return false;
+  const bool act = p.act != ICSG3D_ACT_NONE;
+  if (p.post == ICSG3D_POST_POOL2) {
+    if (static_cast<long long>(p.B) * p.D * p.H * p.W / 8 >= (1ll << 31)) return false;  // 32-bit window arithmetic
+    if (act) bn_bwd_lean_launch<kApply, ICSG3D_POST_POOL2, true>(p, grid, smem, st);
+    else bn_bwd_lean_launch<kApply, ICSG3D_POST_POOL2, false>(p, grid, smem, st);
+  } else if (!kApply && bn_plain_u8()) {
+    if constexpr (!kApply) {
+      if (act) bn_bwd_lean_launch<false, ICSG3D_POST_NONE, true, 8>(p, grid, smem, st);
+      else bn_bwd_lean_launch<false, ICSG3D_POST_NONE, false, 8>(p, grid, smem, st);
+    }
+  } else {
+    if (act) bn_bwd_lean_launch<kApply, ICSG3D_POST_NONE, true>(p, grid, smem, st);
+    else bn_bwd_lean_launch<kApply, ICSG3D_POST_NONE, false>(p, grid, smem, st);
+  }
+  return true;
+}
+
+template <typename T, bool kApply>
+static void bn_bwd_dispatch(const BnBwdParams& p, int grid, size_t smem, cudaStream_t st) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (bn_bwd_try_lean<kApply>(p, grid, smem, st)) return;
+  }
+  if (p.post == ICSG3D_POST_POOL2) bn_bwd_dispatch_minb<T, kApply, ICSG3D_POST_POOL2>(p, grid, smem, st);
+  else if (p.post == ICSG3D_POST_UP2) bn_bwd_dispatch_minb<T, kApply, ICSG3D_POST_UP2>(p, grid, smem, st);
+  else bn_bwd_dispatch_minb<T, kApply, ICSG3D_POST_NONE>(p, grid, smem, st);
+}
+
 static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype, const float* mean,
                          const float* rstd, const float* scale, const float* shift, int act, float alpha, int post,
                          const uint8_t* pool_idx, int B, int D, int H, int W, int C, double* partials, int nparts,
@@ -1117,7 +1496,7 @@ static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* dy2, 
   ICSG_REQUIRE(!tap_other || dtype == ICSG3D_DT_BF16, "bn_bwd: tap gradient needs bf16 activations");
   long long rows = static_cast<long long>(B) * D * H * W;
   if (post == ICSG3D_POST_POOL2) rows /= 8;
-  const int grid = bn_grid(rows, C, V);
+  const int grid = bn_bwd_grid(rows, C, dtype, post, apply);
   BnBwdParams p{};
   p.dy = dy; p.lddy = lddy; p.dy2 = dy2; p.lddy2 = lddy2; p.x = x; p.ldx = ldx; p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
   p.act = act; p.alpha = alpha; p.post = post; p.pool_idx = pool_idx; p.B = B; p.D = D; p.H = H; p.W = W; p.C = C;
@@ -1128,18 +1507,13 @@ static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* dy2, 
   if (!apply) {
     ICSG_REQUIRE(partials && nparts == grid, "bn_bwd_reduce: nparts %d != expected %d", nparts, grid);
     const size_t smem = bn_red_smem(C, V);
-    if (dtype == ICSG3D_DT_BF16) {
-      if (smem > 48 * 1024) ICSG_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      bn_bwd_kernel<__nv_bfloat16, false><<<grid, kBnThreads, smem, st>>>(p);
-    } else {
-      bn_bwd_kernel<float, false><<<grid, kBnThreads, smem, st>>>(p);
-    }
+    if (dtype == ICSG3D_DT_BF16) bn_bwd_dispatch<__nv_bfloat16, false>(p, grid, smem, st);
+    else bn_bwd_dispatch<float, false>(p, grid, smem, st);
   } else {
     ICSG_REQUIRE(sums && dx && count > 0, "bn_bwd_apply: bad arguments");
     ICSG_REQUIRE(lddx % 4 == 0, "bn_bwd_apply: lddx must be a multiple of 4");
-    const int g2 = grid * 2 < 148 * 8 ? grid * 2 : grid;
-    if (dtype == ICSG3D_DT_BF16) bn_bwd_kernel<__nv_bfloat16, true><<<g2, kBnThreads, 0, st>>>(p);
-    else bn_bwd_kernel<float, true><<<g2, kBnThreads, 0, st>>>(p);
+    if (dtype == ICSG3D_DT_BF16) bn_bwd_dispatch<__nv_bfloat16, true>(p, grid, 0, st);
+    else bn_bwd_dispatch<float, true>(p, grid, 0, st);
   }
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -1149,7 +1523,7 @@ extern "C" int icsg3d_bn_bwd_nparts(int B, int D, int H, int W, int C, int dtype
   if (!bn_shape_ok(C, dtype)) return -1;
   long long rows = static_cast<long long>(B) * D * H * W;
   if (post == ICSG3D_POST_POOL2) rows /= 8;
-  return bn_grid(rows, C, dtype == ICSG3D_DT_BF16 ? 8 : 4);
+  return bn_bwd_grid(rows, C, dtype, post, false);
 }
 
 extern "C" int icsg3d_bn_bwd_reduce(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, int dtype, const float* mean,
