@@ -588,6 +588,12 @@ extern "C" int icsg3d_conv3d_set_impl(int impl) {
   return ICSG3D_OK;
 }
 
+extern "C" int icsg3d_conv3d_stream_debug(void* buf, int steps) {
+  ICSG_REQUIRE(steps >= 0 && (buf || steps == 0), "conv3d_stream_debug: bad arguments");
+  conv_stream_set_debug(static_cast<long long*>(buf), steps);
+  return ICSG3D_OK;
+}
+
 // Diagnostic: which kernel and tiling the dispatcher picks for a layer shape (host only; no device needed).
 // out[0..9] = {impl (0 = per-tap TMA kernel, 1 = halo kernel), TD, TH, G, NT, a_bufs, b_stages, items, kc, smem_bytes}
 extern "C" int icsg3d_conv3d_k3_plan(int B, int D, int H, int W, int cin, int nout, int sms, int* out) {

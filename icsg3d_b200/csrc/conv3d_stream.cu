@@ -34,74 +34,96 @@ static constexpr int kStreamMaxR = 8;
 
 // One epilogue item: NC accumulator columns of 32 rows (TMEM -> bias/activation -> global, + BatchNorm running sums).
 // NC = 32 gives the warp two independent 16-column chains per TMEM round trip (the epilogue is latency bound).
+// tcgen05.wait::ld that also names the loaded registers as in/out operands: no use of them can be scheduled above it
 template <int NC>
-__device__ __forceinline__ void stream_epi_item(const ConvStreamParams& p, uint32_t taddr, int c0, bool ok, long long pixel,
-                                                const float* s_bias, float slope, float (&sacc)[32], float (&qacc)[32]) {
-  uint32_t v[NC];
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[NC]) {
+  if constexpr (NC == 32) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+  }
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NC]) {
   if constexpr (NC == 32) tmem_ld32(taddr, v);
   else tmem_ld16(taddr, v);
-  tmem_ld_wait();
-  float fv[NC];
-#pragma unroll
-  for (int i = 0; i < NC; i += 4) {
-    const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + i]);
-    const float x0 = fmaf(__uint_as_float(v[i]), p.oscale, b4.x), x1 = fmaf(__uint_as_float(v[i + 1]), p.oscale, b4.y);
-    const float x2 = fmaf(__uint_as_float(v[i + 2]), p.oscale, b4.z), x3 = fmaf(__uint_as_float(v[i + 3]), p.oscale, b4.w);
-    fv[i] = fmaxf(x0, slope * x0);
-    fv[i + 1] = fmaxf(x1, slope * x1);
-    fv[i + 2] = fmaxf(x2, slope * x2);
-    fv[i + 3] = fmaxf(x3, slope * x3);
-  }
+}
+
+// One drained accumulator item (32 lanes x NC columns, already in registers): scale + bias + activation, store,
+// BatchNorm running sums.
+template <int NC>
+__device__ __forceinline__ void stream_epi_math(const ConvStreamParams& p, const uint32_t (&v)[NC], int c0, bool ok, long long pixel,
+                                                const float* s_bias, float slope, float (&sacc)[32], float (&qacc)[32]) {
   const int nvalid = min(NC, p.n_store - c0);
-  if (p.y_dtype == ICSG3D_DT_BF16) {
-    uint4 qv[NC / 8];
+  const bool bf16 = p.y_dtype == ICSG3D_DT_BF16;
+  const bool vec = nvalid == NC && (p.ldy & (bf16 ? 7 : 3)) == 0;
+  const bool stats = p.stats != nullptr && ok;
+  __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + c0;
+  float* dst32 = reinterpret_cast<float*>(p.y) + pixel * p.ldy + c0;
+  // 8 columns at a time (few live temporaries: the next item's TMEM load occupies 32 registers meanwhile)
 #pragma unroll
-    for (int j = 0; j < NC / 8; ++j) {
-      qv[j].x = pack_bf16x2(fv[8 * j], fv[8 * j + 1]);
-      qv[j].y = pack_bf16x2(fv[8 * j + 2], fv[8 * j + 3]);
-      qv[j].z = pack_bf16x2(fv[8 * j + 4], fv[8 * j + 5]);
-      qv[j].w = pack_bf16x2(fv[8 * j + 6], fv[8 * j + 7]);
+  for (int j = 0; j < NC / 8; ++j) {
+    float fv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + 8 * j + i]);
+      const float x0 = fmaf(__uint_as_float(v[8 * j + i]), p.oscale, b4.x), x1 = fmaf(__uint_as_float(v[8 * j + i + 1]), p.oscale, b4.y);
+      const float x2 = fmaf(__uint_as_float(v[8 * j + i + 2]), p.oscale, b4.z), x3 = fmaf(__uint_as_float(v[8 * j + i + 3]), p.oscale, b4.w);
+      fv[i] = fmaxf(x0, slope * x0);
+      fv[i + 1] = fmaxf(x1, slope * x1);
+      fv[i + 2] = fmaxf(x2, slope * x2);
+      fv[i + 3] = fmaxf(x3, slope * x3);
     }
-    if (ok) {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pixel * p.ldy + c0;
-      if (nvalid == NC && (p.ldy & 7) == 0) {
+    if (bf16) {
+      uint4 qv;
+      qv.x = pack_bf16x2(fv[0], fv[1]);
+      qv.y = pack_bf16x2(fv[2], fv[3]);
+      qv.z = pack_bf16x2(fv[4], fv[5]);
+      qv.w = pack_bf16x2(fv[6], fv[7]);
+      if (ok) {
+        if (vec) {
+          reinterpret_cast<uint4*>(dst16)[j] = qv;
+        } else {
 #pragma unroll
-        for (int j = 0; j < NC / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = qv[j];
+          for (int i = 0; i < 8; ++i)
+            if (8 * j + i < nvalid) dst16[8 * j + i] = f2bf(fv[i]);
+        }
+      }
+      if (stats) {  // statistics of the values as stored (bf16-rounded)
+        float2 u;
+        u = unpack_bf16x2(qv.x); fv[0] = u.x; fv[1] = u.y;
+        u = unpack_bf16x2(qv.y); fv[2] = u.x; fv[3] = u.y;
+        u = unpack_bf16x2(qv.z); fv[4] = u.x; fv[5] = u.y;
+        u = unpack_bf16x2(qv.w); fv[6] = u.x; fv[7] = u.y;
+      }
+    } else if (ok) {
+      if (vec) {
+        reinterpret_cast<float4*>(dst32)[2 * j] = make_float4(fv[0], fv[1], fv[2], fv[3]);
+        reinterpret_cast<float4*>(dst32)[2 * j + 1] = make_float4(fv[4], fv[5], fv[6], fv[7]);
+      } else if (nvalid == 4 && (p.ldy & 3) == 0) {
+        if (j == 0) reinterpret_cast<float4*>(dst32)[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
       } else {
 #pragma unroll
-        for (int i = 0; i < NC; ++i)
-          if (i < nvalid) dst[i] = f2bf(fv[i]);
+        for (int i = 0; i < 8; ++i)
+          if (8 * j + i < nvalid) dst32[8 * j + i] = fv[i];
       }
     }
-    if (p.stats) {  // statistics of the values as stored (bf16-rounded)
+    if (stats) {
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) {
-        float2 u;
-        u = unpack_bf16x2(qv[j].x); fv[8 * j] = u.x; fv[8 * j + 1] = u.y;
-        u = unpack_bf16x2(qv[j].y); fv[8 * j + 2] = u.x; fv[8 * j + 3] = u.y;
-        u = unpack_bf16x2(qv[j].z); fv[8 * j + 4] = u.x; fv[8 * j + 5] = u.y;
-        u = unpack_bf16x2(qv[j].w); fv[8 * j + 6] = u.x; fv[8 * j + 7] = u.y;
+      for (int i = 0; i < 8; ++i) {
+        sacc[8 * j + i] += fv[i];
+        qacc[8 * j + i] = fmaf(fv[i], fv[i], qacc[8 * j + i]);
       }
-    }
-  } else if (ok) {
-    float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + c0;
-    if (nvalid == NC && (p.ldy & 3) == 0) {
-#pragma unroll
-      for (int i = 0; i < NC / 4; ++i)
-        reinterpret_cast<float4*>(dst)[i] = make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
-    } else if (nvalid == 4 && (p.ldy & 3) == 0) {
-      reinterpret_cast<float4*>(dst)[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < NC; ++i)
-        if (i < nvalid) dst[i] = fv[i];
-    }
-  }
-  if (p.stats && ok) {
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      sacc[i] += fv[i];
-      qacc[i] = fmaf(fv[i], fv[i], qacc[i]);
     }
   }
 }
@@ -164,6 +186,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0;  // CTA 1: a full-length interior segment
   const int s_begin = blockIdx.x * p.steps_per_cta;
   const int s_end = min(p.total_steps, s_begin + p.steps_per_cta);
 
@@ -188,6 +211,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int stage = astep & (p.stages - 1);
         mbar_wait(&a_empty[stage], (static_cast<uint32_t>(astep >> p.st_log2) & 1u) ^ 1u);
         if (leader) {
+          if (dbg_on && astep < p.dbg_steps) p.dbg[(0 * p.dbg_steps + astep) * 4] = clock64();
           mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
           for (int ch = 0; ch < p.chunks; ++ch)
             tma_load_5d(sm + a_off + static_cast<size_t>(stage) * p.a_stage_bytes + static_cast<size_t>(ch) * p.a_chunk_bytes,
@@ -222,13 +246,18 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           const int o_lo = max(db, i - 1), o_hi = min(de - 1, i + 1);
           const int o_f = (i == 0) ? o_lo : min(i + 1, o_hi + 1);  // outputs [o_f, o_hi] are touched for the first time
           const int rmask = p.R - 1;
+          const bool dbg_i = dbg_on && issuer == 0 && leader && astep < p.dbg_steps;
+          long long* dbg_row = dbg_i ? p.dbg + (1 * p.dbg_steps + astep) * 4 : nullptr;
+          if (dbg_i) dbg_row[0] = clock64();
           for (int o = o_f; o <= o_hi; ++o) {
             const int q = qbase + o - db;
             mbar_wait(&slot_empty[q & rmask], static_cast<uint32_t>(q >> p.r_log2) & 1u);  // zeroed by the epilogue
           }
+          if (dbg_i) dbg_row[1] = clock64();
           const int stage = astep & (p.stages - 1);
           mbar_wait(&a_full[stage], static_cast<uint32_t>(astep >> p.st_log2) & 1u);
           tc_fence_after();
+          if (dbg_i) dbg_row[2] = clock64();
           // outputs o_lo..o_hi = consecutive ring positions; split once at the ring wrap: op0 (n0 blocks), op1 (n1 blocks)
           const int q_lo = qbase + o_lo - db;
           const int cnt = o_hi - o_lo + 1;
@@ -290,6 +319,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
               }
             }
             umma_commit(&a_empty[stage]);
+            if (dbg_i) dbg_row[3] = clock64();
             if (i - 1 >= db) umma_commit(&slot_full[(qbase + i - 1 - db) & rmask]);            // output plane i-1 is complete
             if (i == p.D - 1 && de == p.D) umma_commit(&slot_full[(qbase + i - db) & rmask]);  // and the last plane of the column
           }
@@ -306,13 +336,13 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int half = (warp - 1 - kStreamMaxIssuers) >> 2;
     const bool split_cols = p.C == 64;
     const int c0 = split_cols ? 32 * half : 0;
-    const int t_first = split_cols ? 0 : half, t_step = split_cols ? 1 : 2;
+    const int t_step = split_cols ? 1 : 2;
+    const uint32_t wp_magic = ((1u << 20) + static_cast<uint32_t>(p.WP) - 1u) / static_cast<uint32_t>(p.WP);
     ConvStreamParams q_ = p;  // this CTA's view of the output: channels [n_off, n_off + C)
     q_.n_store = p.n_store - n_off;
     q_.y = static_cast<char*>(p.y) + static_cast<size_t>(n_off) * (p.y_dtype == ICSG3D_DT_BF16 ? 2 : 4);
     const ConvStreamParams& pe = q_;
     const bool active = c0 < pe.n_store;
-    const float inv_wp = 1.0f / static_cast<float>(p.WP);
     // LeakyReLU / ReLU / identity as max(x, slope * x)
     const float slope = p.act == ICSG3D_ACT_RELU ? 0.f : (p.act == ICSG3D_ACT_LEAKY ? p.alpha : 1.f);
     // BatchNorm statistics of the stored values: per-thread fp32 running sums for this warp's (at most 32) columns,
@@ -339,30 +369,71 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       for (int o = db; o < de; ++o, ++q) {
         const int slot = q & (p.R - 1);
         const long long plane0 = ((static_cast<long long>(n) * p.D + o) * p.H + hb * p.TH) * p.W;
+        const bool dbg_e = dbg_on && quarter == 0 && lane == 0 && q < p.dbg_steps;
+        long long* dbg_row = dbg_e ? p.dbg + ((2 + half) * p.dbg_steps + q) * 4 : nullptr;
+        if (dbg_e) dbg_row[0] = clock64();
         mbar_wait(&slot_full[slot], static_cast<uint32_t>(q >> p.r_log2) & 1u);
         tc_fence_after();
-        {
-          for (int t = t_first; t < t_valid; t += t_step) {
-            const int f = t * 128 + quarter * 32 + lane;
-            const int hl = static_cast<int>((static_cast<float>(f) + 0.5f) * inv_wp);
-            const int wl = f - hl * p.WP;
-            const bool ok = hl < th_valid && wl < p.W;
-            const long long pixel = plane0 + hl * p.W + wl;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                   static_cast<uint32_t>((t * p.R + slot) * p.C + c0);
-            if (p.C >= 32) {
-              if (active) stream_epi_item<32>(pe, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
-              tmem_st_zero<32>(taddr);
-            } else {
-              if (active) stream_epi_item<16>(pe, taddr, c0, ok, pixel, s_bias, slope, sacc, qacc);
-              tmem_st_zero<16>(taddr);
-            }
+        if (dbg_e) dbg_row[1] = clock64();
+        // This warp's tiles of the plane, software-pipelined: the TMEM load of the next tile is in flight while the
+        // current one is converted and stored; a drained item is zeroed as soon as its load has completed.
+        // C <= 32: the two warps of a quarter take alternate tiles, alternating with the plane as well (odd T balances).
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * p.C + c0);
+        const uint32_t t_stride = static_cast<uint32_t>(p.R * p.C);
+        int t = split_cols ? 0 : ((half + q) & 1);
+        auto coords = [&](int tt, bool& ok, long long& pixel) {
+          const uint32_t f = static_cast<uint32_t>(tt * 128 + quarter * 32 + lane);
+          const uint32_t hl = (f * wp_magic) >> 20;  // f / WP (exact for f < 4096, WP < 130)
+          const uint32_t wl = f - hl * static_cast<uint32_t>(p.WP);
+          ok = static_cast<int>(hl) < th_valid && static_cast<int>(wl) < p.W;
+          pixel = plane0 + static_cast<long long>(hl * static_cast<uint32_t>(p.W) + wl);
+        };
+        if (!active) {
+          for (; t < t_valid; t += t_step) {
+            if (p.C >= 32) tmem_st_zero<32>(tq + t * t_stride);
+            else tmem_st_zero<16>(tq + t * t_stride);
+          }
+        } else if (p.C >= 32) {
+          uint32_t v[32];
+          if (t < t_valid) tmem_ld_cols<32>(tq + t * t_stride, v);
+          while (t < t_valid) {
+            const int tn = t + t_step;
+            uint32_t cur[32];
+            tmem_ld_wait_regs<32>(v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cur[i] = v[i];
+            tmem_st_zero<32>(tq + t * t_stride);
+            if (tn < t_valid) tmem_ld_cols<32>(tq + tn * t_stride, v);
+            bool ok;
+            long long pixel;
+            coords(t, ok, pixel);
+            stream_epi_math<32>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc);
+            t = tn;
+          }
+        } else {
+          uint32_t v[16];
+          if (t < t_valid) tmem_ld_cols<16>(tq + t * t_stride, v);
+          while (t < t_valid) {
+            const int tn = t + t_step;
+            uint32_t cur[16];
+            tmem_ld_wait_regs<16>(v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = v[i];
+            tmem_st_zero<16>(tq + t * t_stride);
+            if (tn < t_valid) tmem_ld_cols<16>(tq + tn * t_stride, v);
+            bool ok;
+            long long pixel;
+            coords(t, ok, pixel);
+            stream_epi_math<16>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc);
+            t = tn;
           }
         }
+        if (dbg_e) dbg_row[2] = clock64();
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_empty[slot]);
+        if (dbg_e) dbg_row[3] = clock64();
       }
       s += de - db;
     }
@@ -479,6 +550,13 @@ bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, Co
 
 int conv_stream_grid(const ConvStreamParams& p) { return (p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta; }
 
+static long long* g_stream_dbg = nullptr;
+static int g_stream_dbg_steps = 0;
+void conv_stream_set_debug(long long* buf, int steps) {
+  g_stream_dbg = buf;
+  g_stream_dbg_steps = steps;
+}
+
 int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                        int n_store, int cin, int nout, int act, float alpha, double* stats, ConvStreamParams p,
                        cudaStream_t st, float oscale) {
@@ -501,6 +579,8 @@ int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* b
   }
   p.y = y; p.ldy = ldy; p.y_dtype = y_dtype; p.n_store = n_store; p.bias = bias; p.act = act; p.alpha = alpha;
   p.stats = stats;
+  p.dbg = g_stream_dbg;
+  p.dbg_steps = g_stream_dbg_steps;
   p.oscale = oscale;
   static bool configured = false;
   if (!configured) {

@@ -25,11 +25,14 @@ struct ConvStreamParams {
   float alpha;
   float oscale;  // output = accumulator * oscale + bias (1 unless the weights were pre-scaled: fp16 split mode)
   double* stats;         // optional per-CTA BatchNorm partials [grid][2][C] (sum, sum of squares of the stored values)
+  long long* dbg;        // optional role timeline of CTA (0, 0): [4 roles][dbg_steps][4] clock64 stamps (tools/stream_timeline.py)
+  int dbg_steps;
 };
 
 // false when the layer shape does not fit the streaming scheme (the dispatcher then falls back to the other kernels).
 bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvStreamParams* out);
 int conv_stream_grid(const ConvStreamParams& p);
+void conv_stream_set_debug(long long* buf, int steps);  // role timeline of CTA 1 into buf[4][steps][4] (nullptr: off)
 int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                        int n_store, int cin, int nout, int act, float alpha, double* stats, ConvStreamParams p,
                        cudaStream_t st, float oscale = 1.0f);

@@ -96,6 +96,12 @@ int icsg3d_conv3d_k3_plan(int B, int D, int H, int W, int cin, int nout, int sms
  * 1 per-tap TMA kernel only, 2 halo-reuse kernel (no plane-streaming kernel).  Same as env ICSG3D_CONV_IMPL=v1|halo. */
 int icsg3d_conv3d_set_impl(int impl);
 
+/* Diagnostic: role timeline of the plane-streaming kernel.  While buf != NULL, CTA 1 of every streaming launch writes
+ * clock64 stamps into buf[4][steps][4] (device int64): role 0 producer {TMA issued}, 1 first MMA issuer {enter, ring slot
+ * free, input plane landed, MMAs issued}, 2/3 the two epilogue warps of lane quarter 0 {enter, accumulators complete,
+ * items drained, slot released}.  buf = NULL switches it off (default).  tools/stream_timeline.py. */
+int icsg3d_conv3d_stream_debug(void* buf, int steps);
+
 /* Conv3D 1x1x1 (the U-Net heads `soft`/`sig`, unet.py:339-352) through the same tcgen05 kernel with a single tap:
  * wpack bf16 [1][nout][cin]. */
 int icsg3d_conv3d_k1_igemm(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
