@@ -27,6 +27,7 @@
 namespace icsg3d {
 
 static constexpr int kStreamMaxIssuers = 3;  // 1 + 3 + 8 = 12 warps = 3 per SM sub-partition: up to 168 registers per thread
+static constexpr int kStreamDefaultIssuers = 3;
 static constexpr int kStreamEpiWarps = 8;
 static constexpr int kStreamThreads = (1 + kStreamMaxIssuers + kStreamEpiWarps) * 32;
 static constexpr int kStreamMaxStages = 6;
@@ -395,18 +396,21 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           }
         } else if (p.C >= 32) {
           uint32_t v[32];
-          if (t < t_valid) tmem_ld_cols<32>(tq + t * t_stride, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+          if (t < t_valid && !(p.exp_flags & 2)) tmem_ld_cols<32>(tq + t * t_stride, v);
           while (t < t_valid) {
             const int tn = t + t_step;
             uint32_t cur[32];
             tmem_ld_wait_regs<32>(v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) cur[i] = v[i];
-            tmem_st_zero<32>(tq + t * t_stride);
-            if (tn < t_valid) tmem_ld_cols<32>(tq + tn * t_stride, v);
+            if (!(p.exp_flags & 1)) tmem_st_zero<32>(tq + t * t_stride);
+            if (tn < t_valid && !(p.exp_flags & 2)) tmem_ld_cols<32>(tq + tn * t_stride, v);
             bool ok;
             long long pixel;
             coords(t, ok, pixel);
+            if (p.exp_flags & 4) ok = false;
             stream_epi_math<32>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc);
             t = tn;
           }
@@ -468,6 +472,16 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
 }
 
+// MMA issuer warps used (tiles are dealt round-robin); ICSG3D_STREAM_ISSUERS = 1..3 overrides for A/B timing
+static int stream_max_issuers() {
+  static const int v = [] {
+    const char* e = getenv("ICSG3D_STREAM_ISSUERS");
+    const int n = e ? atoi(e) : kStreamDefaultIssuers;
+    return n < 1 ? 1 : (n > kStreamMaxIssuers ? kStreamMaxIssuers : n);
+  }();
+  return v;
+}
+
 static bool stream_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvStreamParams* out) {
@@ -525,7 +539,7 @@ bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, Co
       bp.st_log2 = stages == 4 ? 2 : 1;
       bp.kc = kc; bp.chunks = chunks; bp.row_bytes = row_bytes;
       bp.stages = stages;
-      bp.issuers = T < kStreamMaxIssuers ? T : kStreamMaxIssuers;
+      bp.issuers = T < stream_max_issuers() ? T : stream_max_issuers();
       bp.a_chunk_bytes = a_chunk; bp.a_stage_bytes = a_stage;
       bp.a_tx_bytes = static_cast<uint32_t>(HP * WP) * row_bytes * chunks;
       bp.w_bytes = w_bytes; bp.blk_bytes = static_cast<uint32_t>(C) * row_bytes;
@@ -581,6 +595,8 @@ int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* b
   p.stats = stats;
   p.dbg = g_stream_dbg;
   p.dbg_steps = g_stream_dbg_steps;
+  static const int exp_flags = [] { const char* e = getenv("ICSG3D_STREAM_EXP"); return e ? atoi(e) : 0; }();
+  p.exp_flags = exp_flags;
   p.oscale = oscale;
   static bool configured = false;
   if (!configured) {

@@ -27,6 +27,8 @@ struct ConvStreamParams {
   double* stats;         // optional per-CTA BatchNorm partials [grid][2][C] (sum, sum of squares of the stored values)
   long long* dbg;        // optional role timeline of CTA (0, 0): [4 roles][dbg_steps][4] clock64 stamps (tools/stream_timeline.py)
   int dbg_steps;
+  int exp_flags;         // TIMING EXPERIMENTS ONLY (env ICSG3D_STREAM_EXP, results are wrong when set): 1 = no slot zeroing,
+                         // 2 = no TMEM loads in the epilogue, 4 = no global stores
 };
 
 // false when the layer shape does not fit the streaming scheme (the dispatcher then falls back to the other kernels).
