@@ -681,7 +681,22 @@ struct BnBwdParams {
   float tap_coef;
   __nv_bfloat16* dx;
   int lddx;
+  double* tap_sq;  // optional (apply pass with a tap): per-block sum (x - tap_other)^2, the DFC feature loss of the layer
 };
+
+// per-block partial of the fused DFC feature loss: partial[blockIdx.x] = sum over the block's threads
+__device__ __forceinline__ void bn_tap_sq_store(double* partials, double v) {
+  __shared__ double tap_red[kBnThreads / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) tap_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBnThreads / 32; ++w) t += tap_red[w];
+    partials[blockIdx.x] = t;
+  }
+}
 
 // g for one x row given the matching dy vector: g_i = dyv_i * act'(scale*x+shift)
 template <int V>
@@ -692,7 +707,9 @@ __device__ __forceinline__ void g_from(const float (&xv)[V], const float (&dyv)[
 }
 
 template <typename T, bool kApply, int kPost = -1>
-__device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p) {
+__device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p, double* tap_sq_out = nullptr) {
+  double tap_sq = 0.0;
+  const bool want_sq = kApply && p.tap_sq != nullptr;
   // kPost >= 0 fixes the post-op at compile time (registers are then sized for that path alone), -1 reads p.post
   const int post = kPost >= 0 ? kPost : p.post;
   // HBM-bound: every thread keeps 4 independent rows (x, dy, optional skip gradient / tap) in flight before it
@@ -735,8 +752,14 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p) {
       if (has_tap) {
         float ov[V];
         VecIO<T>::cvt(tapraw, ov);
+        float sq = 0.f;
 #pragma unroll
-        for (int i = 0; i < V; ++i) o[i] += p.tap_coef * (xv[i] - ov[i]);
+        for (int i = 0; i < V; ++i) {
+          const float d = xv[i] - ov[i];
+          o[i] += p.tap_coef * d;
+          sq = fmaf(d, d, sq);
+        }
+        if (want_sq) tap_sq += static_cast<double>(sq);
       }
       if (p.pre_relu) {
 #pragma unroll
@@ -888,6 +911,7 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p) {
       }
     }
   }
+  if (tap_sq_out) *tap_sq_out = tap_sq;
   if (!kApply) {
     extern __shared__ double sred[];
     double* out = p.partials + static_cast<size_t>(blockIdx.x) * 2 * p.C;
@@ -914,7 +938,9 @@ constexpr int kBnBwdMinBlocks() { return 2; }
 
 template <typename T, bool kApply, int kPost, int kMinBlocks>
 __global__ void __launch_bounds__(kBnThreads, kMinBlocks) bn_bwd_kernel(const BnBwdParams p) {
-  bn_bwd_body<T, kApply, kPost>(p);
+  double tap_sq = 0.0;
+  bn_bwd_body<T, kApply, kPost>(p, &tap_sq);
+  if (kApply && p.tap_sq) bn_tap_sq_store(p.tap_sq, tap_sq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -948,6 +974,13 @@ bn_bwd_lean_kernel(const BnBwdParams p) {
   const bool pre_relu = p.pre_relu != 0;
   const float tap_coef = p.tap_coef;
   const float slope = p.act == ICSG3D_ACT_RELU ? 0.f : p.alpha;  // act'(z) = z > 0 ? 1 : slope
+  const bool want_sq = kApply && p.tap_sq != nullptr;
+  double tap_sq = 0.0;
+  float tap_sqf = 0.f;
+  auto tap_flush = [&]() {
+    if (want_sq) tap_sq += static_cast<double>(tap_sqf);
+    tap_sqf = 0.f;
+  };
   float sc[V], sh[V], mu[V], s1[V], s2[V], ca[V], cb[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
@@ -967,8 +1000,14 @@ bn_bwd_lean_kernel(const BnBwdParams p) {
     if (has_tap) {
       float ov[V];
       cvt8(tq, ov);
+      float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < V; ++i) o[i] += tap_coef * (xv[i] - ov[i]);
+      for (int i = 0; i < V; ++i) {
+        const float d = xv[i] - ov[i];
+        o[i] += tap_coef * d;
+        sq = fmaf(d, d, sq);
+      }
+      tap_sqf += sq;  // fused DFC feature loss of the layer: fp32 within one loop iteration (<= 64 terms), then fp64
     }
     if (pre_relu) {
 #pragma unroll
@@ -1019,6 +1058,7 @@ bn_bwd_lean_kernel(const BnBwdParams p) {
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) row(xr[j], dr[j], tr[j], kApply ? po + j * so : nullptr);
+        if (kApply) tap_flush();
         px += U * sx;
         pd += U * sd;
         if (has_tap) pt += U * st;
@@ -1028,6 +1068,7 @@ bn_bwd_lean_kernel(const BnBwdParams p) {
         uint4 tq = make_uint4(0, 0, 0, 0);
         if (has_tap) tq = ldg16(pt);
         row(ldg16(px), ldg16(pd), tq, po);
+        if (kApply) tap_flush();
         px += sx;
         pd += sd;
         if (has_tap) pt += st;
@@ -1104,10 +1145,12 @@ bn_bwd_lean_kernel(const BnBwdParams p) {
               finish(xv, ov, tr[j], ob + (k >> 2) * dD + ((k >> 1) & 1) * dH + (k & 1) * dW);
             }
           }
+          tap_flush();
         }
       }
     }
   }
+  if (kApply && p.tap_sq) bn_tap_sq_store(p.tap_sq, tap_sq);
   if (!kApply) {
     extern __shared__ double sred[];
     double* out = p.partials + static_cast<size_t>(blockIdx.x) * 2 * p.C;
@@ -1487,7 +1530,7 @@ static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* dy2, 
                          const float* rstd, const float* scale, const float* shift, int act, float alpha, int post,
                          const uint8_t* pool_idx, int B, int D, int H, int W, int C, double* partials, int nparts,
                          const double* sums, double count, int pre_relu, const void* tap_other, int ld_other,
-                         float tap_coef, void* dx, int lddx, void* stream) {
+                         float tap_coef, void* dx, int lddx, void* stream, double* tap_sq = nullptr, int tap_sq_nparts = 0) {
   ICSG_REQUIRE(dy && x && mean && rstd && scale && shift, "bn_bwd: null pointer");
   ICSG_REQUIRE(bn_shape_ok(C, dtype), "bn_bwd: unsupported C=%d for dtype %d", C, dtype);
   const int V = dtype == ICSG3D_DT_BF16 ? 8 : 4;
@@ -1512,6 +1555,9 @@ static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* dy2, 
   } else {
     ICSG_REQUIRE(sums && dx && count > 0, "bn_bwd_apply: bad arguments");
     ICSG_REQUIRE(lddx % 4 == 0, "bn_bwd_apply: lddx must be a multiple of 4");
+    ICSG_REQUIRE(!tap_sq || (tap_other && tap_sq_nparts == grid), "bn_bwd_apply: tap_sq needs a tap and %d partials (got %d)",
+                 grid, tap_sq_nparts);
+    p.tap_sq = tap_sq;
     if (dtype == ICSG3D_DT_BF16) bn_bwd_dispatch<__nv_bfloat16, true>(p, grid, 0, st);
     else bn_bwd_dispatch<float, true>(p, grid, 0, st);
   }
@@ -1541,6 +1587,25 @@ extern "C" int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* dy2, in
                                    float tap_coef, void* dx, int lddx, void* stream) {
   return bn_bwd_launch(true, dy, lddy, dy2, lddy2, x, ldx, dtype, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D, H, W, C,
                        nullptr, 0, sums, count, pre_relu, tap_other, ld_other, tap_coef, dx, lddx, stream);
+}
+
+extern "C" int icsg3d_bn_bwd_apply_nblocks(int B, int D, int H, int W, int C, int dtype, int post) {
+  if (!bn_shape_ok(C, dtype)) return -1;
+  long long rows = static_cast<long long>(B) * D * H * W;
+  if (post == ICSG3D_POST_POOL2) rows /= 8;
+  return bn_bwd_grid(rows, C, dtype, post, true);
+}
+
+extern "C" int icsg3d_bn_bwd_apply_tapsq(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+                                         const float* rstd, const float* scale, const float* shift, int act, float alpha,
+                                         int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C,
+                                         const double* sums, double count, int pre_relu, const void* tap_other,
+                                         int ld_other, float tap_coef, void* dx, int lddx, double* tap_sq, int tap_sq_nparts,
+                                         void* stream) {
+  ICSG_REQUIRE(tap_sq && tap_other, "bn_bwd_apply_tapsq: tap_sq and tap_other are required");
+  return bn_bwd_launch(true, dy, lddy, nullptr, 0, x, ldx, dtype, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D, H, W,
+                       C, nullptr, 0, sums, count, pre_relu, tap_other, ld_other, tap_coef, dx, lddx, stream, tap_sq,
+                       tap_sq_nparts);
 }
 
 extern "C" int icsg3d_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream) {

@@ -234,6 +234,9 @@ class VAEEngine:
         # Measured slower inside the step (3.59 vs 3.35 ms: the co-resident grid is half as wide and the cooperative launch
         # does not overlap with the filter-gradient side stream), so it is opt-in: ICSG3D_FUSE_BN_BWD=1.
         self.fuse_bn_bwd = os.environ.get("ICSG3D_FUSE_BN_BWD", "0") == "1" and (self.world == 1 or self.peer is not None)
+        # DFC feature-loss sums out of the BatchNorm-backward apply pass of the tapped layers (ICSG3D_FUSE_TAP_LOSS=0: separate pass)
+        self.fuse_tap_loss = os.environ.get("ICSG3D_FUSE_TAP_LOSS", "1") != "0"
+        self._defer_taps = False
         self.fuse_stats = True  # BatchNorm statistics from the conv epilogue where the streaming kernel serves the layer
 
     # ------------------------------------------------------------------------------------------
@@ -298,8 +301,9 @@ class VAEEngine:
         ops.bn_apply_fwd(x, C, st.scale, st.shift, act, post, y=y, y32=y32, pool_idx=idx)
 
     def _bn_bwd(self, dy, x, C, st: _BN, act, post, idx, dx, pre_relu=False, tap_other=None, tap_coef=0.0, dgamma=None,
-                dbeta=None):
+                dbeta=None, tap_sq=None):
         rows = x.numel() // x.shape[-1]
+        assert tap_sq is None or not self.fuse_bn_bwd
         if self.fuse_bn_bwd:
             # one cooperative launch: partial sums -> grid barrier -> fixed-order reduction (+ peer-memory all-reduce in
             # data-parallel mode) -> grid barrier -> dx; the second read of dy / x comes from L2 where the layer fits
@@ -316,7 +320,8 @@ class VAEEngine:
         if self.peer is not None:
             ops.bn_reduce_allreduce_grads(part, st.bsums_g, dgamma=dgamma, dbeta=dbeta, **self.peer.args((id(st), "bwd")))
             ops.bn_bwd_apply(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, st.bsums_g,
-                             float(rows * self.world), dx, pre_relu=pre_relu, tap_other=tap_other, tap_coef=tap_coef)
+                             float(rows * self.world), dx, pre_relu=pre_relu, tap_other=tap_other, tap_coef=tap_coef,
+                             tap_sq=tap_sq)
             return
         ops.bn_reduce_grads(part, st.bsums, dgamma, dbeta)  # local sums: the gradient all-reduce adds the ranks
         sums = st.bsums
@@ -325,7 +330,7 @@ class VAEEngine:
             self.dist.all_reduce_sum(st.bsums_g)
             sums = st.bsums_g
         ops.bn_bwd_apply(dy, x, C, st.mean, st.rstd, st.scale, st.shift, act, post, idx, sums, float(rows * self.world), dx,
-                         pre_relu=pre_relu, tap_other=tap_other, tap_coef=tap_coef)
+                         pre_relu=pre_relu, tap_other=tap_other, tap_coef=tap_coef, tap_sq=tap_sq)
 
     def _wgrad(self, x, dy, name, cin, cout, cin_pad, cout_pad, fold=None):
         """dW of conv `name` into the flat gradient buffer (Keras layout).  Off the critical path (only Adam needs it):
@@ -461,19 +466,37 @@ class VAEEngine:
         self.loss_nparts.copy_(torch.tensor(nparts, dtype=torch.int32))
         self.loss_scales.copy_(torch.tensor(scales, dtype=F64))
         self._nparts_host = nparts
+        # train step: the feature-loss sums of the tapped layers that have a BatchNorm backward (all but the last) come
+        # out of bn_bwd_apply (which reads both feature maps anyway) instead of a separate pass over them
+        fused = list(nparts)
+        k = 1
+        for li, L in enumerate(self.pm):
+            if L["tap"]:
+                if li < len(self.pm) - 1:
+                    fused[k] = ops.bn_bwd_apply_nblocks(L["a"][1], L["cout"], POST_POOL2 if L["pool"] else POST_NONE)
+                k += 1
+        assert max(fused) <= self.loss_stride
+        self._nparts_fused_host = fused
+        self.loss_nparts_fused = torch.tensor(fused, dtype=torch.int32, device=self.loss_nparts.device)
         self._loss_meta_ready = True
 
-    def losses(self):
-        """[loss, pm, mse, kld] (lattice_vae.py:241-255) into self.metrics (local batch means)."""
+    def losses(self, defer_taps=False):
+        """[loss, pm, mse, kld] (lattice_vae.py:241-255) into self.metrics (local batch means).  defer_taps (train step):
+        the tapped layers' sums are produced by backward(), which then assembles the metrics (assemble_losses)."""
         self._loss_meta()
         ops.sqdiff_partials(self.M, self.xhat, self.loss_partials[0], self._nparts_host[0])
         k = 1
-        for L in self.pm:
+        for li, L in enumerate(self.pm):
             if L["tap"]:
-                ops.sqdiff_partials(L["a"][0], L["a"][1], self.loss_partials[k], self._nparts_host[k])
+                if not (defer_taps and li < len(self.pm) - 1):
+                    ops.sqdiff_partials(L["a"][0], L["a"][1], self.loss_partials[k], self._nparts_host[k])
                 k += 1
-        ops.vae_loss_assemble(self.loss_partials, self.loss_nparts, self.loss_scales, self.kl, 1.0 / self.B, self.alpha,
-                              self.beta, self.metrics)
+        if not defer_taps:
+            self.assemble_losses(False)
+
+    def assemble_losses(self, fused):
+        ops.vae_loss_assemble(self.loss_partials, self.loss_nparts_fused if fused else self.loss_nparts, self.loss_scales,
+                              self.kl, 1.0 / self.B, self.alpha, self.beta, self.metrics)
 
     # ------------------------------------------------------------------------------------------
     # backward
@@ -491,16 +514,28 @@ class VAEEngine:
         ops.tap_grad_relu(last["a"][1], last["a"][0], coef[last["name"]], last["dc"])
         dy = self.pm[-2]["dy"]
         self._conv(last["dc"], last["wd"], None, out=dy, tag="pm1.c10.dgrad")
+        tap_slot = {}
+        k = 1
+        for L in self.pm:
+            if L["tap"]:
+                tap_slot[L["name"]] = k
+                k += 1
         for li in range(len(self.pm) - 2, -1, -1):
             L = self.pm[li]
+            tap_sq = None
+            if self._defer_taps and L["tap"]:
+                ks = tap_slot[L["name"]]
+                tap_sq = self.loss_partials[ks][: self._nparts_fused_host[ks]]
             self._bn_bwd(dy, L["a"][1], L["cout"], L["bnst"][1], ACT_NONE, POST_POOL2 if L["pool"] else POST_NONE,
                          L["idx"][1], L["dc"], pre_relu=True, tap_other=L["a"][0] if L["tap"] else None,
-                         tap_coef=coef.get(L["name"], 0.0))
+                         tap_coef=coef.get(L["name"], 0.0), tap_sq=tap_sq)
             if li > 0:
                 dy = self.pm[li - 1]["dy"]
                 self._conv(L["dc"], L["wd"], None, out=dy, tag=f"pm1.{L['name']}.dgrad")
             else:
                 self._conv(L["dc"], L["wd"], None, out=self.dxh16, tag="pm1.c1.dgrad", nominal=(L["cout"], 4))
+        if self._defer_taps:
+            self.assemble_losses(True)
         # ---- decoder ----
         ops.xhat_grad(self.M, self.xhat, 2.0 / (self.M.numel() // self.B * Bg), self.dxh16, self.dxhat)
         self._bn_bwd(self.dxhat, self.c5, 4, self.bn5, ACT_RELU, POST_NONE, None, self.dc5, dgamma=g["dec_bn5/gamma"],
@@ -591,7 +626,8 @@ class VAEEngine:
             self.decode(True)
             self.pm_forward(0, True)
             self.pm_forward(1, True)
-        self.losses()
+        self._defer_taps = self.fuse_tap_loss and not self.fuse_bn_bwd
+        self.losses(defer_taps=self._defer_taps)
         self.backward()
         self.optimizer_step()
 

@@ -388,9 +388,26 @@ def _bn_bwd_reduce(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, part
               _ptr(shift), act, alpha, post, _ptr(pool_idx), B, D, H, W, C, _ptr(partials), partials.shape[0], _stream())
 
 
+def bn_bwd_apply_nblocks(x, C, post):
+    """Partials written by bn_bwd_apply(..., tap_sq=...) for this layer shape."""
+    B, D, H, W, _ = x.shape
+    n = _lib.lib().icsg3d_bn_bwd_apply_nblocks(B, D, H, W, C, _dt(x), post)
+    if n <= 0:
+        raise _lib.Icsg3dError("bn_bwd_apply_nblocks: unsupported shape")
+    return n
+
+
 def bn_bwd_apply(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums, count, dx, pre_relu=False,
-                 tap_other=None, tap_coef=0.0, alpha=LEAKY_ALPHA, dy2=None):
+                 tap_other=None, tap_coef=0.0, alpha=LEAKY_ALPHA, dy2=None, tap_sq=None):
+    """tap_sq (fp64 [bn_bwd_apply_nblocks]): also return the per-block sums (x - tap_other)^2 of a tapped layer."""
     with _timed(("bn", "bwd_apply"), _nbytes(dy, x, pool_idx, dy2, dx, tap_other)):
+        if tap_sq is not None:
+            assert dy2 is None and tap_other is not None and tap_sq.dtype == torch.float64
+            B, D, H, W, _ = x.shape
+            return _lib.call("icsg3d_bn_bwd_apply_tapsq", _ptr(dy), _ld(dy), _ptr(x), _ld(x), _dt(x), _ptr(mean), _ptr(rstd),
+                             _ptr(scale), _ptr(shift), act, alpha, post, _ptr(pool_idx), B, D, H, W, C, _ptr(sums),
+                             ctypes.c_double(count), 1 if pre_relu else 0, _ptr(tap_other), tap_other.shape[-1], tap_coef,
+                             _ptr(dx), _ld(dx), _ptr(tap_sq), tap_sq.numel(), _stream())
         return _bn_bwd_apply(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums, count, dx, pre_relu, tap_other,
                              tap_coef, alpha, dy2)
 

@@ -257,6 +257,15 @@ int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* dy2, int lddy2, co
                         int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C, const double* sums,
                         double count, int pre_relu, const void* tap_other, int ld_other, float tap_coef,
                         void* dx, int lddx, void* stream);
+/* bn_bwd_apply of a tapped layer that also returns the layer's DFC feature loss (lattice_vae.py:257-270):
+ * tap_sq[b] = this block's sum (x - tap_other)^2 (fp64), tap_sq_nparts = icsg3d_bn_bwd_apply_nblocks(...) partials that the
+ * caller sums (icsg3d_vae_loss_assemble): the separate icsg3d_sqdiff_partials pass over the two feature maps is not needed. */
+int icsg3d_bn_bwd_apply_nblocks(int B, int D, int H, int W, int C, int dtype, int post);
+int icsg3d_bn_bwd_apply_tapsq(const void* dy, int lddy, const void* x, int ldx, int dtype, const float* mean,
+                              const float* rstd, const float* scale, const float* shift, int act, float alpha,
+                              int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C, const double* sums,
+                              double count, int pre_relu, const void* tap_other, int ld_other, float tap_coef,
+                              void* dx, int lddx, double* tap_sq, int tap_sq_nparts, void* stream);
 int icsg3d_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

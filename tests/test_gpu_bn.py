@@ -88,6 +88,17 @@ def test_bn_fwd_bwd(B, D, C, act, post, order):
                      tap_other=tap_other.to(dev) if tap_other is not None else None, tap_coef=tap_coef)
     torch.cuda.synchronize()
     assert rel_l2(dx.float(), dx_ref) < 1e-2
+    if tap_other is not None:
+        # fused DFC feature loss: the apply pass also returns sum (x - tap_other)^2 as per-block fp64 partials, dx unchanged
+        nsq = ops.bn_bwd_apply_nblocks(xd, C, P)
+        sq = torch.full((nsq,), -1.0, dtype=torch.float64, device=dev)
+        dx_sq = torch.zeros_like(dx)
+        ops.bn_bwd_apply(dyd, xd, C, mean, rstd, scale, shift, A, P, idx, bsums, float(rows), dx_sq, pre_relu=True,
+                         tap_other=tap_other.to(dev), tap_coef=tap_coef, tap_sq=sq)
+        torch.cuda.synchronize()
+        want_sq = ((x.double() - tap_other.double()) ** 2).sum().item()
+        assert abs(sq.sum().item() - want_sq) <= 1e-5 * want_sq, (sq.sum().item(), want_sq)
+        assert torch.equal(dx_sq, dx)
     # the same backward in ONE cooperative launch (reduce -> grid barrier -> fixed-order sums -> grid barrier -> apply)
     nf = ops.bn_bwd_fused_nparts(C, torch.bfloat16)
     fpart = torch.zeros(nf, 2, C, dtype=torch.float64, device=dev)
