@@ -235,6 +235,8 @@ class VAEEngine:
         # does not overlap with the filter-gradient side stream), so it is opt-in: ICSG3D_FUSE_BN_BWD=1.
         self.fuse_bn_bwd = os.environ.get("ICSG3D_FUSE_BN_BWD", "0") == "1" and (self.world == 1 or self.peer is not None)
         # DFC feature-loss sums out of the BatchNorm-backward apply pass of the tapped layers (ICSG3D_FUSE_TAP_LOSS=0: separate pass)
+        self._fuse_small_ok = self.world == 1 or self.peer is not None
+        self.fuse_bn_bwd_small_bytes = int(float(os.environ.get("ICSG3D_FUSE_BN_BWD_SMALL_MB", "0")) * (1 << 20))
         self.fuse_tap_loss = os.environ.get("ICSG3D_FUSE_TAP_LOSS", "1") != "0"
         self._defer_taps = False
         self.fuse_stats = True  # BatchNorm statistics from the conv epilogue where the streaming kernel serves the layer
@@ -304,7 +306,10 @@ class VAEEngine:
                 dbeta=None, tap_sq=None):
         rows = x.numel() // x.shape[-1]
         assert tap_sq is None or not self.fuse_bn_bwd
-        if self.fuse_bn_bwd:
+        # optional (ICSG3D_FUSE_BN_BWD_SMALL_MB > 0; measured 3.04 vs 2.99 ms/step at 6 MB, so off by default): layers of a
+        # few MB take the one-launch cooperative kernel
+        small = tap_sq is None and self._fuse_small_ok and x.numel() * x.element_size() <= self.fuse_bn_bwd_small_bytes
+        if self.fuse_bn_bwd or small:
             # one cooperative launch: partial sums -> grid barrier -> fixed-order reduction (+ peer-memory all-reduce in
             # data-parallel mode) -> grid barrier -> dx; the second read of dy / x comes from L2 where the layer fits
             n = ops.bn_bwd_fused_nparts(C, x.dtype)
