@@ -281,10 +281,19 @@ def run_cuda(args):
                                     for (_, t), v in sorted(bn.items())}}
         achieved = tot_f / (tot_ms * 1e-3) / 1e12
         dom = max(by_kernel, key=lambda k: by_kernel[k]["ms_per_step"])
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of its largest launch (static
+        # evidence, never measured under the profiler in this run): bytes per launch of THAT launch (c2 fprop)
+        traffic, traffic_detail = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_dominant_kernel.json")) as f:
+                traffic_detail = json.load(f)
+            traffic = traffic_detail["dram_bytes_read"] + traffic_detail["dram_bytes_write"]
+        except (OSError, KeyError, ValueError):
+            pass
         roof = {"bound": "tensor",
                 "kernel": "all tcgen05 Conv3D launches of the step (fprop, dgrad, wgrad); dominant by time: " + names[dom],
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_detail": traffic_detail,
                 "peak_source": peaks["src"] + " (sustained: kernels timed inside a long step)",
                 "algorithmic_gflop_per_launch": tot_f / n_all / 1e9, "avg_launch_ms": tot_ms / n_all,
                 "launches_per_step": n_all // reps, "kernel_ms_per_step": tot_ms / reps, "by_kernel": by_kernel,
