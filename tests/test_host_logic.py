@@ -137,3 +137,21 @@ def test_conv_dispatch_plans_respect_hardware_limits():
                     TD, TH, G, NT, a_bufs, b_stages, items, kc, smem = (out[i] for i in range(1, 10))
                     assert 2 * G * NT <= 512 and smem <= 225 * 1024 and D % TH == 0 and items >= 1 and D >= 8
     assert seen == {0, 1, 2}
+
+
+def test_bn_backward_grids_are_one_wave():
+    """Host-only contract of the BatchNorm backward partial counts (one wave of resident blocks on 148 SMs; no device
+    needed): bf16 reduce = 3 blocks/SM (plain, max-pool), apply = 2 blocks/SM, upsample / fp32 keep the 4-per-SM cap."""
+    from icsg3d_b200 import _lib
+    L = _lib.lib()
+    from icsg3d_b200 import ops
+    BF16, F32, NONE, POOL, UP = ops.DT_BF16, ops.DT_F32, ops.POST_NONE, ops.POST_POOL2, ops.POST_UP2
+    assert L.icsg3d_bn_bwd_nparts(32, 32, 32, 32, 64, BF16, POOL) == 148 * 3      # pm.c2
+    assert L.icsg3d_bn_bwd_nparts(32, 32, 32, 32, 32, BF16, NONE) == 148 * 3      # pm.c1
+    assert L.icsg3d_bn_bwd_apply_nblocks(32, 32, 32, 32, 64, BF16, POOL) == 148 * 2
+    assert L.icsg3d_bn_bwd_apply_nblocks(32, 32, 32, 32, 32, BF16, NONE) == 148 * 2
+    assert L.icsg3d_bn_bwd_nparts(32, 16, 16, 16, 32, BF16, UP) == 148 * 4        # dec3: generic kernel
+    assert L.icsg3d_bn_bwd_nparts(32, 32, 32, 32, 4, F32, NONE) == 148 * 4        # dec_bn5 (fp32 logits)
+    # small layers: one block per rows-per-block group, never more than the rows
+    assert L.icsg3d_bn_bwd_nparts(2, 4, 4, 4, 512, BF16, NONE) == 2 * 64 // (256 // 64)
+    assert L.icsg3d_bn_bwd_nparts(2, 4, 4, 4, 12, BF16, NONE) < 0                 # C must be a multiple of the vector width
