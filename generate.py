@@ -10,6 +10,7 @@ import time
 import numpy as np
 
 from icsg3d_b200 import utils
+from icsg3d_b200.pipeline import GeneratePipeline
 from icsg3d_b200.unet.unet import AtomUnet
 from icsg3d_b200.vae.lattice_vae import LatticeDFCVAE
 
@@ -47,18 +48,22 @@ if __name__ == "__main__":
         M_base = np.concatenate([Mb, Cb], axis=-1)
         cond = np.eye(a.ncond, dtype=np.float32)[[int(df[df["task_id"] == base]["interval"].values[0])]]
     z_mu, z_logvar, z = vae.encoder.predict([M_base, cond])
+    # decode -> lattice parameters -> U-Net -> argmax / 0.8 threshold, device resident (icsg3d_b200/pipeline.py): the decoder
+    # output never visits the host; only labels, mask, density channel and lattice / voxel parameters come back
+    pipe = GeneratePipeline(vae, unet, a.batch_size, threshold=0.8, eps_frac=a.eps_frac)
+    cond_tensor = np.tile(cond, (a.batch_size, 1))
     t0 = time.time()
     n_done = 0
     for b in range(a.nsamples // a.batch_size):
         z_s = np.random.normal(z_mu, a.var, size=(a.batch_size, vae.latent_dim))   # generate.py:204 (`var` used as a std)
-        M_prime = vae.decoder.predict([z_s, np.tile(cond, (a.batch_size, 1))])
-        l_prime = utils.to_lattice_params(M_prime[..., 1:], eps_frac=a.eps_frac, d=d)
-        dv = utils.to_voxel_params(l_prime, eps=a.eps_frac, d=d)
-        S_prime, S_b = unet.predict_labels(M_prime, threshold=0.8)                  # generate.py:220-225
+        r = pipe.run(z_s, cond_tensor)                                              # generate.py:208-225
+        S_prime, S_b = r["species"].cpu().numpy(), r["mask"].cpu().numpy().astype(bool)
+        l_prime, dv = r["lattice"].cpu().numpy(), r["voxel"].cpu().numpy()
         n_done += a.batch_size
         if a.out:
             os.makedirs(a.out, exist_ok=True)
-            np.savez_compressed(os.path.join(a.out, f"batch_{b}.npz"), M=M_prime[..., 0], S=S_prime, mask=S_b, lattice=l_prime, dv=dv)
+            np.savez_compressed(os.path.join(a.out, f"batch_{b}.npz"), M=r["density"].cpu().numpy(), S=S_prime, mask=S_b,
+                                lattice=l_prime, dv=dv)
     dt = time.time() - t0
     print("generated %d samples in %.2f s (%.1f samples/s): decoded densities, species labels, atom masks, lattice params"
           % (n_done, dt, n_done / max(dt, 1e-9)))

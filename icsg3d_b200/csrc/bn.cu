@@ -286,6 +286,7 @@ struct BnPeerParams {
   const unsigned long long* peers;  // device array [world]: base address of every rank's symmetric buffer
   int world, rank, slot, nslots, cmax;
   const long long* epoch;           // device scalar, >= 1, incremented once per step
+  long long timeout;                // spin budget in clock64 ticks (peer_timeout_cycles())
 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(1024) bn_reduce_allreduce_kernel(const double*
                                       (slot_idx * pp.world + r) * 64 + blockIdx.x;
     const long long t_start = clock64();
     while (ld_acquire_sys_u64(lflag) != epoch) {
-      if (clock64() - t_start > 8000000000ll) {
+      if (clock64() - t_start > pp.timeout) {
         printf("icsg3d: bn all-reduce timeout rank %d slot %d block %d waiting for rank %d (epoch %llu)\n", pp.rank, pp.slot,
                blockIdx.x, r, epoch);
         __trap();
@@ -1256,7 +1257,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
                                             (slot_idx * pp.world + r) * 64 + blockIdx.x;
           const long long t_start = clock64();
           while (ld_acquire_sys_u64(lflag) != epoch) {
-            if (clock64() - t_start > 8000000000ll) {
+            if (clock64() - t_start > pp.timeout) {
               printf("icsg3d: bn backward all-reduce timeout rank %d slot %d block %d waiting for rank %d\n", pp.rank, pp.slot,
                      blockIdx.x, r);
               __trap();
@@ -1660,7 +1661,7 @@ extern "C" int icsg3d_bn_reduce_allreduce_finalize(const double* partials, int n
   int rc = bn_peer_check(peers, world, rank, slot, nslots, cmax, epoch, C);
   if (rc) return rc;
   BnPeerParams pp{reinterpret_cast<const unsigned long long*>(peers), world, rank, slot, nslots, cmax,
-                  reinterpret_cast<const long long*>(epoch)};
+                  reinterpret_cast<const long long*>(epoch), peer_timeout_cycles()};
   bn_reduce_allreduce_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, nparts, C, 0, count_global, gamma, beta, eps, sums, mean, rstd, scale, shift, moving_mean, moving_var, momentum,
       nullptr, nullptr, pp);
@@ -1675,7 +1676,7 @@ extern "C" int icsg3d_bn_reduce_allreduce_grads(const double* partials, int npar
   int rc = bn_peer_check(peers, world, rank, slot, nslots, cmax, epoch, C);
   if (rc) return rc;
   BnPeerParams pp{reinterpret_cast<const unsigned long long*>(peers), world, rank, slot, nslots, cmax,
-                  reinterpret_cast<const long long*>(epoch)};
+                  reinterpret_cast<const long long*>(epoch), peer_timeout_cycles()};
   bn_reduce_allreduce_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, nparts, C, 1, 1.0, nullptr, nullptr, 0.f, sums_global, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f,
       dgamma, dbeta, pp);
@@ -1715,7 +1716,7 @@ extern "C" int icsg3d_bn_bwd_fused(const void* dy, int lddy, const void* dy2, in
   BnFusedExtra e{};
   e.sums = sums; e.dgamma = dgamma; e.dbeta = dbeta;
   e.pp = BnPeerParams{reinterpret_cast<const unsigned long long*>(peers), peers ? world : 1, rank, slot, nslots, cmax,
-                      reinterpret_cast<const long long*>(epoch)};
+                      reinterpret_cast<const long long*>(epoch), peer_timeout_cycles()};
   if (peers) {
     int rc = bn_peer_check(peers, world, rank, slot, nslots, cmax, epoch, C);
     if (rc) return rc;

@@ -44,6 +44,9 @@ extern unsigned long long g_launches;
   } while (0)
 
 int sm_count();
+// Spin budget (SM clock cycles) of the peer-memory all-reduce kernels before they trap: ICSG3D_PEER_TIMEOUT_S seconds
+// (default 600 s, i.e. NCCL-like tolerance of host-side rank skew), or icsg3d_set_peer_timeout().
+long long peer_timeout_cycles();
 
 // Tensor-map encode (driver entry point fetched at run time; no link against libcuda).
 // dims/strides innermost-first; strides in BYTES for dims 1..rank-1.

@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(float* __restrict__
                                                              float* __restrict__ v, const double* __restrict__ state, float b1,
                                                              float b2, float eps, float grad_scale, long long n,
                                                              const unsigned long long* __restrict__ peers, int world, int rank,
-                                                             int nchunks, size_t data_off, const long long* __restrict__ epoch_p) {
+                                                             int nchunks, size_t data_off, const long long* __restrict__ epoch_p,
+                                                             long long timeout) {
   const unsigned long long epoch = static_cast<unsigned long long>(*epoch_p);
   const int par = static_cast<int>(epoch & 1ull);
   const long long i0 = static_cast<long long>(blockIdx.x) * kAdamChunk;
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(float* __restrict__
     unsigned long long seen;
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(lflag) : "memory");
-      if (seen != epoch && clock64() - t_start > 8000000000ll) {
+      if (seen != epoch && clock64() - t_start > timeout) {
         printf("icsg3d: gradient all-reduce timeout rank %d chunk %d waiting for rank %d (epoch %llu)\n", rank, blockIdx.x, r,
                epoch);
         __trap();
@@ -582,7 +583,7 @@ extern "C" int icsg3d_adam_keras_allreduce_step(float* p, float* g, float* m, fl
   adam_allreduce_kernel<<<static_cast<int>(nchunks), 256, 0, ST>>>(
       p, g, m, v, state, static_cast<float>(beta1), static_cast<float>(beta2), static_cast<float>(eps), grad_scale, n,
       reinterpret_cast<const unsigned long long*>(peers), world, rank, static_cast<int>(nchunks), data_off,
-      reinterpret_cast<const long long*>(epoch));
+      reinterpret_cast<const long long*>(epoch), peer_timeout_cycles());
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

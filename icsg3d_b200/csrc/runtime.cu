@@ -1,6 +1,7 @@
 // Host runtime bits of libicsg3d: error reporting, device queries, TMA tensor-map encoding.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -22,6 +23,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return ICSG3D_ERR_CUDA;
 }
 
+void set_peer_timeout(double seconds);
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -33,6 +36,20 @@ int sm_count() {
   }
   return cached[dev];
 }
+
+static long long g_peer_timeout = -1;
+long long peer_timeout_cycles() {
+  if (g_peer_timeout < 0) {
+    double sec = 600.0;
+    if (const char* e = getenv("ICSG3D_PEER_TIMEOUT_S")) {
+      const double v = atof(e);
+      if (v > 0.0) sec = v;
+    }
+    g_peer_timeout = static_cast<long long>(sec * 2.0e9);  // clock64 ticks at <= 2 GHz
+  }
+  return g_peer_timeout;
+}
+void set_peer_timeout(double seconds) { g_peer_timeout = static_cast<long long>(seconds * 2.0e9); }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -98,5 +115,14 @@ int icsg3d_version(void) { return 100; }
 int icsg3d_sm_count(void) { return icsg3d::sm_count(); }
 
 int64_t icsg3d_launch_count(void) { return static_cast<int64_t>(icsg3d::g_launches); }
+
+int icsg3d_set_peer_timeout(double seconds) {
+  if (!(seconds > 0.0)) {
+    icsg3d::set_error("set_peer_timeout: seconds must be > 0");
+    return ICSG3D_ERR_INVALID;
+  }
+  icsg3d::set_peer_timeout(seconds);
+  return ICSG3D_OK;
+}
 
 }  // extern "C"

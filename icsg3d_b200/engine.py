@@ -7,7 +7,10 @@ CUDA graph and replayed).
 
 Every FLOP runs in libicsg3d.so (icsg3d_b200/ops.py); this file only orders launches and owns buffers.
 Data-parallel mode: batch sharded over ranks; BatchNorm statistic sums (forward and backward)
-and the flat gradient buffer are summed with NCCL all-reduce; nothing else is exchanged.
+and the flat gradient buffer are summed INSIDE the consuming kernels over NVLink peer (symmetric) memory
+(PeerBN below; csrc/bn.cu::bn_reduce_allreduce_kernel, csrc/misc.cu::adam_allreduce_kernel), so the whole
+data-parallel step is one CUDA graph without a NCCL call; ICSG3D_DP_PEER=0 falls back to NCCL all-reduces between
+graph segments.  Nothing else is exchanged.
 """
 from __future__ import annotations
 
@@ -131,6 +134,9 @@ class VAEEngine:
         # pm(x) does not depend on the encoder/decoder: it runs on a side stream (forked/joined inside the captured
         # graph) so that its large convs overlap the small, latency-bound VAE kernels.  Own scratch per stream.
         self.ctx2 = _Ctx(dev, max_dw=16, conv_ws_bytes=ws_bytes)
+        # filter-gradient scratch: owned by this engine (all its wgrad launches are ordered on one stream), sized once for
+        # the largest layer and never reallocated — its address is baked into the captured step graph
+        self.wg_ws = torch.empty(max(self._wgrad_ws_bytes(batch, d, filters), 16), dtype=torch.uint8, device=dev)
         # Data parallel: BatchNorm statistic sums are exchanged INSIDE the finalize kernels over NVLink peer memory
         # (PeerBN); only the flat gradient goes through NCCL.  ICSG3D_DP_PEER=0 (or no symmetric memory) falls back to
         # NCCL all-reduces of the sums, which also forces a single stream (collectives split the captured graph).
@@ -265,6 +271,22 @@ class VAEEngine:
             need = max(need, ops.conv3d_k3_workspace_bytes(B, D_, ci, co), ops.conv3d_k3_workspace_bytes(B, D_, co, ci))
         return need
 
+    @staticmethod
+    def _wgrad_ws_bytes(B, d, filters):
+        """Largest filter-gradient workspace any layer of the step asks for."""
+        f = list(filters)
+        shapes, D, cin = [], d, 16
+        for c in f:  # encoder: (D, cin_pad, cout)
+            shapes.append((D, cin, c))
+            cin, D = c, D // 2
+        shapes.append((D, f[-1], 16))  # enc_conv5
+        S, cin = d // 8, 16
+        for i, c in enumerate(f[::-1]):
+            shapes.append((S, cin, c))
+            cin, S = c, (S * 2 if i < len(f) - 1 else S)
+        shapes.append((S, f[0], 16))  # decoder_output
+        return max(ops.conv3d_k3_wgrad_workspace_bytes(B, D_, ci, co) for D_, ci, co in shapes)
+
     def _conv(self, x, w, bias, ctx=None, **kw):
         """Conv3D through the dispatcher with this stream's split-K workspace (used by the 4^3 / 2^3 layers)."""
         return ops.conv3d_k3(x, w, bias, ws=(ctx or self.ctx).conv_ws, **kw)
@@ -358,10 +380,12 @@ class VAEEngine:
     def _wgrad_now(self, x, dy, name, cin, cout, cin_pad, cout_pad, fold=None):
         g = self.vp.g[name + "/kernel"]
         if cin == cin_pad and cout == cout_pad and fold is None:
-            ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=g.view(27, cin, cout), tag=name + ".wgrad")
+            ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=g.view(27, cin, cout), tag=name + ".wgrad",
+                                ws=self.wg_ws)
             return
         scratch = self.ctx.dw_pad[: 27 * cin_pad * cout_pad].view(27, cin_pad, cout_pad)
-        ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=scratch, tag=name + ".wgrad", nominal=(cin, cout))
+        ops.conv3d_k3_wgrad(x, dy, cin=cin_pad, cout=cout_pad, out=scratch, tag=name + ".wgrad", nominal=(cin, cout),
+                            ws=self.wg_ws)
         if fold is None:
             ops.unpack_conv_dw(scratch, cin, cout, out=g)
         else:

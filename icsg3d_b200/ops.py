@@ -206,17 +206,35 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
     return out
 
 
-_wgrad_ws = {}
+def conv3d_k3_wgrad_workspace_bytes(B, D, cin, cout, k1=False):
+    """Scratch bytes the filter-gradient kernel needs for this layer shape (split partials before the fixed-order sum)."""
+    fn = _lib.lib().icsg3d_conv3d_k1_wgrad_workspace if k1 else _lib.lib().icsg3d_conv3d_k3_wgrad_workspace
+    need = int(fn(B, D, D, D, cin, cout))
+    if need < 0:
+        raise _lib.Icsg3dError("conv3d wgrad workspace: invalid shape")
+    return need
 
 
-def conv3d_k3_wgrad(x, dy, *, cin=None, cout=None, out=None, ref=False, nominal=None, tag="wgrad"):
-    """dW[27][cin][cout] (fp32) = sum_v x[v+tap, ci] * dy[v, co]; x,dy bf16 NDHWC."""
+def _wgrad_scratch(need, ws, device):
+    """Engines pass their own pre-sized workspace (one per stream; its address is baked into captured CUDA graphs, so it
+    is never reallocated).  Direct callers without one get a fresh allocation per call — never a shared module-level
+    buffer that a later, larger request could free under a captured graph."""
+    if ws is None:
+        return torch.empty(max(int(need), 16), dtype=torch.uint8, device=device)
+    if ws.numel() * ws.element_size() < need:
+        raise _lib.Icsg3dError(f"conv3d wgrad: workspace of {ws.numel() * ws.element_size()} B is smaller than the {need} B "
+                               "this layer needs (size it with conv3d_k3_wgrad_workspace_bytes at construction)")
+    return ws
+
+
+def conv3d_k3_wgrad(x, dy, *, cin=None, cout=None, out=None, ref=False, nominal=None, tag="wgrad", ws=None):
+    """dW[27][cin][cout] (fp32) = sum_v x[v+tap, ci] * dy[v, co]; x,dy bf16 NDHWC (channel slices allowed)."""
     _chk(x, torch.bfloat16, "x")
     _chk(dy, torch.bfloat16, "dy")
-    B, D, H, W, ldx = x.shape
-    ldy = dy.shape[-1]
-    cin = cin or ldx
-    cout = cout or ldy
+    B, D, H, W, _ = x.shape
+    ldx, ldy = _ld(x), _ld(dy)
+    cin = cin or x.shape[-1]
+    cout = cout or dy.shape[-1]
     if out is None:
         out = torch.empty((27, cin, cout), dtype=torch.float32, device=x.device)
     if ref:
@@ -225,15 +243,11 @@ def conv3d_k3_wgrad(x, dy, *, cin=None, cout=None, out=None, ref=False, nominal=
     need = _lib.lib().icsg3d_conv3d_k3_wgrad_workspace(B, D, H, W, cin, cout)
     if need < 0:
         raise _lib.Icsg3dError("conv3d_k3_wgrad_workspace: invalid shape")
-    key = (x.device.index,)
-    ws = _wgrad_ws.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(int(need), dtype=torch.uint8, device=x.device)
-        _wgrad_ws[key] = ws
+    ws = _wgrad_scratch(need, ws, x.device)
     nc, no = nominal if nominal else (cin, cout)
     with _timed(("wgrad", tag), 2.0 * B * D * H * W * 27 * nc * no):
         _lib.call("icsg3d_conv3d_k3_wgrad", _ptr(x), ldx, _ptr(dy), ldy, _ptr(out), B, D, H, W, cin, cout, _ptr(ws),
-                  ctypes.c_int64(ws.numel()), _stream())
+                  ctypes.c_int64(ws.numel() * ws.element_size()), _stream())
     return out
 
 
@@ -548,18 +562,14 @@ def adam_keras_allreduce_step(p, g, m, v, state, lr, peers, world, rank, epoch, 
 # ------------------------------------------------------------------------------------------------
 # U-Net heads
 # ------------------------------------------------------------------------------------------------
-def conv3d_k1_wgrad(x, dy, *, cin, cout, out):
+def conv3d_k1_wgrad(x, dy, *, cin, cout, out, ws=None):
     """dW[1][cin][cout] of a 1x1x1 conv (tcgen05, same kernel as the 3x3x3 filter gradient)."""
     B, D, H, W, _ = x.shape
     need = _lib.lib().icsg3d_conv3d_k1_wgrad_workspace(B, D, H, W, cin, cout)
-    key = (x.device.index,)
-    ws = _wgrad_ws.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(int(need), dtype=torch.uint8, device=x.device)
-        _wgrad_ws[key] = ws
+    ws = _wgrad_scratch(need, ws, x.device)
     with _timed(("wgrad", "heads.wgrad"), 2.0 * B * D * H * W * cin * cout):
         _lib.call("icsg3d_conv3d_k1_wgrad", _ptr(x), _ld(x), _ptr(dy), _ld(dy), _ptr(out), B, D, H, W, cin, cout, _ptr(ws),
-                  ctypes.c_int64(ws.numel()), _stream())
+                  ctypes.c_int64(ws.numel() * ws.element_size()), _stream())
     return out
 
 
@@ -589,3 +599,23 @@ def heads_loss(logits, c1, species, class_w, inv_count, partials, argmax_out=Non
 def heads_loss_finalize(partials, count, out, raw=None):
     _lib.call("icsg3d_heads_loss_finalize", _ptr(partials), partials.shape[0], ctypes.c_double(count), _ptr(out), _ptr(raw),
               _stream())
+
+
+def heads_predict(logits, c1, threshold, argmax=None, mask=None, sig_prob=None):
+    """generate.py:221-225 on the fp32 head logits: argmax species (uint8), sigmoid >= threshold mask (uint8), sigmoid."""
+    _chk(logits, torch.float32, "logits")
+    M = logits.numel() // logits.shape[-1]
+    _lib.call("icsg3d_heads_predict", _ptr(logits), logits.shape[-1], c1, ctypes.c_int64(M), float(threshold), _ptr(argmax),
+              _ptr(mask), _ptr(sig_prob), _stream())
+
+
+def metric_counts(y_true, y_pred):
+    """unet.py:159-193: the five K.round(K.clip(.)) sums over (y_true, y_pred) fp32 [..., C] -> fp64 [5] device tensor."""
+    _chk(y_true, torch.float32, "y_true")
+    _chk(y_pred, torch.float32, "y_pred")
+    if y_true.shape != y_pred.shape or not (y_true.is_contiguous() and y_pred.is_contiguous()):
+        raise ValueError("metric_counts: y_true / y_pred must be contiguous tensors of the same shape")
+    counts = torch.empty(5, dtype=torch.float64, device=y_true.device)
+    _lib.call("icsg3d_metric_counts", _ptr(y_true), _ptr(y_pred), ctypes.c_int64(y_true.numel()), y_true.shape[-1],
+              _ptr(counts), _stream())
+    return counts

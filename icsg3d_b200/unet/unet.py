@@ -17,7 +17,7 @@ from ..engine import Dist
 from ..optimizers import Adam
 from ..params import ParamStore, unet_specs
 from ..unet_engine import UNetEngine
-from ..weights_io import load_npz, save_npz
+from ..weights_io import load_weights_file, save_weights_file
 
 
 class _LossSpec:
@@ -32,14 +32,42 @@ def weighted_categorical_crossentropy(weights):
     return _LossSpec(weights)
 
 
-def _metric(name):
-    def f(y_true, y_pred):
-        raise RuntimeError(f"{name} is computed inside the fused head kernel (metrics of train/test_on_batch)")
-    f.__name__ = name
-    return f
+K_EPSILON = 1e-7  # keras.backend.epsilon()
 
 
-r_m, wr_m, p_m, f1_m = _metric("r_m"), _metric("wr_m"), _metric("p_m"), _metric("f1_m")
+def _counts(y_true, y_pred):
+    """The K.round(K.clip(., 0, 1)) sums of unet.py:159-193 on the device (csrc/post.cu::metric_counts_kernel):
+    [tp, possible, predicted, tp without class 0, possible without class 0]."""
+    from .. import ops
+    dev = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cuda"
+    t = _to_dev(y_true, dev, torch.float32).contiguous()
+    p = _to_dev(y_pred, dev, torch.float32).contiguous()
+    return ops.metric_counts(t, p).cpu().tolist()
+
+
+def r_m(y_true, y_pred):
+    """unet.py:159-167 recall over all classes."""
+    tp, possible, _, _, _ = _counts(y_true, y_pred)
+    return tp / (possible + K_EPSILON)
+
+
+def wr_m(y_true, y_pred):
+    """unet.py:170-179 recall without the zero (background) class (hard-coded np.ones(95) weights with w[0] = 0)."""
+    _, _, _, tp_w, possible_w = _counts(y_true, y_pred)
+    return tp_w / (possible_w + K_EPSILON)
+
+
+def p_m(y_true, y_pred):
+    """unet.py:182-187 precision."""
+    tp, _, predicted, _, _ = _counts(y_true, y_pred)
+    return tp / (predicted + K_EPSILON)
+
+
+def f1_m(y_true, y_pred):
+    """unet.py:189-193."""
+    tp, possible, predicted, _, _ = _counts(y_true, y_pred)
+    precision, recall = tp / (predicted + K_EPSILON), tp / (possible + K_EPSILON)
+    return 2 * ((precision * recall) / (precision + recall + K_EPSILON))
 
 
 def _to_dev(a, dev, dtype):
@@ -79,10 +107,15 @@ class _Model:
         return [np.concatenate([o[0] for o in outs]), np.concatenate([o[1] for o in outs])]
 
     def save_weights(self, path):
-        save_npz(path, self._o.params.to_dict())
+        """Keras HDF5 for .h5/.hdf5 paths (one group per layer, readable by the reference's `load_weights`), else .npz.
+        Data parallel: rank 0 alone writes."""
+        o = self._o
+        if o.dist is not None and o.dist.world > 1 and o.dist.rank != 0:
+            return
+        save_weights_file(path, o.params.to_dict(), o.params.specs, model="unet")
 
     def load_weights(self, path):
-        self._o.params.load_dict(load_npz(path))
+        self._o.params.load_dict(load_weights_file(path, self._o.params.specs))
 
     def save(self, path):
         self.save_weights(path)
@@ -90,7 +123,11 @@ class _Model:
 
 class AtomUnet:
     def __init__(self, num_classes=95, class_weights=None, weights=None, input_shape=(32, 32, 32, 4), lr=1e-6, device=None,
-                 dist: Dist | None = None, seed=2, loss_weight=None, use_cuda_graph=True):
+                 dist: Dist | None = None, seed=2, loss_weight=None, use_cuda_graph=True, dtype="bf16"):
+        if dtype not in ("bf16", "fp32"):
+            raise ValueError("dtype must be 'bf16' (throughput mode) or 'fp32' (fp32-class split operands, parity mode)")
+        self.dtype = dtype
+        self._x3 = {}
         self.class_weights = class_weights
         self.input_shape = tuple(input_shape)
         self.optimizer = Adam(lr)
@@ -113,13 +150,20 @@ class AtomUnet:
         else:
             self.filepath = "./saved_models/unet_%d_channel_weights.best.hdf5" % self.input_shape[-1]
 
-    def engine(self, batch) -> UNetEngine:
-        eng = self._engines.get(batch)
+    def engine(self, batch, train=True) -> UNetEngine:
+        """train=False: inference-only engine (no gradient / Adam buffers, no dgrad weight copies)."""
+        key = (batch, bool(train))
+        eng = self._engines.pop(key, None)
+        if eng is None and not train:  # a training engine of that batch can serve inference too
+            eng = self._engines.pop((batch, True), None)
+            key = (batch, True) if eng is not None else key
         if eng is None:
+            while len(self._engines) >= 2:  # keep at most two engines (buffers + captured graph) alive, evict the LRU one
+                self._engines.pop(next(iter(self._engines)))
             eng = UNetEngine(batch, d=self.input_shape[0], channels=self.input_shape[-1], classes=self.num_classes,
                              device=self.device, params=self.params, lr=self.optimizer.lr, class_weight=self.loss_weight,
-                             dist=self.dist)
-            self._engines[batch] = eng
+                             dist=self.dist, train=train)
+        self._engines[key] = eng
         return eng
 
     def _step(self, x, labels, train):
@@ -134,29 +178,56 @@ class AtomUnet:
             eng.eval_step()
         return eng.metrics_host()
 
-    def _predict(self, x, want_probs=False, batch=None):
+    def _predict(self, x, want_probs=False, batch=None, threshold=0.8):
         n = len(x)
         B = min(n, batch or 8)
-        eng = self.engine(B)
+        eng = self.engine(B, train=False)
         d, C = self.input_shape[0], self.num_classes
         x = _to_dev(x, self.device, torch.float32)
         probs = torch.empty(B, d, d, d, C, dtype=torch.float32, device=self.device) if want_probs else None
-        soft, sig, lab = [], [], []
+        soft, sig, lab, msk = [], [], [], []
         for s in range(0, n, B):
             k = min(s + B, n) - s
             eng.X[:k].copy_(x[s:s + k].reshape(k, d, d, d, -1))
-            eng.predict(probs)
+            eng.predict(probs, threshold=threshold)
             if want_probs:
                 soft.append(probs[:k].cpu().numpy().copy())
             sig.append(eng.sigp[:k].cpu().numpy().copy()[..., None])
             lab.append(eng.argmax[:k].cpu().numpy().copy())
+            msk.append(eng.mask[:k].cpu().numpy().copy())
+        self._last_mask = np.concatenate(msk)
         return (np.concatenate(soft) if want_probs else None), np.concatenate(sig), np.concatenate(lab)
 
     def predict_labels(self, x, threshold=0.8, batch=None):
-        """Fused post-processing of generate.py:221-225: argmax species labels (uint8) and the thresholded atom mask,
-        without materialising the (n,d,d,d,95) probability tensor."""
-        _, sig, lab = self._predict(x, want_probs=False, batch=batch)
-        return lab, (sig[..., 0] >= threshold)
+        """Fused post-processing of generate.py:221-225: argmax species labels (uint8) and the thresholded atom mask
+        (bool), both produced on the device (csrc/post.cu::heads_predict_kernel) without materialising the
+        (n,d,d,d,95) probability tensor.  With AtomUnet(dtype="fp32") the pass runs on fp32-class split operands
+        (engine_x3.py), the mode in which the labels are bit-exact against the fp32 reference graph."""
+        if self.dtype == "fp32":
+            return self._predict_labels_x3(x, threshold, batch)
+        _, _, lab = self._predict(x, want_probs=False, batch=batch, threshold=threshold)
+        return lab, self._last_mask.astype(bool)
+
+    def _predict_labels_x3(self, x, threshold, batch):
+        from .. import ops
+        from ..engine_x3 import UNetForwardX3
+        n, d = len(x), self.input_shape[0]
+        B = min(n, batch or 8)
+        x = _to_dev(x, self.device, torch.float32).reshape(n, d, d, d, -1)
+        lab, msk = [], []
+        for s in range(0, n, B):
+            k = min(s + B, n) - s
+            un = self._x3.get(k)
+            if un is None:
+                un = self._x3[k] = UNetForwardX3(k, d=d, channels=self.input_shape[-1], classes=self.num_classes,
+                                                 device=self.device, params=self.params)
+            logits, _, _ = un.predict(x[s:s + k])
+            am = torch.empty(k, d, d, d, dtype=torch.uint8, device=self.device)
+            mk = torch.empty(k, d, d, d, dtype=torch.uint8, device=self.device)
+            ops.heads_predict(logits, self.num_classes, float(threshold), argmax=am, mask=mk)
+            lab.append(am.cpu().numpy())
+            msk.append(mk.cpu().numpy().astype(bool))
+        return np.concatenate(lab), np.concatenate(msk)
 
     def train_generator(self, train_gen, val_gen, epochs=100, output_dir="output/unet/"):
         """unet.py:357-381: fit_generator + ModelCheckpoint(save_best_only on val_loss); plotting callback omitted."""

@@ -93,6 +93,7 @@ class UNetEngine:
         self.h_bias = z(self.nout_h, dt=F32)
         self.logits = z(B, d, d, d, self.nout_h, dt=F32)
         self.argmax = z(B, d, d, d, dt=torch.uint8)
+        self.mask = z(B, d, d, d, dt=torch.uint8)
         self.sigp = z(B, d, d, d, dt=F32)
         self.h_nparts = ops.heads_loss_nparts(B * d ** 3)
         self.h_partials = torch.zeros(self.h_nparts, 6, dtype=F64, device=dev)
@@ -108,6 +109,11 @@ class UNetEngine:
             self.colsum = torch.zeros(2 * 512, dtype=F64, device=dev)
         self._graph = None
         self.use_graph = False
+        self.wg_ws = None
+        if train:  # filter-gradient scratch owned by this engine (see VAEEngine.wg_ws)
+            need = max(ops.conv3d_k3_wgrad_workspace_bytes(B, L["D"], L["cin_pad"], L["cout"]) for L in self.L.values())
+            need = max(need, ops.conv3d_k3_wgrad_workspace_bytes(B, d, 128, self.nout_h, k1=True))
+            self.wg_ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
 
     # ------------------------------------------------------------------------------------------
     def pack_weights(self, dgrad=True):
@@ -153,10 +159,14 @@ class UNetEngine:
             if L.get("pool"):
                 ops.bn_apply_fwd(x, C, st.scale, st.shift, ACT_NONE, POST_POOL2, y=L["p"], pool_idx=L["idx"])
 
-    def forward(self, training, want_probs=None, with_grad=False):
-        """unet_3d_multiclass (unet.py:272-355) on self.X [+ losses on self.species]."""
+    def forward(self, training, want_probs=None, with_grad=False, x_packed=False, losses=True):
+        """unet_3d_multiclass (unet.py:272-355) on self.X [+ losses on self.species].  x_packed: self.x16 already holds
+        the bf16 input (written by the producer, e.g. utils.lattice_params_device's fused pack); losses=False stops at
+        the head logits (inference: generate.py:220)."""
         p = self.pp.p
-        if self.channels == 4:
+        if x_packed:
+            pass
+        elif self.channels == 4:
             ops.pack_vae_input(self.X, None, None, self.x16)
         else:
             ops.f32_to_bf16_rows(self.X, 1, self.x16)
@@ -166,6 +176,8 @@ class UNetEngine:
             self._bn_fwd(L, training)
         ops.conv3d_k3(self.L["c18"]["y"], self.h_wf, self.h_bias, out=self.logits, tag="unet.heads.fprop",
                       nominal=(128, self.classes + 1))
+        if not losses:
+            return
         M = self.B * self.d ** 3
         ops.heads_loss(self.logits, self.classes, self.species, self.class_w, 1.0 / (M * self.world), self.h_partials,
                        argmax_out=self.argmax, sig_prob=self.sigp, dlogits=self.dlogits if with_grad else None,
@@ -202,7 +214,7 @@ class UNetEngine:
         p, g = self.pp.p, self.pp.g
         c18 = self.L["c18"]
         # heads: dW, db, and the gradient w.r.t. c18's BN output
-        ops.conv3d_k1_wgrad(c18["y"], self.dlogits, cin=128, cout=self.nout_h, out=self.dwcat)
+        ops.conv3d_k1_wgrad(c18["y"], self.dlogits, cin=128, cout=self.nout_h, out=self.dwcat, ws=self.wg_ws)
         rows = self.dlogits.numel() // self.nout_h
         n = ops.bn_nparts(rows, self.nout_h, BF16)
         part = self.ctx.partials[: n * 2 * self.nout_h].view(n, 2, self.nout_h)
@@ -232,11 +244,11 @@ class UNetEngine:
             gk = g[nme + "/kernel"]
             if L["cin_real"] == L["cin_pad"]:
                 ops.conv3d_k3_wgrad(xin, L["dc"], cin=L["cin_pad"], cout=C, out=gk.view(27, L["cin_real"], C),
-                                    tag=f"unet.{nme}.wgrad")
+                                    tag=f"unet.{nme}.wgrad", ws=self.wg_ws)
             else:
                 scratch = self.ctx.dw_pad[: 27 * L["cin_pad"] * C].view(27, L["cin_pad"], C)
                 ops.conv3d_k3_wgrad(xin, L["dc"], cin=L["cin_pad"], cout=C, out=scratch, tag=f"unet.{nme}.wgrad",
-                                    nominal=(L["cin_real"], C))
+                                    nominal=(L["cin_real"], C), ws=self.wg_ws)
                 ops.unpack_conv_dw(scratch, L["cin_real"], C, out=gk)
             if nme != "c1":
                 ops.conv3d_k3(L["dc"], L["wd"], None, out=self._dst_of_input_grad(L), tag=f"unet.{nme}.dgrad")
@@ -267,6 +279,11 @@ class UNetEngine:
         return self.metrics
 
     def capture_train_graph(self):
+        if self.world > 1:
+            # the data-parallel U-Net step issues NCCL all-reduces (BatchNorm sums, flat gradient); capturing those inside
+            # one graph is not covered by a test, so the data-parallel U-Net runs eagerly
+            self.use_graph = False
+            return
         saved = [t.clone() for t in (self.pp.theta, self.pp.state, self.pp.adam_m, self.pp.adam_v, self.pp.adam_state)]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -288,10 +305,13 @@ class UNetEngine:
         self.forward(False)
         return self.metrics
 
-    def predict(self, probs_out=None):
-        """Learning phase 0 forward (generate.py:220): fills self.argmax / self.sigp (+ softmax probabilities)."""
-        self.pack_weights(dgrad=False)
-        self.forward(False, want_probs=probs_out)
+    def predict(self, probs_out=None, x_packed=False, threshold=0.8, repack=True):
+        """Learning phase 0 forward (generate.py:220-225): fills self.argmax (species labels), self.mask
+        (sigmoid >= threshold) and self.sigp; with probs_out also the softmax probabilities `model.predict` returns."""
+        if repack:
+            self.pack_weights(dgrad=False)
+        self.forward(False, want_probs=probs_out, x_packed=x_packed, losses=probs_out is not None)
+        ops.heads_predict(self.logits, self.classes, float(threshold), argmax=self.argmax, mask=self.mask, sig_prob=self.sigp)
 
     def metrics_host(self):
         m = self.metrics.clone()

@@ -36,6 +36,9 @@ class VAEDataGenerator:
         self.list_IDs_temp = [self.list_IDs[k] for k in idx]
         M = np.empty((self.batch_size, *self.dim, self.n_channels))
         cond = np.zeros((self.batch_size, self.n_bins))
+        if self.return_S:  # vae/data.py:72-86: species grids + binary atom mask ride along with the condition
+            S = np.empty((self.batch_size, *self.dim, 1))
+            S_b = np.empty((self.batch_size, *self.dim, 1))
         for i, ID in enumerate(self.list_IDs_temp):
             M[i, ..., 0] = np.load(os.path.join(self.data_path, "density_matrices", ID)).reshape(self.dim)
             if self.n_channels > 1:
@@ -43,6 +46,12 @@ class VAEDataGenerator:
             cif_id = re.split(r"_|\.", ID)[0]
             b = self.property_df[self.property_df["task_id"] == cif_id]["bin"].values
             cond[i, int(b[0])] = 1.0
+            if self.return_S:
+                S[i] = np.load(os.path.join(self.data_path, "species_matrices", ID)).reshape(*self.dim, 1)
+                S_b[i] = np.where(S[i] != 0, 1, 0)
+        if self.return_S:
+            onehot = np.eye(self.n_classes, dtype=np.float32)[S[..., 0].astype(np.int64)]  # keras.utils.to_categorical
+            return M, [cond, onehot, S_b]
         return M, cond
 
 

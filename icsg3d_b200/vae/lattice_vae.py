@@ -17,7 +17,7 @@ import torch
 from ..engine import Dist, VAEEngine
 from ..optimizers import Adam
 from ..params import ParamStore, unet_specs, vae_specs
-from ..weights_io import load_npz, save_npz
+from ..weights_io import load_weights_file, save_weights_file
 
 
 def _to_dev(a, dev, dtype=torch.float32):
@@ -67,10 +67,16 @@ class _Model(_Facade):
         return self._o._step(M, cond, train=False)
 
     def save_weights(self, path):
-        save_npz(path, self._o.params.to_dict())
+        """Keras HDF5 when the path says so (.h5/.hdf5: `encoder`/`decoder` groups in Keras' nested-model weight order,
+        readable by the reference's `model.load_weights`), the native .npz container otherwise.  Data parallel: every
+        rank holds identical weights, rank 0 alone writes."""
+        o = self._o
+        if o.dist is not None and o.dist.world > 1 and o.dist.rank != 0:
+            return
+        save_weights_file(path, o.params.to_dict(), o.params.specs, model="vae")
 
     def load_weights(self, path):
-        self._o.params.load_dict(load_npz(path))
+        self._o.params.load_dict(load_weights_file(path, self._o.params.specs))
 
     def save(self, path):
         self.save_weights(path)
@@ -104,19 +110,21 @@ class LatticeDFCVAE:
         self.seed = seed
         self.use_cuda_graph = use_cuda_graph
         # --- perceptual model: the pre-trained U-Net (lattice_vae.py:120 load_model) ---
-        self.pm = ParamStore(unet_specs(self.channels), self.device, with_grads=False, with_adam=False)
+        new_pm = lambda: ParamStore(unet_specs(self.channels), self.device, with_grads=False, with_adam=False)
         if isinstance(perceptual_model, ParamStore):
             self.pm = perceptual_model
         elif hasattr(perceptual_model, "params"):
             self.pm = perceptual_model.params
         elif perceptual_model is None:
-            self.pm.init(seed + 1)  # synthetic run: seeded Glorot U-Net (no pre-trained blobs exist)
+            self.pm = new_pm().init(seed + 1)  # synthetic run: seeded Glorot U-Net (no pre-trained blobs exist)
         else:
             if not os.path.exists(perceptual_model):
                 raise OSError(f"perceptual model weights not found: {perceptual_model}")
-            self.pm.load_dict(load_npz(perceptual_model))
+            # Keras HDF5 (`unet.model.save`, unet.py:378-379; weights-only or full-model file) or the native .npz
+            self.pm = new_pm().load_dict(load_weights_file(perceptual_model, unet_specs(self.channels)))
         self.params = None
         self._engines = {}
+        self.max_engines = 2  # engines (activation buffers + captured graph) kept alive, least recently used evicted
         self.encoder = self.decoder = self.model = None
 
     # ---- reference API -------------------------------------------------------------------------
@@ -195,13 +203,15 @@ class LatticeDFCVAE:
     def engine(self, batch) -> VAEEngine:
         if self.params is None:
             self._set_model()
-        eng = self._engines.get(batch)
+        eng = self._engines.pop(batch, None)
         if eng is None:
+            while len(self._engines) >= self.max_engines:  # dicts keep insertion order: the first key is the LRU engine
+                self._engines.pop(next(iter(self._engines)))
             eng = VAEEngine(batch, d=self.input_shape[0], channels=self.channels, ncond=self.cond_shape, latent=self.latent_dim,
                             filters=self.filters, device=self.device, vae_params=self.params, pm_params=self.pm,
                             alpha=self.alpha, beta=self.beta, pm_layer_weights=self.pm_layer_weights,
                             lr=self.optimizer.lr, dist=self.dist)
-            self._engines[batch] = eng
+        self._engines[batch] = eng  # (re-)inserted last = most recently used
         return eng
 
     def _step(self, M, cond, train):
@@ -220,7 +230,11 @@ class LatticeDFCVAE:
     def _predict(self, a, cond, what):
         n = len(a)
         B = min(n, self.batch_size or 20)
-        eng = self.engine(B)
+        # partial batches run on an existing larger engine (learning phase 0: samples are independent) instead of
+        # allocating a new set of activation buffers per distinct batch size
+        fits = [b for b in self._engines if b >= n]
+        eng = self.engine(min(fits) if fits else B)
+        B = eng.B
         outs = []
         a = _to_dev(a, self.device)
         cond = _to_dev(cond, self.device)

@@ -41,6 +41,7 @@ extern "C" {
 
 #define ICSG3D_DT_BF16 0
 #define ICSG3D_DT_F32 1
+#define ICSG3D_DT_F64 2
 
 const char* icsg3d_last_error(void);
 int icsg3d_version(void);
@@ -48,6 +49,12 @@ int icsg3d_version(void);
 int icsg3d_sm_count(void);
 /* Number of kernels this library has launched (or captured into a CUDA graph) in this process. */
 int64_t icsg3d_launch_count(void);
+/* Spin budget of the peer-memory all-reduce kernels (data parallel, see icsg3d_bn_reduce_allreduce_* and
+ * icsg3d_adam_keras_allreduce_step): a rank that waits longer than `seconds` for a peer traps its context.  Default 600 s
+ * (or the environment variable ICSG3D_PEER_TIMEOUT_S), so that ordinary host-side rank skew (batch loading, checkpoint
+ * writes, a lazy graph capture) does not kill training; launches captured into a CUDA graph keep the value they were
+ * captured with. */
+int icsg3d_set_peer_timeout(double seconds);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv3D 3x3x3, stride 1, "same" — Keras Conv3D(kernel_size=(3,3,3), padding="same")
@@ -339,6 +346,36 @@ int icsg3d_heads_loss(const float* logits, int ld, int c1, const uint8_t* specie
 /* out = [loss, soft_loss, sig_loss, f1_m, wr_m]; raw (optional) = the six term sums (for data-parallel reduction) */
 int icsg3d_heads_loss_finalize(const double* partials, int nparts, double count, float* out, double* raw,
                                void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device post-processing of the generate.py loop (generate.py:208-225) and the augmentation of create_matrices.py
+ * (csrc/post.cu).
+ *
+ * to_lattice_params / to_voxel_params (utils.py:160-190): per-sample min/max over the three coordinate channels
+ * [c0, c0+3) of p ([B][vox][ld], fp32 or fp64), in two launches:
+ *   coord_minmax    -> partials [B][nsplit][6] (same dtype; nsplit = icsg3d_lattice_nsplit(B, vox)); with x16 != NULL
+ *                      (fp32, ld == 4, c0 == 1: the decoder output) it ALSO writes the bf16 [B][vox][16] U-Net input, so
+ *                      the decoder output is read once on its way into the segmentation network;
+ *   lattice_finalize -> lp [B][3] = ((max-min)/(1+2 eps)/(1-1/d)) * (1-1/d as `ap -= ap/d`: the reference's quirk),
+ *                       dv [B][3] = (lp + 2 lp eps)/d (optional), evaluated op by op in the array dtype with
+ *                       round-to-nearest intrinsics => bit-identical to numpy on the same min/max.
+ * heads_predict (generate.py:221-225): argmax species label (first index on ties) and the sigmoid >= threshold atom mask
+ *   from the fp32 head logits [M][ld] (c1 soft columns + the sigmoid logit in column c1); every output is optional.
+ * rotate90_batch (utils.py:193-222 random_rotation_3d, create_matrices.py:174-207): exact signed axis permutation of a
+ *   batch of d^3 grids with `voxel_bytes` bytes per voxel; xforms int32 [B][6] = (perm0,perm1,perm2, flip0,flip1,flip2):
+ *   out[b][o0][o1][o2] = in[b][s0][s1][s2], s_x = flip_x ? d-1-o[perm_x] : o[perm_x].  in != out.
+ * metric_counts (unet.py:159-193 r_m / p_m / f1_m / wr_m): counts fp64 [5] = { sum round(clip(yt*yp,0,1)),
+ *   sum round(clip(yt)), sum round(clip(yp)), the first two again without class 0 } over fp32 [n/C][C] tensors.
+ * ---------------------------------------------------------------------------------------------- */
+int icsg3d_lattice_nsplit(int B, int64_t vox);
+int icsg3d_coord_minmax(const void* p, int dtype, int ld, int c0, int B, int64_t vox, int nsplit, void* partials, void* x16,
+                        void* stream);
+int icsg3d_lattice_finalize(const void* partials, int dtype, int B, int nsplit, double eps_frac, int d, void* lp, void* dv,
+                            void* stream);
+int icsg3d_heads_predict(const float* logits, int ld, int c1, int64_t M, float threshold, uint8_t* argmax_out,
+                         uint8_t* mask_out, float* sig_prob, void* stream);
+int icsg3d_rotate90_batch(const void* in, void* out, int B, int d, int voxel_bytes, const int* xforms, void* stream);
+int icsg3d_metric_counts(const float* y_true, const float* y_pred, int64_t n, int C, double* counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Gaussian atomic-density voxeliser — utils.py:97-144 density_matrix + utils.py:88-94 coordinate_grid

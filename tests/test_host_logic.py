@@ -108,10 +108,32 @@ def test_generators_keep_reference_contract(tmp_path):
     M, cond = g[0]
     assert len(g) == 3 and M.shape == (3, d, d, d, 4) and M.dtype == np.float64 and cond.shape == (3, 3)
     assert np.all(cond.sum(1) == 1) and len(g.list_IDs_temp) == 3
+    gs = VAEDataGenerator(tr, str(root), batch_size=3, dim=(d, d, d), property_csv=str(csv), n_bins=3, return_S=True)
+    M2, (cond2, S1h, Sb) = gs[0]  # vae/data.py:72-86: [cond, to_categorical(S), S != 0]
+    assert np.array_equal(M2, M) and np.array_equal(cond2, cond)
+    assert S1h.shape == (3, d, d, d, 95) and Sb.shape == (3, d, d, d, 1)
+    assert np.array_equal(Sb[..., 0], (S1h.argmax(-1) != 0).astype(np.float64))
     u = UnetDataGenerator(va, str(root), batch_size=2, dim=(d, d, d), n_channels=4)
     X, (y, b) = u[0]
     assert X.shape == (2, d, d, d, 4) and y.shape == (2, d, d, d, 95) and b.shape == (2, d, d, d, 1)
     assert np.array_equal(b[..., 0], (y.argmax(-1) != 0).astype(np.float32))
+
+
+def test_rot90_transform_composes_like_numpy_rot90():
+    """Host logic of the rotation augmentation (utils.py:193-222): the composed signed permutation the kernel applies
+    equals chained np.rot90(., 1, axes) = scipy.ndimage.rotate(., 90, axes, reshape=False) for all 27 axis sequences."""
+    import itertools
+    from icsg3d_b200 import utils
+    d = 5
+    X = np.random.default_rng(0).random((d, d, d))
+    o = np.indices((d, d, d))
+    for seq in itertools.product(utils.ROT_AXES, repeat=3):
+        Y = X
+        for ax in seq:
+            Y = np.rot90(Y, 1, axes=ax)
+        perm, flip = utils.rot90_transform(seq)
+        s = [(d - 1 - o[perm[x]]) if flip[x] else o[perm[x]] for x in range(3)]
+        assert np.array_equal(Y, X[s[0], s[1], s[2]]), seq
 
 
 def test_conv_dispatch_plans_respect_hardware_limits():
