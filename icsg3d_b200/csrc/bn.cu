@@ -682,6 +682,7 @@ struct BnBwdParams {
   float tap_coef;
   __nv_bfloat16* dx;
   int lddx;
+  int dx_f32;      // 1: dx is an fp32 tensor (fp32-class backward), else bf16
   double* tap_sq;  // optional (apply pass with a tap): per-block sum (x - tap_other)^2, the DFC feature loss of the layer
 };
 
@@ -766,7 +767,13 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdParams& p, double* tap_sq
 #pragma unroll
         for (int i = 0; i < V; ++i) o[i] = xv[i] > 0.f ? o[i] : 0.f;
       }
-      store_bf16_vec<V>(p.dx + r * p.lddx + g * V, o);
+      if (p.dx_f32) {
+        float* d32 = reinterpret_cast<float*>(p.dx) + r * p.lddx + g * V;
+#pragma unroll
+        for (int i = 0; i < V; i += 4) *reinterpret_cast<float4*>(d32 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+      } else {
+        store_bf16_vec<V>(p.dx + r * p.lddx + g * V, o);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < V; ++i) {
@@ -1531,13 +1538,14 @@ static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* dy2, 
                          const float* rstd, const float* scale, const float* shift, int act, float alpha, int post,
                          const uint8_t* pool_idx, int B, int D, int H, int W, int C, double* partials, int nparts,
                          const double* sums, double count, int pre_relu, const void* tap_other, int ld_other,
-                         float tap_coef, void* dx, int lddx, void* stream, double* tap_sq = nullptr, int tap_sq_nparts = 0) {
+                         float tap_coef, void* dx, int lddx, void* stream, double* tap_sq = nullptr, int tap_sq_nparts = 0,
+                         int dx_f32 = 0) {
   ICSG_REQUIRE(dy && x && mean && rstd && scale && shift, "bn_bwd: null pointer");
   ICSG_REQUIRE(bn_shape_ok(C, dtype), "bn_bwd: unsupported C=%d for dtype %d", C, dtype);
   const int V = dtype == ICSG3D_DT_BF16 ? 8 : 4;
   ICSG_REQUIRE(ldx % V == 0 && lddy % V == 0 && (!dy2 || lddy2 % V == 0), "bn_bwd: ld must be a multiple of %d", V);
   ICSG_REQUIRE(post != ICSG3D_POST_POOL2 || pool_idx, "bn_bwd: pool needs pool_idx");
-  ICSG_REQUIRE(!tap_other || dtype == ICSG3D_DT_BF16, "bn_bwd: tap gradient needs bf16 activations");
+  ICSG_REQUIRE(!dx_f32 || dtype == ICSG3D_DT_F32, "bn_bwd: an fp32 dx needs fp32 activations / gradients");
   long long rows = static_cast<long long>(B) * D * H * W;
   if (post == ICSG3D_POST_POOL2) rows /= 8;
   const int grid = bn_bwd_grid(rows, C, dtype, post, apply);
@@ -1546,7 +1554,7 @@ static int bn_bwd_launch(bool apply, const void* dy, int lddy, const void* dy2, 
   p.act = act; p.alpha = alpha; p.post = post; p.pool_idx = pool_idx; p.B = B; p.D = D; p.H = H; p.W = W; p.C = C;
   p.partials = partials; p.sums = sums; p.count = count; p.pre_relu = pre_relu;
   p.tap_other = static_cast<const __nv_bfloat16*>(tap_other); p.ld_other = ld_other; p.tap_coef = tap_coef;
-  p.dx = static_cast<__nv_bfloat16*>(dx); p.lddx = lddx;
+  p.dx = static_cast<__nv_bfloat16*>(dx); p.lddx = lddx; p.dx_f32 = dx_f32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!apply) {
     ICSG_REQUIRE(partials && nparts == grid, "bn_bwd_reduce: nparts %d != expected %d", nparts, grid);
@@ -1588,6 +1596,15 @@ extern "C" int icsg3d_bn_bwd_apply(const void* dy, int lddy, const void* dy2, in
                                    float tap_coef, void* dx, int lddx, void* stream) {
   return bn_bwd_launch(true, dy, lddy, dy2, lddy2, x, ldx, dtype, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D, H, W, C,
                        nullptr, 0, sums, count, pre_relu, tap_other, ld_other, tap_coef, dx, lddx, stream);
+}
+
+extern "C" int icsg3d_bn_bwd_apply_f32(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const float* mean,
+                                       const float* rstd, const float* scale, const float* shift, int act, float alpha,
+                                       int post, const uint8_t* pool_idx, int B, int D, int H, int W, int C,
+                                       const double* sums, double count, int pre_relu, const void* tap_other, int ld_other,
+                                       float tap_coef, float* dx, int lddx, void* stream) {
+  return bn_bwd_launch(true, dy, lddy, dy2, lddy2, x, ldx, ICSG3D_DT_F32, mean, rstd, scale, shift, act, alpha, post, pool_idx, B, D,
+                       H, W, C, nullptr, 0, sums, count, pre_relu, tap_other, ld_other, tap_coef, dx, lddx, stream, nullptr, 0, 1);
 }
 
 extern "C" int icsg3d_bn_bwd_apply_nblocks(int B, int D, int H, int W, int C, int dtype, int post) {

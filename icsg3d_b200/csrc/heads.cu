@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_loss_kernel(const float* 
                                                                    float* __restrict__ sig_prob,
                                                                    float* __restrict__ probs,
                                                                    __nv_bfloat16* __restrict__ dlogits, int ldd,
-                                                                   double* __restrict__ partials) {
+                                                                   double* __restrict__ partials, int dl_f32) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int warps = kHeadsThreads / 32;
   double acc[kHeadsTerms] = {0, 0, 0, 0, 0, 0};
@@ -126,13 +126,16 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_loss_kernel(const float* 
         if (col[j] < c1) probs[v * c1 + col[j]] = e[j] * inv;
     }
     if (dlogits) {
-      __nv_bfloat16* drow = dlogits + v * ldd;
       const float gs = in_range ? wt * inv_count : 0.f;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        if (col[j] < c1) drow[col[j]] = f2bf(gs * (e[j] * inv - (col[j] == t ? 1.f : 0.f)));
-        else if (col[j] == c1) drow[col[j]] = f2bf((sp - tb) * inv_count);
-        else if (col[j] < ldd) drow[col[j]] = f2bf(0.f);
+        float gv = 0.f;
+        if (col[j] < c1) gv = gs * (e[j] * inv - (col[j] == t ? 1.f : 0.f));
+        else if (col[j] == c1) gv = (sp - tb) * inv_count;
+        if (col[j] < ldd) {
+          if (dl_f32) reinterpret_cast<float*>(dlogits)[v * ldd + col[j]] = gv;  // fp32-class backward
+          else dlogits[v * ldd + col[j]] = f2bf(gv);
+        }
       }
     }
   }
@@ -204,18 +207,32 @@ extern "C" int icsg3d_heads_loss_nparts(int64_t M) {
   return static_cast<int>(b < 1 ? 1 : b);
 }
 
-extern "C" int icsg3d_heads_loss(const float* logits, int ld, int c1, const uint8_t* species, const float* class_w,
-                                 int64_t M, float inv_count, uint8_t* argmax_out, float* sig_prob, float* probs, void* dlogits,
-                                 int ldd, double* partials, int nparts, void* stream) {
+static int heads_loss_impl(const float* logits, int ld, int c1, const uint8_t* species, const float* class_w, int64_t M,
+                           float inv_count, uint8_t* argmax_out, float* sig_prob, float* probs, void* dlogits, int ldd,
+                           double* partials, int nparts, int dl_f32, void* stream) {
   ICSG_REQUIRE(logits && partials, "heads_loss: null pointer");
   ICSG_REQUIRE(c1 >= 1 && c1 <= 95 && ld > c1, "heads_loss: c1 must be in [1,95] and ld > c1 (three columns per lane)");
   ICSG_REQUIRE(!dlogits || (species && ldd > c1 && ldd <= 96), "heads_loss: gradient needs labels and c1 < ldd <= 96");
   ICSG_REQUIRE(nparts == icsg3d_heads_loss_nparts(M), "heads_loss: nparts mismatch");
   heads_loss_kernel<<<nparts, kHeadsThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, ld, c1, species, class_w, M, inv_count, argmax_out, sig_prob, probs, static_cast<__nv_bfloat16*>(dlogits), ldd,
-      partials);
+      partials, dl_f32);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_heads_loss(const float* logits, int ld, int c1, const uint8_t* species, const float* class_w,
+                                 int64_t M, float inv_count, uint8_t* argmax_out, float* sig_prob, float* probs, void* dlogits,
+                                 int ldd, double* partials, int nparts, void* stream) {
+  return heads_loss_impl(logits, ld, c1, species, class_w, M, inv_count, argmax_out, sig_prob, probs, dlogits, ldd, partials,
+                         nparts, 0, stream);
+}
+
+extern "C" int icsg3d_heads_loss_f32grad(const float* logits, int ld, int c1, const uint8_t* species, const float* class_w,
+                                         int64_t M, float inv_count, uint8_t* argmax_out, float* sig_prob, float* probs,
+                                         float* dlogits, int ldd, double* partials, int nparts, void* stream) {
+  return heads_loss_impl(logits, ld, c1, species, class_w, M, inv_count, argmax_out, sig_prob, probs, dlogits, ldd, partials,
+                         nparts, 1, stream);
 }
 
 extern "C" int icsg3d_heads_loss_finalize(const double* partials, int nparts, double count, float* out, double* raw,

@@ -57,7 +57,7 @@ __global__ void unpack_dw_kernel(const float* __restrict__ dwp, float* __restric
 }
 
 // All weight packs of a model in ONE launch: jobs[j] = {w, wp, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode}
-// (int64 each; mode 0 = fprop layout, 1 = dgrad layout); blockIdx.y = job.
+// (int64 each; mode 0 = fprop layout, 1 = dgrad layout, 2 / 3 = the same as bf16-pair split operands); blockIdx.y = job.
 __global__ void pack_w_batch_kernel(const long long* __restrict__ jobs) {
   const long long* jb = jobs + static_cast<size_t>(blockIdx.y) * 10;
   const float* w = reinterpret_cast<const float*>(jb[0]);
@@ -70,7 +70,7 @@ __global__ void pack_w_batch_kernel(const long long* __restrict__ jobs) {
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v = 0.f;
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
       const int ci = static_cast<int>(idx % cin_pad);
       const int co = static_cast<int>((idx / cin_pad) % cout_pad);
       const int tap = static_cast<int>(idx / (static_cast<long long>(cin_pad) * cout_pad));
@@ -90,7 +90,18 @@ __global__ void pack_w_batch_kernel(const long long* __restrict__ jobs) {
       const int tap = static_cast<int>(idx / (static_cast<long long>(cin_pad) * cout_pad));
       if (ci < cin && co < cout) v = w[(static_cast<long long>(26 - tap) * cin + ci) * cout + co];
     }
-    wp[idx] = f2bf(v);
+    if (mode < 2) {
+      wp[idx] = f2bf(v);
+    } else {
+      // fp32-class split operands as bf16 pairs (csrc/split3.cu): K parts [w_hi | w_hi | w_lo]; mode 2 = fprop layout
+      // [27][cout_pad][3*cin_pad], mode 3 = dgrad layout [27][cin_pad][3*cout_pad]
+      const __nv_bfloat16 hi = f2bf(v), lo = f2bf(v - __bfloat162float(hi));
+      const int kpad = mode == 2 ? cin_pad : cout_pad;
+      __nv_bfloat16* d = wp + (idx / kpad) * 3 * kpad + (idx % kpad);
+      d[0] = hi;
+      d[kpad] = hi;
+      d[2 * kpad] = lo;
+    }
   }
 }
 

@@ -41,10 +41,33 @@ __global__ void f32_to_split3_kernel(const float* __restrict__ src, int ld_src, 
   }
 }
 
-// VAE encoder / perceptual inputs in split form: xe3 [rows][48] from (M 4ch, cond one-hot ncond, 0..), xp3 [rows][48] from M
+// VAE encoder / perceptual inputs in split form: xe3 [rows][48] from (M 4ch, cond one-hot ncond, 0..), xp3 [rows][48] from M;
+// xp16 (optional): the plain bf16 [rows][16] perceptual-model operand (M, 0..) in the same pass.
+// One row per thread, assembled in registers and written as whole 16-byte vectors (96 contiguous bytes per row).
+__device__ __forceinline__ uint32_t pack_raw2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+__device__ __forceinline__ void store_split_row(__nv_bfloat16* dst, const float (&v)[16], int fmt) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[2 * i], h0, l0, fmt);
+    split_bf16(v[2 * i + 1], h1, l1, fmt);
+    hi[i] = pack_raw2(h0, h1);
+    lo[i] = pack_raw2(l0, l1);
+  }
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  d[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  d[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  d[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  d[4] = d[0];
+  d[5] = d[1];
+}
 __global__ void pack_vae_input_split3_kernel(const float* __restrict__ m, const float* __restrict__ cond, int ncond,
                                              long long vox, long long total, __nv_bfloat16* __restrict__ xe,
-                                             __nv_bfloat16* __restrict__ xp, int fmt) {
+                                             __nv_bfloat16* __restrict__ xp, __nv_bfloat16* __restrict__ xp16, int fmt) {
   for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < total;
        r += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v[16];
@@ -52,27 +75,18 @@ __global__ void pack_vae_input_split3_kernel(const float* __restrict__ m, const 
     for (int i = 0; i < 16; ++i) v[i] = 0.f;
     const float4 q = *reinterpret_cast<const float4*>(m + r * 4);
     v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    if (xp) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(v[i], hi, lo, fmt);
-        xp[r * 48 + i] = hi;
-        xp[r * 48 + 16 + i] = lo;
-        xp[r * 48 + 32 + i] = hi;
-      }
+    if (xp) store_split_row(xp + r * 48, v, fmt);
+    if (xp16) {
+      uint4* d = reinterpret_cast<uint4*>(xp16 + r * 16);
+      d[0] = make_uint4(pack_bf16x2(q.x, q.y), pack_bf16x2(q.z, q.w), 0u, 0u);
+      d[1] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (xe) {
       const float* c = cond + (r / vox) * ncond;
-      for (int i = 0; i < ncond && i < 12; ++i) v[4 + i] = c[i];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(v[i], hi, lo, fmt);
-        xe[r * 48 + i] = hi;
-        xe[r * 48 + 16 + i] = lo;
-        xe[r * 48 + 32 + i] = hi;
-      }
+      for (int i = 0; i < 12; ++i)
+        if (i < ncond) v[4 + i] = c[i];
+      store_split_row(xe + r * 48, v, fmt);
     }
   }
 }
@@ -107,6 +121,78 @@ __global__ void pack_w_fprop_x3_kernel(const float* __restrict__ w, __nv_bfloat1
   }
 }
 
+// dgrad operand in split form: w fp32 (27|1, Cin, Cout) -> bf16 [ntaps][cin_pad][3*cout_pad] = [w_hi | w_hi | w_lo] along
+// Cout (the K dimension of the input-gradient GEMM), taps mirrored like pack_w_dgrad_kernel.
+__global__ void pack_w_dgrad_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int ntaps, int cin, int cout,
+                                       int cin_pad, int cout_pad, int fmt, float wscale) {
+  const long long total = static_cast<long long>(ntaps) * cin_pad * cout_pad;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(idx % cout_pad);
+    const int ci = static_cast<int>((idx / cout_pad) % cin_pad);
+    const int tap = static_cast<int>(idx / (static_cast<long long>(cin_pad) * cout_pad));
+    float v = 0.f;
+    if (ci < cin && co < cout) v = w[(static_cast<long long>(ntaps - 1 - tap) * cin + ci) * cout + co];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v * wscale, hi, lo, fmt);
+    __nv_bfloat16* d = wp + (static_cast<long long>(tap) * cin_pad + ci) * 3 * cout_pad + co;
+    d[0] = hi;
+    d[cout_pad] = hi;
+    d[2 * cout_pad] = lo;
+  }
+}
+
+// Filter gradient from split operands: the ordinary wgrad kernel run on x = [x_hi | x_lo] (2*cin_pad channels) and
+// dy = [dy_hi | dy_lo] (2*cout_pad) yields P [ntaps][2 cin_pad][2 cout_pad]; dW = hi*hi + lo*hi + hi*lo (lo*lo dropped).
+__global__ void wgrad_combine_x3_kernel(const float* __restrict__ P, float* __restrict__ dw, int ntaps, int cin_pad,
+                                        int cout_pad) {
+  const long long total = static_cast<long long>(ntaps) * cin_pad * cout_pad;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(idx % cout_pad);
+    const int ci = static_cast<int>((idx / cout_pad) % cin_pad);
+    const int tap = static_cast<int>(idx / (static_cast<long long>(cin_pad) * cout_pad));
+    const float* Pt = P + static_cast<long long>(tap) * 4 * cin_pad * cout_pad;
+    const long long ld = 2ll * cout_pad;
+    dw[idx] = Pt[ci * ld + co] + (Pt[(cin_pad + ci) * ld + co] + Pt[ci * ld + cout_pad + co]);
+  }
+}
+
+// ---- fp32 loss-gradient seeds of the fp32-class backward (same maths as misc.cu's bf16 forms) ----
+// dy = mse_coef*(xhat - x) + dpm   (rows of 4 channels; dpm fp32 with row stride ld, optional)
+__global__ void xhat_grad_f32_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float mse_coef,
+                                     const float* __restrict__ dpm, int ld, long long rows, float* __restrict__ dy) {
+  for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
+       r += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(x)[r];
+    const float4 b = reinterpret_cast<const float4*>(xhat)[r];
+    float4 o = make_float4(mse_coef * (b.x - a.x), mse_coef * (b.y - a.y), mse_coef * (b.z - a.z), mse_coef * (b.w - a.w));
+    if (dpm) {
+      const float4 q = *reinterpret_cast<const float4*>(dpm + r * ld);
+      o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+    }
+    reinterpret_cast<float4*>(dy)[r] = o;
+  }
+}
+// dc = coef * (a - other) * (a > 0)   (DFC tap without a BatchNorm behind it: c10)
+__global__ void tap_grad_relu_f32_kernel(const float* __restrict__ a, const float* __restrict__ other, float coef, long long n,
+                                         float* __restrict__ dc) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = a[i];
+    dc[i] = v > 0.f ? coef * (v - other[i]) : 0.f;
+  }
+}
+// dx = dy * act'(y) given the activation OUTPUT y (LeakyReLU: y > 0 ? 1 : alpha; ReLU: y > 0 ? 1 : 0)
+__global__ void act_bwd_f32_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act, float alpha, long long n,
+                                   float* __restrict__ dx) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float g = act == ICSG3D_ACT_NONE ? 1.f : (y[i] > 0.f ? 1.f : (act == ICSG3D_ACT_LEAKY ? alpha : 0.f));
+    dx[i] = dy[i] * g;
+  }
+}
+
 static int grid1(long long total) {
   long long b = (total + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
@@ -127,15 +213,26 @@ extern "C" int icsg3d_f32_to_split3(const float* src, int ld_src, int c, int64_t
   return ICSG3D_OK;
 }
 
-extern "C" int icsg3d_pack_vae_input_split3(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe,
-                                            void* xp, int fmt, void* stream) {
-  ICSG_REQUIRE(m && (xe || xp), "pack_vae_input_split3: null pointer");
+static int pack_vae_input_split3_impl(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe, void* xp,
+                                      void* xp16, int fmt, void* stream) {
+  ICSG_REQUIRE(m && (xe || xp || xp16), "pack_vae_input_split3: null pointer");
   ICSG_REQUIRE(!xe || (cond && ncond >= 0 && ncond <= 12), "pack_vae_input_split3: ncond must be <= 12");
   const long long total = static_cast<long long>(B) * vox;
   pack_vae_input_split3_kernel<<<grid1(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      m, cond, ncond, vox, total, static_cast<__nv_bfloat16*>(xe), static_cast<__nv_bfloat16*>(xp), fmt);
+      m, cond, ncond, vox, total, static_cast<__nv_bfloat16*>(xe), static_cast<__nv_bfloat16*>(xp),
+      static_cast<__nv_bfloat16*>(xp16), fmt);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_pack_vae_input_split3(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe,
+                                            void* xp, int fmt, void* stream) {
+  return pack_vae_input_split3_impl(m, cond, ncond, B, vox, xe, xp, nullptr, fmt, stream);
+}
+
+extern "C" int icsg3d_pack_vae_input_mixed(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe3,
+                                           void* xp16, int fmt, void* stream) {
+  return pack_vae_input_split3_impl(m, cond, ncond, B, vox, xe3, nullptr, xp16, fmt, stream);
 }
 
 extern "C" int icsg3d_pack_conv_w_fprop_x3(const float* w, void* wpack, int ntaps, int cin, int cout, int cin_pad, int cout_pad,
@@ -149,6 +246,46 @@ extern "C" int icsg3d_pack_conv_w_fprop_x3(const float* w, void* wpack, int ntap
   }
   pack_w_fprop_x3_kernel<<<grid1(static_cast<long long>(ntaps) * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, static_cast<__nv_bfloat16*>(wpack), ntaps, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, fmt, wscale);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_pack_conv_w_dgrad_x3(const float* w, void* wpack, int ntaps, int cin, int cout, int cin_pad, int cout_pad,
+                                           int fmt, float wscale, void* stream) {
+  ICSG_REQUIRE(w && wpack && (ntaps == 27 || ntaps == 1) && (fmt == 0 || fmt == 1), "pack_conv_w_dgrad_x3: bad arguments");
+  ICSG_REQUIRE(cin_pad >= cin && cout_pad >= cout, "pack_conv_w_dgrad_x3: bad padding");
+  pack_w_dgrad_x3_kernel<<<grid1(static_cast<long long>(ntaps) * cin_pad * cout_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(wpack), ntaps, cin, cout, cin_pad, cout_pad, fmt, wscale);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_wgrad_combine_x3(const float* P, float* dw, int ntaps, int cin_pad, int cout_pad, void* stream) {
+  ICSG_REQUIRE(P && dw && ntaps > 0 && cin_pad > 0 && cout_pad > 0, "wgrad_combine_x3: bad arguments");
+  wgrad_combine_x3_kernel<<<grid1(static_cast<long long>(ntaps) * cin_pad * cout_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      P, dw, ntaps, cin_pad, cout_pad);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_xhat_grad_f32(const float* x, const float* xhat, float mse_coef, const float* dpm, int ld, int64_t rows,
+                                    float* dy, void* stream) {
+  ICSG_REQUIRE(x && xhat && dy && (!dpm || ld % 4 == 0), "xhat_grad_f32: bad arguments");
+  xhat_grad_f32_kernel<<<grid1(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, xhat, mse_coef, dpm, ld, rows, dy);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_tap_grad_relu_f32(const float* a, const float* other, float coef, int64_t n, float* dc, void* stream) {
+  ICSG_REQUIRE(a && other && dc, "tap_grad_relu_f32: null pointer");
+  tap_grad_relu_f32_kernel<<<grid1(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, other, coef, n, dc);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_act_bwd_f32(const float* dy, const float* y, int act, float alpha, int64_t n, float* dx, void* stream) {
+  ICSG_REQUIRE(dy && y && dx, "act_bwd_f32: null pointer");
+  act_bwd_f32_kernel<<<grid1(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, act, alpha, n, dx);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

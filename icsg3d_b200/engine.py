@@ -151,28 +151,39 @@ class VAEEngine:
         self._side = None
         B = batch
         z = lambda *s, dt=BF16: torch.zeros(*s, dtype=dt, device=dev)
+        # Encoder FORWARD on fp32-class split operands (bf16 pairs hi + lo on the ordinary tcgen05 kernels, csrc/split3.cu):
+        # the KLD metric is a cancelling sum over mu / log-var whose bf16 error is systematic across the batch (every
+        # rounding point of the encoder — input, weights, conv outputs, pooled outputs — moves it by ~4e-4 relative with a
+        # random sign; measured 1.6e-3 at batch 32), so it is the one part of the step that needs more than bf16 to meet
+        # the 1e-3 loss bar.  The encoder is 3 % of the step's executed FLOPs; its backward stays bf16 on the hi parts.
+        # ICSG3D_ENC_FP32=0 restores the plain bf16 encoder (A/B timing).
+        self.enc_x3 = os.environ.get("ICSG3D_ENC_FP32", "1") != "0"
+        kx = 3 if self.enc_x3 else 1
 
         # ---- static inputs ----
         self.M = z(B, d, d, d, 4, dt=F32)
         self.cond = z(B, ncond, dt=F32)
         self.eps = z(B, latent, dt=F32)
-        self.xe = z(B, d, d, d, 16)
+        self.xe3 = z(B, d, d, d, 16 * kx)     # [hi | lo | hi] when split; the bf16 operand itself otherwise
+        self.xe = self.xe3[..., :16]          # hi part = the bf16 input (filter gradient of enc_conv1)
         self.xp = z(B, d, d, d, 16)
 
         # ---- encoder ----
         self.enc = []
         cin_pad, D = 16, d
+        cdt = F32 if self.enc_x3 else BF16   # conv outputs / incoming gradients of the split layers stay fp32
         for i, f in enumerate(self.filters, 1):
+            y3 = z(B, D // 2, D // 2, D // 2, f * kx)
             L = dict(name=f"enc_conv{i}", bn=f"enc_bn{i}", cin_pad=cin_pad, cout=f, D=D,
-                     c=z(B, D, D, D, f), y=z(B, D // 2, D // 2, D // 2, f), idx=z(B, D // 2, D // 2, D // 2, f, dt=torch.uint8),
-                     dc=z(B, D, D, D, f), dy=z(B, D // 2, D // 2, D // 2, f), bns=_BN(f, dev),
-                     wf=z(27, f, cin_pad), wd=z(27, cin_pad, f) if i > 1 else None)
+                     c=z(B, D, D, D, f, dt=cdt), y3=y3, y=y3[..., :f], idx=z(B, D // 2, D // 2, D // 2, f, dt=torch.uint8),
+                     dc=z(B, D, D, D, f), dy=z(B, D // 2, D // 2, D // 2, f, dt=cdt), bns=_BN(f, dev),
+                     wf=z(27, f, cin_pad * kx), wd=z(27, cin_pad, f) if i > 1 else None)
             self.enc.append(L)
             cin_pad, D = f, D // 2
         self.e_s = D  # spatial edge at enc_conv5 (d/16)
         c4 = self.filters[-1]
         self.e5 = z(B, D, D, D, 4, dt=F32)
-        self.e5_wf, self.e5_wd = z(27, 16, c4), z(27, c4, 16)
+        self.e5_wf, self.e5_wd = z(27, 16, c4 * kx), z(27, c4, 16)
         self.de5 = z(B, D * D * D * 4, dt=F32)
         self.dc_e5 = z(B, D, D, D, 16)
         # ---- bottleneck ----
@@ -259,8 +270,10 @@ class VAEEngine:
         cin = 16
         for c in f:
             shapes.append((D, cin, c))
+            shapes.append((D, 3 * cin, c))  # split-operand encoder forward (3x the K extent)
             cin, D = c, D // 2
         shapes.append((D, f[-1], 16))
+        shapes.append((D, 3 * f[-1], 16))
         S = d // 8
         cin = 16
         for i, c in enumerate(f[::-1]):
@@ -295,7 +308,7 @@ class VAEEngine:
         """Conv3D whose output feeds a BatchNorm: when the layer is served by the plane-streaming kernel the batch
         statistics come out of the conv epilogue (no separate read pass).  Returns the partials view or None."""
         part = None
-        if training and self.fuse_stats and out.dtype == BF16 and out.shape[-1] == C:
+        if training and self.fuse_stats and out.shape[-1] == C:  # bf16 or fp32 output (statistics of the stored values)
             n = ops.conv3d_k3_stats_parts(x, wf)
             if n > 0:
                 part = (ctx or self.ctx).partials[: n * 2 * C].view(n, 2, C)
@@ -303,7 +316,7 @@ class VAEEngine:
         return part
 
     def _bn_fwd(self, x, C, st: _BN, gamma, beta, mm, mv, training, act, post, y=None, y32=None, idx=None, ctx=None,
-                part=None):
+                part=None, y_split=None):
         if training:
             rows = x.numel() // x.shape[-1]
             if part is None:
@@ -322,7 +335,10 @@ class VAEEngine:
                 ops.bn_reduce_finalize(part, float(rows), gamma, beta, st.sums, st.mean, st.rstd, st.scale, st.shift, mm, mv)
         else:
             ops.bn_inference_coeffs(gamma, beta, mm, mv, st.scale, st.shift)
-        ops.bn_apply_fwd(x, C, st.scale, st.shift, act, post, y=y, y32=y32, pool_idx=idx)
+        if y_split is not None:  # fp32 conv output -> [hi | lo | hi] bf16 pairs for the next split conv
+            ops.bn_apply_fwd_split3(x, C, st.scale, st.shift, act, post, y_split, C, 0, pool_idx=idx, fmt=0)
+        else:
+            ops.bn_apply_fwd(x, C, st.scale, st.shift, act, post, y=y, y32=y32, pool_idx=idx)
 
     def _bn_bwd(self, dy, x, C, st: _BN, act, post, idx, dx, pre_relu=False, tap_other=None, tap_coef=0.0, dgamma=None,
                 dbeta=None, tap_sq=None):
@@ -396,13 +412,14 @@ class VAEEngine:
         if self._pack_table is None:
             p = self.vp.p
             jobs = []
+            fm = 2 if self.enc_x3 else 0  # pack mode of the encoder's fprop operands (2 = bf16-pair split)
             for i, L in enumerate(self.enc):
                 if i == 0:
-                    jobs.append((p[L["name"] + "/kernel"], L["wf"], 0, 4, 4, self.ncond))
+                    jobs.append((p[L["name"] + "/kernel"], L["wf"], fm, 4, 4, self.ncond))
                 else:
-                    jobs.append((p[L["name"] + "/kernel"], L["wf"], 0, 0, 1, 0))
+                    jobs.append((p[L["name"] + "/kernel"], L["wf"], fm, 0, 1, 0))
                     jobs.append((p[L["name"] + "/kernel"], L["wd"], 1, 0, 1, 0))
-            jobs.append((p["enc_conv5/kernel"], self.e5_wf, 0, 0, 1, 0))
+            jobs.append((p["enc_conv5/kernel"], self.e5_wf, fm, 0, 1, 0))
             jobs.append((p["enc_conv5/kernel"], self.e5_wd, 1, 0, 1, 0))
             for L in self.dec:
                 jobs.append((p[L["name"] + "/kernel"], L["wf"], 0, 0, 1, 0))
@@ -411,6 +428,14 @@ class VAEEngine:
             jobs.append((p["decoder_output/kernel"], self.out_wd, 1, 0, 1, 0))
             self._pack_table = ops.pack_jobs_table(jobs, self.dev)
         ops.pack_conv_w_batch(self._pack_table)
+
+    def pack_inputs(self):
+        """fp32 batch + one-hot condition -> encoder operand (bf16, or [hi | lo | hi] bf16 pairs for the split encoder) and
+        the perceptual U-Net's bf16 operand."""
+        if self.enc_x3:
+            ops.pack_vae_input_mixed(self.M, self.cond, self.xe3, self.xp, fmt=0)
+        else:
+            ops.pack_vae_input(self.M, self.cond, self.xe3, self.xp)
 
     def repack_pm(self):
         for L in self.pm:
@@ -423,15 +448,16 @@ class VAEEngine:
     def encode(self, training):
         """build_encoder (lattice_vae.py:160-195) on self.xe / self.eps -> self.mu, self.lv, self.z."""
         p = self.vp.p
-        x = self.xe
+        x = self.xe3
         for L in self.enc:
+            nominal = (4 + 4 * self.ncond, L["cout"]) if L is self.enc[0] else (L["cin_pad"], L["cout"])
             part = self._conv_bn(x, L["wf"], p[L["name"] + "/bias"], L["c"], L["cout"], training, tag=L["name"] + ".fprop",
-                                 nominal=(4 + 4 * self.ncond, L["cout"]) if L is self.enc[0] else None)
+                                 nominal=nominal)
             bn = L["bn"]
             self._bn_fwd(L["c"], L["cout"], L["bns"], p[bn + "/gamma"], p[bn + "/beta"],
                          p[bn + "/moving_mean"], p[bn + "/moving_variance"], training, ACT_LEAKY, POST_POOL2, y=L["y"],
-                         idx=L["idx"], part=part)
-            x = L["y"]
+                         idx=L["idx"], part=part, y_split=L["y3"] if self.enc_x3 else None)
+            x = L["y3"]
         self._conv(x, self.e5_wf, p["enc_conv5/bias"], out=self.e5, n_store=4, act=ACT_LEAKY, tag="enc_conv5.fprop",
                       nominal=(self.filters[-1], 4))
         ops.dense_fwd(self.e5.view(self.B, -1), p["enc_dense/kernel"], p["enc_dense/bias"], self.h, act=ACT_RELU)
@@ -638,7 +664,7 @@ class VAEEngine:
         if self.peer is not None:
             self.peer.tick()
         self.pack_weights()
-        ops.pack_vae_input(self.M, self.cond, self.xe, self.xp)
+        self.pack_inputs()
         if self.overlap_pm:
             main = torch.cuda.current_stream()
             if self._side is None:
@@ -743,7 +769,7 @@ class VAEEngine:
     def eval_step(self):
         """test_on_batch (lattice_vae.py:305-310): learning phase 0 -> moving-statistics BN everywhere."""
         self.pack_weights()
-        ops.pack_vae_input(self.M, self.cond, self.xe, self.xp)
+        self.pack_inputs()
         self.encode(False)
         self.decode(False)
         self.pm_forward(0, False)

@@ -94,7 +94,14 @@ def pack_jobs_table(jobs, device):
         _chk(w, torch.float32, "w")
         _chk(wp, torch.bfloat16, "wpack")
         cin, cout = w.shape[3], w.shape[4]
-        cout_pad, cin_pad = (wp.shape[1], wp.shape[2]) if mode == 0 else (wp.shape[2], wp.shape[1])
+        if mode == 0:
+            cout_pad, cin_pad = wp.shape[1], wp.shape[2]
+        elif mode == 1:
+            cout_pad, cin_pad = wp.shape[2], wp.shape[1]
+        elif mode == 2:  # split fprop operand [27][cout_pad][3*cin_pad]
+            cout_pad, cin_pad = wp.shape[1], wp.shape[2] // 3
+        else:            # split dgrad operand [27][cin_pad][3*cout_pad]
+            cout_pad, cin_pad = wp.shape[2] // 3, wp.shape[1]
         rows.append([w.data_ptr(), wp.data_ptr(), cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode])
     return torch.tensor(rows, dtype=torch.int64).to(device)
 
@@ -149,13 +156,15 @@ def conv3d_k3_stats_parts(x, wpack):
 
 
 def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alpha=LEAKY_ALPHA, out=None,
-              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv", stats=None, ws=None, split=False):
+              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv", stats=None, ws=None, split=False, fmt=None):
     """x: bf16 [B,D,H,W,ldx]; wpack: bf16 [27][nout][cin]; returns y [B,D,H,W,n_store].
 
     `ref=True` runs the CUDA-core cross-check kernel (fp32 output) instead of the tcgen05 kernel.
     `stats`: fp64 [parts, 2, nout] with parts = conv3d_k3_stats_parts(x, wpack) > 0 — the kernel also writes the
     per-CTA BatchNorm partials (sum, sum of squares) of the stored output.
-    `split=True`: x / wpack are fp32-class split operands (pack_conv_w_fprop_x3 etc.) in the format ops.SPLIT_FMT.
+    `split=True`: x / wpack are fp32-class split operands (pack_conv_w_fprop_x3 etc.) in the format `fmt` (default
+    ops.SPLIT_FMT): fp16 pairs need the conv to be told (operand-format field, output rescale); bf16 pairs (fmt 0) are
+    ordinary operands with 3x the channels.
     `ws`: optional scratch tensor (any dtype, one per stream): layers with too few tiles (4^3 / 2^3 grids) split K over it.
     """
     _chk(x, torch.bfloat16, "x")
@@ -186,7 +195,7 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
         _lib.lib().icsg3d_conv3d_k3_plan(B, D, H, W, cin, nout, 148, plan)
         kind = ("pertap", "halo", "stream")[plan[0]]
     with _timed((kind, tag), 2.0 * B * D * H * W * wpack.shape[0] * nc * no):
-        if split and SPLIT_FMT == 1:
+        if split and (SPLIT_FMT if fmt is None else fmt) == 1:
             fn = "icsg3d_conv3d_k1_igemm_f16" if wpack.shape[0] == 1 else "icsg3d_conv3d_k3_igemm_f16"
             _lib.call(fn, _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt, n_store, B, D, H, W, cin, nout,
                       act, alpha, 1.0 / SPLIT_WSCALE, _stream())
@@ -346,21 +355,61 @@ SPLIT_FMT = 1  # fp32-class split operands: 0 = bf16 pairs, 1 = IEEE fp16 pairs 
 SPLIT_WSCALE = 1024.0  # fp16 pairs: weights are packed x 2^10 (their lo parts stay normal numbers), the conv output x 2^-10
 
 
-def f32_to_split3(src, c, dst, ctot, coff=0):
+def _fmt(fmt):
+    return SPLIT_FMT if fmt is None else fmt
+
+
+def f32_to_split3(src, c, dst, ctot, coff=0, fmt=None):
     """src fp32 [..., ld] (first c channels) -> dst bf16 [..., 3*ctot] parts [hi | lo | hi] at channel offset coff."""
     rows = src.numel() // src.shape[-1]
-    _lib.call("icsg3d_f32_to_split3", _ptr(src), src.shape[-1], c, ctypes.c_int64(rows), _ptr(dst), ctot, coff, SPLIT_FMT,
+    _lib.call("icsg3d_f32_to_split3", _ptr(src), src.shape[-1], c, ctypes.c_int64(rows), _ptr(dst), ctot, coff, _fmt(fmt),
               _stream())
 
 
-def pack_vae_input_split3(m, cond, xe, xp):
+def pack_vae_input_split3(m, cond, xe, xp, fmt=None):
     B = m.shape[0]
     vox = m.numel() // (B * 4)
     _lib.call("icsg3d_pack_vae_input_split3", _ptr(m), _ptr(cond), cond.shape[1] if cond is not None else 0, B,
-              ctypes.c_int64(vox), _ptr(xe), _ptr(xp), SPLIT_FMT, _stream())
+              ctypes.c_int64(vox), _ptr(xe), _ptr(xp), _fmt(fmt), _stream())
 
 
-def pack_conv_w_fprop_x3(w, cin_pad=None, cout_pad=None, cin_lead=0, fold=1, fold_c=0, out=None):
+def pack_vae_input_mixed(m, cond, xe3, xp16, fmt=0):
+    """Split encoder operand + plain bf16 perceptual operand from one read of the fp32 batch."""
+    B = m.shape[0]
+    vox = m.numel() // (B * 4)
+    _lib.call("icsg3d_pack_vae_input_mixed", _ptr(m), _ptr(cond), cond.shape[1], B, ctypes.c_int64(vox), _ptr(xe3),
+              _ptr(xp16), fmt, _stream())
+
+
+def pack_conv_w_dgrad_x3(w, cin_pad=None, cout_pad=None, out=None, fmt=None):
+    """w fp32 (k,k,k,Cin,Cout) -> bf16 [taps][cin_pad][3*cout_pad] = [w_hi | w_hi | w_lo] along Cout, taps mirrored."""
+    _chk(w, torch.float32, "w")
+    ntaps = w.shape[0] * w.shape[1] * w.shape[2]
+    cin, cout = w.shape[3], w.shape[4]
+    cin_pad, cout_pad = cin_pad or pad16(cin), cout_pad or pad16(cout)
+    if out is None:
+        out = torch.empty((ntaps, cin_pad, 3 * cout_pad), dtype=torch.bfloat16, device=w.device)
+    f = _fmt(fmt)
+    _lib.call("icsg3d_pack_conv_w_dgrad_x3", _ptr(w), _ptr(out), ntaps, cin, cout, cin_pad, cout_pad, f,
+              SPLIT_WSCALE if f == 1 else 1.0, _stream())
+    return out
+
+
+def conv3d_wgrad_x3(x3, dy3, cin_pad, cout_pad, out, k1=False, tag="wgrad.x3"):
+    """Filter gradient from split tensors x3 [..., 3*cin_pad], dy3 [..., 3*cout_pad] (bf16 pairs): the ordinary wgrad
+    kernel on the [hi | lo] channel slices, then the three-block sum -> out fp32 [taps][cin_pad][cout_pad]."""
+    taps = 1 if k1 else 27
+    P = torch.empty((taps, 2 * cin_pad, 2 * cout_pad), dtype=torch.float32, device=x3.device)
+    xs, ds = x3[..., : 2 * cin_pad], dy3[..., : 2 * cout_pad]
+    if k1:
+        conv3d_k1_wgrad(xs, ds, cin=2 * cin_pad, cout=2 * cout_pad, out=P)
+    else:
+        conv3d_k3_wgrad(xs, ds, cin=2 * cin_pad, cout=2 * cout_pad, out=P, tag=tag)
+    _lib.call("icsg3d_wgrad_combine_x3", _ptr(P), _ptr(out), taps, cin_pad, cout_pad, _stream())
+    return out
+
+
+def pack_conv_w_fprop_x3(w, cin_pad=None, cout_pad=None, cin_lead=0, fold=1, fold_c=0, out=None, fmt=None):
     """w fp32 (kd,kh,kw,Cin,Cout) (or (1,1,1,Cin,Cout)) -> bf16 [taps][cout_pad][3*cin_pad] = [w_hi | w_hi | w_lo]."""
     _chk(w, torch.float32, "w")
     ntaps = w.shape[0] * w.shape[1] * w.shape[2]
@@ -371,15 +420,16 @@ def pack_conv_w_fprop_x3(w, cin_pad=None, cout_pad=None, cin_lead=0, fold=1, fol
         cout_pad = pad16(cout)
     if out is None:
         out = torch.empty((ntaps, cout_pad, 3 * cin_pad), dtype=torch.bfloat16, device=w.device)
+    f = _fmt(fmt)
     _lib.call("icsg3d_pack_conv_w_fprop_x3", _ptr(w), _ptr(out), ntaps, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c,
-              SPLIT_FMT, SPLIT_WSCALE if SPLIT_FMT == 1 else 1.0, _stream())
+              f, SPLIT_WSCALE if f == 1 else 1.0, _stream())
     return out
 
 
-def bn_apply_fwd_split3(x, C, scale, shift, act, post, y, ctot, coff=0, pool_idx=None, alpha=LEAKY_ALPHA):
+def bn_apply_fwd_split3(x, C, scale, shift, act, post, y, ctot, coff=0, pool_idx=None, alpha=LEAKY_ALPHA, fmt=None):
     B, D, H, W, _ = x.shape
     _lib.call("icsg3d_bn_apply_fwd_split3", _ptr(x), _ld(x), _dt(x), _ptr(scale), _ptr(shift), act, alpha, post, B, D, H, W, C,
-              _ptr(y), _ld(y), _ptr(pool_idx), ctot, coff, SPLIT_FMT, _stream())
+              _ptr(y), _ld(y), _ptr(pool_idx), ctot, coff, _fmt(fmt), _stream())
 
 
 def bn_bwd_nparts(x, C, post):
@@ -434,6 +484,33 @@ def _bn_bwd_apply(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums,
               _ptr(shift), act, alpha, post, _ptr(pool_idx), B, D, H, W, C, _ptr(sums), ctypes.c_double(count),
               1 if pre_relu else 0, _ptr(tap_other), tap_other.shape[-1] if tap_other is not None else 0,
               tap_coef, _ptr(dx), _ld(dx), _stream())
+
+
+def bn_bwd_apply_f32(dy, x, C, mean, rstd, scale, shift, act, post, pool_idx, sums, count, dx, pre_relu=False,
+                     tap_other=None, tap_coef=0.0, alpha=LEAKY_ALPHA, dy2=None):
+    """bn_bwd_apply with every tensor in fp32 (fp32-class backward): x, dy, dy2, tap_other, dx."""
+    for t, n in ((dy, "dy"), (x, "x"), (dx, "dx"), (dy2, "dy2"), (tap_other, "tap_other")):
+        if t is not None:
+            _chk(t, torch.float32, n)
+    B, D, H, W, _ = x.shape
+    _lib.call("icsg3d_bn_bwd_apply_f32", _ptr(dy), _ld(dy), _ptr(dy2), _ld(dy2) if dy2 is not None else 0, _ptr(x), _ld(x),
+              _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift), act, alpha, post, _ptr(pool_idx), B, D, H, W, C, _ptr(sums),
+              ctypes.c_double(count), 1 if pre_relu else 0, _ptr(tap_other), _ld(tap_other) if tap_other is not None else 0,
+              tap_coef, _ptr(dx), _ld(dx), _stream())
+
+
+def xhat_grad_f32(x, xhat, mse_coef, dpm, dy):
+    rows = x.numel() // 4
+    _lib.call("icsg3d_xhat_grad_f32", _ptr(x), _ptr(xhat), mse_coef, _ptr(dpm), dpm.shape[-1] if dpm is not None else 0,
+              ctypes.c_int64(rows), _ptr(dy), _stream())
+
+
+def tap_grad_relu_f32(a, other, coef, dc):
+    _lib.call("icsg3d_tap_grad_relu_f32", _ptr(a), _ptr(other), coef, ctypes.c_int64(a.numel()), _ptr(dc), _stream())
+
+
+def act_bwd_f32(dy, y, act, dx, alpha=LEAKY_ALPHA):
+    _lib.call("icsg3d_act_bwd_f32", _ptr(dy), _ptr(y), act, alpha, ctypes.c_int64(y.numel()), _ptr(dx), _stream())
 
 
 def bn_bwd_fused_nparts(C, dtype):
@@ -591,6 +668,10 @@ def heads_loss_nparts(M):
 
 def heads_loss(logits, c1, species, class_w, inv_count, partials, argmax_out=None, sig_prob=None, dlogits=None, probs=None):
     M = logits.numel() // logits.shape[-1]
+    if dlogits is not None and dlogits.dtype == torch.float32:  # fp32-class backward
+        return _lib.call("icsg3d_heads_loss_f32grad", _ptr(logits), logits.shape[-1], c1, _ptr(species), _ptr(class_w),
+                         ctypes.c_int64(M), inv_count, _ptr(argmax_out), _ptr(sig_prob), _ptr(probs), _ptr(dlogits),
+                         dlogits.shape[-1], _ptr(partials), partials.shape[0], _stream())
     _lib.call("icsg3d_heads_loss", _ptr(logits), logits.shape[-1], c1, _ptr(species), _ptr(class_w), ctypes.c_int64(M),
               inv_count, _ptr(argmax_out), _ptr(sig_prob), _ptr(probs), _ptr(dlogits), dlogits.shape[-1] if dlogits is not None else 0,
               _ptr(partials), partials.shape[0], _stream())

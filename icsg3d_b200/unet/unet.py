@@ -127,7 +127,7 @@ class AtomUnet:
         if dtype not in ("bf16", "fp32"):
             raise ValueError("dtype must be 'bf16' (throughput mode) or 'fp32' (fp32-class split operands, parity mode)")
         self.dtype = dtype
-        self._x3 = {}
+        self._x3, self._x3t = {}, {}
         self.class_weights = class_weights
         self.input_shape = tuple(input_shape)
         self.optimizer = Adam(lr)
@@ -166,7 +166,33 @@ class AtomUnet:
         self._engines[key] = eng
         return eng
 
+    def _step_x3(self, x, labels, train):
+        from ..engine_x3 import UNetTrainX3
+        B, d = len(x), self.input_shape[0]
+        eng = self._x3t.get(B)
+        if eng is None:
+            self._x3t.clear()
+            eng = self._x3t[B] = UNetTrainX3(B, d=d, channels=self.input_shape[-1], classes=self.num_classes, device=self.device,
+                                             params=self.params, lr=self.optimizer.lr, class_weight=self.loss_weight)
+        x = _to_dev(x, self.device, torch.float32).reshape(B, d, d, d, -1)
+        if train:
+            return eng.train_step(x, labels).cpu().tolist()
+        # test_on_batch: learning phase 0 forward + the losses / metrics on the labels
+        from .. import ops
+        logits = eng.forward(x, training=False)
+        Mv = B * d ** 3
+        part = torch.zeros(ops.heads_loss_nparts(Mv), 6, dtype=torch.float64, device=self.device)
+        out = torch.zeros(5, dtype=torch.float32, device=self.device)
+        sp = labels.to(self.device).to(torch.uint8).reshape(B, d, d, d).contiguous()
+        ops.heads_loss(logits, self.num_classes, sp, eng.class_w, 1.0 / Mv, part)
+        ops.heads_loss_finalize(part, float(Mv), out)
+        return out.cpu().tolist()
+
     def _step(self, x, labels, train):
+        if self.dtype == "fp32":
+            if self.dist is not None and self.dist.world > 1:
+                raise NotImplementedError("the fp32-class mode is single-process (parity mode)")
+            return self._step_x3(x, labels, train)
         B = len(x)
         eng = self.engine(B)
         eng.set_inputs(_to_dev(x, self.device, torch.float32), labels.to(self.device))

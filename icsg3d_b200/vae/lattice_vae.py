@@ -87,7 +87,16 @@ class LatticeDFCVAE:
                  latent_dim=256, beta=3e-4, alpha=0.5, optimizer=None, perceptual_model="saved_models/unet.h5",
                  pm_layers=["re_lu_2", "re_lu_4", "re_lu_6", "re_lu_8"], pm_layer_weights=[1.0, 1.0, 1.0, 1.0],
                  cond_shape=10, custom_objects=None, output_dir="output", device=None, dist: Dist | None = None,
-                 seed=1, use_cuda_graph=True):
+                 seed=1, use_cuda_graph=True, dtype="bf16"):
+        """dtype: "bf16" = the throughput mode (bf16 operands, fp32 accumulation; split-operand encoder forward);
+        "fp32" = fp32-class split operands for every conv, forward AND backward (icsg3d_b200/engine_x3.py) — the parity
+        mode of north_star's 1e-4 tier (activations, gradients), ~3x the tensor-core work, single process."""
+        if dtype not in ("bf16", "fp32"):
+            raise ValueError("dtype must be 'bf16' or 'fp32'")
+        if dtype == "fp32" and dist is not None and dist.world > 1:
+            raise NotImplementedError("the fp32-class mode is single-process (parity mode)")
+        self.dtype = dtype
+        self._x3 = {}
         if tuple(kernel_size) != (3, 3, 3) or tuple(pool_size) != (2, 2, 2):
             raise NotImplementedError("the B200 path implements the reference's 3x3x3 conv / 2x2x2 pool only")
         if list(pm_layers) != ["re_lu_2", "re_lu_4", "re_lu_6", "re_lu_8"]:
@@ -214,7 +223,27 @@ class LatticeDFCVAE:
         self._engines[batch] = eng  # (re-)inserted last = most recently used
         return eng
 
+    def _step_x3(self, M, cond, train):
+        """train_on_batch / test_on_batch in the fp32-class mode (eps drawn on the device like the bf16 engine)."""
+        from ..engine_x3 import VAETrainX3
+        if self.params is None:
+            self._set_model()
+        B = len(M)
+        eng = self._x3.get(B)
+        if eng is None:
+            self._x3.clear()
+            eng = self._x3[B] = VAETrainX3(B, d=self.input_shape[0], ncond=self.cond_shape, latent=self.latent_dim,
+                                           filters=self.filters, device=self.device, vae_params=self.params, pm_params=self.pm,
+                                           alpha=self.alpha, beta=self.beta, pm_layer_weights=self.pm_layer_weights,
+                                           lr=self.optimizer.lr)
+        eps = torch.randn(B, self.latent_dim, device=self.device)
+        M, cond = _to_dev(M, self.device), _to_dev(cond, self.device)
+        m = eng.train_step(M, cond, eps) if train else eng.forward(M, cond, eps, training=False)
+        return m.cpu().tolist()
+
     def _step(self, M, cond, train):
+        if self.dtype == "fp32":
+            return self._step_x3(M, cond, train)
         B = len(M)
         eng = self.engine(B)
         # host batches go straight into the engine's static input buffers (one H2D DMA, no staging allocation)
@@ -253,7 +282,7 @@ class LatticeDFCVAE:
                 eng.eps.normal_()
                 from .. import ops
                 eng.pack_weights()
-                ops.pack_vae_input(eng.M, eng.cond, eng.xe, eng.xp)
+                eng.pack_inputs()
                 eng.encode(False)
                 if what == "encode":
                     outs.append([t[:k].cpu().numpy().copy() for t in (eng.mu, eng.lv, eng.z)])

@@ -149,7 +149,8 @@ int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, int cout, int
                              void* stream);
 
 /* All weight packs of a model in one launch.  jobs: DEVICE array [njobs][10] of int64
- * {w ptr, wpack ptr, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode (0 = fprop layout, 1 = dgrad layout)};
+ * {w ptr, wpack ptr, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode (0 = fprop layout, 1 = dgrad layout,
+ * 2 / 3 = fprop / dgrad layout as bf16-pair split operands [w_hi | w_hi | w_lo] along K, see the fp32-class section)};
  * max_blocks = grid.x (each job strides over its own element count). */
 int icsg3d_pack_conv_w_batch(const int64_t* jobs, int njobs, int max_blocks, void* stream);
 /* dW (padded, from wgrad) -> gradient in Keras layout, undoing padding and the condition fold. */
@@ -223,10 +224,36 @@ int icsg3d_f32_to_split3(const float* src, int ld_src, int c, int64_t rows, void
                          void* stream);
 int icsg3d_pack_vae_input_split3(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe, void* xp,
                                  int fmt, void* stream);
+/* The train step's input pack when only the ENCODER runs on split operands: xe3 bf16 [B*vox][48] = [hi | lo | hi] of
+ * (M, one-hot cond, 0) and xp16 bf16 [B*vox][16] = (M, 0..) for the bf16 perceptual model, one read of m. */
+int icsg3d_pack_vae_input_mixed(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe3, void* xp16,
+                                int fmt, void* stream);
 int icsg3d_pack_conv_w_fprop_x3(const float* w, void* wpack, int ntaps, int cin, int cout, int cin_pad, int cout_pad,
                                 int cin_lead, int fold, int fold_c, int fmt, float wscale, void* stream);
 /* The conv dispatcher on fp16 operands (same kernels and layouts; only the tcgen05 operand-format fields differ).
  * y = accumulator * out_scale + bias: weights packed with wscale = 2^k (lo parts stay normal fp16) use out_scale = 2^-k. */
+/* Backward in the split form.  dgrad: the ordinary conv on dy stored [hi | lo | hi] with this pack of the kernel,
+ * bf16 [ntaps][cin_pad][3*cout_pad] = [w_hi | w_hi | w_lo] along Cout, taps mirrored.  wgrad: the ordinary filter-gradient
+ * kernel on x = [x_hi | x_lo] and dy = [dy_hi | dy_lo] (channel slices of the split tensors) gives P fp32
+ * [ntaps][2*cin_pad][2*cout_pad]; wgrad_combine_x3 sums the three blocks hi*hi + lo*hi + hi*lo into dw [ntaps][cin_pad][cout_pad]. */
+int icsg3d_pack_conv_w_dgrad_x3(const float* w, void* wpack, int ntaps, int cin, int cout, int cin_pad, int cout_pad, int fmt,
+                                float wscale, void* stream);
+int icsg3d_wgrad_combine_x3(const float* P, float* dw, int ntaps, int cin_pad, int cout_pad, void* stream);
+/* fp32 forms of the backward glue for the split (fp32-class) training step: BatchNorm backward apply with an fp32 dx
+ * (x, dy, dy2, tap_other all fp32), the loss-gradient seeds, the activation backward of enc_conv5, and the head losses
+ * with an fp32 d(loss)/d(logits). */
+int icsg3d_bn_bwd_apply_f32(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const float* mean,
+                            const float* rstd, const float* scale, const float* shift, int act, float alpha, int post,
+                            const uint8_t* pool_idx, int B, int D, int H, int W, int C, const double* sums, double count,
+                            int pre_relu, const void* tap_other, int ld_other, float tap_coef, float* dx, int lddx,
+                            void* stream);
+int icsg3d_xhat_grad_f32(const float* x, const float* xhat, float mse_coef, const float* dpm, int ld, int64_t rows, float* dy,
+                         void* stream);
+int icsg3d_tap_grad_relu_f32(const float* a, const float* other, float coef, int64_t n, float* dc, void* stream);
+int icsg3d_act_bwd_f32(const float* dy, const float* y, int act, float alpha, int64_t n, float* dx, void* stream);
+int icsg3d_heads_loss_f32grad(const float* logits, int ld, int c1, const uint8_t* species, const float* class_w, int64_t M,
+                              float inv_count, uint8_t* argmax_out, float* sig_prob, float* probs, float* dlogits, int ldd,
+                              double* partials, int nparts, void* stream);
 int icsg3d_conv3d_k3_igemm_f16(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                                int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                                float leaky_alpha, float out_scale, void* stream);

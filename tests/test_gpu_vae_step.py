@@ -69,13 +69,12 @@ def test_train_step_matches_oracle():
         json.dump(report, f, indent=1)
     print(json.dumps(report, indent=1))
 
-    # losses within 1e-3 (north_star): total, PM, MSE directly; the raw KLD metric enters the loss scaled by
-    # beta = 3e-4, so it is held to 1e-3 AFTER that scaling and to 1e-2 relative as a reported metric
-    # (bf16 activations put ~6e-3 rel-L2 on z_mean/z_log_var and the KL sum cancels heavily).
-    for g_, w_ in zip(got[:3], want[:3]):
+    # losses within 1e-3 (north_star; relative to max(1, |value|)): total, PM, MSE and the raw KLD metric alike.  The KLD
+    # holds that bar because the encoder's forward runs on fp32-class split operands (engine.py enc_x3): in plain bf16
+    # every rounding point of the encoder shifts the cancelling KL sum by ~4e-4 with a batch-independent sign.
+    for g_, w_ in zip(got, want):
         assert abs(g_ - w_) <= 1e-3 * max(1.0, abs(w_)), (got, want)
-    assert abs(got[3] - want[3]) * eng.beta <= 1e-3 and abs(got[3] - want[3]) <= 1e-2 * abs(want[3]), (got, want)
-    assert act["enc_conv1"] < 1e-2 and act["z_mean"] < 3e-2 and act["x_hat"] < 3e-2
+    assert act["enc_conv1"] < 1e-4 and act["z_mean"] < 1e-3 and act["x_hat"] < 3e-2
     assert act["pm_x/c2"] < 1e-2 and act["pm_x/c10"] < 5e-2
     bad = {k: v for k, v in report["grad"].items() if v["cos"] < 0.95 and k.endswith("kernel")}
     assert not bad, bad
@@ -103,9 +102,8 @@ def test_eval_step_matches_oracle():
     got = eng.metrics_host()
     want = [float(loss), float(pm), float(mse), float(kl)]
     print(got, want)
-    for g_, w_ in zip(got[:3], want[:3]):
-        assert abs(g_ - w_) <= 2e-3 * max(1.0, abs(w_)), (got, want)
-    assert abs(got[3] - want[3]) <= 1e-2 * abs(want[3]), (got, want)
+    for g_, w_ in zip(got, want):
+        assert abs(g_ - w_) <= 1e-3 * max(1.0, abs(w_)), (got, want)
 
 
 def test_vae_directional_derivative():
@@ -113,7 +111,7 @@ def test_vae_directional_derivative():
     eng, M, cond, eps, _, _ = _setup(seed=4)
     eng.pack_weights()
     from icsg3d_b200 import ops
-    ops.pack_vae_input(eng.M, eng.cond, eng.xe, eng.xp)
+    eng.pack_inputs()
 
     def fwd():
         eng.pack_weights()

@@ -36,7 +36,7 @@ def main():
         eng.peer.tick()  # the in-kernel BatchNorm all-reduce needs an epoch >= 1 (normally advanced by _train_body)
     eng.pack_weights()
     from icsg3d_b200 import ops
-    ops.pack_vae_input(eng.M, eng.cond, eng.xe, eng.xp)
+    eng.pack_inputs()
     eng.encode(True); eng.decode(True); eng.pm_forward(0, True); eng.pm_forward(1, True); eng.losses(); eng.backward()
     eng.dist.all_reduce_sum(eng.vp.grad)
     torch.cuda.synchronize()
@@ -46,7 +46,7 @@ def main():
         ref = VAEEngine(Bg, d=32, seed=3, device=dev)
         ref.set_inputs(M, cond, eps)
         ref.pack_weights()
-        ops.pack_vae_input(ref.M, ref.cond, ref.xe, ref.xp)
+        ref.pack_inputs()
         ref.encode(True); ref.decode(True); ref.pm_forward(0, True); ref.pm_forward(1, True); ref.losses(); ref.backward()
         torch.cuda.synchronize()
         m_1 = ref.metrics_host()
