@@ -7,7 +7,12 @@
 One "step" = one full train_on_batch of the conditional DFC-VAE against the frozen perceptual U-Net prefix
 (forward, DFC/MSE/KL losses, backward, Keras-Adam) on a batch of synthetic voxelised perovskite grids made on
 the device by the CUDA voxeliser.  N>1: one process per GPU (torchrun), batch 32 per GPU (weak scaling; global
-batch 256 at N=8 = configs[2]), NCCL all-reduce of BatchNorm statistic sums and of the flat gradient buffer.
+batch 256 at N=8 = configs[2]; `--global-batch 256` runs configs[2] literally at any N = strong scaling); BatchNorm
+statistic sums and the flat gradient are exchanged inside the consuming kernels over NVLink peer memory (no NCCL call
+in the step; engine.py PeerBN), the whole data-parallel step is one CUDA graph.
+
+    python bench.py --config {unet_train,vae64,unet64,inference,voxeliser} ...   # the other BASELINE.json configs
+                                                                                  # (bench_configs.py, same JSON contract)
 
 Prints ONE JSON line (rank 0).  Keys: see the round contract — `value` is device-timed with inputs resident in
 HBM (CUDA-graph replay); `e2e` goes through the public API (LatticeDFCVAE.model.train_on_batch) with pinned
@@ -97,6 +102,8 @@ def oracle_cpu_steps(batch, steps, warmup, seed=0):
     import torch
     from oracle import nets, voxelizer as vox
 
+    # all host cores, whatever OMP_NUM_THREADS torchrun exported (it sets 1 for N > 1 launches)
+    torch.set_num_threads(os.cpu_count() or 1)
     rng = np.random.default_rng(seed)
     M = np.zeros((batch, D, D, D, 4), dtype=np.float32)
     for b in range(batch):
@@ -166,8 +173,13 @@ def run_cuda(args):
 
     peaks = load_peaks()
     B = args.batch
-    # N > 1: the step is captured as a sequence of CUDA-graph segments split at the NCCL all-reduces (engine.py
-    # capture_train_graph); --no-graph launches every kernel eagerly instead.
+    scaling = "weak"
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        B, scaling = args.global_batch // world, "strong"
+    # The whole step (N > 1 included: the exchanges run inside kernels over peer memory) is ONE captured CUDA graph;
+    # --no-graph launches every kernel eagerly instead.
     vae = LatticeDFCVAE(perceptual_model=None, device=dev, dist=Dist() if world > 1 else None, seed=1,
                         use_cuda_graph=not args.no_graph)
     vae._set_model(batch_size=B)
@@ -245,15 +257,21 @@ def run_cuda(args):
     rec, ops.TIMING = ops.TIMING, None
     if rank == 0:
         agg = {}
-        for (kind, tag), fl, a, b in rec:
-            d = agg.setdefault((kind, tag), [0.0, 0.0, 0])
+        for (kind, tag), fl, a, b, ex in rec:
+            d = agg.setdefault((kind, tag), [0.0, 0.0, 0, 0.0])
             d[0] += fl
             d[1] += a.elapsed_time(b)
             d[2] += 1
+            d[3] += ex
         names = {"stream": "conv3d_k3_stream_kernel (plane-streaming, kd folded into N; fprop+dgrad, Cout<=64 @ W>=16)",
                  "halo": "conv3d_k3_halo_kernel (halo reuse, tap-outer; fprop+dgrad)",
                  "pertap": "conv3d_k3_igemm_kernel (per-tap TMA; 4^3/2^3 layers)",
                  "wgrad": "conv3d_k3_wgrad(_stream)_kernel (filter gradient)"}
+        # roofline denominator: the BURST bf16 peak unless the clock record of this run shows a power cap (then the
+        # sustained figure) — a 60 ms timed region at ~360 W runs at full clocks
+        capped = bool(clocks and "sw_power_cap" in (clocks.get("reasons") or []))
+        peak_tf = peaks["bf16_tflops_sustained"] if capped else peaks["bf16_tflops"]
+        peak_note = peaks["src"] + (" sustained (sw_power_cap seen during the run)" if capped else " burst (no power cap during the run)")
         by_kernel = {}
         for kind in names:
             f = sum(v[0] for (k, _), v in agg.items() if k == kind)
@@ -261,7 +279,7 @@ def run_cuda(args):
             n = sum(v[2] for (k, _), v in agg.items() if k == kind)
             if n:
                 by_kernel[kind] = {"kernel": names[kind], "tflops": f / (ms * 1e-3) / 1e12,
-                                   "frac_of_peak": f / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                                   "frac_of_peak": f / (ms * 1e-3) / 1e12 / peak_tf,
                                    "launches_per_step": n // reps, "ms_per_step": ms / reps, "gflop_per_step": f / reps / 1e9}
         conv = {k: v for k, v in agg.items() if k[0] in names}
         tot_f = sum(v[0] for v in conv.values())
@@ -270,6 +288,7 @@ def run_cuda(args):
         # the HBM-bound family: BatchNorm(+activation, +pool/upsample) passes, algorithmic bytes = tensors read + written
         bn = {k: v for k, v in agg.items() if k[0] == "bn"}
         bn_b, bn_ms, bn_n = (sum(v[i] for v in bn.values()) for i in range(3))
+        exec_f = sum(v[3] for v in conv.values())
         roof_hbm = None
         if bn_n:
             gbs = bn_b / (bn_ms * 1e-3) / 1e9
@@ -279,10 +298,11 @@ def run_cuda(args):
                         "algorithmic_mb_per_step": bn_b / reps / 1e6,
                         "by_pass": {t: {"GBps": v[0] / (v[1] * 1e-3) / 1e9, "ms_per_step": v[1] / reps, "launches": v[2] // reps}
                                     for (_, t), v in sorted(bn.items())}}
-        achieved = tot_f / (tot_ms * 1e-3) / 1e12
+        agg_tf = tot_f / (tot_ms * 1e-3) / 1e12
         dom = max(by_kernel, key=lambda k: by_kernel[k]["ms_per_step"])
-        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of its largest launch (static
-        # evidence, never measured under the profiler in this run): bytes per launch of THAT launch (c2 fprop)
+        dk = by_kernel[dom]
+        # DRAM traffic of the dominant kernel: STATIC evidence from the committed `ncu --set full` capture of its largest
+        # launch (c2 fprop) — never measured under the profiler in this run
         traffic, traffic_detail = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "r01_ncu_dominant_kernel.json")) as f:
@@ -290,15 +310,23 @@ def run_cuda(args):
             traffic = traffic_detail["dram_bytes_read"] + traffic_detail["dram_bytes_write"]
         except (OSError, KeyError, ValueError):
             pass
-        roof = {"bound": "tensor",
-                "kernel": "all tcgen05 Conv3D launches of the step (fprop, dgrad, wgrad); dominant by time: " + names[dom],
-                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_detail": traffic_detail,
-                "peak_source": peaks["src"] + " (sustained: kernels timed inside a long step)",
-                "algorithmic_gflop_per_launch": tot_f / n_all / 1e9, "avg_launch_ms": tot_ms / n_all,
-                "launches_per_step": n_all // reps, "kernel_ms_per_step": tot_ms / reps, "by_kernel": by_kernel,
-                "profile": "profiles/ (ncu --set full of the dominant kernel on c2 32->64 @32^3: dram bytes, tensor-pipe activity)"}
-        per_layer = {f"{k}:{t}": {"gflop": v[0] / v[2] / 1e9, "ms": v[1] / v[2], "tflops": v[0] / (v[1] * 1e-3) / 1e12}
+        roof = {"bound": "tensor", "kernel": "dominant by time: " + names[dom],
+                "achieved": dk["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": dk["tflops"] / peak_tf,
+                "traffic": traffic, "traffic_source": "static: profiles/r01_ncu_dominant_kernel.json (ncu --set full of this kernel's "
+                                                      "largest launch, c2 fprop; not measured in this run)",
+                "traffic_detail": traffic_detail, "peak_source": peak_note,
+                "algorithmic_gflop_per_launch": dk["gflop_per_step"] / dk["launches_per_step"],
+                "avg_launch_ms": dk["ms_per_step"] / dk["launches_per_step"], "launches_per_step": dk["launches_per_step"],
+                "kernel_ms_per_step": dk["ms_per_step"],
+                "aggregate_all_conv": {"what": "all tcgen05 Conv3D launches of the step (fprop, dgrad, wgrad), nominal FLOPs",
+                                       "achieved": agg_tf, "frac": agg_tf / peak_tf, "launches_per_step": n_all // reps,
+                                       "kernel_ms_per_step": tot_ms / reps, "gflop_per_step": tot_f / reps / 1e9,
+                                       "executed_gflop_per_step": exec_f / reps / 1e9,
+                                       "executed_tflops": exec_f / (tot_ms * 1e-3) / 1e12},
+                "by_kernel": by_kernel,
+                "profile": "profiles/ (ncu --set full summaries: tensor-pipe activity, DRAM bytes)"}
+        per_layer = {f"{k}:{t}": {"gflop": v[0] / v[2] / 1e9, "ms": v[1] / v[2], "tflops": v[0] / (v[1] * 1e-3) / 1e12,
+                                  "executed_gflop": v[3] / v[2] / 1e9, "executed_tflops": v[3] / (v[1] * 1e-3) / 1e12}
                      for (k, t), v in sorted(conv.items(), key=lambda kv: -kv[1][1])}
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "bench_per_layer.json"), "w") as f:
@@ -314,13 +342,15 @@ def run_cuda(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": "VAE+DFC train step @32^3, batch 32/GPU (configs[1]); N>1 = configs[2] data parallel",
                        "grid": D, "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "per-step working set (~2 GB of activations) exceeds the 126 MB L2; no flush needed",
-                       "cuda_graph": (not args.no_graph) if world == 1 else ("segmented at the all-reduces" if not args.no_graph else False),
+                       "cuda_graph": ("one graph per step (peer-memory exchanges inside kernels)" if eng.peer is not None or world == 1
+                                      else "segmented at the NCCL all-reduces (ICSG3D_DP_PEER=0)") if not args.no_graph else False,
+                       "encoder_forward": "fp32-class split operands (KLD parity)" if eng.enc_x3 else "bf16",
                        "gflop_per_sample": GFLOP_PER_SAMPLE},
             "conv_tflops_whole_step": GFLOP_PER_SAMPLE * value / 1e3,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -340,10 +370,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--global-batch", type=int, default=0, help="fixed global batch split over the ranks (configs[2]: 256)")
+    ap.add_argument("--config", default="vae_train",
+                    choices=["vae_train", "unet_train", "vae64", "unet64", "inference", "voxeliser"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config != "vae_train":
+        import bench_configs
+        bench_configs.run(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_cuda(args)

@@ -125,7 +125,9 @@ def unpack_conv_dw(dw_pad, cin, cout, cin_lead=0, fold=1, fold_c=0, out=None):
 TIMING = None
 
 
-def _timed(tag, flops):
+def _timed(tag, flops, executed=None):
+    """flops: algorithmic (nominal channels); executed: what the launch really multiplies (padded / folded
+    / split channel counts) — reported side by side by bench.py."""
     class _T:
         def __enter__(self):
             if TIMING is not None:
@@ -137,7 +139,7 @@ def _timed(tag, flops):
         def __exit__(self, *a):
             if TIMING is not None:
                 self.e1.record()
-                TIMING.append((tag, flops, self.e0, self.e1))
+                TIMING.append((tag, flops, self.e0, self.e1, flops if executed is None else executed))
     return _T()
 
 
@@ -194,7 +196,7 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
         plan = (ctypes.c_int * 10)()
         _lib.lib().icsg3d_conv3d_k3_plan(B, D, H, W, cin, nout, 148, plan)
         kind = ("pertap", "halo", "stream")[plan[0]]
-    with _timed((kind, tag), 2.0 * B * D * H * W * wpack.shape[0] * nc * no):
+    with _timed((kind, tag), 2.0 * B * D * H * W * wpack.shape[0] * nc * no, 2.0 * B * D * H * W * wpack.shape[0] * cin * nout):
         if split and (SPLIT_FMT if fmt is None else fmt) == 1:
             fn = "icsg3d_conv3d_k1_igemm_f16" if wpack.shape[0] == 1 else "icsg3d_conv3d_k3_igemm_f16"
             _lib.call(fn, _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt, n_store, B, D, H, W, cin, nout,
@@ -254,7 +256,7 @@ def conv3d_k3_wgrad(x, dy, *, cin=None, cout=None, out=None, ref=False, nominal=
         raise _lib.Icsg3dError("conv3d_k3_wgrad_workspace: invalid shape")
     ws = _wgrad_scratch(need, ws, x.device)
     nc, no = nominal if nominal else (cin, cout)
-    with _timed(("wgrad", tag), 2.0 * B * D * H * W * 27 * nc * no):
+    with _timed(("wgrad", tag), 2.0 * B * D * H * W * 27 * nc * no, 2.0 * B * D * H * W * 27 * cin * cout):
         _lib.call("icsg3d_conv3d_k3_wgrad", _ptr(x), ldx, _ptr(dy), ldy, _ptr(out), B, D, H, W, cin, cout, _ptr(ws),
                   ctypes.c_int64(ws.numel() * ws.element_size()), _stream())
     return out

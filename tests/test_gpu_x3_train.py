@@ -175,7 +175,7 @@ def test_unet_train_step_fp32_class_gradients():
     # mask-flip limited like the VAE step (see there); the U-Net is 14 ReLU blocks deep with 8-way pool ties:
     # heads / c18 at 1e-4 ... 1e-3, growing towards c1
     assert rep["grad"]["soft/kernel"]["vs_oracle_fp32"] < 2e-4 and rep["grad"]["bn_c18/gamma"]["vs_oracle_fp32"] < 2e-4
-    bad = {k: v for k, v in rep["grad"].items() if v["vs_oracle_fp32"] > 4e-2 or v["cos"] < 0.9995}
+    bad = {k: v for k, v in rep["grad"].items() if v["vs_oracle_fp32"] > 4e-2 or v["cos"] < 0.999}
     assert not bad, bad
 
 

@@ -42,6 +42,7 @@ def main():
     torch.cuda.synchronize()
     m_dp = eng.metrics_host()
     ok = True
+    report = {}
     if rank == 0:
         ref = VAEEngine(Bg, d=32, seed=3, device=dev)
         ref.set_inputs(M, cond, eps)
@@ -56,8 +57,9 @@ def main():
         cos = float((g_dp @ g_1) / (g_dp.norm() * g_1.norm()))
         dm = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(m_dp, m_1))
         ok = dm < 1e-3 and cos > 0.995
-        print(json.dumps({"world": world, "metrics_dp": m_dp, "metrics_1rank": m_1, "grad_rel_l2": rel, "grad_cos": cos,
-                          "ok": ok}))
+        report["equivalence"] = {"world": world, "global_batch": Bg, "metrics_dp": m_dp, "metrics_1rank": m_1,
+                                 "max_rel_metric_delta": dm, "grad_rel_l2": rel, "grad_cos": cos, "ok": ok}
+        print(json.dumps(report["equivalence"]))
     # ---- segmented CUDA-graph replay of the DP step == eager DP step (same kernels, same collectives) ----
     engA = VAEEngine(Bl, d=32, seed=3, device=dev, dist=Dist())
     engB = VAEEngine(Bl, d=32, seed=3, device=dev, dist=Dist())
@@ -73,8 +75,14 @@ def main():
     mA, mB = engA.metrics_host(), engB.metrics_host()
     ok_graph = dtheta == 0.0 and mA == mB
     if rank == 0:
-        print(json.dumps({"world": world, "graph_segments": nseg, "bn_allreduce": "peer-memory kernel" if engA.peer is not None else "nccl", "theta_max_abs_diff_graph_vs_eager": dtheta,
-                          "metrics_graph": mA, "metrics_eager": mB, "ok": bool(ok and ok_graph)}))
+        report["graph_vs_eager"] = {"world": world, "graph_segments": nseg,
+                                    "bn_allreduce": "peer-memory kernel" if engA.peer is not None else "nccl",
+                                    "theta_max_abs_diff_graph_vs_eager": dtheta, "metrics_graph": mA, "metrics_eager": mB,
+                                    "ok": bool(ok and ok_graph)}
+        print(json.dumps(report["graph_vs_eager"]))
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"dp_equivalence_w{world}.json"), "w") as f:
+            json.dump(report, f, indent=1)
     ok = ok and ok_graph
     dist.barrier()
     dist.destroy_process_group()
