@@ -11,6 +11,8 @@
 // Per-site record (8 doubles): x, y, z (Cartesian), thr = sigma*label_frac, zs = Z/sigma^3, two_s2 = 2*sigma^2,
 // Z, unused.  The host wrapper computes thr/zs/two_s2 with numpy for parity runs (np.power is libm pow);
 // icsg3d_synth_perovskite_sites produces them on the device for the benchmark generator.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace icsg3d {
@@ -86,6 +88,123 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const double* __restrict_
   if (species64) species64[o] = spec;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path for the NETWORK outputs only (fp32 4-channel input + uint8 species; no fp64 density / species requested).
+// The exact kernel above is bound by the FP64 pipe (sqrt + exp + divide in double, ~150 DP instructions per voxel and
+// site: 6 TFLOP/s-equivalent at 0.97 M samples/s, 8 % of HBM).  Here:
+//   * species: the distance predicate and the arg-min are decided on the SQUARED distance ss (same fp64 operation order
+//     as cdist, so ss is bit-identical to the reference's) against thr^2 / the running minimum with a 1e-12 relative
+//     guard band; only inside the band (where rounding of sqrt could matter) the exact `sqrt(ss) < thr` of the reference
+//     is evaluated -> the species grid stays BIT-EXACT, the double sqrt disappears from the common path;
+//   * density: exp(-ss / 2 sigma^2) = 2^n * 2^r with the range reduction n = rint(t), r = t - n, t = ss * c_s done in
+//     fp64 (two DP instructions) and 2^r by the SFU (ex2.approx.f32, 2 ulp): relative error ~2e-7 whatever the
+//     magnitude of the argument, i.e. the fp32 output is within ~3 ulp of the rounded fp64 value.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kVoxPerThread = 4;  // voxels per thread of the fast kernel (amortises the per-block site / axis setup)
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(256) voxelize_fast_kernel(const double* __restrict__ sites, const int* __restrict__ nsites,
+                                                            const double* __restrict__ lattice, int max_sites, int d,
+                                                            double eps_frac, float* __restrict__ m32,
+                                                            uint8_t* __restrict__ species) {
+  __shared__ double s_pos[kMaxSites][3];
+  __shared__ double s_thr[kMaxSites], s_thr2lo[kMaxSites], s_thr2hi[kMaxSites], s_c[kMaxSites];
+  __shared__ float s_zs[kMaxSites];
+  __shared__ uint8_t s_z[kMaxSites];
+  extern __shared__ double s_dyn[];  // [3*d] voxel-centre table (fp64) followed by [3*d] coordinate-grid table (fp32)
+  double* s_ctr = s_dyn;
+  float* s_grid = reinterpret_cast<float*>(s_dyn + 3 * d);
+  __shared__ double s_ax[3][4];  // per axis: start, step, dv/2, step2 — the same fp64 expressions as the exact kernel,
+                                 // evaluated once per block instead of once per voxel (9 double divisions per voxel)
+  const int cell = blockIdx.y;
+  const int n = nsites[cell];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double* r = sites + (static_cast<size_t>(cell) * max_sites + i) * kSiteRec;
+    s_pos[i][0] = r[0]; s_pos[i][1] = r[1]; s_pos[i][2] = r[2];
+    const double thr2 = r[3] * r[3];
+    s_thr[i] = r[3];
+    s_thr2lo[i] = thr2 * (1.0 - 1e-12);
+    s_thr2hi[i] = thr2 * (1.0 + 1e-12);
+    s_c[i] = -1.4426950408889634 / r[5];   // t = ss * c = -(ss / 2 sigma^2) * log2(e)
+    s_zs[i] = static_cast<float>(r[4]);
+    s_z[i] = static_cast<uint8_t>(r[6]);
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 35) {
+    const int ax = threadIdx.x - 32;
+    const double a = lattice[cell * 3 + ax];
+    const double dv = (a + ((2.0 * a) * eps_frac)) / static_cast<double>(d);
+    const double start = -a * eps_frac;
+    const double stop = a + (a * eps_frac);
+    s_ax[ax][0] = start;
+    s_ax[ax][1] = (stop - start) / static_cast<double>(d);
+    s_ax[ax][2] = dv / 2.0;
+    const double stop2 = a + ((2.0 * eps_frac) * a);
+    s_ax[ax][3] = (stop2 - 0.0) / static_cast<double>(d);
+  }
+  __syncthreads();
+  // per-axis tables of the voxel-centre coordinate (fp64, for the distances) and the coordinate-grid channel (fp32):
+  // the reference's expressions i*step + start (+ dv/2) evaluated once per block and index, not per voxel
+  for (int t = threadIdx.x; t < 3 * d; t += blockDim.x) {
+    const int ax = t / d, idx = t - ax * d;
+    const double corner = static_cast<double>(idx) * s_ax[ax][1] + s_ax[ax][0];
+    s_ctr[t] = corner + s_ax[ax][2];
+    s_grid[t] = static_cast<float>(static_cast<double>(idx) * s_ax[ax][3] + 0.0);
+  }
+  __syncthreads();
+  const unsigned vox = static_cast<unsigned>(d) * d * d;
+  const unsigned ud = static_cast<unsigned>(d);
+#pragma unroll 1
+  for (int q = 0; q < kVoxPerThread; ++q) {
+    const unsigned v = (blockIdx.x * kVoxPerThread + q) * blockDim.x + threadIdx.x;
+    if (v >= vox) return;
+    const unsigned k = v % ud, j = (v / ud) % ud, i = v / (ud * ud);
+    const double c0 = s_ctr[i], c1 = s_ctr[ud + j], c2 = s_ctr[2 * ud + k];
+    int count = 0, first_in = 0, nearest = 0;
+    double ssmin = 0.0, ssmin_lo = 0.0;
+    float acc = 0.f;
+    for (int s = 0; s < n; ++s) {
+      const double dx = c0 - s_pos[s][0], dy = c1 - s_pos[s][1], dz = c2 - s_pos[s][2];
+      double ss = dx * dx;
+      ss = ss + dy * dy;
+      ss = ss + dz * dz;
+      bool inside = ss < s_thr2lo[s];
+      if (!inside && ss <= s_thr2hi[s]) inside = sqrt(ss) < s_thr[s];   // guard band: the reference's own comparison
+      if (inside) {
+        if (count == 0) first_in = s;
+        ++count;
+      }
+      if (s == 0) {
+        ssmin = ss;
+        ssmin_lo = ss * (1.0 - 1e-12);
+      } else if (ss < ssmin_lo || (ss < ssmin && sqrt(ss) < sqrt(ssmin))) {  // first index wins unless strictly nearer
+        ssmin = ss;
+        ssmin_lo = ss * (1.0 - 1e-12);
+        nearest = s;
+      }
+      // exp(-ss / 2 sigma^2) = 2^t, t = ss * c_s <= 0; round-to-nearest integer part by the 2^52 + 2^51 shift (no
+      // conversion instruction: the integer sits in the low word of the shifted double), fraction to the SFU
+      const double t = fmax(ss * s_c[s], -200.0);
+      const double sh = t + 6755399441055744.0;
+      const int e = __double2loint(sh);
+      const float r = static_cast<float>(t - (sh - 6755399441055744.0));
+      const float scale = e < -126 ? 0.f : __int_as_float((e + 127) << 23);   // flushes below the fp32 normal range
+      acc += ex2_approx(r) * scale * s_zs[s];
+    }
+    const float dens = 0.063493635934240969f * acc;   // 1/(2*pi)^1.5
+    uint8_t spec = 0;
+    if (count == 1) spec = s_z[first_in];
+    else if (count >= 2) spec = s_z[nearest];
+    const size_t o = static_cast<size_t>(cell) * vox + v;
+    if (m32) reinterpret_cast<float4*>(m32)[o] = make_float4(dens, s_grid[i], s_grid[ud + j], s_grid[2 * ud + k]);
+    if (species) species[o] = spec;
+  }
+}
+
 // splitmix64: stateless per-cell random numbers for the synthetic ABX3 generator
 __device__ __forceinline__ uint64_t splitmix(uint64_t& s) {
   s += 0x9E3779B97F4A7C15ull;
@@ -142,8 +261,20 @@ extern "C" int icsg3d_voxelize(const double* sites, const int* nsites, const dou
   ICSG_REQUIRE(ncells >= 1 && ncells <= 65535 && d >= 1 && d <= 512, "voxelize: bad ncells/d");
   const long long vox = static_cast<long long>(d) * d * d;
   dim3 grid(static_cast<unsigned>((vox + 255) / 256), ncells);
-  voxelize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(sites, nsites, lattice, max_sites, d, eps_frac, m32,
-                                                                      m64, species, species64);
+  static int exact_only = -1;  // ICSG3D_VOXELIZE_EXACT=1: always the fp64 kernel (A/B measurements)
+  if (exact_only < 0) {
+    const char* e = getenv("ICSG3D_VOXELIZE_EXACT");
+    exact_only = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!m64 && !species64 && !exact_only) {
+    dim3 gridf(static_cast<unsigned>((vox + 256 * kVoxPerThread - 1) / (256 * kVoxPerThread)), ncells);
+    const size_t smem = static_cast<size_t>(3 * d) * (sizeof(double) + sizeof(float));
+    voxelize_fast_kernel<<<gridf, 256, smem, static_cast<cudaStream_t>(stream)>>>(sites, nsites, lattice, max_sites, d,
+                                                                                 eps_frac, m32, species);
+  }
+  else
+    voxelize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(sites, nsites, lattice, max_sites, d, eps_frac, m32,
+                                                                        m64, species, species64);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
