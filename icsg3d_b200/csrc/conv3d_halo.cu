@@ -46,6 +46,7 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ __align__(8) uint64_t b_all_full;
   __shared__ float s_bias[512];
+  __shared__ float s_stats[2][512];  // per-CTA BatchNorm partials of the stored output (fused statistics)
   __shared__ uint32_t tmem_base_slot;
 
   // warp index through a shuffle: warp-uniform for the compiler, keeps the MMA descriptors in uniform registers
@@ -88,6 +89,7 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < p.nt * p.tiles_n && i < 512; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&s_stats[0][0])[i] = 0.f;
   if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -254,7 +256,8 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         tmem_ld_wait();
         const int col0 = tn * p.nt + c0;
-        if (!ok || col0 >= p.n_store) continue;
+        if (col0 >= p.n_store) continue;        // warp-uniform
+        if (!ok && !p.stats) continue;
         float fv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -273,15 +276,27 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 qv.y = pack_bf16x2(fv[8 * j + 2], fv[8 * j + 3]);
                 qv.z = pack_bf16x2(fv[8 * j + 4], fv[8 * j + 5]);
                 qv.w = pack_bf16x2(fv[8 * j + 6], fv[8 * j + 7]);
-                reinterpret_cast<uint4*>(dst)[j] = qv;
+                if (ok) reinterpret_cast<uint4*>(dst)[j] = qv;
+                if (p.stats) {  // statistics of the values as stored (bf16-rounded)
+                  float2 u;
+                  u = unpack_bf16x2(qv.x); fv[8 * j] = u.x; fv[8 * j + 1] = u.y;
+                  u = unpack_bf16x2(qv.y); fv[8 * j + 2] = u.x; fv[8 * j + 3] = u.y;
+                  u = unpack_bf16x2(qv.z); fv[8 * j + 4] = u.x; fv[8 * j + 5] = u.y;
+                  u = unpack_bf16x2(qv.w); fv[8 * j + 6] = u.x; fv[8 * j + 7] = u.y;
+                }
               }
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nvalid) dst[i] = f2bf(fv[i]);
+            for (int i = 0; i < 32; ++i) {
+              if (i < nvalid) {
+                const __nv_bfloat16 q = f2bf(fv[i]);
+                if (ok) dst[i] = q;
+                fv[i] = bf2f(q);
+              }
+            }
           }
-        } else {
+        } else if (ok) {
           float* dst = reinterpret_cast<float*>(p.y) + pixel * p.ldy + col0;
           if ((p.ldy & 3) == 0 && (nvalid & 3) == 0) {
 #pragma unroll
@@ -294,6 +309,28 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               if (i < nvalid) dst[i] = fv[i];
           }
         }
+        if (p.stats) {
+          // column sums over the warp's 32 rows by a transpose-reduce butterfly (junk rows contribute zero), then one
+          // shared-memory atomic per column and warp: the CTA's partial, written out after the last item
+#pragma unroll
+          for (int j = 0; j < 32; j += 16) {
+            if (j < nvalid) {  // warp-uniform
+              float a[16], b[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float t = ok ? fv[j + i] : 0.f;
+                a[i] = t;
+                b[i] = t * t;
+              }
+              const float s1 = warp_colsum16(a, lane), s2 = warp_colsum16(b, lane);
+              if ((lane & 1) == 0) {
+                const int c = (col0 + j + colsum16_owner(lane)) & 511;
+                atomicAdd(&s_stats[0][c], s1);
+                atomicAdd(&s_stats[1][c], s2);
+              }
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -303,6 +340,13 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    const int nout = p.nt * p.tiles_n;
+    for (int i = threadIdx.x; i < 2 * nout; i += blockDim.x) {
+      const int half = i / nout, c = i - half * nout;
+      p.stats[static_cast<size_t>(blockIdx.x) * 2 * nout + i] = static_cast<double>(s_stats[half][c]);
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -395,7 +439,7 @@ bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, Conv
 
 int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                      int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st,
-                     float oscale) {
+                     float oscale, double* stats) {
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
@@ -416,6 +460,7 @@ int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bia
   }
   p.y = y; p.ldy = ldy; p.y_dtype = y_dtype; p.n_store = n_store; p.bias = bias; p.act = act; p.alpha = alpha;
   p.oscale = oscale;
+  p.stats = stats;
   static bool configured = false;
   if (!configured) {
     ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -424,7 +469,7 @@ int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bia
     configured = true;
   }
   const size_t smem = static_cast<size_t>(p.a_bufs) * p.a_buf_bytes + static_cast<size_t>(p.b_stages) * p.b_unit_bytes + 1024;
-  const int grid = p.total_items < sms ? p.total_items : sms;
+  const int grid = conv_halo_grid(p, sms);
   if (p.kc == 16) conv3d_k3_halo_kernel<1><<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
   else if (p.kc == 32) conv3d_k3_halo_kernel<2><<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
   else conv3d_k3_halo_kernel<4><<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);

@@ -21,12 +21,15 @@ struct ConvHaloParams {
   int act;
   float alpha;
   float oscale;  // output = accumulator * oscale + bias (1 unless the weights were pre-scaled: fp16 split mode)
+  double* stats;  // optional [grid][2][nt*tiles_n]: per-CTA BatchNorm partials (sum, sum of squares) of the STORED output
 };
 
 // Pick (TD, TH, NT) from a simple cycle model; false when the layer shape does not fit the halo scheme.
 bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvHaloParams* out);
 int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                      int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st,
-                     float oscale = 1.0f);
+                     float oscale = 1.0f, double* stats = nullptr);
+// CTAs the halo kernel launches for this plan (= rows of the fused-statistics partials)
+inline int conv_halo_grid(const ConvHaloParams& p, int sms) { return p.total_items < sms ? p.total_items : sms; }
 
 }  // namespace icsg3d

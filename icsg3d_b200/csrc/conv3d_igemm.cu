@@ -420,13 +420,15 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
       return launch_conv_stream(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, stats, sp,
                                 static_cast<cudaStream_t>(stream), oscale);
     }
-    ICSG_REQUIRE(!stats, "conv3d_k3_igemm_stats: this layer shape has no fused-statistics path (stats_parts() == 0)");
     ConvHaloParams hp;
     if (ntaps == 27 && sms0 > 0 && conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp)) {
+      ICSG_REQUIRE(!stats || (nout <= 512 && n_store == nout && stats_parts == conv_halo_grid(hp, sms0)),
+                   "conv3d_k3_igemm_stats: stats_parts %d does not match this layer's plan", stats_parts);
       hp.idesc &= fmt_mask;
       return launch_conv_halo(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, hp, sms0,
-                              static_cast<cudaStream_t>(stream), oscale);
+                              static_cast<cudaStream_t>(stream), oscale, stats);
     }
+    ICSG_REQUIRE(!stats, "conv3d_k3_igemm_stats: this layer shape has no fused-statistics path (stats_parts() == 0)");
   }
   ConvIgemmParams p{};
   p.m_total = static_cast<int>(m_total);
@@ -560,11 +562,33 @@ extern "C" int icsg3d_conv3d_k1_igemm_f16(const void* x, int ldx, const void* wp
                            nullptr, 0, nullptr, 0, true, out_scale);
 }
 
+// Fused statistics in the HALO kernel accumulate per-CTA column sums with fp32 shared-memory atomics: the result depends
+// (in the last bits) on the arrival order of the epilogue warps, which breaks the bit-for-bit reproducibility of a train
+// step (graph replay == eager, N ranks == 1 rank) for a measured gain of 0.8 % of the step.  Off by default;
+// ICSG3D_HALO_STATS=1 or icsg3d_conv3d_set_halo_stats(1) turns it on.
+static int g_halo_stats = -1;
+static bool halo_stats_enabled() {
+  if (g_halo_stats < 0) {
+    const char* e = getenv("ICSG3D_HALO_STATS");
+    g_halo_stats = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_halo_stats == 1;
+}
+extern "C" int icsg3d_conv3d_set_halo_stats(int on) {
+  g_halo_stats = on ? 1 : 0;
+  return ICSG3D_OK;
+}
+
 extern "C" int icsg3d_conv3d_k3_stats_parts(int B, int D, int H, int W, int cin, int nout) {
   const int sms = sm_count();
+  if (sms <= 0) return 0;
   ConvStreamParams sp;
-  if (sms <= 0 || conv_impl_choice() != 0 || !conv_stream_plan(B, D, H, W, cin, nout, sms, &sp)) return 0;
-  return sp.tiles_n == 1 ? conv_stream_grid(sp) : 0;  // fused statistics only for un-split layers
+  if (conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms, &sp))
+    return sp.tiles_n == 1 ? conv_stream_grid(sp) : 0;  // streaming kernel: fused statistics only for un-split layers
+  ConvHaloParams hp;
+  if (halo_stats_enabled() && conv_impl_choice() != 1 && nout <= 512 && conv_halo_plan(B, D, H, W, cin, nout, sms, &hp))
+    return conv_halo_grid(hp, sms);
+  return 0;
 }
 
 extern "C" int icsg3d_conv3d_k3_igemm_stats(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,

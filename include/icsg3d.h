@@ -79,6 +79,11 @@ int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const floa
 /* Same conv with a caller-owned fp32 workspace: layers with too few output tiles to fill the GPU (4^3 / 2^3 grids with a
  * deep K = 27*Cin) run with the K range split over several CTAs and a fixed-order reduction (deterministic).
  * icsg3d_conv3d_k3_workspace_bytes() = bytes needed for this shape (0: the layer is not split; ws may then be NULL). */
+/* Fused BatchNorm statistics in the halo kernel (layers with Cout >= 64 at 16^3 / 8^3): implemented and tested, OFF by
+ * default because its fp32 shared-memory atomics make a train step depend on warp arrival order in the last bits (the
+ * streaming kernel's fused statistics are always on).  icsg3d_conv3d_k3_stats_parts() reports 0 for halo layers unless
+ * enabled here or with ICSG3D_HALO_STATS=1. */
+int icsg3d_conv3d_set_halo_stats(int on);
 int64_t icsg3d_conv3d_k3_workspace_bytes(int B, int D, int H, int W, int cin, int nout);
 int icsg3d_conv3d_k3_igemm_ws(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                               int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,

@@ -143,20 +143,29 @@ def test_wgrad_stream_kernel_full_batch_matches_per_tap_kernel(B, D, cin, cout):
     assert torch.equal(got, got2)
 
 
-@pytest.mark.parametrize("B,D,cin,cout,act", [(3, 32, 32, 64, 1), (2, 32, 16, 16, 0), (5, 16, 64, 32, 2), (2, 32, 16, 32, 1)])
-def test_fused_conv_bn_statistics_match_stored_output(B, D, cin, cout, act):
-    """conv epilogue statistics (icsg3d_conv3d_k3_igemm_stats) == per-channel sum / sum of squares of the stored
-    bf16 output, i.e. what a separate icsg3d_bn_stats pass over the same tensor measures."""
-    from icsg3d_b200 import ops
+@pytest.mark.parametrize("B,D,cin,cout,act,odt", [
+    (3, 32, 32, 64, 1, "bf16"), (2, 32, 16, 16, 0, "bf16"), (5, 16, 64, 32, 2, "bf16"), (2, 32, 16, 32, 1, "bf16"),   # streaming kernel
+    (2, 32, 48, 16, 0, "f32"),                                                # split-operand encoder layer, fp32 output
+    (4, 16, 64, 128, 1, "bf16"), (6, 8, 128, 128, 1, "bf16"), (8, 8, 128, 256, 1, "bf16"), (8, 8, 128, 64, 2, "bf16"),  # halo kernel
+    (32, 8, 96, 64, 0, "f32"), (3, 16, 64, 128, 2, "bf16")])
+def test_fused_conv_bn_statistics_match_stored_output(B, D, cin, cout, act, odt):
+    """conv epilogue statistics (icsg3d_conv3d_k3_igemm_stats; plane-streaming AND halo kernel) == per-channel sum / sum of
+    squares of the STORED output (bf16-rounded or fp32), i.e. what a separate icsg3d_bn_stats pass over it measures."""
+    from icsg3d_b200 import _lib, ops
     x, w, b = _mk(B, D, cin, cout, seed=21)
     xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
     wp = ops.pack_conv_w_fprop(wd)
-    n = ops.conv3d_k3_stats_parts(xd, wp)
-    assert n > 0, "this shape must be served by the plane-streaming kernel"
-    part = torch.full((n, 2, cout), float("nan"), dtype=torch.float64, device="cuda")
-    y = ops.conv3d_k3(xd, wp, bd, act=act, stats=part)
-    y_plain = ops.conv3d_k3(xd, wp, bd, act=act)
-    torch.cuda.synchronize()
+    _lib.call("icsg3d_conv3d_set_halo_stats", 1)   # opt-in for the halo kernel (order-dependent fp32 atomics)
+    try:
+        n = ops.conv3d_k3_stats_parts(xd, wp)
+        assert n > 0, "this shape must be served by a kernel with fused statistics (plane-streaming or halo)"
+        dt = torch.bfloat16 if odt == "bf16" else torch.float32
+        part = torch.full((n, 2, cout), float("nan"), dtype=torch.float64, device="cuda")
+        y = ops.conv3d_k3(xd, wp, bd, act=act, stats=part, out_dtype=dt)
+        y_plain = ops.conv3d_k3(xd, wp, bd, act=act, out_dtype=dt)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("icsg3d_conv3d_set_halo_stats", 0)
     assert torch.equal(y, y_plain)
     yd = y.double().view(-1, cout)
     got = part.sum(0)
