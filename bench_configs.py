@@ -447,11 +447,11 @@ def _run_voxeliser(args):
     e2e_s = _wall_loop(e2e_step, max(3, args.steps // 10), world, dev)
     clocks = sampler.stop() if rank == 0 else None
     gbs = VOX_BYTES * n / (ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "voxelize_kernel (csrc/voxelize.cu)", "achieved": gbs, "peak": peaks["hbm_gbs"],
+    roof = {"bound": "hbm", "kernel": "voxelize_fast_kernel (csrc/voxelize.cu; network outputs: fp32 input tensor + uint8 species)", "achieved": gbs, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
             "algorithmic_bytes_per_launch": VOX_BYTES * n, "avg_launch_ms": ms,
-            "note": "output-write bound is the floor; the fp64 no-FMA distance/exp arithmetic per (voxel, site) sits above it: "
-                    "see profiles/ for the ncu summary of this kernel"}
+            "note": "instruction-issue bound (ncu: issue slots 89 %, FP64 pipe 31 %, DRAM 13 %): the bit-exact species predicate needs ~100 fp64 instructions per (voxel, site); "
+                    "profiles/r02_ncu_voxelize_fast_summary.txt"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sps, _, cores = _cpu_voxeliser(24)
