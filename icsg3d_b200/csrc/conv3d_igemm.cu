@@ -362,6 +362,18 @@ static int conv_impl_choice() {
   }
   return v;
 }
+// Halo kernel or per-tap kernel?  conv_halo_plan() only says whether a halo configuration FITS.  Measured on B200
+// (profiles/r02_conv_halo_vs_pertap.txt): whenever the halo plan has to split N (nt < nout: two passes over the same
+// halo block at the 55-cycle MMA floor, 3-4 weight stages) the per-tap kernel is 1.9-2.5x faster (c18 128->128 @32^3:
+// 453 -> 240 us at batch 8; c16 256->128 @16^3: 204 -> 80 us), and a narrow layer that leaves SMs idle (fewer items than
+// SMs at nt <= 64: dec_conv2 128->64 @8^3) is 1.5x faster per tap with split K.  ICSG3D_CONV_IMPL=halo forces halo.
+static bool conv_use_halo(int B, int D, int H, int W, int cin, int nout, int sms, ConvHaloParams* hp) {
+  if (conv_impl_choice() == 1 || !conv_halo_plan(B, D, H, W, cin, nout, sms, hp)) return false;
+  if (conv_impl_choice() == 2) return true;
+  if (hp->tiles_n > 1) return false;
+  if (hp->total_items < sms && hp->nt <= 64) return false;
+  return true;
+}
 }  // namespace icsg3d
 
 using namespace icsg3d;
@@ -421,7 +433,7 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
                                 static_cast<cudaStream_t>(stream), oscale);
     }
     ConvHaloParams hp;
-    if (ntaps == 27 && sms0 > 0 && conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms0, &hp)) {
+    if (ntaps == 27 && sms0 > 0 && conv_use_halo(B, D, H, W, cin, nout, sms0, &hp)) {
       ICSG_REQUIRE(!stats || (nout <= 512 && n_store == nout && stats_parts == conv_halo_grid(hp, sms0)),
                    "conv3d_k3_igemm_stats: stats_parts %d does not match this layer's plan", stats_parts);
       hp.idesc &= fmt_mask;
@@ -529,7 +541,7 @@ extern "C" int64_t icsg3d_conv3d_k3_workspace_bytes(int B, int D, int H, int W, 
   ConvStreamParams sp;
   ConvHaloParams hp;
   if (conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms, &sp)) return 0;
-  if (conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms, &hp)) return 0;
+  if (conv_use_halo(B, D, H, W, cin, nout, sms, &hp)) return 0;
   const long long m_total = static_cast<long long>(B) * D * H * W;
   const int kc = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
   const int chunks = cin / kc;
@@ -586,7 +598,7 @@ extern "C" int icsg3d_conv3d_k3_stats_parts(int B, int D, int H, int W, int cin,
   if (conv_impl_choice() == 0 && conv_stream_plan(B, D, H, W, cin, nout, sms, &sp))
     return sp.tiles_n == 1 ? conv_stream_grid(sp) : 0;  // streaming kernel: fused statistics only for un-split layers
   ConvHaloParams hp;
-  if (halo_stats_enabled() && conv_impl_choice() != 1 && nout <= 512 && conv_halo_plan(B, D, H, W, cin, nout, sms, &hp))
+  if (halo_stats_enabled() && nout <= 512 && conv_use_halo(B, D, H, W, cin, nout, sms, &hp))
     return conv_halo_grid(hp, sms);
   return 0;
 }
@@ -631,7 +643,7 @@ extern "C" int icsg3d_conv3d_k3_plan(int B, int D, int H, int W, int cin, int no
     return ICSG3D_OK;
   }
   ConvHaloParams hp;
-  if (conv_impl_choice() != 1 && conv_halo_plan(B, D, H, W, cin, nout, sms, &hp)) {
+  if (conv_use_halo(B, D, H, W, cin, nout, sms, &hp)) {
     out[0] = 1; out[1] = hp.TD; out[2] = hp.TH; out[3] = hp.G; out[4] = hp.nt; out[5] = hp.a_bufs; out[6] = hp.b_stages;
     out[7] = hp.total_items; out[8] = hp.kc;
     out[9] = static_cast<int>(hp.a_bufs * hp.a_buf_bytes + hp.b_stages * hp.b_unit_bytes);
