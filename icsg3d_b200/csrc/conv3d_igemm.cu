@@ -372,6 +372,12 @@ static bool conv_use_halo(int B, int D, int H, int W, int cin, int nout, int sms
   if (conv_impl_choice() == 2) return true;
   if (hp->tiles_n > 1) return false;
   if (hp->total_items < sms && hp->nt <= 64) return false;
+  // two or more channel chunks (cin >= 128) shrink the halo block to one 50 %-useful tile per item; with a wide N
+  // (>= 128: the per-tap MMAs are off the 55-cycle floor) and enough voxels to amortise the per-tap pipeline
+  // (>= 256 M tiles) the per-tap kernel wins by 1.2-1.5x (128->256 @16^3 B=8: 90 -> 75 us; 256->128 @8^3 B=100: 190 -> 124;
+  // 128->128 @16^3 B=16: 128 -> 90), while it loses below that size (128->128 @8^3 B=32: 30 vs 45) and for narrow N
+  // (128->64 @16^3 B=100: 237 vs 355)
+  if (cin >= 128 && nout >= 128 && static_cast<long long>(B) * D * H * W >= 32768) return false;
   return true;
 }
 }  // namespace icsg3d
