@@ -305,14 +305,14 @@ def run_cuda(args):
         # launch (c2 fprop) — never measured under the profiler in this run
         traffic, traffic_detail = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_dominant_kernel.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_dominant_kernel.json")) as f:
                 traffic_detail = json.load(f)
             traffic = traffic_detail["dram_bytes_read"] + traffic_detail["dram_bytes_write"]
         except (OSError, KeyError, ValueError):
             pass
         roof = {"bound": "tensor", "kernel": "dominant by time: " + names[dom],
                 "achieved": dk["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": dk["tflops"] / peak_tf,
-                "traffic": traffic, "traffic_source": "static: profiles/r01_ncu_dominant_kernel.json (ncu --set full of this kernel's "
+                "traffic": traffic, "traffic_source": "static: profiles/r02_ncu_dominant_kernel.json (ncu --set full of this kernel's "
                                                       "largest launch, c2 fprop; not measured in this run)",
                 "traffic_detail": traffic_detail, "peak_source": peak_note,
                 "algorithmic_gflop_per_launch": dk["gflop_per_step"] / dk["launches_per_step"],
