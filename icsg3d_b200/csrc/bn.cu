@@ -89,6 +89,7 @@ static constexpr int kBnThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_stats_kernel(const T* __restrict__ x, int ldx, long long M, int C,
                                                              double* __restrict__ partials) {
+  pdl_prologue();
   constexpr int V = VecIO<T>::N;
   extern __shared__ double sred[];  // [2][rows_per_iter][C] would be too big: reduce per channel group instead
   const int cg = C / V;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_stats_kernel(const T* __rest
 // coalesced 32-column reads, then the 8 warp partials are added in warp order.  Block = 32 columns.
 __global__ void __launch_bounds__(256) bn_reduce_partials_kernel(const double* __restrict__ partials, int nparts, int C2,
                                                                  double* __restrict__ sums) {
+  pdl_prologue();
   __shared__ double red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -172,6 +174,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
                                    float* __restrict__ rstd_out, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ moving_mean, float* __restrict__ moving_var, float momentum,
                                    int C) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = sums[c] / count;
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(1024) bn_reduce_fused_kernel(const double* __r
                                                                float* __restrict__ shift, float* __restrict__ moving_mean,
                                                                float* __restrict__ moving_var, float momentum,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_prologue();
   // The reduction is latency bound (a few hundred KB of fp64 partials): 1024 threads keep every load of a column
   // independent and in flight at once; the order of the additions is a function of (nparts) only => deterministic.
   __shared__ double red[kRedSlots][2 * kRedCh + 1];
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__(1024) bn_reduce_allreduce_kernel(const double*
                                                                    float* __restrict__ moving_var, float momentum,
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                    const BnPeerParams pp) {
+  pdl_prologue();
   __shared__ double red[kRedSlots][2 * kRedCh + 1];
   __shared__ double tot[2 * kRedCh];
   const int col = threadIdx.x & (2 * kRedCh - 1);
@@ -409,6 +414,7 @@ __global__ void __launch_bounds__(1024) bn_reduce_allreduce_kernel(const double*
 __global__ void bn_inference_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                            const float* __restrict__ mm, const float* __restrict__ mv, float eps,
                                            float* __restrict__ scale, float* __restrict__ shift, int C) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double rstd = 1.0 / sqrt(static_cast<double>(mv[c]) + static_cast<double>(eps));
@@ -472,6 +478,7 @@ __device__ __forceinline__ void bn_store_out(const BnFwdParams& p, long long row
 
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_kernel(const BnFwdParams p) {
+  pdl_prologue();
   constexpr int V = VecIO<T>::N;
   const T* x = static_cast<const T*>(p.x);
   const int cg = p.C / V;
@@ -596,6 +603,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_kernel(const BnFwd
 // window fetched in one batch from one base pointer, activation fixed at compile time.
 template <int kAct>
 __global__ void __launch_bounds__(kBnThreads, 3) bn_apply_fwd_pool_lean_kernel(const BnFwdParams p) {
+  pdl_prologue();
   constexpr int V = 8;
   typedef __nv_bfloat16 T;
   const T* __restrict__ x = static_cast<const T*>(p.x);
@@ -946,6 +954,7 @@ constexpr int kBnBwdMinBlocks() { return 2; }
 
 template <typename T, bool kApply, int kPost, int kMinBlocks>
 __global__ void __launch_bounds__(kBnThreads, kMinBlocks) bn_bwd_kernel(const BnBwdParams p) {
+  pdl_prologue();
   double tap_sq = 0.0;
   bn_bwd_body<T, kApply, kPost>(p, &tap_sq);
   if (kApply && p.tap_sq) bn_tap_sq_store(p.tap_sq, tap_sq);
@@ -969,6 +978,7 @@ __device__ __forceinline__ void cvt8(const uint4& q, float (&v)[8]) { VecIO<__nv
 template <bool kApply, int kPost, bool kHasAct, int kU = 4>
 __global__ void __launch_bounds__(kBnThreads, (kApply || kU == 8) ? 2 : 3)
 bn_bwd_lean_kernel(const BnBwdParams p) {
+  pdl_prologue();
   constexpr int V = 8;
   typedef __nv_bfloat16 T;
   const T* __restrict__ x = static_cast<const T*>(p.x);
@@ -1201,6 +1211,7 @@ struct BnFusedExtra {
 
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams p, const BnFusedExtra e) {
+  pdl_prologue();
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   bn_bwd_body<T, false>(p);
   __threadfence();
@@ -1308,6 +1319,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
 // dgamma = sum g*xhat, dbeta = sum g  (fp64 sums -> fp32 gradient slots)
 __global__ void bn_param_grads_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
                                       float* __restrict__ dbeta, int C) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (dbeta) dbeta[c] = static_cast<float>(sums[c]);
@@ -1357,9 +1369,9 @@ extern "C" int icsg3d_bn_stats(const void* x, int ldx, int dtype, int64_t rows, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == ICSG3D_DT_BF16) {
     if (smem > 48 * 1024) ICSG_CUDA(cudaFuncSetAttribute(bn_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    bn_stats_kernel<__nv_bfloat16><<<nparts, kBnThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, rows, C, partials);
+    launch_k(bn_stats_kernel<__nv_bfloat16>, nparts, kBnThreads, smem, st, static_cast<const __nv_bfloat16*>(x), ldx, rows, C, partials);
   } else {
-    bn_stats_kernel<float><<<nparts, kBnThreads, smem, st>>>(static_cast<const float*>(x), ldx, rows, C, partials);
+    launch_k(bn_stats_kernel<float>, nparts, kBnThreads, smem, st, static_cast<const float*>(x), ldx, rows, C, partials);
   }
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -1367,7 +1379,7 @@ extern "C" int icsg3d_bn_stats(const void* x, int ldx, int dtype, int64_t rows, 
 
 extern "C" int icsg3d_bn_reduce_partials(const double* partials, int nparts, int C, double* sums, void* stream) {
   ICSG_REQUIRE(partials && sums && nparts > 0, "bn_reduce_partials: bad arguments");
-  bn_reduce_partials_kernel<<<ceil_div(2 * C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, nparts, 2 * C, sums);
+  launch_k(bn_reduce_partials_kernel, ceil_div(2 * C, 32), 256, 0, static_cast<cudaStream_t>(stream), partials, nparts, 2 * C, sums);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -1377,7 +1389,7 @@ extern "C" int icsg3d_bn_finalize(const double* sums, double count, const float*
                                   float* moving_var, float momentum, int C, void* stream) {
   ICSG_REQUIRE(sums && mean && rstd && scale && shift && count > 0, "bn_finalize: bad arguments");
   ICSG_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize: moving_mean/var must both be given");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(bn_finalize_kernel, ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream), 
       sums, count, gamma, beta, eps, mean, rstd, scale, shift, moving_mean, moving_var, momentum, C);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -1387,7 +1399,7 @@ extern "C" int icsg3d_bn_inference_coeffs(const float* gamma, const float* beta,
                                           const float* moving_var, float eps, float* scale, float* shift, int C,
                                           void* stream) {
   ICSG_REQUIRE(moving_mean && moving_var && scale && shift, "bn_inference_coeffs: null pointer");
-  bn_inference_coeffs_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, moving_mean, moving_var,
+  launch_k(bn_inference_coeffs_kernel, ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream), gamma, beta, moving_mean, moving_var,
                                                                                         eps, scale, shift, C);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -1425,14 +1437,14 @@ static int bn_apply_fwd_impl(const void* x, int ldx, int x_dtype, const float* s
     if (lb > static_cast<long long>(sms) * 3) lb = static_cast<long long>(sms) * 3;
     if (lb < 1) lb = 1;
     const int g = static_cast<int>(lb);
-    if (act == ICSG3D_ACT_NONE) bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_NONE><<<g, kBnThreads, 0, st>>>(p);
-    else if (act == ICSG3D_ACT_RELU) bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_RELU><<<g, kBnThreads, 0, st>>>(p);
-    else bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_LEAKY><<<g, kBnThreads, 0, st>>>(p);
+    if (act == ICSG3D_ACT_NONE) launch_k(bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_NONE>, g, kBnThreads, 0, st, p);
+    else if (act == ICSG3D_ACT_RELU) launch_k(bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_RELU>, g, kBnThreads, 0, st, p);
+    else launch_k(bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_LEAKY>, g, kBnThreads, 0, st, p);
     ICSG_CHECK_LAUNCH();
     return ICSG3D_OK;
   }
-  if (x_dtype == ICSG3D_DT_BF16) bn_apply_fwd_kernel<__nv_bfloat16><<<static_cast<int>(blocks), kBnThreads, 0, st>>>(p);
-  else bn_apply_fwd_kernel<float><<<static_cast<int>(blocks), kBnThreads, 0, st>>>(p);
+  if (x_dtype == ICSG3D_DT_BF16) launch_k(bn_apply_fwd_kernel<__nv_bfloat16>, static_cast<int>(blocks), kBnThreads, 0, st, p);
+  else launch_k(bn_apply_fwd_kernel<float>, static_cast<int>(blocks), kBnThreads, 0, st, p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -1478,7 +1490,7 @@ template <typename T, bool kApply, int kPost, int kMinB>
 static void bn_bwd_launch_one(const BnBwdParams& p, int grid, size_t smem, cudaStream_t st) {
   auto* k = bn_bwd_kernel<T, kApply, kPost, kMinB>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  k<<<grid, kBnThreads, smem, st>>>(p);
+  launch_k(k, grid, kBnThreads, smem, st, p);
 }
 template <typename T, bool kApply, int kPost>
 static void bn_bwd_dispatch_minb(const BnBwdParams& p, int grid, size_t smem, cudaStream_t st) {
@@ -1498,7 +1510,7 @@ template <bool kApply, int kPost, bool kHasAct, int kU = 4>
 static void bn_bwd_lean_launch(const BnBwdParams& p, int grid, size_t smem, cudaStream_t st) {
   auto* k = bn_bwd_lean_kernel<kApply, kPost, kHasAct, kU>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  k<<<grid, kBnThreads, smem, st>>>(p);
+  launch_k(k, grid, kBnThreads, smem, st, p);
 }
 template <bool kApply>
 static bool bn_bwd_try_lean(const BnBwdParams& p, int grid, size_t smem, cudaStream_t st) {
@@ -1628,7 +1640,7 @@ extern "C" int icsg3d_bn_bwd_apply_tapsq(const void* dy, int lddy, const void* x
 
 extern "C" int icsg3d_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream) {
   ICSG_REQUIRE(sums, "bn_param_grads: null pointer");
-  bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, dgamma, dbeta, C);
+  launch_k(bn_param_grads_kernel, ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream), sums, dgamma, dbeta, C);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -1639,7 +1651,7 @@ extern "C" int icsg3d_bn_reduce_finalize(const double* partials, int nparts, dou
                                          void* stream) {
   ICSG_REQUIRE(partials && nparts > 0 && mean && rstd && scale && shift && count > 0, "bn_reduce_finalize: bad arguments");
   ICSG_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "bn_reduce_finalize: moving_mean/var must both be given");
-  bn_reduce_fused_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(bn_reduce_fused_kernel, ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream), 
       partials, nparts, C, 0, count, gamma, beta, eps, sums, mean, rstd, scale, shift, moving_mean, moving_var, momentum, nullptr,
       nullptr);
   ICSG_CHECK_LAUNCH();
@@ -1649,7 +1661,7 @@ extern "C" int icsg3d_bn_reduce_finalize(const double* partials, int nparts, dou
 extern "C" int icsg3d_bn_reduce_grads(const double* partials, int nparts, int C, double* sums, float* dgamma, float* dbeta,
                                       void* stream) {
   ICSG_REQUIRE(partials && nparts > 0 && sums, "bn_reduce_grads: bad arguments");
-  bn_reduce_fused_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(bn_reduce_fused_kernel, ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream), 
       partials, nparts, C, 1, 1.0, nullptr, nullptr, 0.f, sums, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, dgamma,
       dbeta);
   ICSG_CHECK_LAUNCH();
@@ -1679,7 +1691,7 @@ extern "C" int icsg3d_bn_reduce_allreduce_finalize(const double* partials, int n
   if (rc) return rc;
   BnPeerParams pp{reinterpret_cast<const unsigned long long*>(peers), world, rank, slot, nslots, cmax,
                   reinterpret_cast<const long long*>(epoch), peer_timeout_cycles()};
-  bn_reduce_allreduce_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(bn_reduce_allreduce_kernel, ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream), 
       partials, nparts, C, 0, count_global, gamma, beta, eps, sums, mean, rstd, scale, shift, moving_mean, moving_var, momentum,
       nullptr, nullptr, pp);
   ICSG_CHECK_LAUNCH();
@@ -1694,7 +1706,7 @@ extern "C" int icsg3d_bn_reduce_allreduce_grads(const double* partials, int npar
   if (rc) return rc;
   BnPeerParams pp{reinterpret_cast<const unsigned long long*>(peers), world, rank, slot, nslots, cmax,
                   reinterpret_cast<const long long*>(epoch), peer_timeout_cycles()};
-  bn_reduce_allreduce_kernel<<<ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(bn_reduce_allreduce_kernel, ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream), 
       partials, nparts, C, 1, 1.0, nullptr, nullptr, 0.f, sums_global, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f,
       dgamma, dbeta, pp);
   ICSG_CHECK_LAUNCH();

@@ -40,6 +40,7 @@ template <int KSTEPS>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const ConvHaloParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2];
   __shared__ __align__(8) uint64_t b_full[kHaloMaxBStages], b_empty[kHaloMaxBStages];
@@ -470,9 +471,9 @@ int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bia
   }
   const size_t smem = static_cast<size_t>(p.a_bufs) * p.a_buf_bytes + static_cast<size_t>(p.b_stages) * p.b_unit_bytes + 1024;
   const int grid = conv_halo_grid(p, sms);
-  if (p.kc == 16) conv3d_k3_halo_kernel<1><<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
-  else if (p.kc == 32) conv3d_k3_halo_kernel<2><<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
-  else conv3d_k3_halo_kernel<4><<<grid, kHaloThreads, smem, st>>>(tmA, tmB, p);
+  if (p.kc == 16) launch_k(conv3d_k3_halo_kernel<1>, grid, kHaloThreads, smem, st, tmA, tmB, p);
+  else if (p.kc == 32) launch_k(conv3d_k3_halo_kernel<2>, grid, kHaloThreads, smem, st, tmA, tmB, p);
+  else launch_k(conv3d_k3_halo_kernel<4>, grid, kHaloThreads, smem, st, tmA, tmB, p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -58,6 +58,7 @@ template <int KSTEPS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const ConvIgemmParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const float* __
                                                                  int ncols, const float* __restrict__ bias, int act, float alpha,
                                                                  void* __restrict__ y, int ldy, int y_dtype, int n_store,
                                                                  float oscale) {
+  pdl_prologue();
   const int c4 = ncols >> 2;
   const long long total = m_total * c4;
   const size_t slice = static_cast<size_t>(m_total) * ncols;
@@ -519,15 +521,15 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   const int total_tiles = p.tiles_m * p.tiles_n * p.ksplit;
   const int grid = total_tiles < sms ? total_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p.kc == 16) conv3d_k3_igemm_kernel<1><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
-  else if (p.kc == 32) conv3d_k3_igemm_kernel<2><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
-  else conv3d_k3_igemm_kernel<4><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
+  if (p.kc == 16) launch_k(conv3d_k3_igemm_kernel<1>, grid, kConvThreads, smem, st, tmA, tmB, p);
+  else if (p.kc == 32) launch_k(conv3d_k3_igemm_kernel<2>, grid, kConvThreads, smem, st, tmA, tmB, p);
+  else launch_k(conv3d_k3_igemm_kernel<4>, grid, kConvThreads, smem, st, tmA, tmB, p);
   ICSG_CHECK_LAUNCH();
   if (p.ksplit > 1) {
     const long long items = m_total * (nout / 4);
     long long blocks = (items + 255) / 256;
     if (blocks > sms * 8) blocks = sms * 8;
-    conv_splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(p.ws, p.ksplit, m_total, nout, bias, act, leaky_alpha, y,
+    launch_k(conv_splitk_reduce_kernel, static_cast<int>(blocks), 256, 0, st, p.ws, p.ksplit, m_total, nout, bias, act, leaky_alpha, y,
                                                                       ldy, y_dtype, n_store, oscale);
     ICSG_CHECK_LAUNCH();
   }

@@ -133,6 +133,7 @@ template <int KSTEPS>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const ConvStreamParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kStreamMaxStages], a_empty[kStreamMaxStages];
   __shared__ __align__(8) uint64_t slot_full[kStreamMaxR], slot_empty[kStreamMaxR];
@@ -607,9 +608,9 @@ int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* b
   }
   const size_t smem = ((p.w_bytes + 1023u) & ~1023u) + static_cast<size_t>(p.stages) * p.a_stage_bytes + 1024;
   const dim3 grid(conv_stream_grid(p), p.tiles_n);
-  if (p.kc == 16) conv3d_k3_stream_kernel<1><<<grid, kStreamThreads, smem, st>>>(tmA, tmB, p);
-  else if (p.kc == 32) conv3d_k3_stream_kernel<2><<<grid, kStreamThreads, smem, st>>>(tmA, tmB, p);
-  else conv3d_k3_stream_kernel<4><<<grid, kStreamThreads, smem, st>>>(tmA, tmB, p);
+  if (p.kc == 16) launch_k(conv3d_k3_stream_kernel<1>, grid, kStreamThreads, smem, st, tmA, tmB, p);
+  else if (p.kc == 32) launch_k(conv3d_k3_stream_kernel<2>, grid, kStreamThreads, smem, st, tmA, tmB, p);
+  else launch_k(conv3d_k3_stream_kernel<4>, grid, kStreamThreads, smem, st, tmA, tmB, p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -45,6 +45,7 @@ static constexpr int kWgradMaxStages = 6;
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                        const WgradParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kWgradMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kWgradMaxStages];
@@ -199,6 +200,7 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 // loads of a column independent and in flight, then the 4 lane sums are added in lane order.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n,
                                                            int splits) {
+  pdl_prologue();
   __shared__ float red[4][64];
   const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
   const long long i = static_cast<long long>(blockIdx.x) * 64 + e;
@@ -326,7 +328,7 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
     const int rc = wgrad_stream_run(x, ldx, dy, ldy, B, D, H, W, cin, cout, sms, static_cast<float*>(workspace), workspace_bytes,
                                     &splits, static_cast<cudaStream_t>(stream));
     if (rc == ICSG3D_OK) {
-      wgrad_reduce_kernel<<<static_cast<int>((n_dw + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      launch_k(wgrad_reduce_kernel, static_cast<int>((n_dw + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream), 
           static_cast<const float*>(workspace), dw, n_dw, splits);
       ICSG_CHECK_LAUNCH();
       return ICSG3D_OK;
@@ -354,9 +356,9 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
   }
   const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
   dim3 grid(p.splits, (p.total_groups + p.groups_per_cta - 1) / p.groups_per_cta, cout / p.ntw);
-  conv3d_k3_wgrad_kernel<<<grid, kWgradThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmDY, p);
+  launch_k(conv3d_k3_wgrad_kernel, grid, kWgradThreads, smem, static_cast<cudaStream_t>(stream), tmX, tmDY, p);
   ICSG_CHECK_LAUNCH();
-  wgrad_reduce_kernel<<<static_cast<int>((n_dw + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(p.ws, dw, n_dw, p.splits);
+  launch_k(wgrad_reduce_kernel, static_cast<int>((n_dw + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream), p.ws, dw, n_dw, p.splits);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -39,6 +39,7 @@ static constexpr uint32_t kWgsDyPad = 1024;  // zeroed bytes in front of every d
 __global__ void __launch_bounds__(kWgsThreads, 1)
 conv3d_k3_wgrad_stream_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                               const WgradStreamParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kWgsMaxStages], empty_bar[kWgsMaxStages];
   __shared__ __align__(8) uint64_t done_bar;
@@ -282,7 +283,7 @@ int launch_wgrad_stream(const void* x, int ldx, const void* dy, int ldy, WgradSt
   }
   const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
   dim3 grid(p.splits, p.chunks, 1);
-  conv3d_k3_wgrad_stream_kernel<<<grid, kWgsThreads, smem, st>>>(tmX, tmDY, p);
+  launch_k(conv3d_k3_wgrad_stream_kernel, grid, kWgsThreads, smem, st, tmX, tmDY, p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

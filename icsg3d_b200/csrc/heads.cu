@@ -16,6 +16,7 @@ __global__ void pack_heads_kernel(const float* __restrict__ w_soft, const float*
                                   const float* __restrict__ b_soft, const float* __restrict__ b_sig, int cin, int c1,
                                   int nout, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
                                   float* __restrict__ bias) {
+  pdl_prologue();
   const int total = cin * nout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i / nout, n = i % nout;
@@ -32,6 +33,7 @@ __global__ void pack_heads_kernel(const float* __restrict__ w_soft, const float*
 __global__ void unpack_heads_grad_kernel(const float* __restrict__ dwcat, const double* __restrict__ colsum, int cin,
                                          int c1, int nout, float* __restrict__ dw_soft, float* __restrict__ dw_sig,
                                          float* __restrict__ db_soft, float* __restrict__ db_sig) {
+  pdl_prologue();
   const int total = cin * (c1 + 1);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i / (c1 + 1), n = i % (c1 + 1);
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_loss_kernel(const float* 
                                                                    float* __restrict__ probs,
                                                                    __nv_bfloat16* __restrict__ dlogits, int ldd,
                                                                    double* __restrict__ partials, int dl_f32) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int warps = kHeadsThreads / 32;
   double acc[kHeadsTerms] = {0, 0, 0, 0, 0, 0};
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_loss_kernel(const float* 
 // out = [loss, soft_loss, sig_loss, f1_m, wr_m] (the order Keras reports; unet.py:249-259), raw[6] = the term sums.
 __global__ void heads_loss_finalize_kernel(const double* __restrict__ partials, int nparts, double count,
                                            float* __restrict__ out, double* __restrict__ raw) {
+  pdl_prologue();
   __shared__ double term[kHeadsTerms];
   if (threadIdx.x < kHeadsTerms) {
     double t = 0.0;
@@ -184,7 +188,7 @@ extern "C" int icsg3d_pack_heads_w(const float* w_soft, const float* w_sig, cons
                                    int c1, int nout, void* wf, void* wd, float* bias, void* stream) {
   ICSG_REQUIRE(w_soft && w_sig && b_soft && b_sig && wf && wd && bias, "pack_heads_w: null pointer");
   ICSG_REQUIRE(nout % 16 == 0 && nout >= c1 + 1 && cin % 16 == 0, "pack_heads_w: bad sizes");
-  pack_heads_kernel<<<ceil_div(cin * nout, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pack_heads_kernel, ceil_div(cin * nout, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w_soft, w_sig, b_soft, b_sig, cin, c1, nout, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd), bias);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -193,7 +197,7 @@ extern "C" int icsg3d_pack_heads_w(const float* w_soft, const float* w_sig, cons
 extern "C" int icsg3d_unpack_heads_grad(const float* dwcat, const double* colsum, int cin, int c1, int nout, float* dw_soft,
                                         float* dw_sig, float* db_soft, float* db_sig, void* stream) {
   ICSG_REQUIRE(dwcat && colsum && dw_soft && dw_sig && db_soft && db_sig, "unpack_heads_grad: null pointer");
-  unpack_heads_grad_kernel<<<ceil_div(cin * (c1 + 1), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(unpack_heads_grad_kernel, ceil_div(cin * (c1 + 1), 256), 256, 0, static_cast<cudaStream_t>(stream), 
       dwcat, colsum, cin, c1, nout, dw_soft, dw_sig, db_soft, db_sig);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -214,7 +218,7 @@ static int heads_loss_impl(const float* logits, int ld, int c1, const uint8_t* s
   ICSG_REQUIRE(c1 >= 1 && c1 <= 95 && ld > c1, "heads_loss: c1 must be in [1,95] and ld > c1 (three columns per lane)");
   ICSG_REQUIRE(!dlogits || (species && ldd > c1 && ldd <= 96), "heads_loss: gradient needs labels and c1 < ldd <= 96");
   ICSG_REQUIRE(nparts == icsg3d_heads_loss_nparts(M), "heads_loss: nparts mismatch");
-  heads_loss_kernel<<<nparts, kHeadsThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(heads_loss_kernel, nparts, kHeadsThreads, 0, static_cast<cudaStream_t>(stream), 
       logits, ld, c1, species, class_w, M, inv_count, argmax_out, sig_prob, probs, static_cast<__nv_bfloat16*>(dlogits), ldd,
       partials, dl_f32);
   ICSG_CHECK_LAUNCH();
@@ -238,7 +242,7 @@ extern "C" int icsg3d_heads_loss_f32grad(const float* logits, int ld, int c1, co
 extern "C" int icsg3d_heads_loss_finalize(const double* partials, int nparts, double count, float* out, double* raw,
                                           void* stream) {
   ICSG_REQUIRE(partials && out && count > 0, "heads_loss_finalize: bad arguments");
-  heads_loss_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials, nparts, count, out, raw);
+  launch_k(heads_loss_finalize_kernel, 1, 32, 0, static_cast<cudaStream_t>(stream), partials, nparts, count, out, raw);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

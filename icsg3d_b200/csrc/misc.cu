@@ -23,6 +23,7 @@ static int grid1d(long long n, int threads = 256, int cap_mult = 8) {
 __global__ void pack_vae_input_kernel(const float* __restrict__ m, const float* __restrict__ cond, int ncond,
                                       long long vox, long long total, __nv_bfloat16* __restrict__ xe,
                                       __nv_bfloat16* __restrict__ xp) {
+  pdl_prologue();
   for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < total;
        r += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = *reinterpret_cast<const float4*>(m + r * 4);
@@ -55,6 +56,7 @@ __global__ void pack_vae_input_kernel(const float* __restrict__ m, const float* 
 // fp32 rows of `c` values -> first c channels of bf16 rows with stride ld (rest untouched), and back.
 __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ src, int c, long long rows,
                                         __nv_bfloat16* __restrict__ dst, int ld) {
+  pdl_prologue();
   const long long total = rows * c;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -62,6 +64,7 @@ __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ src, int c, lo
 }
 __global__ void bf16_rows_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int ld, int c, long long rows,
                                         float* __restrict__ dst) {
+  pdl_prologue();
   const long long total = rows * c;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -74,6 +77,7 @@ __global__ void bf16_rows_to_f32_kernel(const __nv_bfloat16* __restrict__ src, i
 __global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict__ x1, int k1, const float* __restrict__ x2,
                                                         int k2, const float* __restrict__ w, const float* __restrict__ bias,
                                                         int act, int B, int N, float* __restrict__ y) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx, b = blockIdx.y;
@@ -95,12 +99,14 @@ __global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict_
 // dy <- dy * relu'(y) in place when act == RELU (y = saved forward output); then
 // dx[b,k] = sum_n dy[b,n] W[k,n] for k < kx (the first kx rows of W), dW[k,n] = sum_b x[b,k] dy[b,n], db[n] = sum_b dy[b,n]
 __global__ void dense_bwd_mask_kernel(float* __restrict__ dy, const float* __restrict__ y, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && !(y[i] > 0.f)) dy[i] = 0.f;
 }
 // one warp per (b,k): lanes stride over n (coalesced W row), fixed-order shuffle tree
 __global__ void __launch_bounds__(256) dense_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B,
                                                               int N, int kx, float* __restrict__ dx, int accumulate) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (idx >= B * kx) return;
@@ -113,6 +119,7 @@ __global__ void __launch_bounds__(256) dense_bwd_input_kernel(const float* __res
 __global__ void dense_bwd_weight_kernel(const float* __restrict__ x1, int k1, const float* __restrict__ x2, int k2,
                                         const float* __restrict__ dy, int B, int N, float* __restrict__ dw,
                                         float* __restrict__ db) {
+  pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int K = k1 + k2;
   if (idx >= (K + 1) * N) return;
@@ -134,6 +141,7 @@ __global__ void dense_bwd_weight_kernel(const float* __restrict__ x1, int k1, co
 // z = mu + exp(0.5*lv)*eps ; kl[b] = -0.5 * sum_j (1 + lv - mu^2 - exp(lv))   (lattice_vae.py:53-66, 235-239)
 __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
                                    const float* __restrict__ eps, int L, float* __restrict__ z, float* __restrict__ kl) {
+  pdl_prologue();
   const int b = blockIdx.x;
   float acc = 0.f;
   for (int j = threadIdx.x; j < L; j += blockDim.x) {
@@ -155,6 +163,7 @@ __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __
 __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu,
                                    const float* __restrict__ lv, const float* __restrict__ eps, float kl_coef, int n,
                                    float* __restrict__ dmu, float* __restrict__ dlv) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = lv[i];
@@ -165,6 +174,7 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
 // d(pre-activation) of a LeakyReLU output y given d(y), written as bf16 rows (stride ld, first c channels).
 __global__ void leaky_bwd_rows_kernel(const float* __restrict__ dyv, const float* __restrict__ y, float alpha, int c,
                                       long long rows, __nv_bfloat16* __restrict__ dst, int ld) {
+  pdl_prologue();
   const long long total = rows * c;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -176,6 +186,7 @@ __global__ void leaky_bwd_rows_kernel(const float* __restrict__ dyv, const float
 template <typename T>
 __global__ void __launch_bounds__(256) sqdiff_partials_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                                               long long n, double* __restrict__ partials) {
+  pdl_prologue();
   constexpr int V = sizeof(T) == 2 ? 8 : 4;
   const long long nv = n / V;
   double dacc = 0.0;
@@ -226,6 +237,7 @@ __global__ void vae_loss_assemble_kernel(const double* __restrict__ partials, co
                                          int nterms, const double* __restrict__ scales, const float* __restrict__ kl,
                                          int B, double kl_scale, float alpha, float beta, float* __restrict__ out,
                                          double* __restrict__ raw) {
+  pdl_prologue();
   __shared__ double term[8];
   __shared__ double klsum;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,6 +275,7 @@ __global__ void vae_loss_assemble_kernel(const double* __restrict__ partials, co
 // d(loss)/d(x_hat) = mse_coef * (x_hat - x) + dgrad_c1[:, :4]      (fp32 [rows][4]; dgrad bf16 [rows][ld])
 __global__ void xhat_grad_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float mse_coef,
                                  const __nv_bfloat16* __restrict__ dpm, int ld, long long rows, float* __restrict__ dy) {
+  pdl_prologue();
   for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
        r += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(x)[r];
@@ -279,6 +292,7 @@ __global__ void xhat_grad_kernel(const float* __restrict__ x, const float* __res
 // DFC tap without a BatchNorm behind it (c10): dc = coef * (a - a_other) * (a > 0)      bf16, n % 8 == 0
 __global__ void tap_grad_relu_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ other,
                                      float coef, long long n, __nv_bfloat16* __restrict__ dc) {
+  pdl_prologue();
   const long long nv = n / 8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -299,6 +313,7 @@ __global__ void tap_grad_relu_kernel(const __nv_bfloat16* __restrict__ a, const 
 // ---- bias gradient: db[c] = sum_rows dy[r][c]  (bf16 rows; one block per 8-channel group; deterministic) ----
 __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int ld, long long rows,
                                                         int C, float* __restrict__ db) {
+  pdl_prologue();
   const int c = blockIdx.x;
   if (c >= C) return;
   double acc = 0.0;
@@ -328,6 +343,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __r
 // state[0] = t (as double), state[1] = lr_t.  adam_tick advances t and recomputes lr_t on the device so the
 // whole train step (incl. the optimiser) can be replayed from a CUDA graph.
 __global__ void adam_tick_kernel(double* __restrict__ state, double lr, double b1, double b2) {
+  pdl_prologue();
   const double t = state[0] + 1.0;
   state[0] = t;
   state[1] = lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t));
@@ -335,6 +351,7 @@ __global__ void adam_tick_kernel(double* __restrict__ state, double lr, double b
 __global__ void adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                    float* __restrict__ v, const double* __restrict__ state, float b1, float b2, float eps,
                                    float grad_scale, long long n) {
+  pdl_prologue();
   const float lr_t = static_cast<float>(state[1]);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -363,6 +380,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(float* __restrict__
                                                              const unsigned long long* __restrict__ peers, int world, int rank,
                                                              int nchunks, size_t data_off, const long long* __restrict__ epoch_p,
                                                              long long timeout) {
+  pdl_prologue();
   const unsigned long long epoch = static_cast<unsigned long long>(*epoch_p);
   const int par = static_cast<int>(epoch & 1ull);
   const long long i0 = static_cast<long long>(blockIdx.x) * kAdamChunk;
@@ -429,7 +447,7 @@ extern "C" int icsg3d_pack_vae_input(const float* m, const float* cond, int ncon
   ICSG_REQUIRE(m && (xe || xp), "pack_vae_input: null pointer");
   ICSG_REQUIRE(!xe || (cond && ncond >= 0 && ncond <= 12), "pack_vae_input: ncond must be <= 12");
   const long long total = static_cast<long long>(B) * vox;
-  pack_vae_input_kernel<<<grid1d(total), 256, 0, ST>>>(m, cond, ncond, vox, total, static_cast<__nv_bfloat16*>(xe),
+  launch_k(pack_vae_input_kernel, grid1d(total), 256, 0, ST, m, cond, ncond, vox, total, static_cast<__nv_bfloat16*>(xe),
                                                       static_cast<__nv_bfloat16*>(xp));
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -437,14 +455,14 @@ extern "C" int icsg3d_pack_vae_input(const float* m, const float* cond, int ncon
 
 extern "C" int icsg3d_f32_to_bf16_rows(const float* src, int c, int64_t rows, void* dst, int ld, void* stream) {
   ICSG_REQUIRE(src && dst && c <= ld, "f32_to_bf16_rows: bad arguments");
-  f32_to_bf16_rows_kernel<<<grid1d(rows * c), 256, 0, ST>>>(src, c, rows, static_cast<__nv_bfloat16*>(dst), ld);
+  launch_k(f32_to_bf16_rows_kernel, grid1d(rows * c), 256, 0, ST, src, c, rows, static_cast<__nv_bfloat16*>(dst), ld);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
 
 extern "C" int icsg3d_bf16_rows_to_f32(const void* src, int ld, int c, int64_t rows, float* dst, void* stream) {
   ICSG_REQUIRE(src && dst && c <= ld, "bf16_rows_to_f32: bad arguments");
-  bf16_rows_to_f32_kernel<<<grid1d(rows * c), 256, 0, ST>>>(static_cast<const __nv_bfloat16*>(src), ld, c, rows, dst);
+  launch_k(bf16_rows_to_f32_kernel, grid1d(rows * c), 256, 0, ST, static_cast<const __nv_bfloat16*>(src), ld, c, rows, dst);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -452,7 +470,7 @@ extern "C" int icsg3d_bf16_rows_to_f32(const void* src, int ld, int c, int64_t r
 extern "C" int icsg3d_dense_fwd(const float* x1, int k1, const float* x2, int k2, const float* w, const float* bias,
                                 int act, int B, int N, float* y, void* stream) {
   ICSG_REQUIRE(x1 && w && y && (k2 == 0 || x2), "dense_fwd: null pointer");
-  dense_fwd_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, ST>>>(x1, k1, x2, k2, w, bias, act, B, N, y);
+  launch_k(dense_fwd_kernel, dim3(ceil_div(N, 32), B), 256, 0, ST, x1, k1, x2, k2, w, bias, act, B, N, y);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -463,14 +481,14 @@ extern "C" int icsg3d_dense_bwd(const float* x1, int k1, const float* x2, int k2
   ICSG_REQUIRE(x1 && w && dy && dw && db, "dense_bwd: null pointer");
   if (act == ICSG3D_ACT_RELU) {
     ICSG_REQUIRE(y, "dense_bwd: relu needs the forward output");
-    dense_bwd_mask_kernel<<<ceil_div(B * N, 128), 128, 0, ST>>>(dy, y, B * N);
+    launch_k(dense_bwd_mask_kernel, ceil_div(B * N, 128), 128, 0, ST, dy, y, B * N);
     ICSG_CHECK_LAUNCH();
   }
   if (dx1) {
-    dense_bwd_input_kernel<<<ceil_div(B * k1, 8), 256, 0, ST>>>(dy, w, B, N, k1, dx1, accumulate_dx);
+    launch_k(dense_bwd_input_kernel, ceil_div(B * k1, 8), 256, 0, ST, dy, w, B, N, k1, dx1, accumulate_dx);
     ICSG_CHECK_LAUNCH();
   }
-  dense_bwd_weight_kernel<<<ceil_div((k1 + k2 + 1) * N, 128), 128, 0, ST>>>(x1, k1, x2, k2, dy, B, N, dw, db);
+  launch_k(dense_bwd_weight_kernel, ceil_div((k1 + k2 + 1) * N, 128), 128, 0, ST, x1, k1, x2, k2, dy, B, N, dw, db);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -478,7 +496,7 @@ extern "C" int icsg3d_dense_bwd(const float* x1, int k1, const float* x2, int k2
 extern "C" int icsg3d_reparam_fwd(const float* mu, const float* lv, const float* eps, int B, int L, float* z, float* kl,
                                   void* stream) {
   ICSG_REQUIRE(mu && lv && eps && z && kl, "reparam_fwd: null pointer");
-  reparam_fwd_kernel<<<B, 128, 0, ST>>>(mu, lv, eps, L, z, kl);
+  launch_k(reparam_fwd_kernel, B, 128, 0, ST, mu, lv, eps, L, z, kl);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -486,7 +504,7 @@ extern "C" int icsg3d_reparam_fwd(const float* mu, const float* lv, const float*
 extern "C" int icsg3d_reparam_bwd(const float* dz, const float* mu, const float* lv, const float* eps, float kl_coef,
                                   int B, int L, float* dmu, float* dlv, void* stream) {
   ICSG_REQUIRE(dz && mu && lv && eps && dmu && dlv, "reparam_bwd: null pointer");
-  reparam_bwd_kernel<<<ceil_div(B * L, 128), 128, 0, ST>>>(dz, mu, lv, eps, kl_coef, B * L, dmu, dlv);
+  launch_k(reparam_bwd_kernel, ceil_div(B * L, 128), 128, 0, ST, dz, mu, lv, eps, kl_coef, B * L, dmu, dlv);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -494,7 +512,7 @@ extern "C" int icsg3d_reparam_bwd(const float* dz, const float* mu, const float*
 extern "C" int icsg3d_leaky_bwd_rows(const float* dy, const float* y, float alpha, int c, int64_t rows, void* dst, int ld,
                                      void* stream) {
   ICSG_REQUIRE(dy && y && dst && c <= ld, "leaky_bwd_rows: bad arguments");
-  leaky_bwd_rows_kernel<<<grid1d(rows * c), 256, 0, ST>>>(dy, y, alpha, c, rows, static_cast<__nv_bfloat16*>(dst), ld);
+  launch_k(leaky_bwd_rows_kernel, grid1d(rows * c), 256, 0, ST, dy, y, alpha, c, rows, static_cast<__nv_bfloat16*>(dst), ld);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -507,11 +525,11 @@ extern "C" int icsg3d_sqdiff_partials(const void* a, const void* b, int dtype, i
   ICSG_REQUIRE(nparts == icsg3d_sqdiff_nparts(n), "sqdiff_partials: nparts mismatch");
   if (dtype == ICSG3D_DT_BF16) {
     ICSG_REQUIRE(n % 8 == 0, "sqdiff_partials: n must be a multiple of 8 for bf16");
-    sqdiff_partials_kernel<__nv_bfloat16><<<nparts, 256, 0, ST>>>(static_cast<const __nv_bfloat16*>(a),
+    launch_k(sqdiff_partials_kernel<__nv_bfloat16>, nparts, 256, 0, ST, static_cast<const __nv_bfloat16*>(a),
                                                                  static_cast<const __nv_bfloat16*>(b), n, partials);
   } else {
     ICSG_REQUIRE(n % 4 == 0, "sqdiff_partials: n must be a multiple of 4 for fp32");
-    sqdiff_partials_kernel<float><<<nparts, 256, 0, ST>>>(static_cast<const float*>(a), static_cast<const float*>(b), n, partials);
+    launch_k(sqdiff_partials_kernel<float>, nparts, 256, 0, ST, static_cast<const float*>(a), static_cast<const float*>(b), n, partials);
   }
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -522,7 +540,7 @@ extern "C" int icsg3d_vae_loss_assemble(const double* partials, const int* npart
                                         float beta, float* out, double* raw, void* stream) {
   ICSG_REQUIRE(partials && nparts && scales && kl && out, "vae_loss_assemble: null pointer");
   ICSG_REQUIRE(nterms >= 1 && nterms <= 7, "vae_loss_assemble: nterms must be in [1,7]");
-  vae_loss_assemble_kernel<<<1, 256, 0, ST>>>(partials, nparts, stride, nterms, scales, kl, B, kl_scale, alpha, beta, out, raw);
+  launch_k(vae_loss_assemble_kernel, 1, 256, 0, ST, partials, nparts, stride, nterms, scales, kl, B, kl_scale, alpha, beta, out, raw);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -530,14 +548,14 @@ extern "C" int icsg3d_vae_loss_assemble(const double* partials, const int* npart
 extern "C" int icsg3d_xhat_grad(const float* x, const float* xhat, float mse_coef, const void* dpm, int ld, int64_t rows,
                                 float* dy, void* stream) {
   ICSG_REQUIRE(x && xhat && dy, "xhat_grad: null pointer");
-  xhat_grad_kernel<<<grid1d(rows), 256, 0, ST>>>(x, xhat, mse_coef, static_cast<const __nv_bfloat16*>(dpm), ld, rows, dy);
+  launch_k(xhat_grad_kernel, grid1d(rows), 256, 0, ST, x, xhat, mse_coef, static_cast<const __nv_bfloat16*>(dpm), ld, rows, dy);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
 
 extern "C" int icsg3d_tap_grad_relu(const void* a, const void* other, float coef, int64_t n, void* dc, void* stream) {
   ICSG_REQUIRE(a && other && dc && n % 8 == 0, "tap_grad_relu: bad arguments");
-  tap_grad_relu_kernel<<<grid1d(n / 8), 256, 0, ST>>>(static_cast<const __nv_bfloat16*>(a),
+  launch_k(tap_grad_relu_kernel, grid1d(n / 8), 256, 0, ST, static_cast<const __nv_bfloat16*>(a),
                                                      static_cast<const __nv_bfloat16*>(other), coef, n,
                                                      static_cast<__nv_bfloat16*>(dc));
   ICSG_CHECK_LAUNCH();
@@ -546,7 +564,7 @@ extern "C" int icsg3d_tap_grad_relu(const void* a, const void* other, float coef
 
 extern "C" int icsg3d_bias_grad(const void* dy, int ld, int64_t rows, int C, float* db, void* stream) {
   ICSG_REQUIRE(dy && db && C <= ld, "bias_grad: bad arguments");
-  bias_grad_kernel<<<C, 256, 0, ST>>>(static_cast<const __nv_bfloat16*>(dy), ld, rows, C, db);
+  launch_k(bias_grad_kernel, C, 256, 0, ST, static_cast<const __nv_bfloat16*>(dy), ld, rows, C, db);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -554,9 +572,9 @@ extern "C" int icsg3d_bias_grad(const void* dy, int ld, int64_t rows, int C, flo
 extern "C" int icsg3d_adam_keras_step(float* p, const float* g, float* m, float* v, double* state, double lr, double beta1,
                                       double beta2, double eps, float grad_scale, int64_t n, void* stream) {
   ICSG_REQUIRE(p && g && m && v && state, "adam_keras_step: null pointer");
-  adam_tick_kernel<<<1, 1, 0, ST>>>(state, lr, beta1, beta2);
+  launch_k(adam_tick_kernel, 1, 1, 0, ST, state, lr, beta1, beta2);
   ICSG_CHECK_LAUNCH();
-  adam_update_kernel<<<grid1d(n), 256, 0, ST>>>(p, g, m, v, state, static_cast<float>(beta1), static_cast<float>(beta2),
+  launch_k(adam_update_kernel, grid1d(n), 256, 0, ST, p, g, m, v, state, static_cast<float>(beta1), static_cast<float>(beta2),
                                                static_cast<float>(eps), grad_scale, n);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -578,9 +596,9 @@ extern "C" int icsg3d_adam_keras_allreduce_step(float* p, float* g, float* m, fl
   ICSG_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "adam_keras_allreduce_step: g must be 16-byte aligned");
   const int64_t nchunks = (n + kAdamChunk - 1) / kAdamChunk;
   const size_t data_off = static_cast<size_t>(((2 * world * nchunks * 8 + 255) / 256) * 256);
-  adam_tick_kernel<<<1, 1, 0, ST>>>(state, lr, beta1, beta2);
+  launch_k(adam_tick_kernel, 1, 1, 0, ST, state, lr, beta1, beta2);
   ICSG_CHECK_LAUNCH();
-  adam_allreduce_kernel<<<static_cast<int>(nchunks), 256, 0, ST>>>(
+  launch_k(adam_allreduce_kernel, static_cast<int>(nchunks), 256, 0, ST, 
       p, g, m, v, state, static_cast<float>(beta1), static_cast<float>(beta2), static_cast<float>(eps), grad_scale, n,
       reinterpret_cast<const unsigned long long*>(peers), world, rank, static_cast<int>(nchunks), data_off,
       reinterpret_cast<const long long*>(epoch), peer_timeout_cycles());

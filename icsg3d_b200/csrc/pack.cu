@@ -7,6 +7,7 @@ namespace icsg3d {
 
 __global__ void pack_w_fprop_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int cin, int cout,
                                     int cin_pad, int cout_pad, int cin_lead, int fold, int fold_c) {
+  pdl_prologue();
   const long long total = 27ll * cout_pad * cin_pad;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -30,6 +31,7 @@ __global__ void pack_w_fprop_kernel(const float* __restrict__ w, __nv_bfloat16* 
 
 __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int cin, int cout,
                                     int cin_pad, int cout_pad) {
+  pdl_prologue();
   const long long total = 27ll * cin_pad * cout_pad;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -44,6 +46,7 @@ __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* 
 
 __global__ void unpack_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int cin, int cout, int cin_pad,
                                  int cout_pad, int cin_lead, int fold, int fold_c) {
+  pdl_prologue();
   const long long total = 27ll * cin * cout;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -59,6 +62,7 @@ __global__ void unpack_dw_kernel(const float* __restrict__ dwp, float* __restric
 // All weight packs of a model in ONE launch: jobs[j] = {w, wp, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode}
 // (int64 each; mode 0 = fprop layout, 1 = dgrad layout, 2 / 3 = the same as bf16-pair split operands); blockIdx.y = job.
 __global__ void pack_w_batch_kernel(const long long* __restrict__ jobs) {
+  pdl_prologue();
   const long long* jb = jobs + static_cast<size_t>(blockIdx.y) * 10;
   const float* w = reinterpret_cast<const float*>(jb[0]);
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(jb[1]);
@@ -127,7 +131,7 @@ extern "C" int icsg3d_pack_conv_w_fprop(const float* w, void* wpack, int cin, in
   } else {
     ICSG_REQUIRE(cin_pad >= cin, "pack_conv_w_fprop: cin_pad < cin");
   }
-  pack_w_fprop_kernel<<<grid_for(27ll * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pack_w_fprop_kernel, grid_for(27ll * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream), 
       w, static_cast<__nv_bfloat16*>(wpack), cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -137,7 +141,7 @@ extern "C" int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, in
                                         void* stream) {
   ICSG_REQUIRE(w && wpack, "pack_conv_w_dgrad: null pointer");
   ICSG_REQUIRE(cin_pad >= cin && cout_pad >= cout, "pack_conv_w_dgrad: bad padding");
-  pack_w_dgrad_kernel<<<grid_for(27ll * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pack_w_dgrad_kernel, grid_for(27ll * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream), 
       w, static_cast<__nv_bfloat16*>(wpack), cin, cout, cin_pad, cout_pad);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -146,7 +150,7 @@ extern "C" int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, in
 extern "C" int icsg3d_unpack_conv_dw(const float* dw_pad, float* dw, int cin, int cout, int cin_pad, int cout_pad,
                                      int cin_lead, int fold, int fold_c, void* stream) {
   ICSG_REQUIRE(dw_pad && dw, "unpack_conv_dw: null pointer");
-  unpack_dw_kernel<<<grid_for(27ll * cin * cout), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(unpack_dw_kernel, grid_for(27ll * cin * cout), 256, 0, static_cast<cudaStream_t>(stream), 
       dw_pad, dw, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -155,7 +159,7 @@ extern "C" int icsg3d_unpack_conv_dw(const float* dw_pad, float* dw, int cin, in
 
 extern "C" int icsg3d_pack_conv_w_batch(const int64_t* jobs, int njobs, int max_blocks, void* stream) {
   ICSG_REQUIRE(jobs && njobs > 0 && njobs <= 65535 && max_blocks > 0, "pack_conv_w_batch: bad arguments");
-  pack_w_batch_kernel<<<dim3(max_blocks, njobs), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pack_w_batch_kernel, dim3(max_blocks, njobs), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(jobs));
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;

@@ -26,6 +26,7 @@ template <typename T>
 __global__ void __launch_bounds__(kMmThreads) coord_minmax_kernel(const T* __restrict__ p, int ld, int c0, long long vox,
                                                                   int nsplit, T* __restrict__ partials,
                                                                   __nv_bfloat16* __restrict__ x16) {
+  pdl_prologue();
   const int b = blockIdx.y, s = blockIdx.x;
   const long long per = (vox + nsplit - 1) / nsplit;
   const long long v0 = s * per, v1 = (v0 + per < vox) ? v0 + per : vox;
@@ -102,6 +103,7 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 template <typename T>
 __global__ void lattice_finalize_kernel(const T* __restrict__ partials, int B, int nsplit, double eps_frac, int d,
                                         T* __restrict__ lp, T* __restrict__ dv) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 3) return;
   const int b = i / 3, k = i % 3;
@@ -126,6 +128,7 @@ __global__ void lattice_finalize_kernel(const T* __restrict__ partials, int B, i
 __global__ void __launch_bounds__(256) heads_predict_kernel(const float* __restrict__ logits, int ld, int c1, long long M,
                                                             float threshold, uint8_t* __restrict__ argmax_out,
                                                             uint8_t* __restrict__ mask_out, float* __restrict__ sig_prob) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(256) heads_predict_kernel(const float* __restr
 template <typename W>
 __global__ void __launch_bounds__(256) rotate90_kernel(const W* __restrict__ in, W* __restrict__ out, int d, int wpv,
                                                        const int* __restrict__ xf, long long total) {
+  pdl_prologue();
   const long long d3 = static_cast<long long>(d) * d * d;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -203,6 +207,7 @@ __device__ __forceinline__ int rclip(float v) { return static_cast<int>(rintf(fm
 
 __global__ void __launch_bounds__(256) metric_counts_kernel(const float* __restrict__ yt, const float* __restrict__ yp,
                                                             long long n, int C, double* __restrict__ counts) {
+  pdl_prologue();
   long long acc[5] = {0, 0, 0, 0, 0};
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -262,10 +267,10 @@ extern "C" int icsg3d_coord_minmax(const void* p, int dtype, int ld, int c0, int
   ICSG_REQUIRE(!x16 || (dtype == ICSG3D_DT_F32 && ld == 4 && c0 == 1), "coord_minmax: the fused pack needs fp32 [.,4] input");
   dim3 grid(nsplit, B);
   if (dtype == ICSG3D_DT_F32)
-    coord_minmax_kernel<float><<<grid, kMmThreads, 0, ST>>>(static_cast<const float*>(p), ld, c0, vox, nsplit,
+    launch_k(coord_minmax_kernel<float>, grid, kMmThreads, 0, ST, static_cast<const float*>(p), ld, c0, vox, nsplit,
                                                             static_cast<float*>(partials), static_cast<__nv_bfloat16*>(x16));
   else
-    coord_minmax_kernel<double><<<grid, kMmThreads, 0, ST>>>(static_cast<const double*>(p), ld, c0, vox, nsplit,
+    launch_k(coord_minmax_kernel<double>, grid, kMmThreads, 0, ST, static_cast<const double*>(p), ld, c0, vox, nsplit,
                                                              static_cast<double*>(partials), nullptr);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -277,10 +282,10 @@ extern "C" int icsg3d_lattice_finalize(const void* partials, int dtype, int B, i
   ICSG_REQUIRE(dtype == ICSG3D_DT_F32 || dtype == ICSG3D_DT_F64, "lattice_finalize: dtype must be fp32 or fp64");
   const int n = B * 3;
   if (dtype == ICSG3D_DT_F32)
-    lattice_finalize_kernel<float><<<ceil_div(n, 128), 128, 0, ST>>>(static_cast<const float*>(partials), B, nsplit, eps_frac,
+    launch_k(lattice_finalize_kernel<float>, ceil_div(n, 128), 128, 0, ST, static_cast<const float*>(partials), B, nsplit, eps_frac,
                                                                      d, static_cast<float*>(lp), static_cast<float*>(dv));
   else
-    lattice_finalize_kernel<double><<<ceil_div(n, 128), 128, 0, ST>>>(static_cast<const double*>(partials), B, nsplit,
+    launch_k(lattice_finalize_kernel<double>, ceil_div(n, 128), 128, 0, ST, static_cast<const double*>(partials), B, nsplit,
                                                                       eps_frac, d, static_cast<double*>(lp),
                                                                       static_cast<double*>(dv));
   ICSG_CHECK_LAUNCH();
@@ -291,7 +296,7 @@ extern "C" int icsg3d_heads_predict(const float* logits, int ld, int c1, int64_t
                                     uint8_t* mask_out, float* sig_prob, void* stream) {
   ICSG_REQUIRE(logits && M > 0 && (argmax_out || mask_out || sig_prob), "heads_predict: bad arguments");
   ICSG_REQUIRE(c1 >= 1 && c1 <= 95 && ld > c1, "heads_predict: c1 must be in [1,95] and ld > c1");
-  heads_predict_kernel<<<grid_for(M * 32, 256, 16), 256, 0, ST>>>(logits, ld, c1, M, threshold, argmax_out, mask_out, sig_prob);
+  launch_k(heads_predict_kernel, grid_for(M * 32, 256, 16), 256, 0, ST, logits, ld, c1, M, threshold, argmax_out, mask_out, sig_prob);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
@@ -303,18 +308,18 @@ extern "C" int icsg3d_rotate90_batch(const void* in, void* out, int B, int d, in
   const uintptr_t al = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out);
   if (voxel_bytes % 16 == 0 && al % 16 == 0) {
     const int wpv = voxel_bytes / 16;
-    rotate90_kernel<uint4><<<grid_for(vox * wpv, 256, 16), 256, 0, ST>>>(static_cast<const uint4*>(in),
+    launch_k(rotate90_kernel<uint4>, grid_for(vox * wpv, 256, 16), 256, 0, ST, static_cast<const uint4*>(in),
                                                                          static_cast<uint4*>(out), d, wpv, xforms, vox * wpv);
   } else if (voxel_bytes % 8 == 0 && al % 8 == 0) {
     const int wpv = voxel_bytes / 8;
-    rotate90_kernel<uint2><<<grid_for(vox * wpv, 256, 16), 256, 0, ST>>>(static_cast<const uint2*>(in),
+    launch_k(rotate90_kernel<uint2>, grid_for(vox * wpv, 256, 16), 256, 0, ST, static_cast<const uint2*>(in),
                                                                          static_cast<uint2*>(out), d, wpv, xforms, vox * wpv);
   } else if (voxel_bytes % 4 == 0 && al % 4 == 0) {
     const int wpv = voxel_bytes / 4;
-    rotate90_kernel<uint32_t><<<grid_for(vox * wpv, 256, 16), 256, 0, ST>>>(
+    launch_k(rotate90_kernel<uint32_t>, grid_for(vox * wpv, 256, 16), 256, 0, ST, 
         static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), d, wpv, xforms, vox * wpv);
   } else {
-    rotate90_kernel<uint8_t><<<grid_for(vox * voxel_bytes, 256, 16), 256, 0, ST>>>(
+    launch_k(rotate90_kernel<uint8_t>, grid_for(vox * voxel_bytes, 256, 16), 256, 0, ST, 
         static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), d, voxel_bytes, xforms, vox * voxel_bytes);
   }
   ICSG_CHECK_LAUNCH();
@@ -324,7 +329,7 @@ extern "C" int icsg3d_rotate90_batch(const void* in, void* out, int B, int d, in
 extern "C" int icsg3d_metric_counts(const float* y_true, const float* y_pred, int64_t n, int C, double* counts, void* stream) {
   ICSG_REQUIRE(y_true && y_pred && counts && n > 0 && C > 0, "metric_counts: bad arguments");
   ICSG_CUDA(cudaMemsetAsync(counts, 0, 5 * sizeof(double), ST));
-  metric_counts_kernel<<<grid_for(n, 256, 8), 256, 0, ST>>>(y_true, y_pred, n, C, counts);
+  launch_k(metric_counts_kernel, grid_for(n, 256, 8), 256, 0, ST, y_true, y_pred, n, C, counts);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

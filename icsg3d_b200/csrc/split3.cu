@@ -27,6 +27,7 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 // src fp32 [rows][ld_src] (first c channels used) -> dst bf16 [rows][3*ctot]: part*ctot + coff + i  (part = hi, lo, hi)
 __global__ void f32_to_split3_kernel(const float* __restrict__ src, int ld_src, int c, long long rows,
                                      __nv_bfloat16* __restrict__ dst, int ctot, int coff, int fmt) {
+  pdl_prologue();
   const long long total = rows * c;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -68,6 +69,7 @@ __device__ __forceinline__ void store_split_row(__nv_bfloat16* dst, const float 
 __global__ void pack_vae_input_split3_kernel(const float* __restrict__ m, const float* __restrict__ cond, int ncond,
                                              long long vox, long long total, __nv_bfloat16* __restrict__ xe,
                                              __nv_bfloat16* __restrict__ xp, __nv_bfloat16* __restrict__ xp16, int fmt) {
+  pdl_prologue();
   for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < total;
        r += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v[16];
@@ -95,6 +97,7 @@ __global__ void pack_vae_input_split3_kernel(const float* __restrict__ m, const 
 // same channel padding / condition fold as pack_w_fprop_kernel.
 __global__ void pack_w_fprop_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int ntaps, int cin, int cout,
                                        int cin_pad, int cout_pad, int cin_lead, int fold, int fold_c, int fmt, float wscale) {
+  pdl_prologue();
   const long long total = static_cast<long long>(ntaps) * cout_pad * cin_pad;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -125,6 +128,7 @@ __global__ void pack_w_fprop_x3_kernel(const float* __restrict__ w, __nv_bfloat1
 // Cout (the K dimension of the input-gradient GEMM), taps mirrored like pack_w_dgrad_kernel.
 __global__ void pack_w_dgrad_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int ntaps, int cin, int cout,
                                        int cin_pad, int cout_pad, int fmt, float wscale) {
+  pdl_prologue();
   const long long total = static_cast<long long>(ntaps) * cin_pad * cout_pad;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -146,6 +150,7 @@ __global__ void pack_w_dgrad_x3_kernel(const float* __restrict__ w, __nv_bfloat1
 // dy = [dy_hi | dy_lo] (2*cout_pad) yields P [ntaps][2 cin_pad][2 cout_pad]; dW = hi*hi + lo*hi + hi*lo (lo*lo dropped).
 __global__ void wgrad_combine_x3_kernel(const float* __restrict__ P, float* __restrict__ dw, int ntaps, int cin_pad,
                                         int cout_pad) {
+  pdl_prologue();
   const long long total = static_cast<long long>(ntaps) * cin_pad * cout_pad;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -162,6 +167,7 @@ __global__ void wgrad_combine_x3_kernel(const float* __restrict__ P, float* __re
 // dy = mse_coef*(xhat - x) + dpm   (rows of 4 channels; dpm fp32 with row stride ld, optional)
 __global__ void xhat_grad_f32_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float mse_coef,
                                      const float* __restrict__ dpm, int ld, long long rows, float* __restrict__ dy) {
+  pdl_prologue();
   for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
        r += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(x)[r];
@@ -177,6 +183,7 @@ __global__ void xhat_grad_f32_kernel(const float* __restrict__ x, const float* _
 // dc = coef * (a - other) * (a > 0)   (DFC tap without a BatchNorm behind it: c10)
 __global__ void tap_grad_relu_f32_kernel(const float* __restrict__ a, const float* __restrict__ other, float coef, long long n,
                                          float* __restrict__ dc) {
+  pdl_prologue();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float v = a[i];
@@ -186,6 +193,7 @@ __global__ void tap_grad_relu_f32_kernel(const float* __restrict__ a, const floa
 // dx = dy * act'(y) given the activation OUTPUT y (LeakyReLU: y > 0 ? 1 : alpha; ReLU: y > 0 ? 1 : 0)
 __global__ void act_bwd_f32_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act, float alpha, long long n,
                                    float* __restrict__ dx) {
+  pdl_prologue();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float g = act == ICSG3D_ACT_NONE ? 1.f : (y[i] > 0.f ? 1.f : (act == ICSG3D_ACT_LEAKY ? alpha : 0.f));
@@ -207,7 +215,7 @@ using namespace icsg3d;
 extern "C" int icsg3d_f32_to_split3(const float* src, int ld_src, int c, int64_t rows, void* dst, int ctot, int coff,
                                     int fmt, void* stream) {
   ICSG_REQUIRE(src && dst && c > 0 && c <= ld_src && coff >= 0 && coff + c <= ctot, "f32_to_split3: bad arguments");
-  f32_to_split3_kernel<<<grid1(rows * c), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld_src, c, rows,
+  launch_k(f32_to_split3_kernel, grid1(rows * c), 256, 0, static_cast<cudaStream_t>(stream), src, ld_src, c, rows,
                                                                                        static_cast<__nv_bfloat16*>(dst), ctot, coff, fmt);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -218,7 +226,7 @@ static int pack_vae_input_split3_impl(const float* m, const float* cond, int nco
   ICSG_REQUIRE(m && (xe || xp || xp16), "pack_vae_input_split3: null pointer");
   ICSG_REQUIRE(!xe || (cond && ncond >= 0 && ncond <= 12), "pack_vae_input_split3: ncond must be <= 12");
   const long long total = static_cast<long long>(B) * vox;
-  pack_vae_input_split3_kernel<<<grid1(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pack_vae_input_split3_kernel, grid1(total), 256, 0, static_cast<cudaStream_t>(stream), 
       m, cond, ncond, vox, total, static_cast<__nv_bfloat16*>(xe), static_cast<__nv_bfloat16*>(xp),
       static_cast<__nv_bfloat16*>(xp16), fmt);
   ICSG_CHECK_LAUNCH();
@@ -244,7 +252,7 @@ extern "C" int icsg3d_pack_conv_w_fprop_x3(const float* w, void* wpack, int ntap
   } else {
     ICSG_REQUIRE(cin_pad >= cin, "pack_conv_w_fprop_x3: cin_pad < cin");
   }
-  pack_w_fprop_x3_kernel<<<grid1(static_cast<long long>(ntaps) * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pack_w_fprop_x3_kernel, grid1(static_cast<long long>(ntaps) * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream), 
       w, static_cast<__nv_bfloat16*>(wpack), ntaps, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, fmt, wscale);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -254,7 +262,7 @@ extern "C" int icsg3d_pack_conv_w_dgrad_x3(const float* w, void* wpack, int ntap
                                            int fmt, float wscale, void* stream) {
   ICSG_REQUIRE(w && wpack && (ntaps == 27 || ntaps == 1) && (fmt == 0 || fmt == 1), "pack_conv_w_dgrad_x3: bad arguments");
   ICSG_REQUIRE(cin_pad >= cin && cout_pad >= cout, "pack_conv_w_dgrad_x3: bad padding");
-  pack_w_dgrad_x3_kernel<<<grid1(static_cast<long long>(ntaps) * cin_pad * cout_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pack_w_dgrad_x3_kernel, grid1(static_cast<long long>(ntaps) * cin_pad * cout_pad), 256, 0, static_cast<cudaStream_t>(stream), 
       w, static_cast<__nv_bfloat16*>(wpack), ntaps, cin, cout, cin_pad, cout_pad, fmt, wscale);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -262,7 +270,7 @@ extern "C" int icsg3d_pack_conv_w_dgrad_x3(const float* w, void* wpack, int ntap
 
 extern "C" int icsg3d_wgrad_combine_x3(const float* P, float* dw, int ntaps, int cin_pad, int cout_pad, void* stream) {
   ICSG_REQUIRE(P && dw && ntaps > 0 && cin_pad > 0 && cout_pad > 0, "wgrad_combine_x3: bad arguments");
-  wgrad_combine_x3_kernel<<<grid1(static_cast<long long>(ntaps) * cin_pad * cout_pad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(wgrad_combine_x3_kernel, grid1(static_cast<long long>(ntaps) * cin_pad * cout_pad), 256, 0, static_cast<cudaStream_t>(stream), 
       P, dw, ntaps, cin_pad, cout_pad);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -271,21 +279,21 @@ extern "C" int icsg3d_wgrad_combine_x3(const float* P, float* dw, int ntaps, int
 extern "C" int icsg3d_xhat_grad_f32(const float* x, const float* xhat, float mse_coef, const float* dpm, int ld, int64_t rows,
                                     float* dy, void* stream) {
   ICSG_REQUIRE(x && xhat && dy && (!dpm || ld % 4 == 0), "xhat_grad_f32: bad arguments");
-  xhat_grad_f32_kernel<<<grid1(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, xhat, mse_coef, dpm, ld, rows, dy);
+  launch_k(xhat_grad_f32_kernel, grid1(rows), 256, 0, static_cast<cudaStream_t>(stream), x, xhat, mse_coef, dpm, ld, rows, dy);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
 
 extern "C" int icsg3d_tap_grad_relu_f32(const float* a, const float* other, float coef, int64_t n, float* dc, void* stream) {
   ICSG_REQUIRE(a && other && dc, "tap_grad_relu_f32: null pointer");
-  tap_grad_relu_f32_kernel<<<grid1(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, other, coef, n, dc);
+  launch_k(tap_grad_relu_f32_kernel, grid1(n), 256, 0, static_cast<cudaStream_t>(stream), a, other, coef, n, dc);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
 
 extern "C" int icsg3d_act_bwd_f32(const float* dy, const float* y, int act, float alpha, int64_t n, float* dx, void* stream) {
   ICSG_REQUIRE(dy && y && dx, "act_bwd_f32: null pointer");
-  act_bwd_f32_kernel<<<grid1(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, act, alpha, n, dx);
+  launch_k(act_bwd_f32_kernel, grid1(n), 256, 0, static_cast<cudaStream_t>(stream), dy, y, act, alpha, n, dx);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const double* __restrict_
                                                        double eps_frac, float* __restrict__ m32,
                                                        double* __restrict__ m64, uint8_t* __restrict__ species,
                                                        double* __restrict__ species64) {
+  pdl_prologue();
   __shared__ double s_site[kMaxSites * kSiteRec];
   const int cell = blockIdx.y;
   const int n = nsites[cell];
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(256) voxelize_fast_kernel(const double* __rest
                                                             const double* __restrict__ lattice, int max_sites, int d,
                                                             double eps_frac, float* __restrict__ m32,
                                                             uint8_t* __restrict__ species) {
+  pdl_prologue();
   __shared__ double s_pos[kMaxSites][3];
   __shared__ double s_thr[kMaxSites], s_thr2lo[kMaxSites], s_thr2hi[kMaxSites], s_c[kMaxSites];
   __shared__ float s_zs[kMaxSites];
@@ -219,6 +221,7 @@ __device__ __forceinline__ double u01(uint64_t& s) { return static_cast<double>(
 // a,b,c ~ U(3.7,4.3) A; Z_A in {20,38,56,57,58,59,60}, Z_B in 22..30, Z_X in {8,9,17}; radii plausible.
 __global__ void synth_sites_kernel(uint64_t seed, int ncells, int max_sites, double label_frac, double* __restrict__ sites,
                                    int* __restrict__ nsites, double* __restrict__ lattice) {
+  pdl_prologue();
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ncells) return;
   uint64_t s = seed * 0xD1342543DE82EF95ull + static_cast<uint64_t>(cell) * 0x2545F4914F6CDD1Dull + 1;
@@ -269,11 +272,11 @@ extern "C" int icsg3d_voxelize(const double* sites, const int* nsites, const dou
   if (!m64 && !species64 && !exact_only) {
     dim3 gridf(static_cast<unsigned>((vox + 256 * kVoxPerThread - 1) / (256 * kVoxPerThread)), ncells);
     const size_t smem = static_cast<size_t>(3 * d) * (sizeof(double) + sizeof(float));
-    voxelize_fast_kernel<<<gridf, 256, smem, static_cast<cudaStream_t>(stream)>>>(sites, nsites, lattice, max_sites, d,
+    launch_k(voxelize_fast_kernel, gridf, 256, smem, static_cast<cudaStream_t>(stream), sites, nsites, lattice, max_sites, d,
                                                                                  eps_frac, m32, species);
   }
   else
-    voxelize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(sites, nsites, lattice, max_sites, d, eps_frac, m32,
+    launch_k(voxelize_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), sites, nsites, lattice, max_sites, d, eps_frac, m32,
                                                                         m64, species, species64);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
@@ -282,7 +285,7 @@ extern "C" int icsg3d_voxelize(const double* sites, const int* nsites, const dou
 extern "C" int icsg3d_synth_perovskite_sites(uint64_t seed, int ncells, int max_sites, double label_frac, double* sites,
                                              int* nsites, double* lattice, void* stream) {
   ICSG_REQUIRE(sites && nsites && lattice && max_sites >= 5 && max_sites <= kMaxSites, "synth_perovskite_sites: bad arguments");
-  synth_sites_kernel<<<ceil_div(ncells, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(seed, ncells, max_sites, label_frac,
+  launch_k(synth_sites_kernel, ceil_div(ncells, 128), 128, 0, static_cast<cudaStream_t>(stream), seed, ncells, max_sites, label_frac,
                                                                                          sites, nsites, lattice);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;

@@ -55,6 +55,11 @@ int64_t icsg3d_launch_count(void);
  * writes, a lazy graph capture) does not kill training; launches captured into a CUDA graph keep the value they were
  * captured with. */
 int icsg3d_set_peer_timeout(double seconds);
+/* Programmatic dependent launch (every kernel waits on its predecessor with griddepcontrol.wait and is launched with the
+ * programmatic-stream-serialization attribute, so consecutive kernels of a stream overlap launch/prologue with the
+ * predecessor's tail).  Off by default (no measurable gain on the captured train step: 3.173 vs 3.179 ms); 1 (or
+ * ICSG3D_PDL=1) turns it on.  Captured graphs keep the mode they were captured with. */
+int icsg3d_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv3D 3x3x3, stride 1, "same" — Keras Conv3D(kernel_size=(3,3,3), padding="same")
