@@ -257,6 +257,8 @@ class VAEEngine:
         self.fuse_tap_loss = os.environ.get("ICSG3D_FUSE_TAP_LOSS", "1") != "0"
         self._defer_taps = False
         self.fuse_stats = True  # BatchNorm statistics from the conv epilogue where the streaming kernel serves the layer
+        self._exp_skip_wgrad = os.environ.get("ICSG3D_EXP_SKIP_WGRAD", "0") == "1"
+        self._exp_skip_pm0 = os.environ.get("ICSG3D_EXP_SKIP_PM0", "0") == "1"
 
     # ------------------------------------------------------------------------------------------
     # helpers
@@ -378,6 +380,8 @@ class VAEEngine:
     def _wgrad(self, x, dy, name, cin, cout, cin_pad, cout_pad, fold=None):
         """dW of conv `name` into the flat gradient buffer (Keras layout).  Off the critical path (only Adam needs it):
         launched on a side stream that forks here and joins before the optimiser step."""
+        if self._exp_skip_wgrad:  # TIMING EXPERIMENT ONLY (ICSG3D_EXP_SKIP_WGRAD=1): how much of the side-stream work is hidden
+            return
         if not self.overlap_wgrad:
             return self._wgrad_now(x, dy, name, cin, cout, cin_pad, cout_pad, fold)
         main = torch.cuda.current_stream()
@@ -671,7 +675,8 @@ class VAEEngine:
                 self._side = torch.cuda.Stream()
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                self.pm_forward(0, True, ctx=self.ctx2)
+                if not self._exp_skip_pm0:  # TIMING EXPERIMENT ONLY (ICSG3D_EXP_SKIP_PM0=1)
+                    self.pm_forward(0, True, ctx=self.ctx2)
             self.encode(True)
             self.decode(True)
             self.pm_forward(1, True)
