@@ -123,7 +123,7 @@ __global__ void lattice_finalize_kernel(const T* __restrict__ partials, int B, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// generate.py:221-225: species = argmax_c softmax (= argmax of the logits, first index on ties), mask = sigmoid >= thr
+// generate.py:221-225: species = argmax_c of the float32 softmax output (first index on ties), mask = sigmoid >= thr
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) heads_predict_kernel(const float* __restrict__ logits, int ld, int c1, long long M,
                                                             float threshold, uint8_t* __restrict__ argmax_out,
@@ -134,23 +134,43 @@ __global__ void __launch_bounds__(256) heads_predict_kernel(const float* __restr
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long v = warp; v < M; v += nwarps) {
     const float* row = logits + v * ld;
-    float mx = -INFINITY;
+    // The reference takes np.argmax over the float32 SOFTMAX OUTPUT (generate.py:221): two classes whose probabilities
+    // round to the same float tie and the first index wins.  Reproduce exactly that: the same p_j = exp(x_j - max) / sum
+    // that heads_loss_kernel returns as `probs`, then arg-max over p with the first-index rule.
+    float x[3], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int col = lane + 32 * j;
+      x[j] = col < c1 ? row[col] : -INFINITY;
+      mx = fmaxf(mx, x[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float e[3], se = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      e[j] = lane + 32 * j < c1 ? expf(x[j] - mx) : 0.f;
+      se += e[j];
+    }
+    se = warp_sum(se);
+    const float inv = 1.f / se;
+    float pmax = -1.f;
     int amax = 0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int col = lane + 32 * j;
-      const float x = col < c1 ? row[col] : -INFINITY;
-      if (x > mx) {
-        mx = x;
+      const float pj = col < c1 ? e[j] * inv : -1.f;
+      if (pj > pmax) {
+        pmax = pj;
         amax = col;
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const float om = __shfl_xor_sync(0xffffffffu, pmax, o);
       const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
-      if (om > mx || (om == mx && oa < amax)) {
-        mx = om;
+      if (om > pmax || (om == pmax && oa < amax)) {
+        pmax = om;
         amax = oa;
       }
     }

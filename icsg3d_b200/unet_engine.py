@@ -49,7 +49,15 @@ class UNetEngine:
         self.world = dist.world if dist else 1
         dev = self.dev
         self.pp = params or ParamStore(unet_specs(channels, classes), dev, with_grads=train, with_adam=train).init(seed)
-        self.ctx = _Ctx(dev)
+        # split-K scratch of the per-tap conv kernel (the 4^3 / 8^3 layers have too few output tiles to fill 148 SMs
+        # otherwise): largest request over every layer's fprop and dgrad operand shape
+        ws_need = 0
+        for spec in UNET_PLAN:
+            cin_eff = pad16(channels if spec["n"] == "c1" else spec["cin"])
+            D_ = d >> spec["lvl"]
+            ws_need = max(ws_need, ops.conv3d_k3_workspace_bytes(batch, D_, cin_eff, spec["cout"]),
+                          ops.conv3d_k3_workspace_bytes(batch, D_, spec["cout"], cin_eff))
+        self.ctx = _Ctx(dev, conv_ws_bytes=ws_need)
         self.train_enabled = train
         B = batch
         z = lambda *s, dt=BF16: torch.zeros(*s, dtype=dt, device=dev)
@@ -134,16 +142,17 @@ class UNetEngine:
             return self.cat[src[4:]]
         return self.L[src]["y"]
 
-    def _bn_fwd(self, L, training):
+    def _bn_fwd(self, L, training, part=None):
         p = self.pp.p
         n, C, st, x = L["n"], L["cout"], L["bn"], L["a"]
         g, b = p[f"bn_{n}/gamma"], p[f"bn_{n}/beta"]
         mm, mv = p[f"bn_{n}/moving_mean"], p[f"bn_{n}/moving_variance"]
         if training:
             rows = x.numel() // C
-            np_ = ops.bn_nparts(rows, C, x.dtype)
-            part = self.ctx.partials[: np_ * 2 * C].view(np_, 2, C)
-            ops.bn_stats(x, C, part)
+            if part is None:  # no fused statistics from the conv epilogue for this layer shape
+                np_ = ops.bn_nparts(rows, C, x.dtype)
+                part = self.ctx.partials[: np_ * 2 * C].view(np_, 2, C)
+                ops.bn_stats(x, C, part)
             if self.world > 1:
                 ops.bn_reduce_partials(part, st.sums)
                 self.dist.all_reduce_sum(st.sums)
@@ -171,9 +180,14 @@ class UNetEngine:
         else:
             ops.f32_to_bf16_rows(self.X, 1, self.x16)
         for L in self.L.values():
-            ops.conv3d_k3(self._input_of(L), L["wf"], p[L["n"] + "/bias"], out=L["a"], act=ACT_RELU,
-                          tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
-            self._bn_fwd(L, training)
+            xin, part = self._input_of(L), None
+            if training:  # BatchNorm statistics out of the conv epilogue where the serving kernel has them
+                nparts = ops.conv3d_k3_stats_parts(xin, L["wf"])
+                if nparts > 0:
+                    part = self.ctx.partials[: nparts * 2 * L["cout"]].view(nparts, 2, L["cout"])
+            ops.conv3d_k3(xin, L["wf"], p[L["n"] + "/bias"], out=L["a"], act=ACT_RELU, stats=part,
+                          ws=self.ctx.conv_ws, tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
+            self._bn_fwd(L, training, part=part)
         ops.conv3d_k3(self.L["c18"]["y"], self.h_wf, self.h_bias, out=self.logits, tag="unet.heads.fprop",
                       nominal=(128, self.classes + 1))
         if not losses:
@@ -251,7 +265,8 @@ class UNetEngine:
                                     nominal=(L["cin_real"], C), ws=self.wg_ws)
                 ops.unpack_conv_dw(scratch, L["cin_real"], C, out=gk)
             if nme != "c1":
-                ops.conv3d_k3(L["dc"], L["wd"], None, out=self._dst_of_input_grad(L), tag=f"unet.{nme}.dgrad")
+                ops.conv3d_k3(L["dc"], L["wd"], None, out=self._dst_of_input_grad(L), ws=self.ctx.conv_ws,
+                              tag=f"unet.{nme}.dgrad")
 
     def optimizer_step(self):
         if self.world > 1:
