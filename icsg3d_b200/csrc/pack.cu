@@ -70,10 +70,33 @@ __global__ void pack_w_batch_kernel(const long long* __restrict__ jobs) {
   const int cin_pad = static_cast<int>(jb[4]), cout_pad = static_cast<int>(jb[5]);
   const int cin_lead = static_cast<int>(jb[6]), fold = static_cast<int>(jb[7]), fold_c = static_cast<int>(jb[8]);
   const int mode = static_cast<int>(jb[9]);
-  const long long total = 27ll * cout_pad * cin_pad;
+  const long long total = 27ll * cout_pad * (mode == 4 ? 32 : cin_pad);
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v = 0.f;
+    if (mode == 4) {
+      // lean split pack of the encoder's first conv (split3.cu::store_lean_enc_row): [27][cout_pad][32]; cin = cin_lead +
+      // fold * fold_c real channels (4 + 4 x 10), K = [w_hi(M) | w_hi(cond) | w_hi(M 0:2)] [w_hi(M 2:4) | w_lo(M) | w_lo(cond)]
+      const int k = static_cast<int>(idx % 32);
+      const int co = static_cast<int>((idx / 32) % cout_pad);
+      const int tap = static_cast<int>(idx / (32ll * cout_pad));
+      int src = -1, want_lo = 0, folded = 0;  // src: M channel or folded cond index
+      if (k < 4) src = k;
+      else if (k < 14) { src = k - 4; folded = 1; }
+      else if (k < 16) src = k - 14;
+      else if (k < 18) src = k - 16 + 2;
+      else if (k < 22) { src = k - 18; want_lo = 1; }
+      else { src = k - 22; folded = 1; want_lo = 1; }
+      if (co < cout) {
+        const float* wt = w + static_cast<long long>(tap) * cin * cout;
+        if (!folded) v = wt[static_cast<long long>(src) * cout + co];
+        else if (src < fold_c)
+          for (int r = 0; r < fold; ++r) v += wt[static_cast<long long>(cin_lead + r * fold_c + src) * cout + co];
+      }
+      const __nv_bfloat16 hi = f2bf(v);
+      wp[idx] = want_lo ? f2bf(v - __bfloat162float(hi)) : hi;
+      continue;
+    }
     if (mode == 0 || mode == 2) {
       const int ci = static_cast<int>(idx % cin_pad);
       const int co = static_cast<int>((idx / cin_pad) % cout_pad);

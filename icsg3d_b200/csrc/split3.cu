@@ -66,9 +66,28 @@ __device__ __forceinline__ void store_split_row(__nv_bfloat16* dst, const float 
   d[4] = d[0];
   d[5] = d[1];
 }
+// Lean split layout of the ENCODER input (bf16 pairs, 32 channels instead of 48): the one-hot condition is exact in bf16
+// and needs no lo part, so  [M_hi(4) | cond(10) | M_lo(0:2)] [M_lo(2:4) | M_hi(4) | cond(10)]  against the weight pack
+// [w_hi(M) | w_hi(cond) | w_hi(M 0:2)] [w_hi(M 2:4) | w_lo(M) | w_lo(cond)] (pack.cu mode 4) gives the same three products.
+// The first 16 channels start with the plain bf16 operand (M_hi, cond): the bf16 filter gradient reads them in place.
+__device__ __forceinline__ void store_lean_enc_row(__nv_bfloat16* dst, const float4 q, const float* c, int ncond) {
+  const float mv[4] = {q.x, q.y, q.z, q.w};
+  __nv_bfloat16 hi[4], lo[4], cv[10];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_bf16(mv[i], hi[i], lo[i], 0);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) cv[i] = __float2bfloat16_rn(i < ncond ? c[i] : 0.f);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  d[0] = make_uint4(pack_raw2(hi[0], hi[1]), pack_raw2(hi[2], hi[3]), pack_raw2(cv[0], cv[1]), pack_raw2(cv[2], cv[3]));
+  d[1] = make_uint4(pack_raw2(cv[4], cv[5]), pack_raw2(cv[6], cv[7]), pack_raw2(cv[8], cv[9]), pack_raw2(lo[0], lo[1]));
+  d[2] = make_uint4(pack_raw2(lo[2], lo[3]), pack_raw2(hi[0], hi[1]), pack_raw2(hi[2], hi[3]), pack_raw2(cv[0], cv[1]));
+  d[3] = make_uint4(pack_raw2(cv[2], cv[3]), pack_raw2(cv[4], cv[5]), pack_raw2(cv[6], cv[7]), pack_raw2(cv[8], cv[9]));
+}
+
 __global__ void pack_vae_input_split3_kernel(const float* __restrict__ m, const float* __restrict__ cond, int ncond,
                                              long long vox, long long total, __nv_bfloat16* __restrict__ xe,
-                                             __nv_bfloat16* __restrict__ xp, __nv_bfloat16* __restrict__ xp16, int fmt) {
+                                             __nv_bfloat16* __restrict__ xp, __nv_bfloat16* __restrict__ xp16, int fmt,
+                                             int lean) {
   pdl_prologue();
   for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < total;
        r += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -85,10 +104,14 @@ __global__ void pack_vae_input_split3_kernel(const float* __restrict__ m, const 
     }
     if (xe) {
       const float* c = cond + (r / vox) * ncond;
+      if (lean) {
+        store_lean_enc_row(xe + r * 32, q, c, ncond);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 12; ++i)
-        if (i < ncond) v[4 + i] = c[i];
-      store_split_row(xe + r * 48, v, fmt);
+        for (int i = 0; i < 12; ++i)
+          if (i < ncond) v[4 + i] = c[i];
+        store_split_row(xe + r * 48, v, fmt);
+      }
     }
   }
 }
@@ -222,15 +245,21 @@ extern "C" int icsg3d_f32_to_split3(const float* src, int ld_src, int c, int64_t
 }
 
 static int pack_vae_input_split3_impl(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe, void* xp,
-                                      void* xp16, int fmt, void* stream) {
+                                      void* xp16, int fmt, void* stream, int lean = 0) {
+  ICSG_REQUIRE(!lean || (fmt == 0 && ncond <= 10), "pack_vae_input: the lean encoder layout needs bf16 pairs and ncond <= 10");
   ICSG_REQUIRE(m && (xe || xp || xp16), "pack_vae_input_split3: null pointer");
   ICSG_REQUIRE(!xe || (cond && ncond >= 0 && ncond <= 12), "pack_vae_input_split3: ncond must be <= 12");
   const long long total = static_cast<long long>(B) * vox;
   launch_k(pack_vae_input_split3_kernel, grid1(total), 256, 0, static_cast<cudaStream_t>(stream), 
       m, cond, ncond, vox, total, static_cast<__nv_bfloat16*>(xe), static_cast<__nv_bfloat16*>(xp),
-      static_cast<__nv_bfloat16*>(xp16), fmt);
+      static_cast<__nv_bfloat16*>(xp16), fmt, lean);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_pack_vae_input_lean(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe32,
+                                          void* xp16, void* stream) {
+  return pack_vae_input_split3_impl(m, cond, ncond, B, vox, xe32, nullptr, xp16, 0, stream, 1);
 }
 
 extern "C" int icsg3d_pack_vae_input_split3(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe,

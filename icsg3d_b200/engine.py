@@ -164,8 +164,11 @@ class VAEEngine:
         self.M = z(B, d, d, d, 4, dt=F32)
         self.cond = z(B, ncond, dt=F32)
         self.eps = z(B, latent, dt=F32)
-        self.xe3 = z(B, d, d, d, 16 * kx)     # [hi | lo | hi] when split; the bf16 operand itself otherwise
-        self.xe = self.xe3[..., :16]          # hi part = the bf16 input (filter gradient of enc_conv1)
+        # split encoder input: lean 32-channel layout (the one-hot condition needs no lo part; csrc/split3.cu), whose first
+        # 16 channels start with the plain bf16 operand (M_hi, cond) that the bf16 filter gradient of enc_conv1 reads in place
+        self.enc_lean = self.enc_x3 and ncond <= 10 and os.environ.get("ICSG3D_ENC_LEAN", "1") != "0"
+        self.xe3 = z(B, d, d, d, 32 if self.enc_lean else 16 * kx)
+        self.xe = self.xe3[..., :16]
         self.xp = z(B, d, d, d, 16)
 
         # ---- encoder ----
@@ -177,7 +180,7 @@ class VAEEngine:
             L = dict(name=f"enc_conv{i}", bn=f"enc_bn{i}", cin_pad=cin_pad, cout=f, D=D,
                      c=z(B, D, D, D, f, dt=cdt), y3=y3, y=y3[..., :f], idx=z(B, D // 2, D // 2, D // 2, f, dt=torch.uint8),
                      dc=z(B, D, D, D, f), dy=z(B, D // 2, D // 2, D // 2, f, dt=cdt), bns=_BN(f, dev),
-                     wf=z(27, f, cin_pad * kx), wd=z(27, cin_pad, f) if i > 1 else None)
+                     wf=z(27, f, 32 if (i == 1 and self.enc_lean) else cin_pad * kx), wd=z(27, cin_pad, f) if i > 1 else None)
             self.enc.append(L)
             cin_pad, D = f, D // 2
         self.e_s = D  # spatial edge at enc_conv5 (d/16)
@@ -273,6 +276,7 @@ class VAEEngine:
         for c in f:
             shapes.append((D, cin, c))
             shapes.append((D, 3 * cin, c))  # split-operand encoder forward (3x the K extent)
+            shapes.append((D, 2 * cin, c))  # lean split layout of the first layer
             cin, D = c, D // 2
         shapes.append((D, f[-1], 16))
         shapes.append((D, 3 * f[-1], 16))
@@ -419,7 +423,7 @@ class VAEEngine:
             fm = 2 if self.enc_x3 else 0  # pack mode of the encoder's fprop operands (2 = bf16-pair split)
             for i, L in enumerate(self.enc):
                 if i == 0:
-                    jobs.append((p[L["name"] + "/kernel"], L["wf"], fm, 4, 4, self.ncond))
+                    jobs.append((p[L["name"] + "/kernel"], L["wf"], 4 if self.enc_lean else fm, 4, 4, self.ncond))
                 else:
                     jobs.append((p[L["name"] + "/kernel"], L["wf"], fm, 0, 1, 0))
                     jobs.append((p[L["name"] + "/kernel"], L["wd"], 1, 0, 1, 0))
@@ -436,7 +440,9 @@ class VAEEngine:
     def pack_inputs(self):
         """fp32 batch + one-hot condition -> encoder operand (bf16, or [hi | lo | hi] bf16 pairs for the split encoder) and
         the perceptual U-Net's bf16 operand."""
-        if self.enc_x3:
+        if self.enc_lean:
+            ops.pack_vae_input_lean(self.M, self.cond, self.xe3, self.xp)
+        elif self.enc_x3:
             ops.pack_vae_input_mixed(self.M, self.cond, self.xe3, self.xp, fmt=0)
         else:
             ops.pack_vae_input(self.M, self.cond, self.xe3, self.xp)

@@ -98,6 +98,8 @@ def pack_jobs_table(jobs, device):
             cout_pad, cin_pad = wp.shape[1], wp.shape[2]
         elif mode == 1:
             cout_pad, cin_pad = wp.shape[2], wp.shape[1]
+        elif mode == 4:  # lean split pack of the encoder's first conv [27][cout_pad][32]
+            cout_pad, cin_pad = wp.shape[1], 16
         elif mode == 2:  # split fprop operand [27][cout_pad][3*cin_pad]
             cout_pad, cin_pad = wp.shape[1], wp.shape[2] // 3
         else:            # split dgrad operand [27][cin_pad][3*cout_pad]
@@ -381,6 +383,14 @@ def pack_vae_input_mixed(m, cond, xe3, xp16, fmt=0):
     vox = m.numel() // (B * 4)
     _lib.call("icsg3d_pack_vae_input_mixed", _ptr(m), _ptr(cond), cond.shape[1], B, ctypes.c_int64(vox), _ptr(xe3),
               _ptr(xp16), fmt, _stream())
+
+
+def pack_vae_input_lean(m, cond, xe32, xp16):
+    """Lean 32-channel split encoder operand (see icsg3d_pack_vae_input_lean) + plain bf16 perceptual operand."""
+    B = m.shape[0]
+    vox = m.numel() // (B * 4)
+    _lib.call("icsg3d_pack_vae_input_lean", _ptr(m), _ptr(cond), cond.shape[1], B, ctypes.c_int64(vox), _ptr(xe32), _ptr(xp16),
+              _stream())
 
 
 def pack_conv_w_dgrad_x3(w, cin_pad=None, cout_pad=None, out=None, fmt=None):

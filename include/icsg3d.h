@@ -160,7 +160,8 @@ int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, int cout, int
 
 /* All weight packs of a model in one launch.  jobs: DEVICE array [njobs][10] of int64
  * {w ptr, wpack ptr, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode (0 = fprop layout, 1 = dgrad layout,
- * 2 / 3 = fprop / dgrad layout as bf16-pair split operands [w_hi | w_hi | w_lo] along K, see the fp32-class section)};
+ * 2 / 3 = fprop / dgrad layout as bf16-pair split operands [w_hi | w_hi | w_lo] along K, 4 = the lean 32-channel split pack of
+ * the encoder's first conv, see the fp32-class section)};
  * max_blocks = grid.x (each job strides over its own element count). */
 int icsg3d_pack_conv_w_batch(const int64_t* jobs, int njobs, int max_blocks, void* stream);
 /* dW (padded, from wgrad) -> gradient in Keras layout, undoing padding and the condition fold. */
@@ -238,6 +239,11 @@ int icsg3d_pack_vae_input_split3(const float* m, const float* cond, int ncond, i
  * (M, one-hot cond, 0) and xp16 bf16 [B*vox][16] = (M, 0..) for the bf16 perceptual model, one read of m. */
 int icsg3d_pack_vae_input_mixed(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe3, void* xp16,
                                 int fmt, void* stream);
+/* Lean form of the same for the encoder (bf16 pairs): xe32 bf16 [B*vox][32] = [M_hi(4) | cond(10) | M_lo(0:2)]
+ * [M_lo(2:4) | M_hi(4) | cond(10)] — the one-hot condition is exact in bf16 and carries no lo part; pairs with pack mode 4 of
+ * icsg3d_pack_conv_w_batch ([27][cout_pad][32] = [w_hi(M) | w_hi(cond) | w_hi(M 0:2)] [w_hi(M 2:4) | w_lo(M) | w_lo(cond)]). */
+int icsg3d_pack_vae_input_lean(const float* m, const float* cond, int ncond, int B, int64_t vox, void* xe32, void* xp16,
+                               void* stream);
 int icsg3d_pack_conv_w_fprop_x3(const float* w, void* wpack, int ntaps, int cin, int cout, int cin_pad, int cout_pad,
                                 int cin_lead, int fold, int fold_c, int fmt, float wscale, void* stream);
 /* The conv dispatcher on fp16 operands (same kernels and layouts; only the tcgen05 operand-format fields differ).
