@@ -196,26 +196,37 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   }
 }
 
-// dw[i] = sum over splits of ws[s][i], in a FIXED order (deterministic): 4 interleaved split lanes per element keep the
-// loads of a column independent and in flight, then the 4 lane sums are added in lane order.
+// dw[i] = sum over splits of ws[s][i], in a FIXED order (deterministic): 16 interleaved split lanes per element (each with
+// two independent accumulators) keep the short strided columns in flight — with ~148 splits of a few-KB filter gradient the
+// pass is latency-, not bandwidth-bound — then the 16 lane sums are added in a fixed tree.
+static constexpr int kWgRedLanes = 16, kWgRedElems = 16;
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n,
                                                            int splits) {
   pdl_prologue();
-  __shared__ float red[4][64];
-  const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
-  const long long i = static_cast<long long>(blockIdx.x) * 64 + e;
+  __shared__ float red[kWgRedLanes][kWgRedElems + 1];
+  const int e = threadIdx.x & (kWgRedElems - 1), sl = threadIdx.x / kWgRedElems;
+  const long long i = static_cast<long long>(blockIdx.x) * kWgRedElems + e;
   float a0 = 0.f, a1 = 0.f;
   if (i < n) {
     int s = sl;
-    for (; s + 4 < splits; s += 8) {
+    for (; s + kWgRedLanes < splits; s += 2 * kWgRedLanes) {
       a0 += ws[static_cast<long long>(s) * n + i];
-      a1 += ws[static_cast<long long>(s + 4) * n + i];
+      a1 += ws[static_cast<long long>(s + kWgRedLanes) * n + i];
     }
     if (s < splits) a0 += ws[static_cast<long long>(s) * n + i];
   }
   red[sl][e] = a0 + a1;
   __syncthreads();
-  if (sl == 0 && i < n) dw[i] = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+  if (sl == 0 && i < n) {
+    float t[kWgRedLanes];
+#pragma unroll
+    for (int k = 0; k < kWgRedLanes; ++k) t[k] = red[k][e];
+#pragma unroll
+    for (int w = kWgRedLanes / 2; w > 0; w >>= 1)
+#pragma unroll
+      for (int k = 0; k < w; ++k) t[k] += t[k + w];
+    dw[i] = t[0];
+  }
 }
 
 int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H, int W, int c_extent, int kc);
@@ -328,7 +339,7 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
     const int rc = wgrad_stream_run(x, ldx, dy, ldy, B, D, H, W, cin, cout, sms, static_cast<float*>(workspace), workspace_bytes,
                                     &splits, static_cast<cudaStream_t>(stream));
     if (rc == ICSG3D_OK) {
-      launch_k(wgrad_reduce_kernel, static_cast<int>((n_dw + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream), 
+      launch_k(wgrad_reduce_kernel, static_cast<int>((n_dw + kWgRedElems - 1) / kWgRedElems), 256, 0, static_cast<cudaStream_t>(stream), 
           static_cast<const float*>(workspace), dw, n_dw, splits);
       ICSG_CHECK_LAUNCH();
       return ICSG3D_OK;
@@ -358,7 +369,7 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
   dim3 grid(p.splits, (p.total_groups + p.groups_per_cta - 1) / p.groups_per_cta, cout / p.ntw);
   launch_k(conv3d_k3_wgrad_kernel, grid, kWgradThreads, smem, static_cast<cudaStream_t>(stream), tmX, tmDY, p);
   ICSG_CHECK_LAUNCH();
-  launch_k(wgrad_reduce_kernel, static_cast<int>((n_dw + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream), p.ws, dw, n_dw, p.splits);
+  launch_k(wgrad_reduce_kernel, static_cast<int>((n_dw + kWgRedElems - 1) / kWgRedElems), 256, 0, static_cast<cudaStream_t>(stream), p.ws, dw, n_dw, p.splits);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

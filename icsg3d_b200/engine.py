@@ -673,21 +673,30 @@ class VAEEngine:
     def _train_body(self):
         if self.peer is not None:
             self.peer.tick()
-        self.pack_weights()
-        self.pack_inputs()
         if self.overlap_pm:
+            # the weight re-pack (latency-bound index shuffling of 1.7 M values) runs beside the input pack (HBM-bound) on the
+            # filter-gradient stream; pm(x) needs only the input pack (the perceptual weights are frozen and packed once)
             main = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream()
+            if self._wg_side is None:
+                self._wg_side = torch.cuda.Stream()
+            self._wg_side.wait_stream(main)
+            with torch.cuda.stream(self._wg_side):
+                self.pack_weights()
+            self.pack_inputs()
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 if not self._exp_skip_pm0:  # TIMING EXPERIMENT ONLY (ICSG3D_EXP_SKIP_PM0=1)
                     self.pm_forward(0, True, ctx=self.ctx2)
+            main.wait_stream(self._wg_side)
             self.encode(True)
             self.decode(True)
             self.pm_forward(1, True)
             main.wait_stream(self._side)
         else:
+            self.pack_weights()
+            self.pack_inputs()
             self.encode(True)
             self.decode(True)
             self.pm_forward(0, True)
