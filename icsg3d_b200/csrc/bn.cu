@@ -291,7 +291,53 @@ struct BnPeerParams {
   int world, rank, slot, nslots, cmax;
   const long long* epoch;           // device scalar, >= 1, incremented once per step
   long long timeout;                // spin budget in clock64 ticks (peer_timeout_cycles())
+  int ll;                           // 1: flag-in-word exchange (every 8-byte word carries its epoch tag: no fence, no flag round trip)
 };
+
+// Bytes of the classic regions (flags + data) of one rank's symmetric buffer; the flag-in-word region follows them.
+__host__ __device__ __forceinline__ size_t bn_peer_classic_bytes(int world, int nslots, int cmax) {
+  return static_cast<size_t>(nslots) * 2 * world * (64 * 8 + 2 * static_cast<size_t>(cmax) * 8);
+}
+// Flag-in-word ("LL") slot of value v (0 .. 2*cmax) that rank `src` contributes to call site slot_idx, in the buffer at
+// `base`: two 8-byte words, each = 32 data bits | (epoch tag << 32).  An 8-byte store is atomic, so a reader that sees the
+// tag of this epoch in a word also sees that word's data: no __threadfence_system(), no separate flag write to wait for.
+__device__ __forceinline__ unsigned long long* bn_ll_word(unsigned long long base, const BnPeerParams& pp, size_t slot_idx,
+                                                          int src, int v) {
+  return reinterpret_cast<unsigned long long*>(base + bn_peer_classic_bytes(pp.world, pp.nslots, pp.cmax)) +
+         ((slot_idx * pp.world + src) * (2 * static_cast<size_t>(pp.cmax)) + v) * 2;
+}
+__device__ __forceinline__ void bn_ll_push(const BnPeerParams& pp, size_t slot_idx, int v, double val, unsigned long long epoch) {
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(val));
+  const unsigned long long tag = (epoch & 0xffffffffull) << 32;
+  const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+  for (int r = 0; r < pp.world; ++r) {
+    unsigned long long* q = bn_ll_word(pp.peers[r], pp, slot_idx, pp.rank, v);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(q), "l"(w0) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(q + 1), "l"(w1) : "memory");
+  }
+}
+// Sum over the ranks (rank order: identical on every rank) of value v, spinning until every rank's words carry this epoch.
+__device__ __forceinline__ double bn_ll_sum(const BnPeerParams& pp, size_t slot_idx, int v, unsigned long long epoch) {
+  const unsigned long long tag = epoch & 0xffffffffull;
+  double s = 0.0;
+  const long long t_start = clock64();
+  for (int r = 0; r < pp.world; ++r) {
+    const unsigned long long* q = bn_ll_word(pp.peers[pp.rank], pp, slot_idx, r, v);
+    unsigned long long w0, w1;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w0) : "l"(q) : "memory");
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w1) : "l"(q + 1) : "memory");
+      if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+      if (clock64() - t_start > pp.timeout) {
+        printf("icsg3d: bn all-reduce (flag-in-word) timeout rank %d slot %d block %d waiting for rank %d (epoch %llu)\n", pp.rank,
+               pp.slot, blockIdx.x, r, epoch);
+        __trap();
+      }
+    }
+    s += __longlong_as_double(static_cast<long long>((w0 & 0xffffffffull) | (w1 << 32)));
+  }
+  return s;
+}
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -347,43 +393,56 @@ __global__ void __launch_bounds__(1024) bn_reduce_allreduce_kernel(const double*
     }
     const double local = (t0 + t1) + (t2 + t3);
     tot[threadIdx.x] = local;  // local sums (dgamma / dbeta in backward mode: the gradient all-reduce adds the ranks)
-    if (c < C) {
-      for (int r = 0; r < pp.world; ++r) {  // push into every rank's copy (own included)
-        double* data = reinterpret_cast<double*>(pp.peers[r] + flags_bytes) +
-                       (slot_idx * pp.world + pp.rank) * (2 * static_cast<size_t>(pp.cmax));
-        data[(threadIdx.x >> 3) * pp.cmax + c] = local;
+    if (pp.ll) {
+      if (c < C) bn_ll_push(pp, slot_idx, (threadIdx.x >> 3) * pp.cmax + c, local, epoch);
+    } else {
+      if (c < C) {
+        for (int r = 0; r < pp.world; ++r) {  // push into every rank's copy (own included)
+          double* data = reinterpret_cast<double*>(pp.peers[r] + flags_bytes) +
+                         (slot_idx * pp.world + pp.rank) * (2 * static_cast<size_t>(pp.cmax));
+          data[(threadIdx.x >> 3) * pp.cmax + c] = local;
+        }
       }
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (threadIdx.x < pp.world) {
-    const int r = threadIdx.x;
-    // publish: my contribution for block b is complete on rank r
-    unsigned long long* rflag = reinterpret_cast<unsigned long long*>(pp.peers[r]) +
-                                (slot_idx * pp.world + pp.rank) * 64 + blockIdx.x;
-    st_release_sys_u64(rflag, epoch);
-    // wait: rank r's contribution has arrived in MY buffer
-    const unsigned long long* lflag = reinterpret_cast<const unsigned long long*>(pp.peers[pp.rank]) +
-                                      (slot_idx * pp.world + r) * 64 + blockIdx.x;
-    const long long t_start = clock64();
-    while (ld_acquire_sys_u64(lflag) != epoch) {
-      if (clock64() - t_start > pp.timeout) {
-        printf("icsg3d: bn all-reduce timeout rank %d slot %d block %d waiting for rank %d (epoch %llu)\n", pp.rank, pp.slot,
-               blockIdx.x, r, epoch);
-        __trap();
-      }
+      __threadfence_system();
     }
   }
-  __syncthreads();
-  if (threadIdx.x >= kRedCh || c >= C) return;
-  const double* mine = reinterpret_cast<const double*>(pp.peers[pp.rank] + flags_bytes) +
-                       slot_idx * pp.world * (2 * static_cast<size_t>(pp.cmax));
   double s0 = 0.0, s1 = 0.0;
-  for (int r = 0; r < pp.world; ++r) {  // rank order: identical on every rank
-    const volatile double* d = mine + static_cast<size_t>(r) * 2 * pp.cmax;
-    s0 += d[c];
-    s1 += d[pp.cmax + c];
+  if (pp.ll) {
+    __shared__ double gl[2 * kRedCh];
+    if (threadIdx.x < 2 * kRedCh && c < C) gl[threadIdx.x] = bn_ll_sum(pp, slot_idx, (threadIdx.x >> 3) * pp.cmax + c, epoch);
+    __syncthreads();
+    if (threadIdx.x >= kRedCh || c >= C) return;
+    s0 = gl[threadIdx.x];
+    s1 = gl[kRedCh + threadIdx.x];
+  } else {
+    __syncthreads();
+    if (threadIdx.x < pp.world) {
+      const int r = threadIdx.x;
+      // publish: my contribution for block b is complete on rank r
+      unsigned long long* rflag = reinterpret_cast<unsigned long long*>(pp.peers[r]) +
+                                  (slot_idx * pp.world + pp.rank) * 64 + blockIdx.x;
+      st_release_sys_u64(rflag, epoch);
+      // wait: rank r's contribution has arrived in MY buffer
+      const unsigned long long* lflag = reinterpret_cast<const unsigned long long*>(pp.peers[pp.rank]) +
+                                        (slot_idx * pp.world + r) * 64 + blockIdx.x;
+      const long long t_start = clock64();
+      while (ld_acquire_sys_u64(lflag) != epoch) {
+        if (clock64() - t_start > pp.timeout) {
+          printf("icsg3d: bn all-reduce timeout rank %d slot %d block %d waiting for rank %d (epoch %llu)\n", pp.rank, pp.slot,
+                 blockIdx.x, r, epoch);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x >= kRedCh || c >= C) return;
+    const double* mine = reinterpret_cast<const double*>(pp.peers[pp.rank] + flags_bytes) +
+                         slot_idx * pp.world * (2 * static_cast<size_t>(pp.cmax));
+    for (int r = 0; r < pp.world; ++r) {  // rank order: identical on every rank
+      const volatile double* d = mine + static_cast<size_t>(r) * 2 * pp.cmax;
+      s0 += d[c];
+      s1 += d[pp.cmax + c];
+    }
   }
   if (sums) {
     sums[c] = s0;
@@ -1678,7 +1737,9 @@ static int bn_peer_check(const uint64_t* peers, int world, int rank, int slot, i
 
 extern "C" int64_t icsg3d_bn_allreduce_buffer_bytes(int world, int nslots, int cmax) {
   if (world < 1 || nslots < 1 || cmax < 1) return -1;
-  return static_cast<int64_t>(nslots) * 2 * world * (64 * 8 + 2 * static_cast<int64_t>(cmax) * 8);
+  // classic regions (flags + data) followed by the flag-in-word region (two tagged 8-byte words per value)
+  return static_cast<int64_t>(bn_peer_classic_bytes(world, nslots, cmax)) +
+         static_cast<int64_t>(nslots) * 2 * world * (2 * static_cast<int64_t>(cmax)) * 16;
 }
 
 extern "C" int icsg3d_bn_reduce_allreduce_finalize(const double* partials, int nparts, double count_global, const float* gamma,
@@ -1690,7 +1751,7 @@ extern "C" int icsg3d_bn_reduce_allreduce_finalize(const double* partials, int n
   int rc = bn_peer_check(peers, world, rank, slot, nslots, cmax, epoch, C);
   if (rc) return rc;
   BnPeerParams pp{reinterpret_cast<const unsigned long long*>(peers), world, rank, slot, nslots, cmax,
-                  reinterpret_cast<const long long*>(epoch), peer_timeout_cycles()};
+                  reinterpret_cast<const long long*>(epoch), peer_timeout_cycles(), peer_ll_enabled() ? 1 : 0};
   launch_k(bn_reduce_allreduce_kernel, ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream), 
       partials, nparts, C, 0, count_global, gamma, beta, eps, sums, mean, rstd, scale, shift, moving_mean, moving_var, momentum,
       nullptr, nullptr, pp);
@@ -1705,7 +1766,7 @@ extern "C" int icsg3d_bn_reduce_allreduce_grads(const double* partials, int npar
   int rc = bn_peer_check(peers, world, rank, slot, nslots, cmax, epoch, C);
   if (rc) return rc;
   BnPeerParams pp{reinterpret_cast<const unsigned long long*>(peers), world, rank, slot, nslots, cmax,
-                  reinterpret_cast<const long long*>(epoch), peer_timeout_cycles()};
+                  reinterpret_cast<const long long*>(epoch), peer_timeout_cycles(), peer_ll_enabled() ? 1 : 0};
   launch_k(bn_reduce_allreduce_kernel, ceil_div(C, kRedCh), 1024, 0, static_cast<cudaStream_t>(stream), 
       partials, nparts, C, 1, 1.0, nullptr, nullptr, 0.f, sums_global, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f,
       dgamma, dbeta, pp);
@@ -1745,7 +1806,7 @@ extern "C" int icsg3d_bn_bwd_fused(const void* dy, int lddy, const void* dy2, in
   BnFusedExtra e{};
   e.sums = sums; e.dgamma = dgamma; e.dbeta = dbeta;
   e.pp = BnPeerParams{reinterpret_cast<const unsigned long long*>(peers), peers ? world : 1, rank, slot, nslots, cmax,
-                      reinterpret_cast<const long long*>(epoch), peer_timeout_cycles()};
+                      reinterpret_cast<const long long*>(epoch), peer_timeout_cycles(), peer_ll_enabled() ? 1 : 0};
   if (peers) {
     int rc = bn_peer_check(peers, world, rank, slot, nslots, cmax, epoch, C);
     if (rc) return rc;

@@ -74,6 +74,9 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
 // Spin budget (SM clock cycles) of the peer-memory all-reduce kernels before they trap: ICSG3D_PEER_TIMEOUT_S seconds
 // (default 600 s, i.e. NCCL-like tolerance of host-side rank skew), or icsg3d_set_peer_timeout().
 long long peer_timeout_cycles();
+// Flag-in-word exchange of the BatchNorm statistic all-reduce (see bn.cu): ICSG3D_PEER_LL=0 / icsg3d_set_peer_ll(0) selects
+// the classic data + fence + flag protocol.
+bool peer_ll_enabled();
 
 // Tensor-map encode (driver entry point fetched at run time; no link against libcuda).
 // dims/strides innermost-first; strides in BYTES for dims 1..rank-1.

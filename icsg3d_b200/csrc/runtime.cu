@@ -25,6 +25,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 void set_peer_timeout(double seconds);
 void set_pdl(int on);
+void set_peer_ll(int on);
 
 int sm_count() {
   static int cached[64] = {0};
@@ -51,6 +52,16 @@ long long peer_timeout_cycles() {
   return g_peer_timeout;
 }
 void set_peer_timeout(double seconds) { g_peer_timeout = static_cast<long long>(seconds * 2.0e9); }
+
+static int g_peer_ll = -1;
+bool peer_ll_enabled() {
+  if (g_peer_ll < 0) {
+    const char* e = getenv("ICSG3D_PEER_LL");
+    g_peer_ll = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_peer_ll == 1;
+}
+void set_peer_ll(int on) { g_peer_ll = on ? 1 : 0; }
 
 static int g_pdl = -1;
 bool pdl_enabled() {
@@ -126,6 +137,11 @@ int icsg3d_version(void) { return 100; }
 int icsg3d_sm_count(void) { return icsg3d::sm_count(); }
 
 int64_t icsg3d_launch_count(void) { return static_cast<int64_t>(icsg3d::g_launches); }
+
+int icsg3d_set_peer_ll(int on) {
+  icsg3d::set_peer_ll(on);
+  return ICSG3D_OK;
+}
 
 int icsg3d_set_pdl(int on) {
   icsg3d::set_pdl(on);

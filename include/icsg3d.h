@@ -55,6 +55,11 @@ int64_t icsg3d_launch_count(void);
  * writes, a lazy graph capture) does not kill training; launches captured into a CUDA graph keep the value they were
  * captured with. */
 int icsg3d_set_peer_timeout(double seconds);
+/* Protocol of the BatchNorm statistic exchange: 1 (default) = flag-in-word — every 8-byte word pushed to a peer carries
+ * its epoch tag, so there is no system fence and no separate flag round trip per exchange; 0 (or ICSG3D_PEER_LL=0) = data,
+ * fence.sys, release flag, acquire poll.  Both live in the same symmetric buffer (icsg3d_bn_allreduce_buffer_bytes covers
+ * both regions) and give bit-identical sums. */
+int icsg3d_set_peer_ll(int on);
 /* Programmatic dependent launch (every kernel waits on its predecessor with griddepcontrol.wait and is launched with the
  * programmatic-stream-serialization attribute, so consecutive kernels of a stream overlap launch/prologue with the
  * predecessor's tail).  Off by default (no measurable gain on the captured train step: 3.173 vs 3.179 ms); 1 (or
