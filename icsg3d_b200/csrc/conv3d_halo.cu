@@ -356,6 +356,14 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 static bool halo_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// Autotuning hook (tools/halo_autotune.py): when set, only the forced (TD, TH, NT) is considered.
+static int g_halo_force[3] = {0, 0, 0};
+void conv_halo_force(int td, int th, int nt) {
+  g_halo_force[0] = td;
+  g_halo_force[1] = th;
+  g_halo_force[2] = nt;
+}
+
 // Pick (TD, TH, NT) minimising a simple time-per-output model; returns false when no configuration fits.
 bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvHaloParams* out) {
   if (W < 8 || W > 64 || !halo_pow2(W) || !halo_pow2(H) || !halo_pow2(D)) return false;
@@ -374,6 +382,7 @@ bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, Conv
       const int HP = TH + 2;
       const int plane_rows = HP * WP;
       for (int TD = 1; TD <= 8 && TD <= D; ++TD) {
+        if (g_halo_force[0] > 0 && (TD != g_halo_force[0] || TH != g_halo_force[1] || nt != g_halo_force[2])) continue;
         const int out_rows = TD * plane_rows;
         const int G = (out_rows + 127) / 128;
         if (G > kHaloMaxG || 2 * G * nt > 512) continue;  // two accumulator sets

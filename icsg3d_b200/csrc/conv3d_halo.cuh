@@ -24,6 +24,7 @@ struct ConvHaloParams {
   double* stats;  // optional [grid][2][nt*tiles_n]: per-CTA BatchNorm partials (sum, sum of squares) of the STORED output
 };
 
+void conv_halo_force(int td, int th, int nt);  // autotuning hook: consider only this configuration (0,0,0: off)
 // Pick (TD, TH, NT) from a simple cycle model; false when the layer shape does not fit the halo scheme.
 bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvHaloParams* out);
 int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,

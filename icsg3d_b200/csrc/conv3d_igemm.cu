@@ -594,6 +594,11 @@ static bool halo_stats_enabled() {
   }
   return g_halo_stats == 1;
 }
+extern "C" int icsg3d_conv3d_halo_force(int td, int th, int nt) {
+  conv_halo_force(td, th, nt);
+  return ICSG3D_OK;
+}
+
 extern "C" int icsg3d_conv3d_set_halo_stats(int on) {
   g_halo_stats = on ? 1 : 0;
   return ICSG3D_OK;

@@ -94,6 +94,8 @@ int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const floa
  * streaming kernel's fused statistics are always on).  icsg3d_conv3d_k3_stats_parts() reports 0 for halo layers unless
  * enabled here or with ICSG3D_HALO_STATS=1. */
 int icsg3d_conv3d_set_halo_stats(int on);
+/* Autotuning hook (tools/halo_autotune.py): restrict the halo planner to one (TD, TH, NT) configuration; (0,0,0) = off. */
+int icsg3d_conv3d_halo_force(int td, int th, int nt);
 int64_t icsg3d_conv3d_k3_workspace_bytes(int B, int D, int H, int W, int cin, int nout);
 int icsg3d_conv3d_k3_igemm_ws(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                               int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
