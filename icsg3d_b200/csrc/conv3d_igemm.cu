@@ -594,6 +594,11 @@ static bool halo_stats_enabled() {
   }
   return g_halo_stats == 1;
 }
+extern "C" int icsg3d_conv3d_stream_force(int n_hblk) {
+  conv_stream_force_nb(n_hblk);
+  return ICSG3D_OK;
+}
+
 extern "C" int icsg3d_conv3d_halo_force(int td, int th, int nt) {
   conv_halo_force(td, th, nt);
   return ICSG3D_OK;

@@ -485,6 +485,9 @@ static int stream_max_issuers() {
 
 static bool stream_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+static int g_stream_force_nb = 0;
+void conv_stream_force_nb(int nb) { g_stream_force_nb = nb; }
+
 bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvStreamParams* out) {
   if (W < 16 || W > 64 || !stream_pow2(W) || !stream_pow2(H) || !stream_pow2(D) || D < 4) return false;
   if (cin % 16 != 0 || cin > 256) return false;
@@ -507,6 +510,7 @@ bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, Co
   double best = -1.0;
   ConvStreamParams bp{};
   for (int nb = 1; nb <= H; ++nb) {  // balanced h-blocks only: every plane step of the layer costs about the same
+    if (g_stream_force_nb > 0 && nb != g_stream_force_nb) continue;  // autotuning hook
     const int TH = (H + nb - 1) / nb;
     if ((H + TH - 1) / TH != nb) continue;
     const int T = (TH * WP + 127) / 128;

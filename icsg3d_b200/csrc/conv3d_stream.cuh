@@ -34,6 +34,7 @@ struct ConvStreamParams {
 // false when the layer shape does not fit the streaming scheme (the dispatcher then falls back to the other kernels).
 bool conv_stream_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvStreamParams* out);
 int conv_stream_grid(const ConvStreamParams& p);
+void conv_stream_force_nb(int nb);  // autotuning hook: only this number of h-blocks (0: off)
 void conv_stream_set_debug(long long* buf, int steps);  // role timeline of CTA 1 into buf[4][steps][4] (nullptr: off)
 int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                        int n_store, int cin, int nout, int act, float alpha, double* stats, ConvStreamParams p,

@@ -96,6 +96,8 @@ int icsg3d_conv3d_k3_igemm(const void* x, int ldx, const void* wpack, const floa
 int icsg3d_conv3d_set_halo_stats(int on);
 /* Autotuning hook (tools/halo_autotune.py): restrict the halo planner to one (TD, TH, NT) configuration; (0,0,0) = off. */
 int icsg3d_conv3d_halo_force(int td, int th, int nt);
+/* Same for the plane-streaming kernel: only plans with this number of h-blocks per plane (0 = off). */
+int icsg3d_conv3d_stream_force(int n_hblk);
 int64_t icsg3d_conv3d_k3_workspace_bytes(int B, int D, int H, int W, int cin, int nout);
 int icsg3d_conv3d_k3_igemm_ws(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                               int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
