@@ -702,6 +702,21 @@ def heads_predict(logits, c1, threshold, argmax=None, mask=None, sig_prob=None):
               _ptr(mask), _ptr(sig_prob), _stream())
 
 
+def heads_predict_fused(x, wpack, bias, c1, threshold, argmax=None, mask=None, sig_prob=None, cin=None, f16=False,
+                        out_scale=1.0):
+    """generate.py:220-225 without the logits round trip: head GEMM on the features x [..., ld] (first `cin` channels)
+    with the packed head weights [1][nout][cin], soft-max arg-max + sigmoid threshold in the GEMM's epilogue."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(wpack, torch.bfloat16, "wpack")
+    nout, k = wpack.shape[-2], wpack.shape[-1]
+    cin = k if cin is None else cin
+    if cin != k:
+        raise ValueError("heads_predict_fused: wpack does not match cin")
+    M = x.numel() // x.shape[-1]
+    _lib.call("icsg3d_heads_predict_fused", _ptr(x), x.stride(-2), _ptr(wpack), _ptr(bias), ctypes.c_int64(M), cin, nout, c1,
+              1 if f16 else 0, float(out_scale), float(threshold), _ptr(argmax), _ptr(mask), _ptr(sig_prob), _stream())
+
+
 def metric_counts(y_true, y_pred):
     """unet.py:159-193: the five K.round(K.clip(.)) sums over (y_true, y_pred) fp32 [..., C] -> fp64 [5] device tensor."""
     _chk(y_true, torch.float32, "y_true")

@@ -168,7 +168,7 @@ class UNetEngine:
             if L.get("pool"):
                 ops.bn_apply_fwd(x, C, st.scale, st.shift, ACT_NONE, POST_POOL2, y=L["p"], pool_idx=L["idx"])
 
-    def forward(self, training, want_probs=None, with_grad=False, x_packed=False, losses=True):
+    def forward(self, training, want_probs=None, with_grad=False, x_packed=False, losses=True, heads=True):
         """unet_3d_multiclass (unet.py:272-355) on self.X [+ losses on self.species].  x_packed: self.x16 already holds
         the bf16 input (written by the producer, e.g. utils.lattice_params_device's fused pack); losses=False stops at
         the head logits (inference: generate.py:220)."""
@@ -188,6 +188,8 @@ class UNetEngine:
             ops.conv3d_k3(xin, L["wf"], p[L["n"] + "/bias"], out=L["a"], act=ACT_RELU, stats=part,
                           ws=self.ctx.conv_ws, tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
             self._bn_fwd(L, training, part=part)
+        if not heads:
+            return
         ops.conv3d_k3(self.L["c18"]["y"], self.h_wf, self.h_bias, out=self.logits, tag="unet.heads.fprop",
                       nominal=(128, self.classes + 1))
         if not losses:
@@ -325,7 +327,12 @@ class UNetEngine:
         (sigmoid >= threshold) and self.sigp; with probs_out also the softmax probabilities `model.predict` returns."""
         if repack:
             self.pack_weights(dgrad=False)
-        self.forward(False, want_probs=probs_out, x_packed=x_packed, losses=probs_out is not None)
+        if probs_out is None:  # labels only: head GEMM + soft-max arg-max + threshold in one kernel, no logits in HBM
+            self.forward(False, x_packed=x_packed, losses=False, heads=False)
+            ops.heads_predict_fused(self.L["c18"]["y"], self.h_wf, self.h_bias, self.classes, float(threshold),
+                                    argmax=self.argmax, mask=self.mask, sig_prob=self.sigp)
+            return
+        self.forward(False, want_probs=probs_out, x_packed=x_packed, losses=True)
         ops.heads_predict(self.logits, self.classes, float(threshold), argmax=self.argmax, mask=self.mask, sig_prob=self.sigp)
 
     def metrics_host(self):

@@ -426,6 +426,14 @@ int icsg3d_lattice_finalize(const void* partials, int dtype, int B, int nsplit, 
                             void* stream);
 int icsg3d_heads_predict(const float* logits, int ld, int c1, int64_t M, float threshold, uint8_t* argmax_out,
                          uint8_t* mask_out, float* sig_prob, void* stream);
+/* generate.py:220-225 in ONE kernel (csrc/heads_fused.cu): the two 1x1x1 head convolutions (unet.py:338-341) on the
+ * features x [M][ldx] (2-byte operands: bf16, or IEEE fp16 with op_f16 = 1 for the fp32-class split mode) with the packed
+ * head weights of icsg3d_pack_heads_w ([nout][cin], column c1 = sigmoid head), then exactly icsg3d_heads_predict on the
+ * logits = accumulator * out_scale + bias — which stay in tensor memory and are never written to HBM.
+ * cin: multiple of 64, <= 384; nout: multiple of 16, <= 96; 1 <= c1 < nout. */
+int icsg3d_heads_predict_fused(const void* x, int ldx, const void* wpack, const float* bias, int64_t M, int cin, int nout,
+                               int c1, int op_f16, float out_scale, float threshold, uint8_t* argmax_out,
+                               uint8_t* mask_out, float* sig_prob, void* stream);
 int icsg3d_rotate90_batch(const void* in, void* out, int B, int d, int voxel_bytes, const int* xforms, void* stream);
 int icsg3d_metric_counts(const float* y_true, const float* y_pred, int64_t n, int C, double* counts, void* stream);
 

@@ -110,6 +110,73 @@ def test_heads_predict_labels_and_mask():
     assert torch.equal(mk.cpu().bool()[clear], (want_sig >= 0.8)[clear])
     assert torch.equal(mk.bool(), sp >= 0.8)       # mask and probability are consistent with each other
 
+@pytest.mark.parametrize("shape,cin,classes,f16", [((3, 4, 4, 4), 128, 95, False), ((2, 16, 16, 16), 128, 95, False),
+                                                   ((1, 8, 8, 8), 64, 20, False), ((1, 8, 8, 8), 384, 95, False),
+                                                   ((2, 8, 8, 8), 384, 95, True)])
+def test_fused_heads_predict_equals_conv_then_predict(shape, cin, classes, f16):
+    """csrc/heads_fused.cu == 1x1x1 head conv (fp32 logits) + heads_predict, bit for bit (labels, mask, probability),
+    including exact ties between classes and a row count that is not a multiple of the 128-row tile."""
+    from icsg3d_b200 import ops
+    B, D, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    nout = (classes + 1 + 15) // 16 * 16
+    x = (torch.randn(B, D, H, W, cin, device="cuda", generator=g) * 2).to(torch.bfloat16)
+    w_soft = torch.randn(1, 1, 1, cin, classes, device="cuda", generator=g) / cin ** 0.5 * 3
+    w_soft[..., 7] = w_soft[..., 3]                       # classes 3 and 7 tie everywhere: the first index must win
+    w_sig = torch.randn(1, 1, 1, cin, 1, device="cuda", generator=g) / cin ** 0.5
+    b_soft = torch.randn(classes, device="cuda", generator=g) * 0.1
+    b_soft[3] += 2.0                                      # ... and often enough to be seen at every test size
+    b_soft[7] = b_soft[3]
+    if classes > 10:                                      # class 5 a hair BELOW class 9 and before it: its probability
+        w_soft[..., 5] = w_soft[..., 9]                   # rounds to the same float32 for some voxels only (the rare
+        b_soft[9] += 2.0                                  # path of the fused kernel: exp() of a 1-ulp logit difference)
+        b_soft[5] = b_soft[9] - 1.2e-7
+    b_sig = torch.randn(1, device="cuda", generator=g)
+    wf = torch.zeros(1, nout, cin, dtype=torch.bfloat16, device="cuda")
+    wd = torch.zeros(1, cin, nout, dtype=torch.bfloat16, device="cuda")
+    bias = torch.zeros(nout, dtype=torch.float32, device="cuda")
+    ops.pack_heads_w(w_soft, w_sig, b_soft, b_sig, wf, wd, bias)
+    logits = torch.empty(B, D, H, W, nout, dtype=torch.float32, device="cuda")
+    if f16:  # IEEE fp16 operand bits in the same 2-byte buffers (fp32-class split mode), weights pre-scaled by 2^10
+        x = x.float().half().view(torch.bfloat16)
+        wf = (wf.float() * ops.SPLIT_WSCALE).half().view(torch.bfloat16)
+        ops.conv3d_k3(x, wf, bias, out=logits, split=True, fmt=1)
+    else:
+        ops.conv3d_k3(x, wf, bias, out=logits)
+    M = B * D * H * W
+    ref = [torch.empty(M, dtype=dt, device="cuda") for dt in (torch.uint8, torch.uint8, torch.float32)]
+    got = [torch.full((M,), 255, dtype=torch.uint8, device="cuda"), torch.full((M,), 255, dtype=torch.uint8, device="cuda"),
+           torch.full((M,), -1.0, dtype=torch.float32, device="cuda")]
+    ops.heads_predict(logits, classes, 0.6, argmax=ref[0], mask=ref[1], sig_prob=ref[2])
+    ops.heads_predict_fused(x, wf, bias, classes, 0.6, argmax=got[0], mask=got[1], sig_prob=got[2], f16=f16,
+                            out_scale=1.0 / ops.SPLIT_WSCALE if f16 else 1.0)
+    torch.cuda.synchronize()
+    for r, o in zip(ref, got):
+        assert torch.equal(r, o)
+    assert int((ref[0] == 7).sum()) == 0 and int((ref[0] == 3).sum()) > 0     # the tie really occurs and resolves to 3
+    if classes > 10 and M >= 1024:
+        assert int((ref[0] == 5).sum()) > 0 and int((ref[0] == 9).sum()) > 0  # near-ties resolve both ways
+    lab = logits.view(M, nout)[:, :classes].argmax(dim=1)
+    assert float((got[0].long() != lab).float().mean()) < 1e-3
+
+
+def test_fused_heads_predict_on_a_channel_slice_with_row_stride():
+    """Features living in a wider buffer (ldx > cin), as the U-Net's concatenation buffers do."""
+    from icsg3d_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    big = (torch.randn(2, 8, 8, 8, 192, device="cuda", generator=g)).to(torch.bfloat16)
+    x = big[..., 64:192]
+    wf = (torch.randn(1, 96, 128, device="cuda", generator=g) / 6).to(torch.bfloat16)
+    bias = torch.randn(96, device="cuda", generator=g) * 0.1
+    logits = torch.empty(2, 8, 8, 8, 96, dtype=torch.float32, device="cuda")
+    ops.conv3d_k3(x, wf, bias, out=logits)
+    M = 1024
+    a0, a1 = torch.empty(M, dtype=torch.uint8, device="cuda"), torch.empty(M, dtype=torch.uint8, device="cuda")
+    m0, m1 = torch.empty_like(a0), torch.empty_like(a0)
+    ops.heads_predict(logits, 95, 0.8, argmax=a0, mask=m0)
+    ops.heads_predict_fused(x, wf, bias, 95, 0.8, argmax=a1, mask=m1)
+    assert torch.equal(a0, a1) and torch.equal(m0, m1)
+
 
 def test_metric_functions_match_keras_formulas():
     """unet.py:159-193 on one-hot truth / softmax predictions: numpy restatement of the K.round(K.clip()) sums."""
