@@ -91,6 +91,12 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   for (int i = threadIdx.x; i < p.nt * p.tiles_n && i < 512; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&s_stats[0][0])[i] = 0.f;
+  if (p.post_scale != nullptr) {  // inference: the statistics table carries the post-activation affine instead
+    for (int i = threadIdx.x; i < p.nt * p.tiles_n && i < 512; i += blockDim.x) {
+      s_stats[0][i] = p.post_scale[i];
+      s_stats[1][i] = p.post_shift[i];
+    }
+  }
   if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -264,6 +270,10 @@ conv3d_k3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int i = 0; i < 32; ++i) {
           const float x = fmaf(__uint_as_float(v[i]), p.oscale, s_bias[(col0 + i) & 511]);
           fv[i] = fmaxf(x, slope * x);
+        }
+        if (p.post_scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) fv[i] = fmaf(fv[i], s_stats[0][(col0 + i) & 511], s_stats[1][(col0 + i) & 511]);
         }
         const int nvalid = min(ncol, p.n_store - col0);
         if (p.y_dtype == ICSG3D_DT_BF16) {
@@ -449,7 +459,7 @@ bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, Conv
 
 int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                      int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st,
-                     float oscale, double* stats) {
+                     float oscale, double* stats, const float* post_scale, const float* post_shift) {
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
@@ -471,6 +481,8 @@ int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bia
   p.y = y; p.ldy = ldy; p.y_dtype = y_dtype; p.n_store = n_store; p.bias = bias; p.act = act; p.alpha = alpha;
   p.oscale = oscale;
   p.stats = stats;
+  p.post_scale = post_scale;
+  p.post_shift = post_shift;
   static bool configured = false;
   if (!configured) {
     ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

@@ -22,6 +22,8 @@ struct ConvHaloParams {
   float alpha;
   float oscale;  // output = accumulator * oscale + bias (1 unless the weights were pre-scaled: fp16 split mode)
   double* stats;  // optional [grid][2][nt*tiles_n]: per-CTA BatchNorm partials (sum, sum of squares) of the STORED output
+  const float* post_scale;  // optional per-channel affine after the activation (inference BatchNorm); excludes stats
+  const float* post_shift;
 };
 
 void conv_halo_force(int td, int th, int nt);  // autotuning hook: consider only this configuration (0,0,0: off)
@@ -29,7 +31,8 @@ void conv_halo_force(int td, int th, int nt);  // autotuning hook: consider only
 bool conv_halo_plan(int B, int D, int H, int W, int cin, int nout, int sms, ConvHaloParams* out);
 int launch_conv_halo(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                      int n_store, int cin, int nout, int act, float alpha, ConvHaloParams p, int sms, cudaStream_t st,
-                     float oscale = 1.0f, double* stats = nullptr);
+                     float oscale = 1.0f, double* stats = nullptr, const float* post_scale = nullptr,
+                     const float* post_shift = nullptr);
 // CTAs the halo kernel launches for this plan (= rows of the fused-statistics partials)
 inline int conv_halo_grid(const ConvHaloParams& p, int sms) { return p.total_items < sms ? p.total_items : sms; }
 

@@ -49,6 +49,8 @@ struct ConvIgemmParams {
   int act;
   float alpha;
   float oscale;  // output = accumulator * oscale + bias (1 unless the weights were pre-scaled: fp16 split mode)
+  const float* post_scale;  // optional per-channel affine applied AFTER the activation (inference BatchNorm that follows
+  const float* post_shift;  // Conv3D+ReLU in the U-Net, unet.py:277-279): y = post_scale * act(.) + post_shift
 };
 
 static constexpr int kConvThreads = 192;
@@ -222,6 +224,7 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           } else if (p.act == ICSG3D_ACT_LEAKY) {
             x = x > 0.f ? x : p.alpha * x;
           }
+          if (p.post_scale != nullptr) x = fmaf(x, __ldg(p.post_scale + col0 + i), __ldg(p.post_shift + col0 + i));
           f[i] = x;
         }
         const int nvalid = min(16, p.n_store - col0);
@@ -273,7 +276,8 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 __global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, long long m_total,
                                                                  int ncols, const float* __restrict__ bias, int act, float alpha,
                                                                  void* __restrict__ y, int ldy, int y_dtype, int n_store,
-                                                                 float oscale) {
+                                                                 float oscale, const float* __restrict__ post_scale,
+                                                                 const float* __restrict__ post_shift) {
   pdl_prologue();
   const int c4 = ncols >> 2;
   const long long total = m_total * c4;
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const float* __
       float x = o[i] * oscale + (bias ? bias[c + i] : 0.f);
       if (act == ICSG3D_ACT_RELU) x = fmaxf(x, 0.f);
       else if (act == ICSG3D_ACT_LEAKY) x = x > 0.f ? x : alpha * x;
+      if (post_scale != nullptr) x = fmaf(x, post_scale[c + i], post_shift[c + i]);
       o[i] = x;
     }
     const int nv = min(4, n_store - c);
@@ -413,7 +418,8 @@ static void igemm_tiling(int tiles_m, int nout, int iters, int sms, bool allow_s
 static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                              int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                              float leaky_alpha, void* stream, double* stats = nullptr, int stats_parts = 0,
-                             void* ws = nullptr, int64_t ws_bytes = 0, bool op_f16 = false, float oscale = 1.0f) {
+                             void* ws = nullptr, int64_t ws_bytes = 0, bool op_f16 = false, float oscale = 1.0f,
+                             const float* post_scale = nullptr, const float* post_shift = nullptr) {
   // op_f16: the 2-byte operands are IEEE fp16 instead of bf16 (fp32-class split mode): same kernels and layouts, only
   // the a/b format fields (bits 7..9 / 10..12) of the tcgen05 instruction descriptor change from BF16 (1) to F16 (0)
   const uint32_t fmt_mask = op_f16 ? ~((7u << 7) | (7u << 10)) : ~0u;
@@ -427,6 +433,8 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   ICSG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0,
                "conv3d_k3_igemm: x and wpack must be 16-byte aligned");
   ICSG_REQUIRE(y_dtype == ICSG3D_DT_BF16 || y_dtype == ICSG3D_DT_F32, "conv3d_k3_igemm: bad y_dtype");
+  ICSG_REQUIRE((post_scale == nullptr) == (post_shift == nullptr) && !(post_scale && stats),
+               "conv3d_k3_igemm: post_scale / post_shift come together and exclude fused statistics");
   const long long m_total = static_cast<long long>(B) * D * H * W;
   ICSG_REQUIRE(m_total < (1ll << 31), "conv3d_k3_igemm: too many voxels");
 
@@ -438,7 +446,7 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
                    "conv3d_k3_igemm_stats: stats_parts %d does not match this layer's plan", stats_parts);
       for (int i = 0; i < 3; ++i) sp.idesc[i] &= fmt_mask;
       return launch_conv_stream(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, stats, sp,
-                                static_cast<cudaStream_t>(stream), oscale);
+                                static_cast<cudaStream_t>(stream), oscale, post_scale, post_shift);
     }
     ConvHaloParams hp;
     if (ntaps == 27 && sms0 > 0 && conv_use_halo(B, D, H, W, cin, nout, sms0, &hp)) {
@@ -446,7 +454,7 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
                    "conv3d_k3_igemm_stats: stats_parts %d does not match this layer's plan", stats_parts);
       hp.idesc &= fmt_mask;
       return launch_conv_halo(x, ldx, wpack, bias, y, ldy, y_dtype, n_store, cin, nout, act, leaky_alpha, hp, sms0,
-                              static_cast<cudaStream_t>(stream), oscale, stats);
+                              static_cast<cudaStream_t>(stream), oscale, stats, post_scale, post_shift);
     }
     ICSG_REQUIRE(!stats, "conv3d_k3_igemm_stats: this layer shape has no fused-statistics path (stats_parts() == 0)");
   }
@@ -498,6 +506,8 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   p.act = act;
   p.alpha = leaky_alpha;
   p.oscale = oscale;
+  p.post_scale = post_scale;
+  p.post_shift = post_shift;
 
   CUtensorMap tmA, tmB;
   int rc = encode_act_map(&tmA, x, ldx, B, D, H, W, cin, p.kc);
@@ -530,7 +540,7 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
     long long blocks = (items + 255) / 256;
     if (blocks > sms * 8) blocks = sms * 8;
     launch_k(conv_splitk_reduce_kernel, static_cast<int>(blocks), 256, 0, st, p.ws, p.ksplit, m_total, nout, bias, act, leaky_alpha, y,
-                                                                      ldy, y_dtype, n_store, oscale);
+                                                                      ldy, y_dtype, n_store, oscale, post_scale, post_shift);
     ICSG_CHECK_LAUNCH();
   }
   return ICSG3D_OK;
@@ -565,6 +575,17 @@ extern "C" int icsg3d_conv3d_k3_igemm_ws(const void* x, int ldx, const void* wpa
                                          float leaky_alpha, void* ws, int64_t ws_bytes, void* stream) {
   return conv3d_igemm_impl(27, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream,
                            nullptr, 0, ws, ws_bytes);
+}
+
+// Inference form of Conv3D + activation + BatchNorm (unet.py:277-279 in learning phase 0): the per-channel affine of the
+// moving statistics is applied in the conv epilogue, y = post_scale * act(conv + bias) + post_shift
+extern "C" int icsg3d_conv3d_k3_igemm_post(const void* x, int ldx, const void* wpack, const float* bias,
+                                           const float* post_scale, const float* post_shift, void* y, int ldy, int y_dtype,
+                                           int n_store, int B, int D, int H, int W, int cin, int nout, int act,
+                                           float leaky_alpha, void* ws, int64_t ws_bytes, void* stream) {
+  ICSG_REQUIRE(post_scale && post_shift, "conv3d_k3_igemm_post: post_scale and post_shift required");
+  return conv3d_igemm_impl(27, x, ldx, wpack, bias, y, ldy, y_dtype, n_store, B, D, H, W, cin, nout, act, leaky_alpha, stream,
+                           nullptr, 0, ws, ws_bytes, false, 1.0f, post_scale, post_shift);
 }
 
 // fp16 operands (the fp32-class split mode of csrc/split3.cu); same dispatcher, kernels and layouts

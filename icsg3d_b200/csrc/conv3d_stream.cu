@@ -64,7 +64,8 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NC]) 
 // BatchNorm running sums.
 template <int NC>
 __device__ __forceinline__ void stream_epi_math(const ConvStreamParams& p, const uint32_t (&v)[NC], int c0, bool ok, long long pixel,
-                                                const float* s_bias, float slope, float (&sacc)[32], float (&qacc)[32]) {
+                                                const float* s_bias, float slope, float (&sacc)[32], float (&qacc)[32],
+                                                const float* s_post) {
   const int nvalid = min(NC, p.n_store - c0);
   const bool bf16 = p.y_dtype == ICSG3D_DT_BF16;
   const bool vec = nvalid == NC && (p.ldy & (bf16 ? 7 : 3)) == 0;
@@ -84,6 +85,14 @@ __device__ __forceinline__ void stream_epi_math(const ConvStreamParams& p, const
       fv[i + 1] = fmaxf(x1, slope * x1);
       fv[i + 2] = fmaxf(x2, slope * x2);
       fv[i + 3] = fmaxf(x3, slope * x3);
+      if (s_post != nullptr) {  // warp-uniform: inference BatchNorm affine after the activation
+        const float4 s4 = *reinterpret_cast<const float4*>(&s_post[c0 + 8 * j + i]);
+        const float4 t4 = *reinterpret_cast<const float4*>(&s_post[64 + c0 + 8 * j + i]);
+        fv[i] = fmaf(fv[i], s4.x, t4.x);
+        fv[i + 1] = fmaf(fv[i + 1], s4.y, t4.y);
+        fv[i + 2] = fmaf(fv[i + 2], s4.z, t4.z);
+        fv[i + 3] = fmaf(fv[i + 3], s4.w, t4.w);
+      }
     }
     if (bf16) {
       uint4 qv;
@@ -139,6 +148,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __shared__ __align__(8) uint64_t slot_full[kStreamMaxR], slot_empty[kStreamMaxR];
   __shared__ __align__(8) uint64_t w_full;
   __shared__ __align__(16) float s_bias[64];
+  __shared__ __align__(16) float s_post[128];  // [0,64) post-activation scale, [64,128) shift (inference BatchNorm)
   __shared__ double s_stats[2][64];
   __shared__ uint32_t tmem_base_slot;
 
@@ -181,6 +191,10 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   const int n_off = static_cast<int>(blockIdx.y) * p.C;  // N split: this CTA's slice of the output channels
   if (threadIdx.x < 64) s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.C) ? p.bias[n_off + threadIdx.x] : 0.f;
+  if (threadIdx.x < 64 && p.post_scale != nullptr) {
+    s_post[threadIdx.x] = threadIdx.x < p.C ? p.post_scale[n_off + threadIdx.x] : 1.f;
+    s_post[64 + threadIdx.x] = threadIdx.x < p.C ? p.post_shift[n_off + threadIdx.x] : 0.f;
+  }
   if (threadIdx.x < 128) s_stats[threadIdx.x >> 6][threadIdx.x & 63] = 0.0;
   if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
   tc_fence_before();
@@ -412,7 +426,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             long long pixel;
             coords(t, ok, pixel);
             if (p.exp_flags & 4) ok = false;
-            stream_epi_math<32>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc);
+            stream_epi_math<32>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc, p.post_scale != nullptr ? s_post : nullptr);
             t = tn;
           }
         } else {
@@ -429,7 +443,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             bool ok;
             long long pixel;
             coords(t, ok, pixel);
-            stream_epi_math<16>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc);
+            stream_epi_math<16>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc, p.post_scale != nullptr ? s_post : nullptr);
             t = tn;
           }
         }
@@ -578,7 +592,7 @@ void conv_stream_set_debug(long long* buf, int steps) {
 
 int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                        int n_store, int cin, int nout, int act, float alpha, double* stats, ConvStreamParams p,
-                       cudaStream_t st, float oscale) {
+                       cudaStream_t st, float oscale, const float* post_scale, const float* post_shift) {
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
@@ -603,6 +617,8 @@ int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* b
   static const int exp_flags = [] { const char* e = getenv("ICSG3D_STREAM_EXP"); return e ? atoi(e) : 0; }();
   p.exp_flags = exp_flags;
   p.oscale = oscale;
+  p.post_scale = post_scale;
+  p.post_shift = post_shift;
   static bool configured = false;
   if (!configured) {
     ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));

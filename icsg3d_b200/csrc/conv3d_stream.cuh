@@ -25,6 +25,8 @@ struct ConvStreamParams {
   float alpha;
   float oscale;  // output = accumulator * oscale + bias (1 unless the weights were pre-scaled: fp16 split mode)
   double* stats;         // optional per-CTA BatchNorm partials [grid][2][C] (sum, sum of squares of the stored values)
+  const float* post_scale;  // optional per-channel affine after the activation (inference BatchNorm); excludes stats
+  const float* post_shift;
   long long* dbg;        // optional role timeline of CTA (0, 0): [4 roles][dbg_steps][4] clock64 stamps (tools/stream_timeline.py)
   int dbg_steps;
   int exp_flags;         // TIMING EXPERIMENTS ONLY (env ICSG3D_STREAM_EXP, results are wrong when set): 1 = no slot zeroing,
@@ -38,6 +40,7 @@ void conv_stream_force_nb(int nb);  // autotuning hook: only this number of h-bl
 void conv_stream_set_debug(long long* buf, int steps);  // role timeline of CTA 1 into buf[4][steps][4] (nullptr: off)
 int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy, int y_dtype,
                        int n_store, int cin, int nout, int act, float alpha, double* stats, ConvStreamParams p,
-                       cudaStream_t st, float oscale = 1.0f);
+                       cudaStream_t st, float oscale = 1.0f, const float* post_scale = nullptr,
+                       const float* post_shift = nullptr);
 
 }  // namespace icsg3d

@@ -160,7 +160,8 @@ def conv3d_k3_stats_parts(x, wpack):
 
 
 def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alpha=LEAKY_ALPHA, out=None,
-              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv", stats=None, ws=None, split=False, fmt=None):
+              out_dtype=torch.bfloat16, ref=False, nominal=None, tag="conv", stats=None, ws=None, split=False, fmt=None,
+              post=None):
     """x: bf16 [B,D,H,W,ldx]; wpack: bf16 [27][nout][cin]; returns y [B,D,H,W,n_store].
 
     `ref=True` runs the CUDA-core cross-check kernel (fp32 output) instead of the tcgen05 kernel.
@@ -170,6 +171,8 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
     ops.SPLIT_FMT): fp16 pairs need the conv to be told (operand-format field, output rescale); bf16 pairs (fmt 0) are
     ordinary operands with 3x the channels.
     `ws`: optional scratch tensor (any dtype, one per stream): layers with too few tiles (4^3 / 2^3 grids) split K over it.
+    `post=(scale, shift)`: fp32 [nout] per-channel affine applied after the activation in the epilogue (the inference
+    BatchNorm that follows Conv3D+ReLU in the U-Net): y = scale * act(conv + bias) + shift.
     """
     _chk(x, torch.bfloat16, "x")
     _chk(wpack, torch.bfloat16, "wpack")
@@ -203,6 +206,14 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
             fn = "icsg3d_conv3d_k1_igemm_f16" if wpack.shape[0] == 1 else "icsg3d_conv3d_k3_igemm_f16"
             _lib.call(fn, _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(out), _ld(out), ydt, n_store, B, D, H, W, cin, nout,
                       act, alpha, 1.0 / SPLIT_WSCALE, _stream())
+        elif post is not None:
+            if wpack.shape[0] != 27 or split or stats is not None:
+                raise ValueError("conv3d_k3: post= is for plain 3x3x3 layers without fused statistics")
+            _chk(post[0], torch.float32, "post scale")
+            _chk(post[1], torch.float32, "post shift")
+            _lib.call("icsg3d_conv3d_k3_igemm_post", _ptr(x), ldx, _ptr(wpack), _ptr(bias), _ptr(post[0]), _ptr(post[1]),
+                      _ptr(out), _ld(out), ydt, n_store, B, D, H, W, cin, nout, act, alpha, _ptr(ws),
+                      ctypes.c_int64(ws.numel() * ws.element_size() if ws is not None else 0), _stream())
         elif stats is not None:
             _chk(stats, torch.float64, "stats")
             if stats.dim() != 3 or stats.shape[1] != 2 or stats.shape[2] != nout or not stats.is_contiguous():

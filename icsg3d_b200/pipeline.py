@@ -38,6 +38,7 @@ class GeneratePipeline:
         """Re-pack the GEMM operand copies of both networks (after loading / changing weights)."""
         self.veng.pack_weights()
         self.ueng.pack_weights(dgrad=False)
+        self.ueng.inference_coeffs()
         self._graph = None
 
     def _body(self):

@@ -95,6 +95,8 @@ class UNetEngine:
                 if spec.get("pool"):
                     L["dp"] = z(B, D // 2, D // 2, D // 2, cout)
             self.L[n] = L
+        cmax = max(spec["cout"] for spec in UNET_PLAN)
+        self.one, self.zero = torch.ones(cmax, dtype=F32, device=dev), torch.zeros(cmax, dtype=F32, device=dev)
         # heads
         self.nout_h = pad16(classes + 1)
         self.h_wf, self.h_wd = z(1, self.nout_h, 128), z(1, 128, self.nout_h)
@@ -142,7 +144,18 @@ class UNetEngine:
             return self.cat[src[4:]]
         return self.L[src]["y"]
 
-    def _bn_fwd(self, L, training, part=None):
+    def _inference_coeffs(self, L):
+        p, n, st = self.pp.p, L["n"], L["bn"]
+        ops.bn_inference_coeffs(p[f"bn_{n}/gamma"], p[f"bn_{n}/beta"], p[f"bn_{n}/moving_mean"], p[f"bn_{n}/moving_variance"],
+                                st.scale, st.shift)
+
+    def inference_coeffs(self):
+        """BatchNorm scale / shift of every block from the moving statistics (learning phase 0); they change only with
+        the weights, so a serving loop computes them once (predict(repack=False) / forward(coeffs=False))."""
+        for L in self.L.values():
+            self._inference_coeffs(L)
+
+    def _bn_fwd(self, L, training, part=None, coeffs=True):
         p = self.pp.p
         n, C, st, x = L["n"], L["cout"], L["bn"], L["a"]
         g, b = p[f"bn_{n}/gamma"], p[f"bn_{n}/beta"]
@@ -159,7 +172,7 @@ class UNetEngine:
                 ops.bn_finalize(st.sums, float(rows * self.world), g, b, st.mean, st.rstd, st.scale, st.shift, mm, mv)
             else:
                 ops.bn_reduce_finalize(part, float(rows), g, b, st.sums, st.mean, st.rstd, st.scale, st.shift, mm, mv)
-        else:
+        elif coeffs:
             ops.bn_inference_coeffs(g, b, mm, mv, st.scale, st.shift)
         if "up" in L:
             ops.bn_apply_fwd(x, C, st.scale, st.shift, ACT_NONE, POST_UP2, y=L["y"])
@@ -168,10 +181,11 @@ class UNetEngine:
             if L.get("pool"):
                 ops.bn_apply_fwd(x, C, st.scale, st.shift, ACT_NONE, POST_POOL2, y=L["p"], pool_idx=L["idx"])
 
-    def forward(self, training, want_probs=None, with_grad=False, x_packed=False, losses=True, heads=True):
+    def forward(self, training, want_probs=None, with_grad=False, x_packed=False, losses=True, heads=True, coeffs=True):
         """unet_3d_multiclass (unet.py:272-355) on self.X [+ losses on self.species].  x_packed: self.x16 already holds
         the bf16 input (written by the producer, e.g. utils.lattice_params_device's fused pack); losses=False stops at
-        the head logits (inference: generate.py:220)."""
+        the head logits (inference: generate.py:220); coeffs=False (learning phase 0): the BatchNorm scale / shift of the
+        moving statistics are already in place (inference_coeffs() after the last weight change)."""
         p = self.pp.p
         if x_packed:
             pass
@@ -181,13 +195,24 @@ class UNetEngine:
             ops.f32_to_bf16_rows(self.X, 1, self.x16)
         for L in self.L.values():
             xin, part = self._input_of(L), None
+            if not training and "up" not in L:
+                # learning phase 0: BatchNorm is a fixed per-channel affine -> applied in the conv epilogue, which writes
+                # the block output (a plain tensor or its slice of a concatenation buffer) directly
+                st = L["bn"]
+                if coeffs:
+                    self._inference_coeffs(L)
+                ops.conv3d_k3(xin, L["wf"], p[L["n"] + "/bias"], out=L["y"], act=ACT_RELU, post=(st.scale, st.shift),
+                              ws=self.ctx.conv_ws, tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
+                if L.get("pool"):
+                    ops.bn_apply_fwd(L["y"], L["cout"], self.one, self.zero, ACT_NONE, POST_POOL2, y=L["p"])
+                continue
             if training:  # BatchNorm statistics out of the conv epilogue where the serving kernel has them
                 nparts = ops.conv3d_k3_stats_parts(xin, L["wf"])
                 if nparts > 0:
                     part = self.ctx.partials[: nparts * 2 * L["cout"]].view(nparts, 2, L["cout"])
             ops.conv3d_k3(xin, L["wf"], p[L["n"] + "/bias"], out=L["a"], act=ACT_RELU, stats=part,
                           ws=self.ctx.conv_ws, tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
-            self._bn_fwd(L, training, part=part)
+            self._bn_fwd(L, training, part=part, coeffs=coeffs)
         if not heads:
             return
         ops.conv3d_k3(self.L["c18"]["y"], self.h_wf, self.h_bias, out=self.logits, tag="unet.heads.fprop",
@@ -328,11 +353,11 @@ class UNetEngine:
         if repack:
             self.pack_weights(dgrad=False)
         if probs_out is None:  # labels only: head GEMM + soft-max arg-max + threshold in one kernel, no logits in HBM
-            self.forward(False, x_packed=x_packed, losses=False, heads=False)
+            self.forward(False, x_packed=x_packed, losses=False, heads=False, coeffs=repack)
             ops.heads_predict_fused(self.L["c18"]["y"], self.h_wf, self.h_bias, self.classes, float(threshold),
                                     argmax=self.argmax, mask=self.mask, sig_prob=self.sigp)
             return
-        self.forward(False, want_probs=probs_out, x_packed=x_packed, losses=True)
+        self.forward(False, want_probs=probs_out, x_packed=x_packed, losses=True, coeffs=repack)
         ops.heads_predict(self.logits, self.classes, float(threshold), argmax=self.argmax, mask=self.mask, sig_prob=self.sigp)
 
     def metrics_host(self):

@@ -102,6 +102,13 @@ int64_t icsg3d_conv3d_k3_workspace_bytes(int B, int D, int H, int W, int cin, in
 int icsg3d_conv3d_k3_igemm_ws(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                               int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                               float leaky_alpha, void* ws, int64_t ws_bytes, void* stream);
+/* Inference form of Conv3D + activation + BatchNormalization (unet.py:277-279 in learning phase 0): the per-channel affine
+ * of the moving statistics (icsg3d_bn_inference_coeffs) is applied in the conv epilogue,
+ * y = post_scale[c] * act(conv + bias[c]) + post_shift[c], so the BatchNorm pass over the activation disappears. */
+int icsg3d_conv3d_k3_igemm_post(const void* x, int ldx, const void* wpack, const float* bias, const float* post_scale,
+                                const float* post_shift, void* y, int ldy, int y_dtype, int n_store, int B, int D, int H,
+                                int W, int cin, int nout, int act, float leaky_alpha, void* ws, int64_t ws_bytes,
+                                void* stream);
 
 /* Conv3D + BiasAdd(+activation) that also emits the BatchNorm statistics of its own (stored, bf16-rounded) output from the
  * epilogue — replaces a separate icsg3d_bn_stats read pass for the BatchNormalization() that follows the conv

@@ -194,3 +194,37 @@ def test_split_k_per_tap_kernel_matches_unsplit(B, D, cin, cout, act):
     assert rel_l2(yb.float(), y0) < 1e-2
     if (B, D) == (32, 4):
         assert need > 0, "the 4^3 layers at batch 32 must be split"
+
+
+@pytest.mark.parametrize("B,D,cin,cout,act,kind", [
+    (2, 32, 16, 32, 1, 2), (3, 32, 32, 64, 1, 2),          # plane-streaming kernel
+    (4, 16, 64, 128, 1, 1), (6, 8, 128, 128, 2, 1),        # halo kernel
+    (8, 16, 128, 128, 1, 0), (2, 32, 192, 128, 1, 0),      # per-tap kernel (unsplit)
+    (4, 4, 256, 512, 1, 0), (3, 4, 16, 128, 0, 0)])        # per-tap kernel, K split over the workspace
+def test_conv_epilogue_post_affine_matches_conv_then_affine(B, D, cin, cout, act, kind):
+    """icsg3d_conv3d_k3_igemm_post (inference Conv3D + ReLU + BatchNorm in one kernel, unet.py:277-279):
+    y = scale * act(conv + bias) + shift in the epilogue of every conv kernel == the fp32 conv output put through the
+    same affine, rounded to bf16 once; also into a channel slice of a wider buffer (the U-Net's concatenation buffers)."""
+    import ctypes
+    from icsg3d_b200 import _lib, ops
+    x, w, b = _mk(B, D, cin, cout, seed=41)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    wp = ops.pack_conv_w_fprop(wd)
+    plan = (ctypes.c_int * 10)()
+    _lib.lib().icsg3d_conv3d_k3_plan(B, D, D, D, cin, cout, 148, plan)
+    assert plan[0] == kind, f"shape is served by kernel {plan[0]}, the case was written for {kind}"
+    g = torch.Generator(device="cuda").manual_seed(5)
+    scale = torch.rand(cout, device="cuda", generator=g) * 2 - 0.5
+    shift = torch.randn(cout, device="cuda", generator=g)
+    need = ops.conv3d_k3_workspace_bytes(B, D, cin, cout)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+    a32 = ops.conv3d_k3(xd, wp, bd, act=act, out_dtype=torch.float32, ws=ws)
+    want = torch.addcmul(shift, a32, scale)
+    buf = torch.full((B, D, D, D, cout + 32), 7.0, dtype=torch.bfloat16, device="cuda")
+    got = buf[..., 16:16 + cout]
+    ops.conv3d_k3(xd, wp, bd, act=act, out=got, post=(scale, shift), ws=ws)
+    torch.cuda.synchronize()
+    assert torch.all(buf[..., :16] == 7.0) and torch.all(buf[..., 16 + cout:] == 7.0)
+    err = (got.float() - want).abs()
+    assert float((err / (want.abs() + 1e-2)).max()) < 8e-3          # one bf16 rounding of the fp32 result
+    assert rel_l2(got.float(), want) < 3e-3
