@@ -230,6 +230,42 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
     return out
 
 
+def pack_conv_w_upfold(w, c_skip0, c_skip, c_up0, c_up, out=None):
+    """Keras kernel fp32 (3,3,3,cin,cout) -> the K-unit list of conv3d_k3_upfold: 27 taps of the skip channels
+    [c_skip0, c_skip0+c_skip) and, per output phase, the 8 folded taps of the upsampled channels [c_up0, c_up0+c_up)."""
+    _chk(w, torch.float32, "w")
+    cin, cout = w.shape[-2], w.shape[-1]
+    n = int(_lib.lib().icsg3d_conv3d_upfold_wpack_elems(c_skip, c_up, cout))
+    if out is None:
+        out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    if out.numel() != n or not out.is_contiguous():
+        raise ValueError("pack_conv_w_upfold: out has the wrong size")
+    _lib.call("icsg3d_pack_conv_w_upfold", _ptr(w), cin, cout, c_skip0, c_skip, c_up0, c_up, _ptr(out), _stream())
+    return out
+
+
+def conv3d_k3_upfold(x_skip, x_low, wfold, bias, nout, *, act=ACT_NONE, alpha=LEAKY_ALPHA, out=None, post=None,
+                     tag="conv.upfold", nominal=None):
+    """Conv3D(3, same) over concatenate([x_skip, UpSampling3D(2)(x_low)]) without materialising the upsampled tensor
+    (csrc/conv3d_upfold.cu).  x_skip bf16 [B,D,H,W,cs], x_low bf16 [B,D/2,H/2,W/2,cu] (channel slices allowed)."""
+    _chk(x_skip, torch.bfloat16, "x_skip")
+    _chk(x_low, torch.bfloat16, "x_low")
+    _chk(wfold, torch.bfloat16, "wfold")
+    B, D, H, W, cs = x_skip.shape
+    cu = x_low.shape[-1]
+    if tuple(x_low.shape[:4]) != (B, D // 2, H // 2, W // 2):
+        raise ValueError("conv3d_k3_upfold: x_low must have half the extents of x_skip")
+    if out is None:
+        out = torch.empty((B, D, H, W, nout), dtype=torch.bfloat16, device=x_skip.device)
+    _chk(out, torch.bfloat16, "out")
+    ps, pt = post if post is not None else (None, None)
+    vox = 2.0 * B * D * H * W * nout
+    with _timed(("upfold", tag), vox * 27 * (nominal[0] if nominal else cs + cu), vox * (27 * cs + 8 * cu)):
+        _lib.call("icsg3d_conv3d_k3_upfold", _ptr(x_skip), _ld(x_skip), cs, _ptr(x_low), _ld(x_low), cu, _ptr(wfold), _ptr(bias),
+                  _ptr(ps), _ptr(pt), _ptr(out), _ld(out), out.shape[-1], B, D, H, W, nout, act, alpha, _stream())
+    return out
+
+
 def conv3d_k3_wgrad_workspace_bytes(B, D, cin, cout, k1=False):
     """Scratch bytes the filter-gradient kernel needs for this layer shape (split partials before the fixed-order sum)."""
     fn = _lib.lib().icsg3d_conv3d_k1_wgrad_workspace if k1 else _lib.lib().icsg3d_conv3d_k3_wgrad_workspace

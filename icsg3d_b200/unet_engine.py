@@ -8,6 +8,8 @@ backward pass the slices of the concat gradient are read in place.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -95,6 +97,20 @@ class UNetEngine:
                 if spec.get("pool"):
                     L["dp"] = z(B, D // 2, D // 2, D // 2, cout)
             self.L[n] = L
+        # Upsample-into-Conv fold for learning phase 0 (csrc/conv3d_upfold.cu): consumer block -> (skip slice, low tensor)
+        self.fold = os.environ.get("ICSG3D_UPFOLD", "1") != "0"
+        self._wfold_fresh = False
+        for L in self.L.values():
+            if "up" in L:
+                L["ylow"] = z(B, L["D"], L["D"], L["D"], L["cout"])
+        for L in self.L.values():
+            if L["src"].startswith("cat:"):
+                buf = L["src"][4:]
+                sk = next(x for x in self.L.values() if x.get("cat", (None,))[0] == buf)
+                up = next(x for x in self.L.values() if x.get("up", (None,))[0] == buf)
+                L["fold"] = (sk["y"], up["ylow"])
+                L["fold_ch"] = (sk["cat"][1], sk["cout"], up["up"][1], up["cout"])
+                L["wfold"] = None
         cmax = max(spec["cout"] for spec in UNET_PLAN)
         self.one, self.zero = torch.ones(cmax, dtype=F32, device=dev), torch.zeros(cmax, dtype=F32, device=dev)
         # heads
@@ -128,8 +144,11 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------
     def pack_weights(self, dgrad=True):
         p = self.pp.p
+        self._wfold_fresh = not dgrad and self.fold
         for n, L in self.L.items():
             ops.pack_conv_w_fprop(p[n + "/kernel"], cin_pad=L["cin_pad"], out=L["wf"])
+            if not dgrad and self.fold and "fold" in L:  # inference packing: folded taps of the upsampled channels
+                L["wfold"] = ops.pack_conv_w_upfold(p[n + "/kernel"], *L["fold_ch"], out=L["wfold"])
             if dgrad and "wd" in L:
                 ops.pack_conv_w_dgrad(p[n + "/kernel"], cin_pad=L["cin_pad"], out=L["wd"])
         ops.pack_heads_w(p["soft/kernel"], p["sig/kernel"], p["soft/bias"], p["sig/bias"], self.h_wf, self.h_wd, self.h_bias)
@@ -193,16 +212,26 @@ class UNetEngine:
             ops.pack_vae_input(self.X, None, None, self.x16)
         else:
             ops.f32_to_bf16_rows(self.X, 1, self.x16)
+        fold = self.fold and self._wfold_fresh  # folded weights are packed by pack_weights(dgrad=False) only
         for L in self.L.values():
             xin, part = self._input_of(L), None
-            if not training and "up" not in L:
+            if not training and ("up" not in L or fold):
                 # learning phase 0: BatchNorm is a fixed per-channel affine -> applied in the conv epilogue, which writes
-                # the block output (a plain tensor or its slice of a concatenation buffer) directly
+                # the block output (a plain tensor or its slice of a concatenation buffer) directly.  With the
+                # Upsample-into-Conv fold the blocks before an UpSampling3D keep their LOW-resolution output
+                # and the consumer convolves it with 8 folded taps per output phase: no upsampled tensor, no BN pass.
                 st = L["bn"]
                 if coeffs:
                     self._inference_coeffs(L)
-                ops.conv3d_k3(xin, L["wf"], p[L["n"] + "/bias"], out=L["y"], act=ACT_RELU, post=(st.scale, st.shift),
-                              ws=self.ctx.conv_ws, tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
+                dst = L["ylow"] if "up" in L else L["y"]
+                if "fold" in L and fold:
+                    skip, low = L["fold"]
+                    ops.conv3d_k3_upfold(skip, low, L["wfold"], p[L["n"] + "/bias"], L["cout"], act=ACT_RELU, out=dst,
+                                         post=(st.scale, st.shift), tag=f"unet.{L['n']}.fprop",
+                                         nominal=(L["cin_real"], L["cout"]))
+                else:
+                    ops.conv3d_k3(xin, L["wf"], p[L["n"] + "/bias"], out=dst, act=ACT_RELU, post=(st.scale, st.shift),
+                                  ws=self.ctx.conv_ws, tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
                 if L.get("pool"):
                     ops.bn_apply_fwd(L["y"], L["cout"], self.one, self.zero, ACT_NONE, POST_POOL2, y=L["p"])
                 continue

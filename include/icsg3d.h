@@ -102,6 +102,19 @@ int64_t icsg3d_conv3d_k3_workspace_bytes(int B, int D, int H, int W, int cin, in
 int icsg3d_conv3d_k3_igemm_ws(const void* x, int ldx, const void* wpack, const float* bias, void* y, int ldy,
                               int y_dtype, int n_store, int B, int D, int H, int W, int cin, int nout, int act,
                               float leaky_alpha, void* ws, int64_t ws_bytes, void* stream);
+/* Conv3D 3x3x3 "same" over concatenate([skip, UpSampling3D(2)(low)]) (unet.py:309-332: c13 / c15 / c17) without the upsampled
+ * tensor (csrc/conv3d_upfold.cu): each of the 8 output phases is a 2x2x2 convolution of the LOW-resolution
+ * tensor with summed weights (8 taps instead of 27) accumulated with the 27-tap convolution of the skip channels.
+ *   x_skip bf16 [B,D,H,W,ld_skip] (c_skip channels), x_low bf16 [B,D/2,H/2,W/2,ld_low] (c_low channels), both multiples of 64;
+ *   wfold: icsg3d_pack_conv_w_upfold of the Keras kernel fp32 [27][cin][cout] (icsg3d_conv3d_upfold_wpack_elems bf16 elements);
+ *   y bf16 [B,D,H,W,ldy] = post_scale * act(conv + bias) + post_shift (post_* optional, as icsg3d_conv3d_k3_igemm_post). */
+int64_t icsg3d_conv3d_upfold_wpack_elems(int c_skip, int c_up, int nout);
+int icsg3d_pack_conv_w_upfold(const float* w, int cin, int cout, int c_skip0, int c_skip, int c_up0, int c_up, void* wfold,
+                              void* stream);
+int icsg3d_conv3d_k3_upfold(const void* x_skip, int ld_skip, int c_skip, const void* x_low, int ld_low, int c_low,
+                            const void* wfold, const float* bias, const float* post_scale, const float* post_shift, void* y,
+                            int ldy, int n_store, int B, int D, int H, int W, int nout, int act, float leaky_alpha,
+                            void* stream);
 /* Inference form of Conv3D + activation + BatchNormalization (unet.py:277-279 in learning phase 0): the per-channel affine
  * of the moving statistics (icsg3d_bn_inference_coeffs) is applied in the conv epilogue,
  * y = post_scale[c] * act(conv + bias[c]) + post_shift[c], so the BatchNorm pass over the activation disappears. */

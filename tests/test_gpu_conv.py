@@ -228,3 +228,40 @@ def test_conv_epilogue_post_affine_matches_conv_then_affine(B, D, cin, cout, act
     err = (got.float() - want).abs()
     assert float((err / (want.abs() + 1e-2)).max()) < 8e-3          # one bf16 rounding of the fp32 result
     assert rel_l2(got.float(), want) < 3e-3
+
+
+@pytest.mark.parametrize("B,D,cs,cu,cout,exact", [(2, 8, 64, 128, 128, True), (1, 16, 64, 128, 128, True), (3, 8, 128, 256, 256, False),
+                                                  (2, 8, 256, 512, 512, False), (5, 4, 64, 64, 64, True)])
+def test_upsample_conv_fold_matches_materialised_upsample_concat_conv(B, D, cs, cu, cout, exact):
+    """csrc/conv3d_upfold.cu (Conv3D over concatenate([skip, UpSampling3D(2)(low)]) as 27 skip taps + 8 folded
+    taps per output phase) == the conv kernel on the materialised K.upsample x2 + concat tensor (unet.py:309-332)."""
+    from icsg3d_b200 import ops
+    g = torch.Generator().manual_seed(51)
+    cin = cs + cu
+    skip = torch.randn(B, D, D, D, cs, generator=g).to(torch.bfloat16).cuda()
+    low = torch.randn(B, D // 2, D // 2, D // 2, cu, generator=g).to(torch.bfloat16).cuda()
+    if exact:   # multiples of 1/8: the folded sums of up to 8 weights are exact in bf16 -> same products, same result
+        w = (torch.randint(-4, 5, (3, 3, 3, cin, cout), generator=g).float() / 8).cuda()
+    else:
+        w = (torch.randn(3, 3, 3, cin, cout, generator=g) / (27 * cin) ** 0.5).cuda()
+    b = (torch.randn(cout, generator=g) * 0.1).cuda()
+    up = low.repeat_interleave(2, 1).repeat_interleave(2, 2).repeat_interleave(2, 3)
+    cat = torch.cat([skip, up], dim=-1).contiguous()
+    want32 = ops.conv3d_k3(cat, ops.pack_conv_w_fprop(w), b, act=1, out_dtype=torch.float32)
+    wf = ops.pack_conv_w_upfold(w, 0, cs, cs, cu)
+    got = ops.conv3d_k3_upfold(skip, low, wf, b, cout, act=1)
+    # ... and reading both operands as channel slices of wider buffers, writing into a slice, with the inference affine
+    sbuf = torch.zeros(B, D, D, D, cs + 64, dtype=torch.bfloat16, device="cuda")
+    lbuf = torch.zeros(B, D // 2, D // 2, D // 2, cu + 64, dtype=torch.bfloat16, device="cuda")
+    sbuf[..., 64:] = skip
+    lbuf[..., :cu] = low
+    ybuf = torch.full((B, D, D, D, cout + 16), 3.0, dtype=torch.bfloat16, device="cuda")
+    scale, shift = torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda")
+    ops.conv3d_k3_upfold(sbuf[..., 64:], lbuf[..., :cu], wf, b, cout, act=1, out=ybuf[..., :cout], post=(scale, shift))
+    torch.cuda.synchronize()
+    tol = 1e-3 if exact else 4e-3
+    assert rel_l2(got.float(), want32) < tol + 2e-3          # bf16 rounding of the output
+    if exact:
+        assert float((got.float() - want32).abs().max()) <= float(want32.abs().max()) * 2 ** -8
+    assert rel_l2(ybuf[..., :cout].float(), torch.addcmul(shift, want32, scale)) < tol + 2e-3
+    assert torch.all(ybuf[..., cout:] == 3.0)
