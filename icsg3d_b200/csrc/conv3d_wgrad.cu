@@ -30,7 +30,7 @@ struct WgradParams {
   int kcb, ntw, nb_boxes;      // B operand: channels per box, N tile, boxes per tile
   int splits;
   int stages;
-  uint32_t a_box_bytes, b_box_bytes, a_bytes, stage_bytes;
+  uint32_t a_box_bytes, b_box_bytes, a_bytes, b_bytes, stage_bytes;  // stage = the A row-blocks of one group; the dy tile has its own 2-slot ring
   uint32_t sbo_a, lbo_a, sbo_b, lbo_b, layout_a, layout_b, idesc, tmem_cols;
   float* ws;                   // [splits][27*cin*cout]
 };
@@ -50,12 +50,17 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   __shared__ __align__(8) uint64_t full_bar[kWgradMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kWgradMaxStages];
   __shared__ __align__(8) uint64_t done_bar;
+  __shared__ __align__(8) uint64_t b_full[2], b_empty[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t ring_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* ring = smem_raw + (ring_base - smem_u32(smem_raw));
+  // [dy tile slot 0 | dy tile slot 1 | A stage ring]: the dy tile of a voxel tile is loaded ONCE and shared by all the
+  // accumulator groups of the CTA (it used to travel with every group's stage: half of the L2 -> smem traffic)
+  const uint32_t bring_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* bring = smem_raw + (bring_base - smem_u32(smem_raw));
+  const uint32_t ring_base = bring_base + 2u * p.b_bytes;
+  uint8_t* ring = bring + 2u * p.b_bytes;
 
   const int split = blockIdx.x;
   const int g_begin = blockIdx.y * p.groups_per_cta;
@@ -70,6 +75,10 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       mbar_init(&empty_bar[s], kWgradIssuers);
     }
     mbar_init(&done_bar, kWgradIssuers);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], static_cast<uint32_t>(g_end - g_begin));  // one tcgen05.commit per group that read the slot
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_slot, p.tmem_cols);
@@ -83,7 +92,8 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = split; tile < p.tiles_m; tile += p.splits) {
+    int ti = 0;
+    for (int tile = split; tile < p.tiles_m; tile += p.splits, ++ti) {
       int pix = tile * 128;
       const int w0 = pix % p.W;
       pix /= p.W;
@@ -91,16 +101,24 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       pix /= p.H;
       const int d0 = pix % p.D;
       const int n0 = pix / p.D;
+      {
+        const int bs = ti & 1;
+        mbar_wait(&b_empty[bs], (static_cast<uint32_t>(ti >> 1) & 1u) ^ 1u);
+        if (leader) {
+          mbar_expect_tx(&b_full[bs], p.b_bytes);
+          for (int j = 0; j < p.nb_boxes; ++j)
+            tma_load_5d(bring + static_cast<size_t>(bs) * p.b_bytes + static_cast<size_t>(j) * p.b_box_bytes, &tmDY, &b_full[bs],
+                        nz * p.ntw + j * p.kcb, w0, h0, d0, n0);
+        }
+      }
       for (int g = g_begin; g < g_end; ++g) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         const int blk0 = g * p.bpg;
         int nblk = p.total_blocks - blk0;
         if (nblk > p.bpg) nblk = p.bpg;
         uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
-        uint8_t* sb = sa + p.a_bytes;
         if (leader) {
-          mbar_expect_tx(&full_bar[stage],
-                         static_cast<uint32_t>(nblk) * p.a_box_bytes + static_cast<uint32_t>(p.nb_boxes) * p.b_box_bytes);
+          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(nblk) * p.a_box_bytes);
           for (int b = 0; b < nblk; ++b) {
             const int blk = blk0 + b;
             const int tap = blk / p.chunks_a;
@@ -112,9 +130,6 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tma_load_5d(sa + static_cast<size_t>(b) * p.a_box_bytes, &tmX, &full_bar[stage], ch * p.kca, w0 + kw - 1,
                         h0 + kh - 1, d0 + kd - 1, n0);
           }
-          for (int j = 0; j < p.nb_boxes; ++j)
-            tma_load_5d(sb + static_cast<size_t>(j) * p.b_box_bytes, &tmDY, &full_bar[stage], nz * p.ntw + j * p.kcb, w0,
-                        h0, d0, n0);
         }
         if (++stage == p.stages) {
           stage = 0;
@@ -129,7 +144,8 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const int g_cnt = g_end - g_begin;
     const uint32_t a_hi = umma_desc_hi(p.sbo_a, p.layout_a), b_hi = umma_desc_hi(p.sbo_b, p.layout_b);
     const uint32_t ring_lo_a = umma_desc_lo(ring_base, p.lbo_a);
-    const uint32_t ring_lo_b = umma_desc_lo(ring_base + p.a_bytes, p.lbo_b);
+    const uint32_t ring_lo_b = umma_desc_lo(bring_base, p.lbo_b);
+    const uint32_t bslot_lo = p.b_bytes >> 4;
     const uint32_t stage_lo = p.stage_bytes >> 4;
     const uint32_t ka = (2u * p.sbo_a) >> 4, kb = (2u * p.sbo_b) >> 4;
     // Every issuer walks the WHOLE stage sequence and waits on every full barrier in order (mbarrier parity waits are
@@ -138,18 +154,21 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     int ti = 0, stage = 0;
     uint32_t phase = 0;
     for (int tile = split; tile < p.tiles_m; tile += p.splits, ++ti) {
+      const int bs = ti & 1;
+      mbar_wait(&b_full[bs], static_cast<uint32_t>(ti >> 1) & 1u);
       for (int gl = 0; gl < g_cnt; ++gl) {
         mbar_wait(&full_bar[stage], phase);
         if (gl % kWgradIssuers == issuer) {
           tc_fence_after();
           const uint32_t a_lo = ring_lo_a + static_cast<uint32_t>(stage) * stage_lo;
-          const uint32_t b_lo = ring_lo_b + static_cast<uint32_t>(stage) * stage_lo;
+          const uint32_t b_lo = ring_lo_b + static_cast<uint32_t>(bs) * bslot_lo;
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(gl * p.ntw);
           if (leader) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)  // 8 x 16 voxels
               umma_bf16_lohi(d_tmem, a_lo + k * ka, a_hi, b_lo + k * kb, b_hi, p.idesc, (ti | k) != 0 ? 1u : 0u);
             umma_commit(&empty_bar[stage]);
+            umma_commit(&b_empty[bs]);
           }
         } else if (leader) {
           mbar_arrive(&empty_bar[stage]);
@@ -196,37 +215,47 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   }
 }
 
-// dw[i] = sum over splits of ws[s][i], in a FIXED order (deterministic): 16 interleaved split lanes per element (each with
-// two independent accumulators) keep the short strided columns in flight — with ~148 splits of a few-KB filter gradient the
-// pass is latency-, not bandwidth-bound — then the 16 lane sums are added in a fixed tree.
-static constexpr int kWgRedLanes = 16, kWgRedElems = 16;
+// dw[i] = sum over splits of ws[s][i], in a FIXED order (deterministic): LANES interleaved split lanes per element (each
+// with two independent accumulators), then the lane sums are added in a fixed tree.  Two shapes of the same kernel: many
+// splits of a few-KB filter gradient (the VAE step: ~148 splits, latency bound) take 16 lanes x 16 elements so that the
+// short strided columns stay in flight; few splits of a multi-MB gradient (the U-Net's 256..512-channel layers: 1..13
+// splits of up to 28 MB, bandwidth bound) take 4 lanes x 64 elements so that the lanes are not idle.
+template <int LANES, int ELEMS>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n,
                                                            int splits) {
+  static_assert(LANES * ELEMS == 256, "one thread per (lane, element)");
   pdl_prologue();
-  __shared__ float red[kWgRedLanes][kWgRedElems + 1];
-  const int e = threadIdx.x & (kWgRedElems - 1), sl = threadIdx.x / kWgRedElems;
-  const long long i = static_cast<long long>(blockIdx.x) * kWgRedElems + e;
+  __shared__ float red[LANES][ELEMS + 1];
+  const int e = threadIdx.x & (ELEMS - 1), sl = threadIdx.x / ELEMS;
+  const long long i = static_cast<long long>(blockIdx.x) * ELEMS + e;
   float a0 = 0.f, a1 = 0.f;
   if (i < n) {
     int s = sl;
-    for (; s + kWgRedLanes < splits; s += 2 * kWgRedLanes) {
+    for (; s + LANES < splits; s += 2 * LANES) {
       a0 += ws[static_cast<long long>(s) * n + i];
-      a1 += ws[static_cast<long long>(s + kWgRedLanes) * n + i];
+      a1 += ws[static_cast<long long>(s + LANES) * n + i];
     }
     if (s < splits) a0 += ws[static_cast<long long>(s) * n + i];
   }
   red[sl][e] = a0 + a1;
   __syncthreads();
   if (sl == 0 && i < n) {
-    float t[kWgRedLanes];
+    float t[LANES];
 #pragma unroll
-    for (int k = 0; k < kWgRedLanes; ++k) t[k] = red[k][e];
+    for (int k = 0; k < LANES; ++k) t[k] = red[k][e];
 #pragma unroll
-    for (int w = kWgRedLanes / 2; w > 0; w >>= 1)
+    for (int w = LANES / 2; w > 0; w >>= 1)
 #pragma unroll
       for (int k = 0; k < w; ++k) t[k] += t[k + w];
     dw[i] = t[0];
   }
+}
+
+// The shape is a function of the split count only, and the split count of the layer shape only: a layer is always
+// reduced in the same order (1 rank == N ranks, graph replay == eager).
+void launch_wgrad_reduce(const float* ws, float* dw, long long n, int splits, cudaStream_t st) {
+  if (splits >= 32) launch_k(wgrad_reduce_kernel<16, 16>, static_cast<int>((n + 15) / 16), 256, 0, st, ws, dw, n, splits);
+  else launch_k(wgrad_reduce_kernel<4, 64>, static_cast<int>((n + 63) / 64), 256, 0, st, ws, dw, n, splits);
 }
 
 int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H, int W, int c_extent, int kc);
@@ -262,8 +291,9 @@ static int wgrad_plan(int ntaps, int B, int D, int H, int W, int cin, int cout, 
   p->a_box_bytes = 128u * p->kca * 2u;
   p->b_box_bytes = 128u * p->kcb * 2u;
   p->a_bytes = static_cast<uint32_t>(p->bpg) * p->a_box_bytes;  // 32 KB
-  p->stage_bytes = p->a_bytes + static_cast<uint32_t>(p->nb_boxes) * p->b_box_bytes;
-  int stages = static_cast<int>((200u * 1024u) / p->stage_bytes);
+  p->b_bytes = static_cast<uint32_t>(p->nb_boxes) * p->b_box_bytes;
+  p->stage_bytes = p->a_bytes;
+  int stages = static_cast<int>((200u * 1024u - 2u * p->b_bytes) / p->stage_bytes);
   if (stages > kWgradMaxStages) stages = kWgradMaxStages;
   p->stages = stages;
   p->sbo_a = 8u * p->kca * 2u;
@@ -339,8 +369,7 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
     const int rc = wgrad_stream_run(x, ldx, dy, ldy, B, D, H, W, cin, cout, sms, static_cast<float*>(workspace), workspace_bytes,
                                     &splits, static_cast<cudaStream_t>(stream));
     if (rc == ICSG3D_OK) {
-      launch_k(wgrad_reduce_kernel, static_cast<int>((n_dw + kWgRedElems - 1) / kWgRedElems), 256, 0, static_cast<cudaStream_t>(stream), 
-          static_cast<const float*>(workspace), dw, n_dw, splits);
+      launch_wgrad_reduce(static_cast<const float*>(workspace), dw, n_dw, splits, static_cast<cudaStream_t>(stream));
       ICSG_CHECK_LAUNCH();
       return ICSG3D_OK;
     }
@@ -365,11 +394,11 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
     ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     configured = true;
   }
-  const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
+  const size_t smem = 2u * p.b_bytes + static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
   dim3 grid(p.splits, (p.total_groups + p.groups_per_cta - 1) / p.groups_per_cta, cout / p.ntw);
   launch_k(conv3d_k3_wgrad_kernel, grid, kWgradThreads, smem, static_cast<cudaStream_t>(stream), tmX, tmDY, p);
   ICSG_CHECK_LAUNCH();
-  launch_k(wgrad_reduce_kernel, static_cast<int>((n_dw + kWgRedElems - 1) / kWgRedElems), 256, 0, static_cast<cudaStream_t>(stream), p.ws, dw, n_dw, p.splits);
+  launch_wgrad_reduce(p.ws, dw, n_dw, p.splits, static_cast<cudaStream_t>(stream));
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
