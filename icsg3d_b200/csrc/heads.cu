@@ -154,13 +154,22 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_loss_kernel(const float* 
 }
 
 // out = [loss, soft_loss, sig_loss, f1_m, wr_m] (the order Keras reports; unet.py:249-259), raw[6] = the term sums.
-__global__ void heads_loss_finalize_kernel(const double* __restrict__ partials, int nparts, double count,
-                                           float* __restrict__ out, double* __restrict__ raw) {
+__global__ void __launch_bounds__(256) heads_loss_finalize_kernel(const double* __restrict__ partials, int nparts, double count,
+                                                                  float* __restrict__ out, double* __restrict__ raw) {
   pdl_prologue();
+  // fixed-order two-level sum of the per-block partials (deterministic): 32 strided lanes per term, then lane order
+  __shared__ double lanes[32][8];
   __shared__ double term[kHeadsTerms];
+  const int tm = threadIdx.x & 7, ln = threadIdx.x >> 3;
+  if (tm < kHeadsTerms) {
+    double t = 0.0;
+    for (int p = ln; p < nparts; p += 32) t += partials[static_cast<size_t>(p) * kHeadsTerms + tm];
+    lanes[ln][tm] = t;
+  }
+  __syncthreads();
   if (threadIdx.x < kHeadsTerms) {
     double t = 0.0;
-    for (int p = 0; p < nparts; ++p) t += partials[static_cast<size_t>(p) * kHeadsTerms + threadIdx.x];
+    for (int l = 0; l < 32; ++l) t += lanes[l][threadIdx.x];
     term[threadIdx.x] = t;
     if (raw) raw[threadIdx.x] = t;
   }
@@ -242,7 +251,7 @@ extern "C" int icsg3d_heads_loss_f32grad(const float* logits, int ld, int c1, co
 extern "C" int icsg3d_heads_loss_finalize(const double* partials, int nparts, double count, float* out, double* raw,
                                           void* stream) {
   ICSG_REQUIRE(partials && out && count > 0, "heads_loss_finalize: bad arguments");
-  launch_k(heads_loss_finalize_kernel, 1, 32, 0, static_cast<cudaStream_t>(stream), partials, nparts, count, out, raw);
+  launch_k(heads_loss_finalize_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), partials, nparts, count, out, raw);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

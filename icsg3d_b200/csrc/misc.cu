@@ -348,20 +348,39 @@ __global__ void adam_tick_kernel(double* __restrict__ state, double lr, double b
   state[0] = t;
   state[1] = lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t));
 }
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float eps, float lr_t,
+                                         float grad_scale) {
+  const float gi = g * grad_scale;
+  const float mi = b1 * m + (1.f - b1) * gi;
+  const float vi = b2 * v + (1.f - b2) * gi * gi;
+  m = mi;
+  v = vi;
+  p -= lr_t * mi / (sqrtf(vi) + eps);
+}
 __global__ void adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                    float* __restrict__ v, const double* __restrict__ state, float b1, float b2, float eps,
-                                   float grad_scale, long long n) {
+                                   float grad_scale, long long n, int vec4) {
   pdl_prologue();
   const float lr_t = static_cast<float>(state[1]);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * grad_scale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long done = 0;
+  if (vec4) {  // all four arrays 16-byte aligned: 16-byte accesses for the bulk (same per-element arithmetic)
+    const long long n4 = n >> 2;
+    for (long long i = t0; i < n4; i += stride) {
+      float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+      const float4 gg = reinterpret_cast<const float4*>(g)[i];
+      adam_one(pp.x, gg.x, mm.x, vv.x, b1, b2, eps, lr_t, grad_scale);
+      adam_one(pp.y, gg.y, mm.y, vv.y, b1, b2, eps, lr_t, grad_scale);
+      adam_one(pp.z, gg.z, mm.z, vv.z, b1, b2, eps, lr_t, grad_scale);
+      adam_one(pp.w, gg.w, mm.w, vv.w, b1, b2, eps, lr_t, grad_scale);
+      reinterpret_cast<float4*>(m)[i] = mm;
+      reinterpret_cast<float4*>(v)[i] = vv;
+      reinterpret_cast<float4*>(p)[i] = pp;
+    }
+    done = n4 << 2;
   }
+  for (long long i = done + t0; i < n; i += stride) adam_one(p[i], g[i], m[i], v[i], b1, b2, eps, lr_t, grad_scale);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -574,8 +593,10 @@ extern "C" int icsg3d_adam_keras_step(float* p, const float* g, float* m, float*
   ICSG_REQUIRE(p && g && m && v && state, "adam_keras_step: null pointer");
   launch_k(adam_tick_kernel, 1, 1, 0, ST, state, lr, beta1, beta2);
   ICSG_CHECK_LAUNCH();
-  launch_k(adam_update_kernel, grid1d(n), 256, 0, ST, p, g, m, v, state, static_cast<float>(beta1), static_cast<float>(beta2),
-                                               static_cast<float>(eps), grad_scale, n);
+  const int vec4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  launch_k(adam_update_kernel, grid1d(vec4 ? (n + 3) / 4 : n), 256, 0, ST, p, g, m, v, state, static_cast<float>(beta1),
+           static_cast<float>(beta2), static_cast<float>(eps), grad_scale, n, vec4);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

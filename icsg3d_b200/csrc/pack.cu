@@ -44,6 +44,47 @@ __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// Fast forms for the wide layers (no padding, no fold): the U-Net repacks 30 M weights per train step.
+// fprop is a per-tap transpose [ci][co] -> [co][ci]: 64 x 32 tile through shared memory, 128-byte rows on both sides.
+__global__ void __launch_bounds__(256) pack_w_fprop_tiled_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                                 int cin, int cout) {
+  pdl_prologue();
+  __shared__ float tile[64][33];
+  const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 32, tap = blockIdx.z;
+  const int lane = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+  const float* src = w + (static_cast<long long>(tap) * cin + ci0) * cout + co0 + lane;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tile[r0 + 8 * k][lane] = src[static_cast<long long>(r0 + 8 * k) * cout];
+  __syncthreads();
+  uint32_t* dst = reinterpret_cast<uint32_t*>(wp + (static_cast<long long>(tap) * cout + co0) * cin + ci0) + lane;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = r0 + 8 * k;
+    dst[static_cast<long long>(c) * (cin >> 1)] = pack_bf16x2(tile[2 * lane][c], tile[2 * lane + 1][c]);
+  }
+}
+
+// dgrad keeps the orientation (taps mirrored): 8 output channels per thread, 16-byte stores
+__global__ void __launch_bounds__(256) pack_w_dgrad_vec_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                               int cin, int cout) {
+  pdl_prologue();
+  const int c8 = cout >> 3;
+  const long long per_tap = static_cast<long long>(cin) * c8, total = 27 * per_tap;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(idx / per_tap);
+    const long long r = idx - tap * per_tap;  // (ci, co8) of this tap
+    const float4* src = reinterpret_cast<const float4*>(w + (static_cast<long long>(26 - tap) * per_tap + r) * 8);
+    const float4 a = src[0], b = src[1];
+    uint4 q;
+    q.x = pack_bf16x2(a.x, a.y);
+    q.y = pack_bf16x2(a.z, a.w);
+    q.z = pack_bf16x2(b.x, b.y);
+    q.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(wp)[idx] = q;
+  }
+}
+
 __global__ void unpack_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int cin, int cout, int cin_pad,
                                  int cout_pad, int cin_lead, int fold, int fold_c) {
   pdl_prologue();
@@ -154,6 +195,13 @@ extern "C" int icsg3d_pack_conv_w_fprop(const float* w, void* wpack, int cin, in
   } else {
     ICSG_REQUIRE(cin_pad >= cin, "pack_conv_w_fprop: cin_pad < cin");
   }
+  if (fold <= 1 && cin_pad == cin && cout_pad == cout && cin % 64 == 0 && cout % 32 == 0 && cout / 32 <= 65535 &&
+      (reinterpret_cast<uintptr_t>(wpack) & 3) == 0) {
+    launch_k(pack_w_fprop_tiled_kernel, dim3(cin / 64, cout / 32, 27), 256, 0, static_cast<cudaStream_t>(stream), w,
+             static_cast<__nv_bfloat16*>(wpack), cin, cout);
+    ICSG_CHECK_LAUNCH();
+    return ICSG3D_OK;
+  }
   launch_k(pack_w_fprop_kernel, grid_for(27ll * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream), 
       w, static_cast<__nv_bfloat16*>(wpack), cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c);
   ICSG_CHECK_LAUNCH();
@@ -164,6 +212,13 @@ extern "C" int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, in
                                         void* stream) {
   ICSG_REQUIRE(w && wpack, "pack_conv_w_dgrad: null pointer");
   ICSG_REQUIRE(cin_pad >= cin && cout_pad >= cout, "pack_conv_w_dgrad: bad padding");
+  if (cin_pad == cin && cout_pad == cout && cout % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(wpack) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+    launch_k(pack_w_dgrad_vec_kernel, grid_for(27ll * cin * (cout / 8)), 256, 0, static_cast<cudaStream_t>(stream), w,
+             static_cast<__nv_bfloat16*>(wpack), cin, cout);
+    ICSG_CHECK_LAUNCH();
+    return ICSG3D_OK;
+  }
   launch_k(pack_w_dgrad_kernel, grid_for(27ll * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream), 
       w, static_cast<__nv_bfloat16*>(wpack), cin, cout, cin_pad, cout_pad);
   ICSG_CHECK_LAUNCH();
