@@ -251,11 +251,35 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
-// The shape is a function of the split count only, and the split count of the layer shape only: a layer is always
-// reduced in the same order (1 rank == N ranks, graph replay == eager).
+// Few splits of a large gradient (the U-Net's 256..768-channel layers: up to 10.6 M elements, 2..13 splits): a plain
+// streaming sum, one float4 per thread and grid-stride, splits added in index order.
+__global__ void __launch_bounds__(256) wgrad_reduce_stream_kernel(const float4* __restrict__ ws, float4* __restrict__ dw,
+                                                                  long long n4, int splits) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 a = ws[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = ws[static_cast<long long>(s) * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dw[i] = a;
+  }
+}
+
+// The shape is a function of the split count (and the alignment of the destination) only, and the split count of the layer
+// shape only: a layer is always reduced in the same order (1 rank == N ranks, graph replay == eager).
 void launch_wgrad_reduce(const float* ws, float* dw, long long n, int splits, cudaStream_t st) {
-  if (splits >= 32) launch_k(wgrad_reduce_kernel<16, 16>, static_cast<int>((n + 15) / 16), 256, 0, st, ws, dw, n, splits);
-  else launch_k(wgrad_reduce_kernel<4, 64>, static_cast<int>((n + 63) / 64), 256, 0, st, ws, dw, n, splits);
+  if (splits >= 32) {
+    launch_k(wgrad_reduce_kernel<16, 16>, static_cast<int>((n + 15) / 16), 256, 0, st, ws, dw, n, splits);
+  } else if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0) {
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    launch_k(wgrad_reduce_stream_kernel, static_cast<int>(blocks), 256, 0, st, reinterpret_cast<const float4*>(ws),
+             reinterpret_cast<float4*>(dw), n / 4, splits);
+  } else {
+    launch_k(wgrad_reduce_kernel<4, 64>, static_cast<int>((n + 63) / 64), 256, 0, st, ws, dw, n, splits);
+  }
 }
 
 int encode_act_map(CUtensorMap* map, const void* x, int ldx, int B, int D, int H, int W, int c_extent, int kc);
@@ -381,7 +405,9 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
   const int64_t need = static_cast<int64_t>(p.splits) * ntaps * cin * cout * 4;
   ICSG_REQUIRE(workspace_bytes >= need, "conv3d_k3_wgrad: workspace too small (%lld < %lld)",
                static_cast<long long>(workspace_bytes), static_cast<long long>(need));
-  p.ws = static_cast<float*>(workspace);
+  // a single split IS the gradient: written in place (16-byte stores), no reduction pass
+  const bool direct = p.splits == 1 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0;
+  p.ws = direct ? dw : static_cast<float*>(workspace);
 
   CUtensorMap tmX, tmDY;
   int rc = encode_act_map(&tmX, x, ldx, B, D, H, W, cin, p.kca);
@@ -398,7 +424,7 @@ static int wgrad_impl(int ntaps, const void* x, int ldx, const void* dy, int ldy
   dim3 grid(p.splits, (p.total_groups + p.groups_per_cta - 1) / p.groups_per_cta, cout / p.ntw);
   launch_k(conv3d_k3_wgrad_kernel, grid, kWgradThreads, smem, static_cast<cudaStream_t>(stream), tmX, tmDY, p);
   ICSG_CHECK_LAUNCH();
-  launch_wgrad_reduce(p.ws, dw, n_dw, p.splits, static_cast<cudaStream_t>(stream));
+  if (!direct) launch_wgrad_reduce(p.ws, dw, n_dw, p.splits, static_cast<cudaStream_t>(stream));
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -179,6 +179,70 @@ extern "C" int icsg3d_probe_mma_rate(int64_t* out, int m, int n, int reps, int n
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Probe 2b: the same for MN-MAJOR operands as the filter-gradient kernels use them (A = [voxel][64 channels] boxes, two
+// boxes side by side along M; B = [voxel][64 channels] boxes along N; K = voxels, 16 per MMA = two 8-row groups):
+// cycles per MMA when consecutive MMAs walk the 8 k-steps of a 128-voxel tile.  mn = 0 runs the K-major form of probe 2
+// with the same shared-memory footprint for comparison.
+// ------------------------------------------------------------------------------------------------------
+namespace icsg3d {
+__global__ void __launch_bounds__(128, 1) probe_mma_rate_mn_kernel(long long* out, int n, int reps, int nacc, int mn) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0u;
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t box = 128u * 128u;  // [128 voxels][64 channels] bf16
+    const uint32_t idesc = umma_idesc_bf16(n, mn, mn);
+    const uint32_t hi = umma_desc_hi(1024u, umma_layout_for_swizzle(128));
+    const uint32_t a_lo = umma_desc_lo(base, mn ? box : 16u), b_lo = umma_desc_lo(base + 32u * 1024u, mn ? box : 16u);
+    const uint32_t kstep = mn ? (2u * 1024u) >> 4 : 2u;  // 16 voxels = two 8-row groups | 32 bytes along the 128-byte row
+    const uint32_t mask = static_cast<uint32_t>(nacc - 1);
+    const long long t0 = clock64();
+#pragma unroll 8
+    for (int r = 0; r < reps; ++r) {
+      const uint32_t k = static_cast<uint32_t>(r) & (mn ? 7u : 3u);
+      umma_bf16_lohi(tmem + (static_cast<uint32_t>(r >> 3) & mask) * static_cast<uint32_t>(n), a_lo + k * kstep, hi, b_lo + k * kstep, hi,
+                     idesc, 1u);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[0] = reps;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+}  // namespace icsg3d
+
+extern "C" int icsg3d_probe_mma_rate_mn(int64_t* out, int n, int reps, int nacc, int mn, void* stream) {
+  ICSG_REQUIRE(out && n % 16 == 0 && n >= 16 && n <= 256 && nacc >= 1 && nacc * n <= 512 && (mn == 0 || mn == 1),
+               "probe_mma_rate_mn: bad arguments");
+  ICSG_CUDA(cudaFuncSetAttribute(icsg3d::probe_mma_rate_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  icsg3d::probe_mma_rate_mn_kernel<<<1, 128, 98 * 1024, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<long long*>(out), n, reps,
+                                                                                            nacc, mn);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Probe 3: the halo kernel's exact MMA issue pattern (tap-outer, G accumulators, KSTEPS k-steps, per-tap row
 // shifts into a resident A block, resident B tiles) with NO TMA, NO barriers and NO epilogue: isolates the
 // tensor-pipe cost of the pattern itself.  out[0] = cycles for `items` items, out[1] = MMAs issued.

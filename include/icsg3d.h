@@ -488,6 +488,7 @@ int icsg3d_probe_mn_fold(const void* x, const void* y, float* out, int rows, int
  * cycles, out[1] = cycles until the commit barrier fires. */
 int icsg3d_probe_mma_rate(int64_t* out, int m, int n, int reps, int nacc, int swizzle_bytes, int a_step, int b_step,
                           void* stream);
+int icsg3d_probe_mma_rate_mn(int64_t* out, int n, int reps, int nacc, int mn, void* stream);
 
 /* Hardware probe: the halo kernel's MMA issue pattern without TMA/barriers/epilogue (see csrc/probe.cu). */
 int icsg3d_probe_halo_pattern(int64_t* out, int G, int nt, int plane_rows, int WP, int row_bytes, int ksteps, int items,
