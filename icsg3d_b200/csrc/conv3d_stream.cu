@@ -62,7 +62,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NC]) 
 
 // One drained accumulator item (32 lanes x NC columns, already in registers): scale + bias + activation, store,
 // BatchNorm running sums.
-template <int NC>
+template <int NC, bool kPost>
 __device__ __forceinline__ void stream_epi_math(const ConvStreamParams& p, const uint32_t (&v)[NC], int c0, bool ok, long long pixel,
                                                 const float* s_bias, float slope, float (&sacc)[32], float (&qacc)[32],
                                                 const float* s_post) {
@@ -85,7 +85,7 @@ __device__ __forceinline__ void stream_epi_math(const ConvStreamParams& p, const
       fv[i + 1] = fmaxf(x1, slope * x1);
       fv[i + 2] = fmaxf(x2, slope * x2);
       fv[i + 3] = fmaxf(x3, slope * x3);
-      if (s_post != nullptr) {  // warp-uniform: inference BatchNorm affine after the activation
+      if constexpr (kPost) {  // inference BatchNorm affine after the activation
         const float4 s4 = *reinterpret_cast<const float4*>(&s_post[c0 + 8 * j + i]);
         const float4 t4 = *reinterpret_cast<const float4*>(&s_post[64 + c0 + 8 * j + i]);
         fv[i] = fmaf(fv[i], s4.x, t4.x);
@@ -138,7 +138,7 @@ __device__ __forceinline__ void stream_epi_math(const ConvStreamParams& p, const
   }
 }
 
-template <int KSTEPS>
+template <int KSTEPS, bool kPost>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const ConvStreamParams p) {
@@ -191,7 +191,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   const int n_off = static_cast<int>(blockIdx.y) * p.C;  // N split: this CTA's slice of the output channels
   if (threadIdx.x < 64) s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.C) ? p.bias[n_off + threadIdx.x] : 0.f;
-  if (threadIdx.x < 64 && p.post_scale != nullptr) {
+  if (kPost && threadIdx.x < 64) {
     s_post[threadIdx.x] = threadIdx.x < p.C ? p.post_scale[n_off + threadIdx.x] : 1.f;
     s_post[64 + threadIdx.x] = threadIdx.x < p.C ? p.post_shift[n_off + threadIdx.x] : 0.f;
   }
@@ -426,7 +426,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             long long pixel;
             coords(t, ok, pixel);
             if (p.exp_flags & 4) ok = false;
-            stream_epi_math<32>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc, p.post_scale != nullptr ? s_post : nullptr);
+            stream_epi_math<32, kPost>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc, s_post);
             t = tn;
           }
         } else {
@@ -443,7 +443,7 @@ conv3d_k3_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             bool ok;
             long long pixel;
             coords(t, ok, pixel);
-            stream_epi_math<16>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc, p.post_scale != nullptr ? s_post : nullptr);
+            stream_epi_math<16, kPost>(pe, cur, c0, ok, pixel, s_bias, slope, sacc, qacc, s_post);
             t = tn;
           }
         }
@@ -621,16 +621,27 @@ int launch_conv_stream(const void* x, int ldx, const void* wpack, const float* b
   p.post_shift = post_shift;
   static bool configured = false;
   if (!configured) {
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_stream_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     configured = true;
   }
   const size_t smem = ((p.w_bytes + 1023u) & ~1023u) + static_cast<size_t>(p.stages) * p.a_stage_bytes + 1024;
   const dim3 grid(conv_stream_grid(p), p.tiles_n);
-  if (p.kc == 16) launch_k(conv3d_k3_stream_kernel<1>, grid, kStreamThreads, smem, st, tmA, tmB, p);
-  else if (p.kc == 32) launch_k(conv3d_k3_stream_kernel<2>, grid, kStreamThreads, smem, st, tmA, tmB, p);
-  else launch_k(conv3d_k3_stream_kernel<4>, grid, kStreamThreads, smem, st, tmA, tmB, p);
+  // the inference form (BatchNorm affine after the activation) is its own instantiation: the training kernel's epilogue
+  // is latency bound and carries nothing it does not need
+  if (post_scale != nullptr) {
+    if (p.kc == 16) launch_k(conv3d_k3_stream_kernel<1, true>, grid, kStreamThreads, smem, st, tmA, tmB, p);
+    else if (p.kc == 32) launch_k(conv3d_k3_stream_kernel<2, true>, grid, kStreamThreads, smem, st, tmA, tmB, p);
+    else launch_k(conv3d_k3_stream_kernel<4, true>, grid, kStreamThreads, smem, st, tmA, tmB, p);
+  } else {
+    if (p.kc == 16) launch_k(conv3d_k3_stream_kernel<1, false>, grid, kStreamThreads, smem, st, tmA, tmB, p);
+    else if (p.kc == 32) launch_k(conv3d_k3_stream_kernel<2, false>, grid, kStreamThreads, smem, st, tmA, tmB, p);
+    else launch_k(conv3d_k3_stream_kernel<4, false>, grid, kStreamThreads, smem, st, tmA, tmB, p);
+  }
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }
