@@ -736,6 +736,28 @@ def heads_loss(logits, c1, species, class_w, inv_count, partials, argmax_out=Non
               _ptr(partials), partials.shape[0], _stream())
 
 
+def heads_loss_fused_nparts(M):
+    return _lib.lib().icsg3d_heads_loss_fused_nparts(ctypes.c_int64(M))
+
+
+def heads_loss_fused(x, wpack, bias, c1, species, class_w, inv_count, partials, argmax_out=None, sig_prob=None, dlogits=None):
+    """Head GEMM + both losses + metric counts + bf16 d(loss)/d(logits) in one kernel (csrc/heads_fused.cu); `partials`
+    fp64 [>= heads_loss_fused_nparts(M), 6]: only the first nparts rows are written — pass exactly that view to
+    heads_loss_finalize."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(wpack, torch.bfloat16, "wpack")
+    if dlogits is not None:
+        _chk(dlogits, torch.bfloat16, "dlogits")
+    nout, cin = wpack.shape[-2], wpack.shape[-1]
+    M = x.numel() // x.shape[-1]
+    n = heads_loss_fused_nparts(M)
+    if partials.shape[0] != n or not partials.is_contiguous():
+        raise ValueError(f"heads_loss_fused: partials must be a contiguous [{n}, 6] fp64 tensor")
+    _lib.call("icsg3d_heads_loss_fused", _ptr(x), x.stride(-2), _ptr(wpack), _ptr(bias), ctypes.c_int64(M), cin, nout, c1,
+              _ptr(species), _ptr(class_w), inv_count, _ptr(partials), _ptr(argmax_out), _ptr(sig_prob), _ptr(dlogits),
+              dlogits.shape[-1] if dlogits is not None else 0, _stream())
+
+
 def heads_loss_finalize(partials, count, out, raw=None):
     _lib.call("icsg3d_heads_loss_finalize", _ptr(partials), partials.shape[0], ctypes.c_double(count), _ptr(out), _ptr(raw),
               _stream())

@@ -123,6 +123,9 @@ class UNetEngine:
         self.sigp = z(B, d, d, d, dt=F32)
         self.h_nparts = ops.heads_loss_nparts(B * d ** 3)
         self.h_partials = torch.zeros(self.h_nparts, 6, dtype=F64, device=dev)
+        self.h_partials_fused = torch.zeros(ops.heads_loss_fused_nparts(B * d ** 3), 6, dtype=F64, device=dev)
+        self.fuse_heads = os.environ.get("ICSG3D_FUSE_HEADS", "1") != "0"
+        self.keep_logits = False  # diagnostics / parity tests: also materialise the fp32 head logits the fused kernel skips
         self.h_raw = torch.zeros(6, dtype=F64, device=dev)
         self.metrics = torch.zeros(5, dtype=F32, device=dev)
         cw = torch.full((classes,), float(classes)) if class_weight is None else torch.as_tensor(class_weight, dtype=F32)
@@ -243,6 +246,16 @@ class UNetEngine:
                           ws=self.ctx.conv_ws, tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
             self._bn_fwd(L, training, part=part, coeffs=coeffs)
         if not heads:
+            return
+        M = self.B * self.d ** 3
+        if losses and want_probs is None and self.fuse_heads:
+            # head GEMM + losses + metric counts + bf16 gradient in one kernel: the fp32 logits never exist in HBM
+            ops.heads_loss_fused(self.L["c18"]["y"], self.h_wf, self.h_bias, self.classes, self.species, self.class_w,
+                                 1.0 / (M * self.world), self.h_partials_fused, argmax_out=self.argmax, sig_prob=self.sigp,
+                                 dlogits=self.dlogits if with_grad else None)
+            ops.heads_loss_finalize(self.h_partials_fused, float(M), self.metrics, self.h_raw)
+            if self.keep_logits:
+                ops.conv3d_k3(self.L["c18"]["y"], self.h_wf, self.h_bias, out=self.logits)
             return
         ops.conv3d_k3(self.L["c18"]["y"], self.h_wf, self.h_bias, out=self.logits, tag="unet.heads.fprop",
                       nominal=(128, self.classes + 1))

@@ -454,6 +454,15 @@ int icsg3d_heads_predict(const float* logits, int ld, int c1, int64_t M, float t
 int icsg3d_heads_predict_fused(const void* x, int ldx, const void* wpack, const float* bias, int64_t M, int cin, int nout,
                                int c1, int op_f16, float out_scale, float threshold, uint8_t* argmax_out,
                                uint8_t* mask_out, float* sig_prob, void* stream);
+/* Training form of the same kernel (unet.py:196-221, 252-259 in one pass over the features): head GEMM, weighted
+ * categorical cross-entropy on the clipped soft-max + binary cross-entropy on the sigmoid head, the f1 / weighted-recall
+ * counts (unet.py:159-193) and d(loss)/d(logits) as bf16 [M][ldd] — what icsg3d_conv3d_k1_igemm + icsg3d_heads_loss
+ * compute through 384 B/voxel of fp32 logits in HBM.  partials: fp64 [icsg3d_heads_loss_fused_nparts(M)][6] for
+ * icsg3d_heads_loss_finalize.  species uint8 [M] (binary target = species != 0), class_w fp32 [c1] or null. */
+int icsg3d_heads_loss_fused_nparts(int64_t M);
+int icsg3d_heads_loss_fused(const void* x, int ldx, const void* wpack, const float* bias, int64_t M, int cin, int nout, int c1,
+                            const uint8_t* species, const float* class_w, float inv_count, double* partials,
+                            uint8_t* argmax_out, float* sig_prob, void* dlogits, int ldd, void* stream);
 int icsg3d_rotate90_batch(const void* in, void* out, int B, int d, int voxel_bytes, const int* xforms, void* stream);
 int icsg3d_metric_counts(const float* y_true, const float* y_pred, int64_t n, int C, double* counts, void* stream);
 

@@ -91,6 +91,7 @@ def _unet_case(B, d, tag):
     taps = {}
     out, soft, sig = nets.unet_loss(pp, M, S.long(), training=True, weight=95.0, taps=taps)
     grads = dict(zip(names, torch.autograd.grad(out[0], [leaves[k] for k in names])))
+    eng.keep_logits = True   # the fused head kernel keeps the logits in tensor memory; materialise them for the taps
     eng.train_step()
     torch.cuda.synchronize()
     got = eng.metrics_host()

@@ -177,6 +177,49 @@ def test_fused_heads_predict_on_a_channel_slice_with_row_stride():
     ops.heads_predict_fused(x, wf, bias, 95, 0.8, argmax=a1, mask=m1)
     assert torch.equal(a0, a1) and torch.equal(m0, m1)
 
+@pytest.mark.parametrize("shape,classes", [((2, 16, 16, 16), 95), ((3, 4, 4, 4), 95), ((1, 8, 8, 8), 20)])
+def test_fused_heads_loss_equals_conv_then_heads_loss(shape, classes):
+    """csrc/heads_fused.cu, training form == 1x1x1 head conv (fp32 logits) + heads_loss: losses, f1 / weighted-recall
+    counts, arg-max, sigmoid probability and the bf16 gradient w.r.t. the logits."""
+    from icsg3d_b200 import ops
+    B, D, H, W = shape
+    cin, M = 128, B * D * H * W
+    g = torch.Generator(device="cuda").manual_seed(13)
+    nout = (classes + 1 + 15) // 16 * 16
+    x = (torch.randn(B, D, H, W, cin, device="cuda", generator=g) * 2).to(torch.bfloat16)
+    w_soft = torch.randn(1, 1, 1, cin, classes, device="cuda", generator=g) / cin ** 0.5 * 2
+    w_sig = torch.randn(1, 1, 1, cin, 1, device="cuda", generator=g) / cin ** 0.5
+    b_soft = torch.randn(classes, device="cuda", generator=g) * 0.1
+    b_sig = torch.randn(1, device="cuda", generator=g)
+    wf = torch.zeros(1, nout, cin, dtype=torch.bfloat16, device="cuda")
+    wd = torch.zeros(1, cin, nout, dtype=torch.bfloat16, device="cuda")
+    bias = torch.zeros(nout, dtype=torch.float32, device="cuda")
+    ops.pack_heads_w(w_soft, w_sig, b_soft, b_sig, wf, wd, bias)
+    species = torch.randint(0, classes, (M,), device="cuda", generator=g).to(torch.uint8)
+    species[::3] = 0
+    cw = torch.rand(classes, device="cuda", generator=g) * 3 + 0.5
+    logits = torch.empty(B, D, H, W, nout, dtype=torch.float32, device="cuda")
+    ops.conv3d_k3(x, wf, bias, out=logits)
+    p0 = torch.zeros(ops.heads_loss_nparts(M), 6, dtype=torch.float64, device="cuda")
+    a0, s0 = torch.empty(M, dtype=torch.uint8, device="cuda"), torch.empty(M, dtype=torch.float32, device="cuda")
+    d0 = torch.zeros(M, nout, dtype=torch.bfloat16, device="cuda")
+    ops.heads_loss(logits, classes, species, cw, 1.0 / M, p0, argmax_out=a0, sig_prob=s0, dlogits=d0)
+    p1 = torch.zeros(ops.heads_loss_fused_nparts(M), 6, dtype=torch.float64, device="cuda")
+    a1, s1 = torch.full_like(a0, 255), torch.full_like(s0, -1.0)
+    d1 = torch.full((M, nout), 9.0, dtype=torch.bfloat16, device="cuda")
+    ops.heads_loss_fused(x, wf, bias, classes, species, cw, 1.0 / M, p1, argmax_out=a1, sig_prob=s1, dlogits=d1)
+    m0, m1 = torch.zeros(5, device="cuda"), torch.zeros(5, device="cuda")
+    r0, r1 = torch.zeros(6, dtype=torch.float64, device="cuda"), torch.zeros(6, dtype=torch.float64, device="cuda")
+    ops.heads_loss_finalize(p0, float(M), m0, r0)
+    ops.heads_loss_finalize(p1, float(M), m1, r1)
+    torch.cuda.synchronize()
+    assert torch.equal(a0, a1) and torch.equal(s0, s1)
+    assert torch.equal(r0[2:], r1[2:])                                   # the four metric counts are integers
+    assert torch.allclose(r0[:2], r1[:2], rtol=1e-6) and torch.allclose(m0, m1, rtol=1e-5)
+    diff = (d0.float() - d1.float()).abs()
+    assert float(diff.max()) <= float(d0.float().abs().max()) * 2 ** -7   # one bf16 ulp of the largest entry
+    assert float((d0 != d1).float().mean()) < 0.02                        # soft-max sum order differs in the last bit only
+
 
 def test_metric_functions_match_keras_formulas():
     """unet.py:159-193 on one-hot truth / softmax predictions: numpy restatement of the K.round(K.clip()) sums."""

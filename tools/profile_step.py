@@ -1,5 +1,5 @@
 """Per-entry-point device time of one eager VAE+DFC train step (B=32, 32^3), warm, in the real launch order
-(no side-stream overlap so that each call is timed alone).  usage: profile_step.py [batch] [reps] [tag]"""
+(no side-stream overlap so that each call is timed alone).  usage: profile_step.py [batch] [reps] [tag] [d]"""
 import collections
 import json
 import os
@@ -14,10 +14,11 @@ from icsg3d_b200.engine import VAEEngine
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 tag = sys.argv[3] if len(sys.argv) > 3 else "step"
-eng = VAEEngine(B, d=32, seed=1)
+d = int(sys.argv[4]) if len(sys.argv) > 4 else 32
+eng = VAEEngine(B, d=d, seed=1)
 eng.overlap_pm = False
 eng.overlap_wgrad = False
-M, cond, _ = utils.synthetic_batch(B, d=32, seed=1000)
+M, cond, _ = utils.synthetic_batch(B, d=d, seed=1000)
 eng.set_inputs(M, cond, torch.randn(B, 256, device="cuda"))
 for _ in range(3):
     eng._train_body()
