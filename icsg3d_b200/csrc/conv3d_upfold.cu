@@ -26,6 +26,9 @@ struct TmSet8 {
 };
 
 struct ConvUpfoldParams {
+  int mode;             // 0: fprop (tile = phase x low voxels, skip + folded units, output scattered to 2i + r)
+                        // 1: dgrad w.r.t. the LOW tensor (tile = low voxels, 64 (phase, tap) x cout/64 units read from the
+                        //    parity classes of dY, plain low-resolution output)
   int m_low;            // B * Dl * Hl * Wl
   int Dl, Hl, Wl;       // low-resolution extents (output: 2x)
   int cs, cu;           // 64-channel chunks of the skip / upsampled part
@@ -83,9 +86,9 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
   const uint32_t tmem_base = tmem_base_slot;
 
   // tile index = (tm * 8 + phase) * tiles_n + tn: the 8 phases of one low-resolution box run side by side (L2 reuse)
-  const int total_tiles = p.tiles_m * 8 * p.tiles_n;
-  const int skip_units = 27 * p.cs;
-  const int units = skip_units + 8 * p.cu;
+  const int total_tiles = p.mode == 0 ? p.tiles_m * 8 * p.tiles_n : p.tiles_m * p.tiles_n;
+  const int skip_units = p.mode == 0 ? 27 * p.cs : 0;
+  const int units = p.mode == 0 ? skip_units + 8 * p.cu : 64 * p.cs;  // mode 1: cs = cout / 64 chunks of dY
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -96,7 +99,7 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tn = tile % p.tiles_n;
       const int tmp = tile / p.tiles_n;
-      const int ph = tmp & 7, tm = tmp >> 3;
+      const int ph = p.mode == 0 ? (tmp & 7) : 0, tm = p.mode == 0 ? (tmp >> 3) : tmp;
       const int rd = ph >> 2, rh = (ph >> 1) & 1, rw = ph & 1;
       int pix = tm * 128;
       const int w0 = pix % p.Wl;
@@ -112,7 +115,13 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
         uint8_t* sb = sa + kUfAUnit;
         if (leader) {
           mbar_expect_tx(&full_bar[stage], tx_bytes);
-          if (u < skip_units) {
+          if (p.mode == 1) {
+            // dLow[i] += Wf[r][t]^T dY[2 (i - o(r,t)) + r]: `tap` counts the 64 (phase r, tap t) pairs
+            const int r = tap >> 3, t = tap & 7;
+            const int od = ((t >> 2) & 1) - (((r >> 2) & 1) ^ 1), oh = ((t >> 1) & 1) - (((r >> 1) & 1) ^ 1), ow = (t & 1) - ((r & 1) ^ 1);
+            tma_load_5d(sa, &tmSkip.m[r], &full_bar[stage], ch * 64, w0 - ow, h0 - oh, d0 - od, n0);
+            tma_load_3d(sb, &tmB, &full_bar[stage], 0, tn * p.nt, u);
+          } else if (u < skip_units) {
             // full-resolution voxel 2i + r + (k - 1) = 2 (i + o) + r' of parity class r'
             const int kd = tap / 9, kh = (tap - kd * 9) / 3, kw = tap - kd * 9 - kh * 3;
             const int qd = rd + kd - 1, qh = rh + kh - 1, qw = rw + kw - 1;  // in [-1, 2]
@@ -126,7 +135,7 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
             tma_load_3d(sb, &tmB, &full_bar[stage], 0, tn * p.nt, skip_units + (ph * 8 + tap) * p.cu + ch);
           }
         }
-        if (++ch == (u < skip_units ? p.cs : p.cu)) {
+        if (++ch == ((p.mode == 1 || u < skip_units) ? p.cs : p.cu)) {
           ch = 0;
           ++tap;
           if (u + 1 == skip_units) tap = 0;
@@ -178,18 +187,21 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
       const int acc = local & 1;
       const int tn = tile % p.tiles_n;
       const int tmp = tile / p.tiles_n;
-      const int ph = tmp & 7, tm = tmp >> 3;
+      const int ph = p.mode == 0 ? (tmp & 7) : 0, tm = p.mode == 0 ? (tmp >> 3) : tmp;
       const int pl = tm * 128 + row;  // low-resolution voxel of this row
       const bool row_ok = pl < p.m_low;
-      int t = pl;
-      const int wl = t % p.Wl;
-      t /= p.Wl;
-      const int hl = t % p.Hl;
-      t /= p.Hl;
-      const int dl = t % p.Dl;
-      const int n = t / p.Dl;
-      const long long pixel = ((static_cast<long long>(n) * (2 * p.Dl) + 2 * dl + (ph >> 2)) * (2 * p.Hl) + 2 * hl + ((ph >> 1) & 1)) *
-                                  (2 * p.Wl) + 2 * wl + (ph & 1);
+      long long pixel = pl;
+      if (p.mode == 0) {
+        int t = pl;
+        const int wl = t % p.Wl;
+        t /= p.Wl;
+        const int hl = t % p.Hl;
+        t /= p.Hl;
+        const int dl = t % p.Dl;
+        const int n = t / p.Dl;
+        pixel = ((static_cast<long long>(n) * (2 * p.Dl) + 2 * dl + (ph >> 2)) * (2 * p.Hl) + 2 * hl + ((ph >> 1) & 1)) * (2 * p.Wl) +
+                2 * wl + (ph & 1);
+      }
       mbar_wait(&tmem_full_bar[acc], static_cast<uint32_t>(local >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.nt);
@@ -287,6 +299,37 @@ __global__ void pack_w_upfold_kernel(const float* __restrict__ w, int cin, int c
   }
 }
 
+// Folded weights for the gradient w.r.t. the LOW tensor (mode 1): out bf16 [64 * cc][cup_pad][64], cc = ceil(cout / 64):
+//   unit (r*8 + t)*cc + ch, row n, column k  =  Wf[r][t][c_up0 + n][64 ch + k]   (the same tap sums, N = low channel, K = cout)
+__global__ void pack_w_upfold_dgrad_kernel(const float* __restrict__ w, int cin, int cout, int c_up0, int c_up, int cup_pad,
+                                           __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
+  const int cc = (cout + 63) / 64;
+  const long long total = 64ll * cc * cup_pad * 64;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(idx & 63);
+    const int n = static_cast<int>((idx >> 6) % cup_pad);
+    const int unit = static_cast<int>((idx >> 6) / cup_pad);
+    const int co = (unit % cc) * 64 + k;
+    const int pt = unit / cc, ph = pt >> 3, t = pt & 7;
+    float v = 0.f;
+    if (n < c_up && co < cout) {
+      const int lo[3] = {((ph >> 2) & 1) == 0 ? ((t >> 2) & 1 ? 1 : 0) : ((t >> 2) & 1 ? 2 : 0),
+                         ((ph >> 1) & 1) == 0 ? ((t >> 1) & 1 ? 1 : 0) : ((t >> 1) & 1 ? 2 : 0),
+                         (ph & 1) == 0 ? (t & 1 ? 1 : 0) : (t & 1 ? 2 : 0)};
+      const int hi[3] = {((ph >> 2) & 1) == 0 ? ((t >> 2) & 1 ? 2 : 0) : ((t >> 2) & 1 ? 2 : 1),
+                         ((ph >> 1) & 1) == 0 ? ((t >> 1) & 1 ? 2 : 0) : ((t >> 1) & 1 ? 2 : 1),
+                         (ph & 1) == 0 ? (t & 1 ? 2 : 0) : (t & 1 ? 2 : 1)};
+      for (int kd = lo[0]; kd <= hi[0]; ++kd)
+        for (int kh = lo[1]; kh <= hi[1]; ++kh)
+          for (int kw = lo[2]; kw <= hi[2]; ++kw)
+            v += w[(static_cast<long long>((kd * 3 + kh) * 3 + kw) * cin + c_up0 + n) * cout + co];
+    }
+    out[idx] = f2bf(v);
+  }
+}
+
 static bool uf_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 }  // namespace icsg3d
@@ -314,22 +357,12 @@ extern "C" int icsg3d_pack_conv_w_upfold(const float* w, int cin, int cout, int 
   return ICSG3D_OK;
 }
 
-extern "C" int icsg3d_conv3d_k3_upfold(const void* x_skip, int ld_skip, int c_skip, const void* x_low, int ld_low, int c_low,
-                                       const void* wfold, const float* bias, const float* post_scale, const float* post_shift,
-                                       void* y, int ldy, int n_store, int B, int D, int H, int W, int nout, int act,
-                                       float leaky_alpha, void* stream) {
-  ICSG_REQUIRE(x_skip && x_low && wfold && y, "conv3d_k3_upfold: null pointer");
-  ICSG_REQUIRE(B > 0 && uf_pow2(D) && uf_pow2(H) && uf_pow2(W) && D >= 4 && H >= 4 && W >= 4 && W <= 256,
-               "conv3d_k3_upfold: D,H,W (output extents) must be powers of two in [4,256] (got %d %d %d)", D, H, W);
-  ICSG_REQUIRE(c_skip >= 64 && c_skip % 64 == 0 && c_low >= 64 && c_low % 64 == 0,
-               "conv3d_k3_upfold: channel counts must be multiples of 64 (got %d skip, %d low)", c_skip, c_low);
-  ICSG_REQUIRE(nout >= 16 && nout % 16 == 0, "conv3d_k3_upfold: nout must be a multiple of 16 (got %d)", nout);
-  ICSG_REQUIRE(ld_skip % 8 == 0 && ld_skip >= c_skip && ld_low % 8 == 0 && ld_low >= c_low && ldy >= n_store && n_store > 0 &&
-                   n_store <= nout,
-               "conv3d_k3_upfold: bad leading dimensions");
-  ICSG_REQUIRE(((reinterpret_cast<uintptr_t>(x_skip) | reinterpret_cast<uintptr_t>(x_low) | reinterpret_cast<uintptr_t>(wfold)) & 15) == 0,
-               "conv3d_k3_upfold: operands must be 16-byte aligned");
-  ICSG_REQUIRE((post_scale == nullptr) == (post_shift == nullptr), "conv3d_k3_upfold: post_scale / post_shift come together");
+// Shared launcher.  x_par: the full-resolution tensor read through its 8 parity classes (mode 0: the skip input with
+// c_par channels; mode 1: dY with c_par = cout channels); x_low (mode 0 only): the low-resolution input.
+static int upfold_launch(int mode, const void* x_par, int ld_par, int c_par, const void* x_low, int ld_low, int c_low,
+                         const void* wpack, int n_units, const float* bias, const float* post_scale, const float* post_shift,
+                         void* y, int ldy, int n_store, int B, int D, int H, int W, int nout, int act, float leaky_alpha,
+                         void* stream) {
   const int Dl = D / 2, Hl = H / 2, Wl = W / 2;
   const long long m_low = static_cast<long long>(B) * Dl * Hl * Wl;
   ICSG_REQUIRE(m_low * 8 < (1ll << 31), "conv3d_k3_upfold: too many voxels");
@@ -337,17 +370,19 @@ extern "C" int icsg3d_conv3d_k3_upfold(const void* x_skip, int ld_skip, int c_sk
   if (sms <= 0) return cuda_fail(cudaGetLastError(), "sm_count", __FILE__, __LINE__);
 
   ConvUpfoldParams p{};
+  p.mode = mode;
   p.m_low = static_cast<int>(m_low);
   p.Dl = Dl;
   p.Hl = Hl;
   p.Wl = Wl;
-  p.cs = c_skip / 64;
+  p.cs = c_par / 64;
   p.cu = c_low / 64;
   p.tiles_m = static_cast<int>((m_low + 127) / 128);
+  const int phases = mode == 0 ? 8 : 1;
   int nt = nout < 256 ? nout : 256;
   while (nt > 16 && nout % nt != 0) nt -= 16;
-  while (nt > 64 && nt % 32 == 0 && static_cast<long long>(p.tiles_m) * 8 * (nout / nt) < sms) nt /= 2;  // small problems: more tiles
-  ICSG_REQUIRE(nout % nt == 0, "conv3d_k3_upfold: unsupported nout %d", nout);
+  while (nt > 64 && nt % 32 == 0 && static_cast<long long>(p.tiles_m) * phases * (nout / nt) < sms) nt /= 2;  // small problems: more tiles
+  ICSG_REQUIRE(nout % nt == 0, "conv3d_k3_upfold: unsupported N %d", nout);
   p.nt = nt;
   p.tiles_n = nout / nt;
   p.b_unit_bytes = static_cast<uint32_t>(nt) * 128u;
@@ -379,34 +414,36 @@ extern "C" int icsg3d_conv3d_k3_upfold(const void* x_skip, int ld_skip, int c_sk
   const int bn = rem;
   const uint32_t box[5] = {64u, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bd),
                            static_cast<uint32_t>(bn)};
-  TmSet8 tmSkip;
+  TmSet8 tmPar;
   CUtensorMap tmLow, tmB;
   {
-    // parity class (pd, ph, pw) of the full-resolution skip tensor: voxel (2i + p) -> index i, strides doubled
-    const uint64_t dims[5] = {static_cast<uint64_t>(c_skip), static_cast<uint64_t>(Wl), static_cast<uint64_t>(Hl),
+    // parity class (pd, ph, pw) of the full-resolution tensor: voxel (2i + p) -> index i, strides doubled
+    const uint64_t dims[5] = {static_cast<uint64_t>(c_par), static_cast<uint64_t>(Wl), static_cast<uint64_t>(Hl),
                               static_cast<uint64_t>(Dl), static_cast<uint64_t>(B)};
-    const uint64_t sW = static_cast<uint64_t>(ld_skip) * 2, sH = sW * W, sD = sH * H, sN = sD * D;
+    const uint64_t sW = static_cast<uint64_t>(ld_par) * 2, sH = sW * W, sD = sH * H, sN = sD * D;
     const uint64_t strides[4] = {2 * sW, 2 * sH, 2 * sD, sN};
     for (int c = 0; c < 8; ++c) {
-      const uint8_t* base = static_cast<const uint8_t*>(x_skip) + ((c >> 2) & 1) * sD + ((c >> 1) & 1) * sH + (c & 1) * sW;
-      int rc = encode_tiled_bf16(&tmSkip.m[c], base, 5, dims, strides, box, 128);
+      const uint8_t* base = static_cast<const uint8_t*>(x_par) + ((c >> 2) & 1) * sD + ((c >> 1) & 1) * sH + (c & 1) * sW;
+      int rc = encode_tiled_bf16(&tmPar.m[c], base, 5, dims, strides, box, 128);
       if (rc) return rc;
     }
   }
-  {
+  if (mode == 0) {
     const uint64_t dims[5] = {static_cast<uint64_t>(c_low), static_cast<uint64_t>(Wl), static_cast<uint64_t>(Hl),
                               static_cast<uint64_t>(Dl), static_cast<uint64_t>(B)};
     const uint64_t sW = static_cast<uint64_t>(ld_low) * 2;
     const uint64_t strides[4] = {sW, sW * Wl, sW * Wl * Hl, sW * Wl * Hl * Dl};
     int rc = encode_tiled_bf16(&tmLow, x_low, 5, dims, strides, box, 128);
     if (rc) return rc;
+  } else {
+    tmLow = tmPar.m[0];  // unused in mode 1
   }
   {
     const int np = (nout + 15) / 16 * 16;
-    const uint64_t dims[3] = {64, static_cast<uint64_t>(np), static_cast<uint64_t>(27 * p.cs + 64 * p.cu)};
+    const uint64_t dims[3] = {64, static_cast<uint64_t>(np), static_cast<uint64_t>(n_units)};
     const uint64_t strides[2] = {128, static_cast<uint64_t>(np) * 128};
     const uint32_t bbox[3] = {64, static_cast<uint32_t>(nt), 1};
-    int rc = encode_tiled_bf16(&tmB, wfold, 3, dims, strides, bbox, 128);
+    int rc = encode_tiled_bf16(&tmB, wpack, 3, dims, strides, bbox, 128);
     if (rc) return rc;
   }
   const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
@@ -415,9 +452,63 @@ extern "C" int icsg3d_conv3d_k3_upfold(const void* x_skip, int ld_skip, int c_sk
     ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_upfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     configured = true;
   }
-  const int total_tiles = p.tiles_m * 8 * p.tiles_n;
+  const int total_tiles = p.tiles_m * phases * p.tiles_n;
   const int grid = total_tiles < sms ? total_tiles : sms;
-  launch_k(conv3d_k3_upfold_kernel, grid, kUfThreads, smem, static_cast<cudaStream_t>(stream), tmSkip, tmLow, tmB, p);
+  launch_k(conv3d_k3_upfold_kernel, grid, kUfThreads, smem, static_cast<cudaStream_t>(stream), tmPar, tmLow, tmB, p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
+}
+
+extern "C" int icsg3d_conv3d_k3_upfold(const void* x_skip, int ld_skip, int c_skip, const void* x_low, int ld_low, int c_low,
+                                       const void* wfold, const float* bias, const float* post_scale, const float* post_shift,
+                                       void* y, int ldy, int n_store, int B, int D, int H, int W, int nout, int act,
+                                       float leaky_alpha, void* stream) {
+  ICSG_REQUIRE(x_skip && x_low && wfold && y, "conv3d_k3_upfold: null pointer");
+  ICSG_REQUIRE(B > 0 && uf_pow2(D) && uf_pow2(H) && uf_pow2(W) && D >= 4 && H >= 4 && W >= 4 && W <= 256,
+               "conv3d_k3_upfold: D,H,W (output extents) must be powers of two in [4,256] (got %d %d %d)", D, H, W);
+  ICSG_REQUIRE(c_skip >= 64 && c_skip % 64 == 0 && c_low >= 64 && c_low % 64 == 0,
+               "conv3d_k3_upfold: channel counts must be multiples of 64 (got %d skip, %d low)", c_skip, c_low);
+  ICSG_REQUIRE(nout >= 16 && nout % 16 == 0, "conv3d_k3_upfold: nout must be a multiple of 16 (got %d)", nout);
+  ICSG_REQUIRE(ld_skip % 8 == 0 && ld_skip >= c_skip && ld_low % 8 == 0 && ld_low >= c_low && ldy >= n_store && n_store > 0 &&
+                   n_store <= nout,
+               "conv3d_k3_upfold: bad leading dimensions");
+  ICSG_REQUIRE(((reinterpret_cast<uintptr_t>(x_skip) | reinterpret_cast<uintptr_t>(x_low) | reinterpret_cast<uintptr_t>(wfold)) & 15) == 0,
+               "conv3d_k3_upfold: operands must be 16-byte aligned");
+  ICSG_REQUIRE((post_scale == nullptr) == (post_shift == nullptr), "conv3d_k3_upfold: post_scale / post_shift come together");
+  return upfold_launch(0, x_skip, ld_skip, c_skip, x_low, ld_low, c_low, wfold, 27 * (c_skip / 64) + 64 * (c_low / 64), bias,
+                       post_scale, post_shift, y, ldy, n_store, B, D, H, W, nout, act, leaky_alpha, stream);
+}
+
+extern "C" int64_t icsg3d_conv3d_upfold_dgrad_wpack_elems(int cout, int c_up) {
+  if (cout <= 0 || c_up <= 0) return -1;
+  return 64ll * ((cout + 63) / 64) * ((c_up + 15) / 16 * 16) * 64;
+}
+
+extern "C" int icsg3d_pack_conv_w_upfold_dgrad(const float* w, int cin, int cout, int c_up0, int c_up, void* wpack, void* stream) {
+  ICSG_REQUIRE(w && wpack && cin > 0 && cout > 0 && c_up > 0 && c_up0 >= 0 && c_up0 + c_up <= cin,
+               "pack_conv_w_upfold_dgrad: bad channel range");
+  const long long total = icsg3d_conv3d_upfold_dgrad_wpack_elems(cout, c_up);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_k(pack_w_upfold_dgrad_kernel, static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream), w, cin, cout, c_up0,
+           c_up, (c_up + 15) / 16 * 16, static_cast<__nv_bfloat16*>(wpack));
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+// Gradient of the folded convolution w.r.t. the LOW-resolution input: dlow [B,D/2,H/2,W/2,ld_low] (c_up channels) from
+// dy [B,D,H,W,ld_dy] (cout channels) — what UpSampling3D's backward (the sum over the 8 children) of the full-resolution
+// data gradient gives, at 8/27 of its multiply-adds and without the full-resolution gradient of those channels.
+extern "C" int icsg3d_conv3d_k3_upfold_dgrad_low(const void* dy, int ld_dy, int cout, const void* wpack, void* dlow, int ld_low,
+                                                 int c_up, int B, int D, int H, int W, void* stream) {
+  ICSG_REQUIRE(dy && wpack && dlow, "conv3d_k3_upfold_dgrad_low: null pointer");
+  ICSG_REQUIRE(B > 0 && uf_pow2(D) && uf_pow2(H) && uf_pow2(W) && D >= 4 && H >= 4 && W >= 4 && W <= 256,
+               "conv3d_k3_upfold_dgrad_low: D,H,W (extents of dy) must be powers of two in [4,256] (got %d %d %d)", D, H, W);
+  ICSG_REQUIRE(cout >= 64 && cout % 64 == 0 && c_up >= 16 && c_up % 16 == 0,
+               "conv3d_k3_upfold_dgrad_low: cout must be a multiple of 64 and c_up of 16 (got %d, %d)", cout, c_up);
+  ICSG_REQUIRE(ld_dy % 8 == 0 && ld_dy >= cout && ld_low >= c_up, "conv3d_k3_upfold_dgrad_low: bad leading dimensions");
+  ICSG_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(wpack)) & 15) == 0,
+               "conv3d_k3_upfold_dgrad_low: operands must be 16-byte aligned");
+  return upfold_launch(1, dy, ld_dy, cout, nullptr, 0, 0, wpack, 64 * (cout / 64), nullptr, nullptr, nullptr, dlow, ld_low, c_up,
+                       B, D, H, W, c_up, ICSG3D_ACT_NONE, 0.f, stream);
 }

@@ -64,9 +64,10 @@ __global__ void __launch_bounds__(256) pack_w_fprop_tiled_kernel(const float* __
   }
 }
 
-// dgrad keeps the orientation (taps mirrored): 8 output channels per thread, 16-byte stores
+// dgrad keeps the orientation (taps mirrored): 8 output channels per thread, 16-byte stores; the input channels may be a
+// slice [ci0, ci0 + cin) of a kernel with cin_total input channels (the skip half of a folded Upsample + Conv layer)
 __global__ void __launch_bounds__(256) pack_w_dgrad_vec_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
-                                                               int cin, int cout) {
+                                                               int cin, int cout, int cin_total, int ci0) {
   pdl_prologue();
   const int c8 = cout >> 3;
   const long long per_tap = static_cast<long long>(cin) * c8, total = 27 * per_tap;
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(256) pack_w_dgrad_vec_kernel(const float* __re
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int tap = static_cast<int>(idx / per_tap);
     const long long r = idx - tap * per_tap;  // (ci, co8) of this tap
-    const float4* src = reinterpret_cast<const float4*>(w + (static_cast<long long>(26 - tap) * per_tap + r) * 8);
+    const float4* src = reinterpret_cast<const float4*>(
+        w + ((static_cast<long long>(26 - tap) * cin_total + ci0) * c8 + r) * 8);
     const float4 a = src[0], b = src[1];
     uint4 q;
     q.x = pack_bf16x2(a.x, a.y);
@@ -215,12 +217,25 @@ extern "C" int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, in
   if (cin_pad == cin && cout_pad == cout && cout % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(wpack) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
     launch_k(pack_w_dgrad_vec_kernel, grid_for(27ll * cin * (cout / 8)), 256, 0, static_cast<cudaStream_t>(stream), w,
-             static_cast<__nv_bfloat16*>(wpack), cin, cout);
+             static_cast<__nv_bfloat16*>(wpack), cin, cout, cin, 0);
     ICSG_CHECK_LAUNCH();
     return ICSG3D_OK;
   }
   launch_k(pack_w_dgrad_kernel, grid_for(27ll * cout_pad * cin_pad), 256, 0, static_cast<cudaStream_t>(stream), 
       w, static_cast<__nv_bfloat16*>(wpack), cin, cout, cin_pad, cout_pad);
+  ICSG_CHECK_LAUNCH();
+  return ICSG3D_OK;
+}
+
+// dgrad operand of the input-channel slice [ci0, ci0 + cin) of a kernel fp32 [27][cin_total][cout]: bf16 [27][cin][cout]
+extern "C" int icsg3d_pack_conv_w_dgrad_slice(const float* w, void* wpack, int cin_total, int ci0, int cin, int cout,
+                                              void* stream) {
+  ICSG_REQUIRE(w && wpack && ci0 >= 0 && cin > 0 && ci0 + cin <= cin_total && cout % 8 == 0 && cin % 16 == 0 && cout % 16 == 0,
+               "pack_conv_w_dgrad_slice: bad channel slice");
+  ICSG_REQUIRE(((reinterpret_cast<uintptr_t>(wpack) | reinterpret_cast<uintptr_t>(w)) & 15) == 0,
+               "pack_conv_w_dgrad_slice: operands must be 16-byte aligned");
+  launch_k(pack_w_dgrad_vec_kernel, grid_for(27ll * cin * (cout / 8)), 256, 0, static_cast<cudaStream_t>(stream), w,
+           static_cast<__nv_bfloat16*>(wpack), cin, cout, cin_total, ci0);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

@@ -230,6 +230,16 @@ def conv3d_k3(x, wpack, bias=None, *, cin=None, n_store=None, act=ACT_NONE, alph
     return out
 
 
+def pack_conv_w_dgrad_slice(w, ci0, cin, out=None):
+    """dgrad operand bf16 [27][cin][cout] of the input-channel slice [ci0, ci0+cin) of w fp32 (3,3,3,cin_total,cout)."""
+    _chk(w, torch.float32, "w")
+    cin_total, cout = w.shape[-2], w.shape[-1]
+    if out is None:
+        out = torch.empty((27, cin, cout), dtype=torch.bfloat16, device=w.device)
+    _lib.call("icsg3d_pack_conv_w_dgrad_slice", _ptr(w), _ptr(out), cin_total, ci0, cin, cout, _stream())
+    return out
+
+
 def pack_conv_w_upfold(w, c_skip0, c_skip, c_up0, c_up, out=None):
     """Keras kernel fp32 (3,3,3,cin,cout) -> the K-unit list of conv3d_k3_upfold: 27 taps of the skip channels
     [c_skip0, c_skip0+c_skip) and, per output phase, the 8 folded taps of the upsampled channels [c_up0, c_up0+c_up)."""
@@ -263,6 +273,34 @@ def conv3d_k3_upfold(x_skip, x_low, wfold, bias, nout, *, act=ACT_NONE, alpha=LE
     with _timed(("upfold", tag), vox * 27 * (nominal[0] if nominal else cs + cu), vox * (27 * cs + 8 * cu)):
         _lib.call("icsg3d_conv3d_k3_upfold", _ptr(x_skip), _ld(x_skip), cs, _ptr(x_low), _ld(x_low), cu, _ptr(wfold), _ptr(bias),
                   _ptr(ps), _ptr(pt), _ptr(out), _ld(out), out.shape[-1], B, D, H, W, nout, act, alpha, _stream())
+    return out
+
+
+def pack_conv_w_upfold_dgrad(w, c_up0, c_up, out=None):
+    """Keras kernel fp32 (3,3,3,cin,cout) -> transposed folded weights for conv3d_k3_upfold_dgrad_low."""
+    _chk(w, torch.float32, "w")
+    cin, cout = w.shape[-2], w.shape[-1]
+    n = int(_lib.lib().icsg3d_conv3d_upfold_dgrad_wpack_elems(cout, c_up))
+    if out is None:
+        out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    if out.numel() != n or not out.is_contiguous():
+        raise ValueError("pack_conv_w_upfold_dgrad: out has the wrong size")
+    _lib.call("icsg3d_pack_conv_w_upfold_dgrad", _ptr(w), cin, cout, c_up0, c_up, _ptr(out), _stream())
+    return out
+
+
+def conv3d_k3_upfold_dgrad_low(dy, wpack, c_up, out=None, tag="conv.upfold.dgrad_low", nominal=None):
+    """Gradient of conv3d_k3_upfold w.r.t. its low-resolution input: dy bf16 [B,D,H,W,cout] -> bf16 [B,D/2,H/2,W/2,c_up]."""
+    _chk(dy, torch.bfloat16, "dy")
+    _chk(wpack, torch.bfloat16, "wpack")
+    B, D, H, W, cout = dy.shape
+    if out is None:
+        out = torch.empty((B, D // 2, H // 2, W // 2, c_up), dtype=torch.bfloat16, device=dy.device)
+    _chk(out, torch.bfloat16, "out")
+    vox = 2.0 * B * D * H * W * cout * c_up
+    with _timed(("upfold", tag), vox * 27 if nominal is None else nominal, vox * 8):
+        _lib.call("icsg3d_conv3d_k3_upfold_dgrad_low", _ptr(dy), _ld(dy), cout, _ptr(wpack), _ptr(out), _ld(out), c_up, B, D, H, W,
+                  _stream())
     return out
 
 

@@ -59,6 +59,9 @@ class UNetEngine:
             D_ = d >> spec["lvl"]
             ws_need = max(ws_need, ops.conv3d_k3_workspace_bytes(batch, D_, cin_eff, spec["cout"]),
                           ops.conv3d_k3_workspace_bytes(batch, D_, spec["cout"], cin_eff))
+            if spec["src"].startswith("cat:"):  # data gradient of the skip half alone (Upsample-into-Conv fold)
+                cs = next(x["cout"] for x in UNET_PLAN if x.get("cat", (None,))[0] == spec["src"][4:])
+                ws_need = max(ws_need, ops.conv3d_k3_workspace_bytes(batch, D_, spec["cout"], cs))
         self.ctx = _Ctx(dev, conv_ws_bytes=ws_need)
         self.train_enabled = train
         B = batch
@@ -99,10 +102,14 @@ class UNetEngine:
             self.L[n] = L
         # Upsample-into-Conv fold for learning phase 0 (csrc/conv3d_upfold.cu): consumer block -> (skip slice, low tensor)
         self.fold = os.environ.get("ICSG3D_UPFOLD", "1") != "0"
+        # ... and in the train step for the forward and the data gradient (the filter gradient still reads the
+        # materialised upsampled tensor, so the BatchNorm pass of the producer writes both forms)
+        self.fold_train = train and self.fold and os.environ.get("ICSG3D_UPFOLD_TRAIN", "1") != "0"
         self._wfold_fresh = False
         for L in self.L.values():
             if "up" in L:
                 L["ylow"] = z(B, L["D"], L["D"], L["D"], L["cout"])
+                L["dylow"] = z(B, L["D"], L["D"], L["D"], L["cout"]) if self.fold_train else None
         for L in self.L.values():
             if L["src"].startswith("cat:"):
                 buf = L["src"][4:]
@@ -110,7 +117,16 @@ class UNetEngine:
                 up = next(x for x in self.L.values() if x.get("up", (None,))[0] == buf)
                 L["fold"] = (sk["y"], up["ylow"])
                 L["fold_ch"] = (sk["cat"][1], sk["cout"], up["up"][1], up["cout"])
-                L["wfold"] = None
+                L["fold_up"] = up["n"]
+                # in the TRAIN step the fold pays where the low-resolution grid alone fills the SMs (>= 128 tiles of 128
+                # voxels): the folded weights are re-packed every step and the deep layers' data gradient has too few
+                # tiles without a K split (measured at batch 8: folding c13 / c15 too costs 0.4 ms, c17 alone gains)
+                L["fold_tr"] = up["fold_tr"] = self.fold_train and B * (L["D"] // 2) ** 3 >= 16384
+                s0, cs, u0, cu = L["fold_ch"]
+                lib = ops._lib.lib()
+                L["wfold"] = z(int(lib.icsg3d_conv3d_upfold_wpack_elems(cs, cu, L["cout"])))
+                L["wd_skip"] = z(27, cs, L["cout"]) if L["fold_tr"] else None
+                L["wdlow"] = z(int(lib.icsg3d_conv3d_upfold_dgrad_wpack_elems(L["cout"], cu))) if L["fold_tr"] else None
         cmax = max(spec["cout"] for spec in UNET_PLAN)
         self.one, self.zero = torch.ones(cmax, dtype=F32, device=dev), torch.zeros(cmax, dtype=F32, device=dev)
         # heads
@@ -150,8 +166,14 @@ class UNetEngine:
         self._wfold_fresh = not dgrad and self.fold
         for n, L in self.L.items():
             ops.pack_conv_w_fprop(p[n + "/kernel"], cin_pad=L["cin_pad"], out=L["wf"])
-            if not dgrad and self.fold and "fold" in L:  # inference packing: folded taps of the upsampled channels
+            if "fold" in L and ((not dgrad and self.fold) or (dgrad and L["fold_tr"])):
+                # folded taps of the upsampled channels (+ in training the data-gradient operands of both halves)
                 L["wfold"] = ops.pack_conv_w_upfold(p[n + "/kernel"], *L["fold_ch"], out=L["wfold"])
+                if dgrad:
+                    s0, cs, u0, cu = L["fold_ch"]
+                    L["wd_skip"] = ops.pack_conv_w_dgrad_slice(p[n + "/kernel"], s0, cs, out=L["wd_skip"])
+                    L["wdlow"] = ops.pack_conv_w_upfold_dgrad(p[n + "/kernel"], u0, cu, out=L["wdlow"])
+                    continue
             if dgrad and "wd" in L:
                 ops.pack_conv_w_dgrad(p[n + "/kernel"], cin_pad=L["cin_pad"], out=L["wd"])
         ops.pack_heads_w(p["soft/kernel"], p["sig/kernel"], p["soft/bias"], p["sig/bias"], self.h_wf, self.h_wd, self.h_bias)
@@ -198,6 +220,8 @@ class UNetEngine:
             ops.bn_inference_coeffs(g, b, mm, mv, st.scale, st.shift)
         if "up" in L:
             ops.bn_apply_fwd(x, C, st.scale, st.shift, ACT_NONE, POST_UP2, y=L["y"])
+            if training and L.get("fold_tr"):  # the folded consumer reads the low-resolution output
+                ops.bn_apply_fwd(x, C, st.scale, st.shift, ACT_NONE, POST_NONE, y=L["ylow"])
         else:
             ops.bn_apply_fwd(x, C, st.scale, st.shift, ACT_NONE, POST_NONE, y=L["y"])
             if L.get("pool"):
@@ -237,6 +261,13 @@ class UNetEngine:
                                   ws=self.ctx.conv_ws, tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
                 if L.get("pool"):
                     ops.bn_apply_fwd(L["y"], L["cout"], self.one, self.zero, ACT_NONE, POST_POOL2, y=L["p"])
+                continue
+            if training and L.get("fold_tr") and "fold" in L:
+                # train step: the upsampled half of the input as 8 folded taps on the producer's low-resolution output
+                skip, low = L["fold"]
+                ops.conv3d_k3_upfold(skip, low, L["wfold"], p[L["n"] + "/bias"], L["cout"], act=ACT_RELU, out=L["a"],
+                                     tag=f"unet.{L['n']}.fprop", nominal=(L["cin_real"], L["cout"]))
+                self._bn_fwd(L, training, part=None, coeffs=coeffs)
                 continue
             if training:  # BatchNorm statistics out of the conv epilogue where the serving kernel has them
                 nparts = ops.conv3d_k3_stats_parts(xin, L["wf"])
@@ -278,6 +309,8 @@ class UNetEngine:
     def _grad_wrt_output(self, L):
         """(dy, post, idx, dy2) describing the gradient reaching block L's BN output."""
         if "up" in L:
+            if L.get("fold_tr"):  # written at low resolution by the folded consumer's data-gradient kernel
+                return L["dylow"], POST_NONE, None, None
             buf, off = L["up"]
             return self.dcat[buf][..., off:off + L["cout"]], POST_UP2, None, None
         if "cat" in L:
@@ -333,7 +366,15 @@ class UNetEngine:
                 ops.conv3d_k3_wgrad(xin, L["dc"], cin=L["cin_pad"], cout=C, out=scratch, tag=f"unet.{nme}.wgrad",
                                     nominal=(L["cin_real"], C), ws=self.wg_ws)
                 ops.unpack_conv_dw(scratch, L["cin_real"], C, out=gk)
-            if nme != "c1":
+            if L.get("fold_tr") and "fold" in L:
+                # data gradient of the folded layer: 27 taps for the skip channels only, 64 folded (phase, tap) pairs
+                # straight to the LOW-resolution gradient of the upsampled producer
+                s0, cs, u0, cu = L["fold_ch"]
+                ops.conv3d_k3(L["dc"], L["wd_skip"], None, out=self._dst_of_input_grad(L)[..., s0:s0 + cs], ws=self.ctx.conv_ws,
+                              tag=f"unet.{nme}.dgrad", nominal=(C, cs))
+                ops.conv3d_k3_upfold_dgrad_low(L["dc"], L["wdlow"], cu, out=self.L[L["fold_up"]]["dylow"],
+                                               tag=f"unet.{nme}.dgrad_low")
+            elif nme != "c1":
                 ops.conv3d_k3(L["dc"], L["wd"], None, out=self._dst_of_input_grad(L), ws=self.ctx.conv_ws,
                               tag=f"unet.{nme}.dgrad")
 

@@ -115,6 +115,14 @@ int icsg3d_conv3d_k3_upfold(const void* x_skip, int ld_skip, int c_skip, const v
                             const void* wfold, const float* bias, const float* post_scale, const float* post_shift, void* y,
                             int ldy, int n_store, int B, int D, int H, int W, int nout, int act, float leaky_alpha,
                             void* stream);
+/* Backward of the folded convolution w.r.t. its LOW-resolution input (the training step's use of the fold): dlow bf16
+ * [B,D/2,H/2,W/2,ld_low] (c_up channels) from dy bf16 [B,D,H,W,ld_dy] (cout channels, multiple of 64) with the transposed
+ * folded weights of icsg3d_pack_conv_w_upfold_dgrad (icsg3d_conv3d_upfold_dgrad_wpack_elems bf16 elements).  Equals
+ * UpSampling3D's backward (sum over the 8 children) of the full-resolution data gradient of those channels. */
+int64_t icsg3d_conv3d_upfold_dgrad_wpack_elems(int cout, int c_up);
+int icsg3d_pack_conv_w_upfold_dgrad(const float* w, int cin, int cout, int c_up0, int c_up, void* wpack, void* stream);
+int icsg3d_conv3d_k3_upfold_dgrad_low(const void* dy, int ld_dy, int cout, const void* wpack, void* dlow, int ld_low, int c_up,
+                                      int B, int D, int H, int W, void* stream);
 /* Inference form of Conv3D + activation + BatchNormalization (unet.py:277-279 in learning phase 0): the per-channel affine
  * of the moving statistics (icsg3d_bn_inference_coeffs) is applied in the conv epilogue,
  * y = post_scale[c] * act(conv + bias[c]) + post_shift[c], so the BatchNorm pass over the activation disappears. */
@@ -186,6 +194,8 @@ int icsg3d_pack_conv_w_fprop(const float* w, void* wpack, int cin, int cout, int
                              int cin_lead, int fold, int fold_c, void* stream);
 int icsg3d_pack_conv_w_dgrad(const float* w, void* wpack, int cin, int cout, int cin_pad, int cout_pad,
                              void* stream);
+/* Same for the input-channel slice [ci0, ci0 + cin) of a kernel with cin_total input channels: bf16 [27][cin][cout]. */
+int icsg3d_pack_conv_w_dgrad_slice(const float* w, void* wpack, int cin_total, int ci0, int cin, int cout, void* stream);
 
 /* All weight packs of a model in one launch.  jobs: DEVICE array [njobs][10] of int64
  * {w ptr, wpack ptr, cin, cout, cin_pad, cout_pad, cin_lead, fold, fold_c, mode (0 = fprop layout, 1 = dgrad layout,

@@ -265,3 +265,25 @@ def test_upsample_conv_fold_matches_materialised_upsample_concat_conv(B, D, cs, 
         assert float((got.float() - want32).abs().max()) <= float(want32.abs().max()) * 2 ** -8
     assert rel_l2(ybuf[..., :cout].float(), torch.addcmul(shift, want32, scale)) < tol + 2e-3
     assert torch.all(ybuf[..., cout:] == 3.0)
+
+
+@pytest.mark.parametrize("B,D,cs,cu,cout", [(2, 8, 64, 128, 128), (1, 16, 64, 128, 128), (3, 8, 128, 256, 256), (2, 8, 256, 512, 512),
+                                            (5, 4, 64, 64, 64)])
+def test_upsample_conv_fold_dgrad_low_matches_upsample_backward_of_dgrad(B, D, cs, cu, cout):
+    """Backward of the folded conv w.r.t. its low-resolution input == UpSampling3D's backward (sum over the 8 children) of
+    the data-gradient conv on the materialised concat tensor (weights exactly representable: same products)."""
+    from icsg3d_b200 import ops
+    g = torch.Generator().manual_seed(61)
+    cin = cs + cu
+    dy = torch.randn(B, D, D, D, cout, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randint(-4, 5, (3, 3, 3, cin, cout), generator=g).float() / 8).cuda()
+    dcat32 = ops.conv3d_k3(dy, ops.pack_conv_w_dgrad(w), None, out_dtype=torch.float32)           # [B,D,D,D,cin]
+    want = dcat32[..., cs:].reshape(B, D // 2, 2, D // 2, 2, D // 2, 2, cu).sum(dim=(2, 4, 6))
+    wt = ops.pack_conv_w_upfold_dgrad(w, cs, cu)
+    buf = torch.full((B, D // 2, D // 2, D // 2, cu + 32), 5.0, dtype=torch.bfloat16, device="cuda")
+    ops.conv3d_k3_upfold_dgrad_low(dy, wt, cu, out=buf[..., 16:16 + cu])
+    torch.cuda.synchronize()
+    got = buf[..., 16:16 + cu].float()
+    assert rel_l2(got, want) < 3e-3
+    assert float((got - want).abs().max()) <= float(want.abs().max()) * 2 ** -7
+    assert torch.all(buf[..., :16] == 5.0) and torch.all(buf[..., 16 + cu:] == 5.0)
