@@ -15,7 +15,7 @@ in the step; engine.py PeerBN), the whole data-parallel step is one CUDA graph.
                                                                                   # (bench_configs.py, same JSON contract)
 
 Prints ONE JSON line (rank 0).  Keys: see the round contract — `value` is device-timed with inputs resident in
-HBM (CUDA-graph replay); `e2e` goes through the public API (LatticeDFCVAE.model.train_on_batch) with pinned
+HBM (CUDA-graph replay); `e2e` goes through the public API (LatticeDFCVAE.fit_epoch, the batch loop of train()) with pinned
 host inputs copied H2D and the metrics read back D2H every step; `roofline` is the tcgen05 implicit-GEMM conv
 kernel (all fprop/dgrad launches of a step) timed live with CUDA events; `cpu_baseline` is the oracle port
 timed on the host cores on a bounded sample.
@@ -222,14 +222,23 @@ def run_cuda(args):
     metrics = eng.metrics_host()
 
     # ---- end-to-end arm through the public API with host buffers ----
+    # LatticeDFCVAE.fit_epoch is the batch loop of the reference's train() (lattice_vae.py:289-299: train_on_batch per
+    # batch of the generator, metrics averaged at the end of the epoch): every step copies its batch from pinned host
+    # memory and returns its four metrics to the host; the copy of batch b+1 runs under step b.
     Mh = M.cpu().pin_memory()
     ch = cond.cpu().pin_memory()
-    for _ in range(3):
-        vae.model.train_on_batch([Mh, ch], Mh)
+
+    class _HostBatches:
+        def __len__(self):
+            return args.steps
+
+        def __getitem__(self, b):
+            return Mh, ch
+
+    vae.fit_epoch(_HostBatches(), 3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        vae.model.train_on_batch([Mh, ch], Mh)
+    vae.fit_epoch(_HostBatches(), args.steps)
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:

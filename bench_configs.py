@@ -301,7 +301,19 @@ def _run_unet_train(args, d, B):
     ms = _timed_loop(eng.train_step, args.steps, args.warmup, world, dev, sampler if rank == 0 else None)
     value = B * world / (ms * 1e-3)
     Mh, Sh = M.cpu().pin_memory(), S.cpu().pin_memory()
-    e2e_s = _wall_loop(lambda: unet.model.train_on_batch(Mh, Sh), max(3, args.steps // 4), world, dev)
+    # the batch loop of fit_generator (AtomUnet.fit_epoch): H2D of every batch from pinned memory, metrics D2H every step
+    n_e2e = max(3, args.steps // 4)
+    unet.fit_epoch([(Mh, Sh)] * 3)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    unet.fit_epoch([(Mh, Sh)] * n_e2e)
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item()) / n_e2e
     clocks = sampler.stop() if rank == 0 else None
     roof = _conv_roofline(eng._train_body, peaks, clocks) if rank == 0 or world > 1 else None
     cpu = None
@@ -345,7 +357,19 @@ def _run_vae64(args):
     ms = _timed_loop(eng.train_step, args.steps, args.warmup, world, dev, sampler if rank == 0 else None)
     value = B * world / (ms * 1e-3)
     Mh, ch = M.cpu().pin_memory(), cond.cpu().pin_memory()
-    e2e_s = _wall_loop(lambda: vae.model.train_on_batch([Mh, ch], Mh), max(3, args.steps // 4), world, dev)
+    # the batch loop of train() (LatticeDFCVAE.fit_epoch): H2D of every batch from pinned memory, metrics D2H every step
+    n_e2e = max(3, args.steps // 4)
+    vae.fit_epoch([(Mh, ch)] * 3)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    vae.fit_epoch([(Mh, ch)] * n_e2e)
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item()) / n_e2e
     clocks = sampler.stop() if rank == 0 else None
     eng.overlap_pm = eng.overlap_wgrad = False
     roof = _conv_roofline(eng._train_body, peaks, clocks)

@@ -255,14 +255,77 @@ class AtomUnet:
             msk.append(mk.cpu().numpy().astype(bool))
         return np.concatenate(lab), np.concatenate(msk)
 
+    def fit_epoch(self, gen, steps=None, train=True):
+        """The batch loop of fit_generator (unet.py:357-381): one train_on_batch (test_on_batch) per gen[b] -> (x, y),
+        returned as a [steps, 5] array of [loss, soft_loss, sig_loss, soft_f1_m, soft_wr_m].  Pipelined like
+        LatticeDFCVAE.fit_epoch: the next batch's host -> device copy runs on a copy stream under the current step, the
+        metrics return through a pinned ring, the host waits once at the end."""
+        steps = len(gen) if steps is None else int(steps)
+        if steps <= 0:
+            return np.zeros((0, 5))
+        if self.dtype == "fp32":
+            return np.array([self._step(gen[b][0], self.model._labels(gen[b][1]), train=train) for b in range(steps)])
+        x0, y0 = gen[0]
+        B = len(x0)
+        eng = self.engine(B)
+        h = lambda a: a if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a))
+        f32 = lambda a: a if a.dtype == torch.float32 else a.float()
+        if train and self.use_cuda_graph and not eng.use_graph:
+            eng.set_inputs(_to_dev(x0, self.device, torch.float32), self.model._labels(y0).to(self.device))
+            eng.capture_train_graph()
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream, self._stage = torch.cuda.Stream(), {}
+        if B not in self._stage:
+            self._stage = {B: [(torch.empty_like(eng.X), torch.empty_like(eng.species), torch.cuda.Event(), torch.cuda.Event())
+                               for _ in range(2)]}
+        stage, cs = self._stage[B], self._copy_stream
+        ring = torch.empty(steps, 5, dtype=torch.float32).pin_memory()
+        keep = []
+
+        def prefetch(b):
+            xb, yb = (x0, y0) if b == 0 else gen[b]
+            xh, yh = f32(h(xb)).reshape(eng.X.shape), self.model._labels(yb).reshape(eng.species.shape)
+            keep.append((xh, yh))
+            sx, sy, ready, free = stage[b & 1]
+            with torch.cuda.stream(cs):
+                cs.wait_event(free)
+                sx.copy_(xh, non_blocking=True)
+                sy.copy_(yh, non_blocking=True)
+                ready.record(cs)
+
+        cs.wait_stream(main)
+        prefetch(0)
+        for b in range(steps):
+            if b + 1 < steps:
+                prefetch(b + 1)
+            sx, sy, ready, free = stage[b & 1]
+            main.wait_event(ready)
+            eng.set_inputs(sx, sy)
+            free.record(main)
+            if train:
+                eng.train_step()
+            else:
+                eng.eval_step()
+            ring[b].copy_(eng.metrics, non_blocking=True)
+            if len(keep) > 4:
+                del keep[0]
+        main.synchronize()
+        out = ring.double()
+        if self.dist is not None and self.dist.world > 1:
+            t = out.to(self.device)
+            self.dist.all_reduce_sum(t)
+            out = (t / self.dist.world).cpu()
+        return out.numpy()
+
     def train_generator(self, train_gen, val_gen, epochs=100, output_dir="output/unet/"):
         """unet.py:357-381: fit_generator + ModelCheckpoint(save_best_only on val_loss); plotting callback omitted."""
         print("Training...")
         best = np.inf
         for e in range(epochs):
-            tm = [self.model.train_on_batch(*train_gen[i]) for i in range(len(train_gen))]
-            vm = [self.model.test_on_batch(*val_gen[i]) for i in range(len(val_gen))]
-            tm, vm = np.mean(tm, axis=0), (np.mean(vm, axis=0) if vm else np.mean(tm, axis=0))
+            tm = self.fit_epoch(train_gen, train=True)
+            vm = self.fit_epoch(val_gen, train=False)
+            tm, vm = np.mean(tm, axis=0), (np.mean(vm, axis=0) if len(vm) else np.mean(tm, axis=0))
             print("Epoch %d/%d - loss: %.4f - soft_loss: %.4f - sig_loss: %.4f - soft_f1_m: %.4f - soft_wr_m: %.4f - "
                   "val_loss: %.4f" % (e + 1, epochs, tm[0], tm[1], tm[2], tm[3], tm[4], vm[0]))
             if vm[0] < best:

@@ -168,16 +168,8 @@ class LatticeDFCVAE:
         for e in range(self.num_epochs):
             print("Epoch %s:" % e)
             t0 = time.time()
-            tm = []
-            for b in range(train_steps):
-                batch, cond = train_gen[b]
-                tm.append(np.array(self.model.train_on_batch([batch, cond], batch)))
-            tm = np.mean(tm, axis=0)
-            vm = []
-            for b in range(val_steps):
-                batch, cond = val_gen[b]
-                vm.append(np.array(self.model.test_on_batch([batch, cond], batch)))
-            vm = np.mean(vm, axis=0) if vm else tm
+            tm = np.mean(self.fit_epoch(train_gen, train_steps, train=True), axis=0)
+            vm = np.mean(self.fit_epoch(val_gen, val_steps, train=False), axis=0) if val_steps else tm
             s = "Time: %.3f s   " % (time.time() - t0)
             for m in range(4):
                 s += "Train %s: %.3f    " % (self.metric_names[m], tm[m])
@@ -194,6 +186,70 @@ class LatticeDFCVAE:
         self.model.load_weights(self.filepath)
         self.model.save(os.path.splitext(self.filepath)[0] + ".h5")
         print("Model saved")
+
+    def fit_epoch(self, gen, steps=None, train=True):
+        """The batch loop of train() (lattice_vae.py:289-299, 301-305): one train_on_batch (test_on_batch) per gen[b] ->
+        (batch, cond), returned as a [steps, 4] array of [loss, perceptual, mse, kld].  Unlike a loop of train_on_batch
+        calls it does not stop the GPU between batches: batch b+1 travels host -> device on a copy stream into a second
+        staging buffer while step b computes, every step's metrics come back through a pinned ring, and the host waits
+        once at the end.  Pinned host batches (torch tensors) are copied asynchronously; numpy / pageable batches work
+        and simply copy synchronously."""
+        steps = len(gen) if steps is None else int(steps)
+        if steps <= 0:
+            return np.zeros((0, 4))
+        if self.dtype == "fp32":
+            return np.array([self._step(*gen[b], train=train) for b in range(steps)])
+        M0, c0 = gen[0]
+        B = len(M0)
+        eng = self.engine(B)
+        if train and self.use_cuda_graph and not eng.use_graph:
+            eng.M.copy_(_as_f32(M0))         # capture needs valid inputs; no eps draw here, so the random stream of the
+            eng.cond.copy_(_as_f32(c0))      # epoch is the one a loop of train_on_batch calls consumes
+            eng.capture_train_graph()
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream, self._stage = torch.cuda.Stream(), {}
+        if B not in self._stage:
+            self._stage = {B: [(torch.empty_like(eng.M), torch.empty_like(eng.cond), torch.cuda.Event(), torch.cuda.Event())
+                               for _ in range(2)]}
+        stage, cs = self._stage[B], self._copy_stream
+        ring = torch.empty(steps, 4, dtype=torch.float32).pin_memory()
+        keep = []  # host tensors of copies in flight
+
+        def prefetch(b):
+            Mb, cb = (M0, c0) if b == 0 else gen[b]
+            Mh, ch = _as_f32(Mb), _as_f32(cb)
+            keep.append((Mh, ch))
+            sm, sc, ready, free = stage[b & 1]
+            with torch.cuda.stream(cs):
+                cs.wait_event(free)          # the step two batches back has consumed this staging buffer
+                sm.copy_(Mh, non_blocking=True)
+                sc.copy_(ch, non_blocking=True)
+                ready.record(cs)
+
+        cs.wait_stream(main)
+        prefetch(0)
+        for b in range(steps):
+            if b + 1 < steps:
+                prefetch(b + 1)
+            sm, sc, ready, free = stage[b & 1]
+            main.wait_event(ready)
+            eng.set_inputs(sm, sc)           # device -> device into the engine's static buffers (+ fresh eps)
+            free.record(main)
+            if train:
+                eng.train_step()
+            else:
+                eng.eval_step()
+            ring[b].copy_(eng.metrics, non_blocking=True)
+            if len(keep) > 4:
+                del keep[0]
+        main.synchronize()
+        out = ring.double()
+        if self.dist is not None and self.dist.world > 1:
+            t = out.to(self.device)
+            self.dist.all_reduce_sum(t)
+            out = (t / self.dist.world).cpu()
+        return out.numpy()
 
     def save_(self, weights, model="saved_models/vae.h5"):
         self.model.load_weights(weights)

@@ -184,3 +184,29 @@ def test_training_curve_tracks_oracle():
     # the moving averages of the VAE's BatchNorm layers follow Keras' update (R3) on both sides
     mm = eng.vp.p["enc_bn1/moving_mean"].cpu()
     assert rel_l2(mm, pv["enc_bn1/moving_mean"]) < 5e-2  # 6 steps of slowly diverging bf16/fp32 trajectories (measured 2.4e-2)
+
+
+def test_fit_epoch_pipelined_equals_train_on_batch_loop():
+    """LatticeDFCVAE.fit_epoch (the batch loop of train(), lattice_vae.py:289-299, with the next batch's host->device copy
+    under the current step and one host sync per epoch) == the same batches through train_on_batch one by one: identical
+    per-batch metrics and identical weights afterwards; numpy batches work too."""
+    import numpy as np
+    from icsg3d_b200 import utils
+    from icsg3d_b200.vae.lattice_vae import LatticeDFCVAE
+    batches = []
+    for i in range(5):
+        M, cond, _ = utils.synthetic_batch(4, d=32, seed=70 + i)
+        batches.append((M.cpu().pin_memory(), cond.cpu().pin_memory()))
+    a = LatticeDFCVAE(perceptual_model=None, seed=3)
+    b = LatticeDFCVAE(perceptual_model=None, seed=3)
+    a._set_model(batch_size=4)
+    b._set_model(batch_size=4)
+    torch.manual_seed(11)
+    want = np.array([a.model.train_on_batch([M, c], M) for M, c in batches])
+    torch.manual_seed(11)
+    got = b.fit_epoch(batches, train=True)
+    assert got.shape == (5, 4) and np.array_equal(got.astype(np.float32), want.astype(np.float32))
+    assert torch.equal(a.params.theta, b.params.theta)
+    ev = b.fit_epoch([(M.numpy(), c.numpy()) for M, c in batches[:2]], train=False)   # test_on_batch loop, numpy inputs
+    assert ev.shape == (2, 4) and np.isfinite(ev).all()
+
