@@ -27,6 +27,8 @@ struct ConvIgemmParams {
   int kc;               // channels per k-unit: 16, 32 or 64
   int nt;               // N tile
   int tiles_n, tiles_m;
+  int mt;               // M tiles (128 voxels each) that share one weight tile per stage: 1, or 2 for the wide layers
+                        // (operand traffic per FLOP 3/4: the per-tap kernel is bound by L2 -> shared-memory traffic)
   int ups;              // k-units per pipeline stage
   int ntaps;            // 27 (3x3x3) or 1 (1x1x1)
   int iters;            // ntaps*chunks/ups
@@ -56,7 +58,7 @@ struct ConvIgemmParams {
 static constexpr int kConvThreads = 192;
 static constexpr int kMaxStages = 8;
 
-template <int KSTEPS>
+template <int KSTEPS, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const ConvIgemmParams p) {
@@ -93,33 +95,38 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int total_tiles = p.tiles_m * p.tiles_n * p.ksplit;  // tile index = (tm * tiles_n + tn) * ksplit + ks
+  const int tiles_mg = (p.tiles_m + MT - 1) / MT;        // groups of mt M tiles
+  const int total_tiles = tiles_mg * p.tiles_n * p.ksplit;   // tile index = (tm * tiles_n + tn) * ksplit + ks
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>(p.ups) * (p.a_unit_bytes + p.b_unit_bytes);
+    const uint32_t tx_bytes = static_cast<uint32_t>(p.ups) * (static_cast<uint32_t>(MT) * p.a_unit_bytes + p.b_unit_bytes);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ks = tile % p.ksplit;
       const int tmn = tile / p.ksplit;
       const int tm = tmn / p.tiles_n;
       const int tn = tmn - tm * p.tiles_n;
-      int pix = tm * 128;
-      const int w0 = pix % p.W;
-      pix /= p.W;
-      const int h0 = pix % p.H;
-      pix /= p.H;
-      const int d0 = pix % p.D;
-      const int n0 = pix / p.D;
+      int w0[MT], h0[MT], d0[MT], n0[MT];
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {  // a tile past the end (odd tile count) lies beyond the last sample: zero filled
+        int pix = (tm * MT + t) * 128;
+        w0[t] = pix % p.W;
+        pix /= p.W;
+        h0[t] = pix % p.H;
+        pix /= p.H;
+        d0[t] = pix % p.D;
+        n0[t] = pix / p.D;
+      }
       const int it0 = ks * p.ips, it1 = min(p.iters, it0 + p.ips);
       const int unit0 = it0 * p.ups;
       int tap = unit0 / p.chunks, ch = unit0 - tap * p.chunks;
       for (int it = it0; it < it1; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
-        uint8_t* sb = sa + static_cast<size_t>(p.ups) * p.a_unit_bytes;
+        uint8_t* sb = sa + static_cast<size_t>(p.ups * MT) * p.a_unit_bytes;
         if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
         for (int j = 0; j < p.ups; ++j) {
           int kd = tap / 9;
@@ -127,8 +134,10 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           int kw = tap - kd * 9 - kh * 3;
           if (p.ntaps == 1) kd = kh = kw = 1;  // 1x1x1: no spatial shift
           if (leader) {
-            tma_load_5d(sa + static_cast<size_t>(j) * p.a_unit_bytes, &tmA, &full_bar[stage], ch * p.kc, w0 + kw - 1,
-                        h0 + kh - 1, d0 + kd - 1, n0);
+#pragma unroll
+            for (int t = 0; t < MT; ++t)
+              tma_load_5d(sa + static_cast<size_t>(j * MT + t) * p.a_unit_bytes, &tmA, &full_bar[stage], ch * p.kc,
+                          w0[t] + kw - 1, h0[t] + kh - 1, d0[t] + kd - 1, n0[t]);
             tma_load_3d(sb + static_cast<size_t>(j) * p.b_unit_bytes, &tmB, &full_bar[stage], ch * p.kc, tn * p.nt, tap);
           }
           if (++ch == p.chunks) {
@@ -156,21 +165,25 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t acc_phase = static_cast<uint32_t>(local >> 1) & 1u;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.nt);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MT * p.nt);
       const int ks = tile % p.ksplit;
       const int it0 = ks * p.ips, it1 = min(p.iters, it0 + p.ips);
       for (int it = it0; it < it1; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         uint32_t a_lo = ring_lo + static_cast<uint32_t>(stage) * stage_lo;
-        uint32_t b_lo = a_lo + static_cast<uint32_t>(p.ups) * a_unit_lo;
+        uint32_t b_lo = a_lo + static_cast<uint32_t>(p.ups * MT) * a_unit_lo;
         for (int j = 0; j < p.ups; ++j) {
           if (leader) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              umma_bf16_lohi(d_tmem, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, p.idesc, ((it - it0) | j | k) != 0 ? 1u : 0u);
+            for (int t = 0; t < MT; ++t) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16_lohi(d_tmem + static_cast<uint32_t>(t * p.nt), a_lo + static_cast<uint32_t>(t) * a_unit_lo + 2u * k, desc_hi,
+                               b_lo + 2u * k, desc_hi, p.idesc, ((it - it0) | j | k) != 0 ? 1u : 0u);
+            }
           }
-          a_lo += a_unit_lo;
+          a_lo += static_cast<uint32_t>(MT) * a_unit_lo;
           b_lo += b_unit_lo;
         }
         if (leader) umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -193,11 +206,12 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int tmn = tile / p.ksplit;
       const int tm = tmn / p.tiles_n;
       const int tn = tmn - tm * p.tiles_n;
-      const long long pixel = static_cast<long long>(tm) * 128 + row;
-      const bool row_ok = pixel < p.m_total;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.nt);
+      for (int t = 0; t < MT; ++t) {
+      const long long pixel = (static_cast<long long>(tm) * MT + t) * 128 + row;
+      const bool row_ok = pixel < p.m_total;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((acc * MT + t) * p.nt);
       for (int c0 = 0; c0 < p.nt; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
@@ -258,6 +272,7 @@ conv3d_k3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
         }
       }
+      }  // t
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -483,10 +498,18 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   p.tiles_n = nout / nt;
   p.ips = (p.iters + ksplit - 1) / ksplit;
   p.ksplit = (p.iters + p.ips - 1) / p.ips;
+  // Two M tiles per weight tile (both accumulator pairs fit the 512 TMEM columns up to N = 128): the kernel is bound by
+  // L2 -> shared-memory operand traffic (ncu: tensor pipe 51 % at N = 128 with 32 KB per 256 MMA cycles), and sharing the
+  // weight tile makes it 48 KB per 512.  Needs enough tiles to keep every SM busy with pairs.
+  static const int mt_env = [] { const char* e = getenv("ICSG3D_IGEMM_MT"); return e ? atoi(e) : 0; }();
+  p.mt = 1;
+  if (mt_env != 1 && p.kc == 64 && p.ups == 1 && p.ksplit == 1 && nt <= 128 &&
+      static_cast<long long>(p.tiles_m / 2) * p.tiles_n >= 2ll * sms)
+    p.mt = 2;
   p.ws = static_cast<float*>(ws);
   p.a_unit_bytes = 128u * p.kc * 2u;
   p.b_unit_bytes = static_cast<uint32_t>(nt) * p.kc * 2u;
-  p.stage_bytes = (static_cast<uint32_t>(p.ups) * (p.a_unit_bytes + p.b_unit_bytes) + 1023u) & ~1023u;
+  p.stage_bytes = (static_cast<uint32_t>(p.ups) * (static_cast<uint32_t>(p.mt) * p.a_unit_bytes + p.b_unit_bytes) + 1023u) & ~1023u;
   const uint32_t smem_budget = 200u * 1024u;
   int stages = static_cast<int>(smem_budget / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -496,7 +519,7 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   p.layout = umma_layout_for_swizzle(p.kc * 2);
   p.idesc = umma_idesc_bf16(nt, 0, 0) & fmt_mask;
   uint32_t cols = 32;
-  while (cols < 2u * nt) cols <<= 1;
+  while (cols < 2u * p.mt * nt) cols <<= 1;
   p.tmem_cols = cols;
   p.y = y;
   p.ldy = ldy;
@@ -523,17 +546,19 @@ static int conv3d_igemm_impl(int ntaps, const void* x, int ldx, const void* wpac
   const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
   static bool configured = false;
   if (!configured) {
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_igemm_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     configured = true;
   }
-  const int total_tiles = p.tiles_m * p.tiles_n * p.ksplit;
+  const int total_tiles = ((p.tiles_m + p.mt - 1) / p.mt) * p.tiles_n * p.ksplit;
   const int grid = total_tiles < sms ? total_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p.kc == 16) launch_k(conv3d_k3_igemm_kernel<1>, grid, kConvThreads, smem, st, tmA, tmB, p);
-  else if (p.kc == 32) launch_k(conv3d_k3_igemm_kernel<2>, grid, kConvThreads, smem, st, tmA, tmB, p);
-  else launch_k(conv3d_k3_igemm_kernel<4>, grid, kConvThreads, smem, st, tmA, tmB, p);
+  if (p.kc == 16) launch_k(conv3d_k3_igemm_kernel<1, 1>, grid, kConvThreads, smem, st, tmA, tmB, p);
+  else if (p.kc == 32) launch_k(conv3d_k3_igemm_kernel<2, 1>, grid, kConvThreads, smem, st, tmA, tmB, p);
+  else if (p.mt == 2) launch_k(conv3d_k3_igemm_kernel<4, 2>, grid, kConvThreads, smem, st, tmA, tmB, p);
+  else launch_k(conv3d_k3_igemm_kernel<4, 1>, grid, kConvThreads, smem, st, tmA, tmB, p);
   ICSG_CHECK_LAUNCH();
   if (p.ksplit > 1) {
     const long long items = m_total * (nout / 4);

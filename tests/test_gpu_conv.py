@@ -287,3 +287,25 @@ def test_upsample_conv_fold_dgrad_low_matches_upsample_backward_of_dgrad(B, D, c
     assert rel_l2(got, want) < 3e-3
     assert float((got - want).abs().max()) <= float(want.abs().max()) * 2 ** -7
     assert torch.all(buf[..., :16] == 5.0) and torch.all(buf[..., 16 + cu:] == 5.0)
+
+
+@pytest.mark.parametrize("B,D,cin,cout,act", [(3, 32, 128, 128, 1), (5, 32, 64, 128, 0), (40, 16, 192, 128, 2), (20, 16, 128, 64, 1)])
+def test_per_tap_kernel_with_paired_m_tiles_matches_cuda_core_reference(B, D, cin, cout, act):
+    """Per-tap kernel in its paired form (two 128-voxel tiles share every weight tile, conv3d_igemm.cu: mt = 2; taken when
+    the layer has >= 2 x SMs tile pairs) against the CUDA-core cross-check kernel, and bit-equal to the unpaired form."""
+    import ctypes
+    from icsg3d_b200 import _lib, ops
+    x, w, b = _mk(B, D, cin, cout, seed=71)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    wp = ops.pack_conv_w_fprop(wd)
+    _lib.call("icsg3d_conv3d_set_impl", 1)          # per-tap kernel regardless of the dispatch rules
+    try:
+        got = ops.conv3d_k3(xd, wp, bd, act=act, out_dtype=torch.float32)
+        gb = ops.conv3d_k3(xd, wp, bd, act=act)
+    finally:
+        _lib.call("icsg3d_conv3d_set_impl", 0)
+    ref = ops.conv3d_k3(xd, wp, bd, act=act, ref=True)
+    torch.cuda.synchronize()
+    assert rel_l2(got, ref) < 1e-5
+    assert rel_l2(gb.float(), ref) < 4e-3
+
