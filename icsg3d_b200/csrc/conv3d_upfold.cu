@@ -49,6 +49,7 @@ static constexpr int kUfThreads = 192;
 static constexpr int kUfMaxStages = 8;
 static constexpr uint32_t kUfAUnit = 128u * 64u * 2u;
 
+template <int MT>  // low-resolution tiles (128 voxels) that share every weight tile: 1, or 2 when there are enough tiles
 __global__ void __launch_bounds__(kUfThreads, 1)
 conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_constant__ CUtensorMap tmLow,
                         const __grid_constant__ CUtensorMap tmB, const ConvUpfoldParams p) {
@@ -86,7 +87,8 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
   const uint32_t tmem_base = tmem_base_slot;
 
   // tile index = (tm * 8 + phase) * tiles_n + tn: the 8 phases of one low-resolution box run side by side (L2 reuse)
-  const int total_tiles = p.mode == 0 ? p.tiles_m * 8 * p.tiles_n : p.tiles_m * p.tiles_n;
+  const int tiles_mg = (p.tiles_m + MT - 1) / MT;
+  const int total_tiles = p.mode == 0 ? tiles_mg * 8 * p.tiles_n : tiles_mg * p.tiles_n;
   const int skip_units = p.mode == 0 ? 27 * p.cs : 0;
   const int units = p.mode == 0 ? skip_units + 8 * p.cu : 64 * p.cs;  // mode 1: cs = cout / 64 chunks of dY
 
@@ -95,31 +97,37 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase_bit = 0;
-    const uint32_t tx_bytes = kUfAUnit + p.b_unit_bytes;
+    const uint32_t tx_bytes = MT * kUfAUnit + p.b_unit_bytes;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tn = tile % p.tiles_n;
       const int tmp = tile / p.tiles_n;
       const int ph = p.mode == 0 ? (tmp & 7) : 0, tm = p.mode == 0 ? (tmp >> 3) : tmp;
       const int rd = ph >> 2, rh = (ph >> 1) & 1, rw = ph & 1;
-      int pix = tm * 128;
-      const int w0 = pix % p.Wl;
-      pix /= p.Wl;
-      const int h0 = pix % p.Hl;
-      pix /= p.Hl;
-      const int d0 = pix % p.Dl;
-      const int n0 = pix / p.Dl;
+      int w0[MT], h0[MT], d0[MT], n0[MT];
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {  // a tile past the end lies beyond the last sample: zero filled, never stored
+        int pix = (tm * MT + t) * 128;
+        w0[t] = pix % p.Wl;
+        pix /= p.Wl;
+        h0[t] = pix % p.Hl;
+        pix /= p.Hl;
+        d0[t] = pix % p.Dl;
+        n0[t] = pix / p.Dl;
+      }
       int tap = 0, ch = 0;
       for (int u = 0; u < units; ++u) {
         mbar_wait(&empty_bar[stage], phase_bit ^ 1u);
         uint8_t* sa = ring + static_cast<size_t>(stage) * p.stage_bytes;
-        uint8_t* sb = sa + kUfAUnit;
+        uint8_t* sb = sa + MT * kUfAUnit;
         if (leader) {
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           if (p.mode == 1) {
             // dLow[i] += Wf[r][t]^T dY[2 (i - o(r,t)) + r]: `tap` counts the 64 (phase r, tap t) pairs
             const int r = tap >> 3, t = tap & 7;
             const int od = ((t >> 2) & 1) - (((r >> 2) & 1) ^ 1), oh = ((t >> 1) & 1) - (((r >> 1) & 1) ^ 1), ow = (t & 1) - ((r & 1) ^ 1);
-            tma_load_5d(sa, &tmSkip.m[r], &full_bar[stage], ch * 64, w0 - ow, h0 - oh, d0 - od, n0);
+#pragma unroll
+            for (int t2 = 0; t2 < MT; ++t2)
+              tma_load_5d(sa + t2 * kUfAUnit, &tmSkip.m[r], &full_bar[stage], ch * 64, w0[t2] - ow, h0[t2] - oh, d0[t2] - od, n0[t2]);
             tma_load_3d(sb, &tmB, &full_bar[stage], 0, tn * p.nt, u);
           } else if (u < skip_units) {
             // full-resolution voxel 2i + r + (k - 1) = 2 (i + o) + r' of parity class r'
@@ -127,11 +135,17 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
             const int qd = rd + kd - 1, qh = rh + kh - 1, qw = rw + kw - 1;  // in [-1, 2]
             const int pd = qd & 1, phh = qh & 1, pw = qw & 1;
             const int od = (qd - pd) >> 1, oh = (qh - phh) >> 1, ow = (qw - pw) >> 1;
-            tma_load_5d(sa, &tmSkip.m[pd * 4 + phh * 2 + pw], &full_bar[stage], ch * 64, w0 + ow, h0 + oh, d0 + od, n0);
+#pragma unroll
+            for (int t2 = 0; t2 < MT; ++t2)
+              tma_load_5d(sa + t2 * kUfAUnit, &tmSkip.m[pd * 4 + phh * 2 + pw], &full_bar[stage], ch * 64, w0[t2] + ow, h0[t2] + oh,
+                          d0[t2] + od, n0[t2]);
             tma_load_3d(sb, &tmB, &full_bar[stage], 0, tn * p.nt, u);
           } else {
             const int td = tap >> 2, th = (tap >> 1) & 1, tw = tap & 1;
-            tma_load_5d(sa, &tmLow, &full_bar[stage], ch * 64, w0 + tw - (rw ^ 1), h0 + th - (rh ^ 1), d0 + td - (rd ^ 1), n0);
+#pragma unroll
+            for (int t2 = 0; t2 < MT; ++t2)
+              tma_load_5d(sa + t2 * kUfAUnit, &tmLow, &full_bar[stage], ch * 64, w0[t2] + tw - (rw ^ 1), h0[t2] + th - (rh ^ 1),
+                          d0[t2] + td - (rd ^ 1), n0[t2]);
             tma_load_3d(sb, &tmB, &full_bar[stage], 0, tn * p.nt, skip_units + (ph * 8 + tap) * p.cu + ch);
           }
         }
@@ -159,16 +173,20 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
       const int acc = local & 1;
       mbar_wait(&tmem_empty_bar[acc], (static_cast<uint32_t>(local >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.nt);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MT * p.nt);
       for (int u = 0; u < units; ++u) {
         mbar_wait(&full_bar[stage], phase_bit);
         tc_fence_after();
         if (leader) {
           const uint32_t a_lo = ring_lo + static_cast<uint32_t>(stage) * stage_lo;
-          const uint32_t b_lo = a_lo + a_unit_lo;
+          const uint32_t b_lo = a_lo + MT * a_unit_lo;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_lohi(d_tmem, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, p.idesc, (u | k) != 0 ? 1u : 0u);
+          for (int t = 0; t < MT; ++t) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lohi(d_tmem + static_cast<uint32_t>(t * p.nt), a_lo + t * a_unit_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi,
+                             p.idesc, (u | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);
         }
         if (++stage == p.stages) {
@@ -188,7 +206,11 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
       const int tn = tile % p.tiles_n;
       const int tmp = tile / p.tiles_n;
       const int ph = p.mode == 0 ? (tmp & 7) : 0, tm = p.mode == 0 ? (tmp >> 3) : tmp;
-      const int pl = tm * 128 + row;  // low-resolution voxel of this row
+      mbar_wait(&tmem_full_bar[acc], static_cast<uint32_t>(local >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t2 = 0; t2 < MT; ++t2) {
+      const int pl = (tm * MT + t2) * 128 + row;  // low-resolution voxel of this row
       const bool row_ok = pl < p.m_low;
       long long pixel = pl;
       if (p.mode == 0) {
@@ -202,9 +224,7 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
         pixel = ((static_cast<long long>(n) * (2 * p.Dl) + 2 * dl + (ph >> 2)) * (2 * p.Hl) + 2 * hl + ((ph >> 1) & 1)) * (2 * p.Wl) +
                 2 * wl + (ph & 1);
       }
-      mbar_wait(&tmem_full_bar[acc], static_cast<uint32_t>(local >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.nt);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((acc * MT + t2) * p.nt);
       for (int c0 = 0; c0 < p.nt; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + static_cast<uint32_t>(c0), v);
@@ -242,6 +262,7 @@ conv3d_k3_upfold_kernel(const __grid_constant__ TmSet8 tmSkip, const __grid_cons
           for (int i = 0; i < nvalid; ++i) dst[i] = f2bf(f[i]);
         }
       }
+      }  // t2
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -386,13 +407,17 @@ static int upfold_launch(int mode, const void* x_par, int ld_par, int c_par, con
   p.nt = nt;
   p.tiles_n = nout / nt;
   p.b_unit_bytes = static_cast<uint32_t>(nt) * 128u;
-  p.stage_bytes = (kUfAUnit + p.b_unit_bytes + 1023u) & ~1023u;
+  // two low-resolution tiles per weight tile where both accumulator pairs fit TMEM and there are enough tiles (as in the
+  // per-tap kernel: the operand traffic L2 -> shared memory bounds the kernel)
+  static const int mt_env = [] { const char* e = getenv("ICSG3D_IGEMM_MT"); return e ? atoi(e) : 0; }();
+  const int mt = (mt_env != 1 && nt <= 128 && static_cast<long long>(p.tiles_m / 2) * phases * p.tiles_n >= 2ll * sms) ? 2 : 1;
+  p.stage_bytes = (mt * kUfAUnit + p.b_unit_bytes + 1023u) & ~1023u;
   int stages = static_cast<int>(200u * 1024u / p.stage_bytes);
   if (stages > kUfMaxStages) stages = kUfMaxStages;
   p.stages = stages;
   p.idesc = umma_idesc_bf16(nt, 0, 0);
   uint32_t cols = 32;
-  while (cols < 2u * nt) cols <<= 1;
+  while (cols < 2u * mt * nt) cols <<= 1;
   p.tmem_cols = cols;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.ldy = ldy;
@@ -449,12 +474,14 @@ static int upfold_launch(int mode, const void* x_par, int ld_par, int c_par, con
   const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
   static bool configured = false;
   if (!configured) {
-    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_upfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_upfold_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    ICSG_CUDA(cudaFuncSetAttribute(conv3d_k3_upfold_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     configured = true;
   }
-  const int total_tiles = p.tiles_m * phases * p.tiles_n;
+  const int total_tiles = ((p.tiles_m + mt - 1) / mt) * phases * p.tiles_n;
   const int grid = total_tiles < sms ? total_tiles : sms;
-  launch_k(conv3d_k3_upfold_kernel, grid, kUfThreads, smem, static_cast<cudaStream_t>(stream), tmPar, tmLow, tmB, p);
+  if (mt == 2) launch_k(conv3d_k3_upfold_kernel<2>, grid, kUfThreads, smem, static_cast<cudaStream_t>(stream), tmPar, tmLow, tmB, p);
+  else launch_k(conv3d_k3_upfold_kernel<1>, grid, kUfThreads, smem, static_cast<cudaStream_t>(stream), tmPar, tmLow, tmB, p);
   ICSG_CHECK_LAUNCH();
   return ICSG3D_OK;
 }

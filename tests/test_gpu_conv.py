@@ -231,7 +231,8 @@ def test_conv_epilogue_post_affine_matches_conv_then_affine(B, D, cin, cout, act
 
 
 @pytest.mark.parametrize("B,D,cs,cu,cout,exact", [(2, 8, 64, 128, 128, True), (1, 16, 64, 128, 128, True), (3, 8, 128, 256, 256, False),
-                                                  (2, 8, 256, 512, 512, False), (5, 4, 64, 64, 64, True)])
+                                                  (2, 8, 256, 512, 512, False), (5, 4, 64, 64, 64, True),
+                                                  (40, 16, 64, 128, 128, True)])   # enough tiles for the paired form
 def test_upsample_conv_fold_matches_materialised_upsample_concat_conv(B, D, cs, cu, cout, exact):
     """csrc/conv3d_upfold.cu (Conv3D over concatenate([skip, UpSampling3D(2)(low)]) as 27 skip taps + 8 folded
     taps per output phase) == the conv kernel on the materialised K.upsample x2 + concat tensor (unet.py:309-332)."""
@@ -268,7 +269,7 @@ def test_upsample_conv_fold_matches_materialised_upsample_concat_conv(B, D, cs, 
 
 
 @pytest.mark.parametrize("B,D,cs,cu,cout", [(2, 8, 64, 128, 128), (1, 16, 64, 128, 128), (3, 8, 128, 256, 256), (2, 8, 256, 512, 512),
-                                            (5, 4, 64, 64, 64)])
+                                            (5, 4, 64, 64, 64), (20, 32, 64, 128, 128)])   # last: paired low-resolution tiles
 def test_upsample_conv_fold_dgrad_low_matches_upsample_backward_of_dgrad(B, D, cs, cu, cout):
     """Backward of the folded conv w.r.t. its low-resolution input == UpSampling3D's backward (sum over the 8 children) of
     the data-gradient conv on the materialised concat tensor (weights exactly representable: same products)."""
