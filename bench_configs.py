@@ -315,6 +315,7 @@ def _run_unet_train(args, d, B):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item()) / n_e2e
     clocks = sampler.stop() if rank == 0 else None
+    eng.overlap_wgrad = False  # one stream: every launch of the roofline pass is timed alone
     roof = _conv_roofline(eng._train_body, peaks, clocks) if rank == 0 or world > 1 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

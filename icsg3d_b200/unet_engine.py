@@ -141,6 +141,8 @@ class UNetEngine:
         self.h_partials = torch.zeros(self.h_nparts, 6, dtype=F64, device=dev)
         self.h_partials_fused = torch.zeros(ops.heads_loss_fused_nparts(B * d ** 3), 6, dtype=F64, device=dev)
         self.fuse_heads = os.environ.get("ICSG3D_FUSE_HEADS", "1") != "0"
+        self.overlap_wgrad = os.environ.get("ICSG3D_UNET_OVERLAP_WGRAD", "1") != "0"
+        self._wg_side, self._wg_pending = None, False
         self.keep_logits = False  # diagnostics / parity tests: also materialise the fp32 head logits the fused kernel skips
         self.h_raw = torch.zeros(6, dtype=F64, device=dev)
         self.metrics = torch.zeros(5, dtype=F32, device=dev)
@@ -358,14 +360,18 @@ class UNetEngine:
             self._bias_grad(L["dc"], C, g[nme + "/bias"])
             xin = self._input_of(L)
             gk = g[nme + "/kernel"]
-            if L["cin_real"] == L["cin_pad"]:
-                ops.conv3d_k3_wgrad(xin, L["dc"], cin=L["cin_pad"], cout=C, out=gk.view(27, L["cin_real"], C),
-                                    tag=f"unet.{nme}.wgrad", ws=self.wg_ws)
-            else:
-                scratch = self.ctx.dw_pad[: 27 * L["cin_pad"] * C].view(27, L["cin_pad"], C)
-                ops.conv3d_k3_wgrad(xin, L["dc"], cin=L["cin_pad"], cout=C, out=scratch, tag=f"unet.{nme}.wgrad",
-                                    nominal=(L["cin_real"], C), ws=self.wg_ws)
-                ops.unpack_conv_dw(scratch, L["cin_real"], C, out=gk)
+            # filter gradient: only Adam needs it -> on a side stream under the BatchNorm-backward / data-gradient chain of
+            # the next layers (HBM-bound passes next to an L2-bound tensor kernel; the per-tap kernels leave registers
+            # and shared memory for a BatchNorm block on the same SM)
+            with self._wgrad_stream():
+                if L["cin_real"] == L["cin_pad"]:
+                    ops.conv3d_k3_wgrad(xin, L["dc"], cin=L["cin_pad"], cout=C, out=gk.view(27, L["cin_real"], C),
+                                        tag=f"unet.{nme}.wgrad", ws=self.wg_ws)
+                else:
+                    scratch = self.ctx.dw_pad[: 27 * L["cin_pad"] * C].view(27, L["cin_pad"], C)
+                    ops.conv3d_k3_wgrad(xin, L["dc"], cin=L["cin_pad"], cout=C, out=scratch, tag=f"unet.{nme}.wgrad",
+                                        nominal=(L["cin_real"], C), ws=self.wg_ws)
+                    ops.unpack_conv_dw(scratch, L["cin_real"], C, out=gk)
             if L.get("fold_tr") and "fold" in L:
                 # data gradient of the folded layer: 27 taps for the skip channels only, 64 folded (phase, tap) pairs
                 # straight to the LOW-resolution gradient of the upsampled producer
@@ -377,6 +383,21 @@ class UNetEngine:
             elif nme != "c1":
                 ops.conv3d_k3(L["dc"], L["wd"], None, out=self._dst_of_input_grad(L), ws=self.ctx.conv_ws,
                               tag=f"unet.{nme}.dgrad")
+        if self._wg_pending:
+            torch.cuda.current_stream().wait_stream(self._wg_side)
+            self._wg_pending = False
+
+    def _wgrad_stream(self):
+        """Context of the filter-gradient launches: the side stream (forked from the current stream here, joined at the
+        end of backward()) or, with overlap_wgrad off, the current stream."""
+        import contextlib
+        if not self.overlap_wgrad:
+            return contextlib.nullcontext()
+        if self._wg_side is None:
+            self._wg_side = torch.cuda.Stream()
+        self._wg_side.wait_stream(torch.cuda.current_stream())
+        self._wg_pending = True
+        return torch.cuda.stream(self._wg_side)
 
     def optimizer_step(self):
         if self.world > 1:

@@ -16,6 +16,7 @@ d = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = torch.device("cuda:0")
 eng = UNetEngine(B, d=d, device=dev, seed=2)
+eng.overlap_wgrad = False  # each call timed alone
 M, _, S = utils.synthetic_batch(B, d=d, seed=2000, device=dev)
 eng.set_inputs(M, S)
 for _ in range(3):
