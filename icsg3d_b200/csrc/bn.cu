@@ -721,6 +721,73 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_apply_fwd_pool_lean_kernel(c
   }
 }
 
+// Lean bf16 BN + activation (+ UpSampling3D(2)) forward with a plain bf16 output: the channel group is fixed per thread
+// (scale / shift in registers instead of 16 table loads per vector), rows walk by pointer increments, 4 rows in flight.
+template <int kAct, bool kUp>
+__global__ void __launch_bounds__(kBnThreads, 4) bn_apply_fwd_lean_kernel(const BnFwdParams p) {
+  pdl_prologue();
+  constexpr int V = 8, U = 4;
+  typedef __nv_bfloat16 T;
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const int cg = p.C / V;
+  const int rpi = kBnThreads / cg;
+  const int g = threadIdx.x % cg;
+  const int rl = threadIdx.x / cg;
+  if (rl >= rpi) return;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sc[i] = p.scale[g * V + i];
+    sh[i] = p.shift[g * V + i];
+  }
+  const float alpha = p.alpha;
+  const uint32_t M = static_cast<uint32_t>(p.B) * p.D * p.H * p.W;
+  const uint32_t stride = gridDim.x * rpi;
+  auto finish = [&](const uint4& q, uint32_t r) {
+    float v[V];
+    VecIO<T>::cvt(q, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float z = fmaf(sc[i], v[i], sh[i]);
+      if (kAct == ICSG3D_ACT_RELU) z = z > 0.f ? z : 0.f;
+      if (kAct == ICSG3D_ACT_LEAKY) z = z > 0.f ? z : alpha * z;
+      v[i] = z;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    if constexpr (!kUp) {
+      *reinterpret_cast<uint4*>(p.y + static_cast<long long>(r) * p.ldy + g * V) = o;
+    } else {
+      const uint32_t t0 = r / p.W, w = r - t0 * p.W;
+      const uint32_t t1 = t0 / p.H, h = t0 - t1 * p.H;
+      const uint32_t n = t1 / p.D, d = t1 - n * p.D;
+      const long long W2 = 2ll * p.W, H2 = 2ll * p.H;
+      T* ob = p.y + (((static_cast<long long>(n) * 2 * p.D + 2 * d) * H2 + 2 * h) * W2 + 2 * w) * p.ldy + g * V;
+      const long long oW = p.ldy, oH = W2 * p.ldy, oD = H2 * W2 * p.ldy;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(ob + (k >> 2) * oD + ((k >> 1) & 1) * oH + (k & 1) * oW) = o;
+    }
+  };
+  uint32_t r = blockIdx.x * rpi + rl;
+  const T* px = x + static_cast<long long>(r) * p.ldx + g * V;
+  const long long sx = static_cast<long long>(stride) * p.ldx;
+  for (; static_cast<unsigned long long>(r) + (U - 1ull) * stride < M; r += U * stride) {
+    uint4 q[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) q[j] = *reinterpret_cast<const uint4*>(px + j * sx);
+#pragma unroll
+    for (int j = 0; j < U; ++j) finish(q[j], r + j * stride);
+    px += U * sx;
+  }
+  for (; r < M; r += stride) {
+    finish(*reinterpret_cast<const uint4*>(px), r);
+    px += sx;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
@@ -1499,6 +1566,25 @@ static int bn_apply_fwd_impl(const void* x, int ldx, int x_dtype, const float* s
     if (act == ICSG3D_ACT_NONE) launch_k(bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_NONE>, g, kBnThreads, 0, st, p);
     else if (act == ICSG3D_ACT_RELU) launch_k(bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_RELU>, g, kBnThreads, 0, st, p);
     else launch_k(bn_apply_fwd_pool_lean_kernel<ICSG3D_ACT_LEAKY>, g, kBnThreads, 0, st, p);
+    ICSG_CHECK_LAUNCH();
+    return ICSG3D_OK;
+  }
+  if (lean && x_dtype == ICSG3D_DT_BF16 && (post == ICSG3D_POST_NONE || post == ICSG3D_POST_UP2) && split_ctot == 0 && y && !y32 &&
+      kBnThreads % (C / V) == 0 && (ldy & 7) == 0 && static_cast<long long>(B) * D * H * W < (1ll << 31) - (1ll << 24)) {
+    const int rpi = kBnThreads / (C / V);
+    const long long rows = static_cast<long long>(B) * D * H * W;
+    long long lb = (rows + rpi - 1) / rpi;
+    if (lb > static_cast<long long>(sms) * 4) lb = static_cast<long long>(sms) * 4;
+    if (lb < 1) lb = 1;
+    const int g = static_cast<int>(lb);
+    const bool up = post == ICSG3D_POST_UP2;
+#define ICSG_BN_LEAN(A)                                                                            \
+  if (up) launch_k(bn_apply_fwd_lean_kernel<A, true>, g, kBnThreads, 0, st, p);                     \
+  else launch_k(bn_apply_fwd_lean_kernel<A, false>, g, kBnThreads, 0, st, p)
+    if (act == ICSG3D_ACT_NONE) { ICSG_BN_LEAN(ICSG3D_ACT_NONE); }
+    else if (act == ICSG3D_ACT_RELU) { ICSG_BN_LEAN(ICSG3D_ACT_RELU); }
+    else { ICSG_BN_LEAN(ICSG3D_ACT_LEAKY); }
+#undef ICSG_BN_LEAN
     ICSG_CHECK_LAUNCH();
     return ICSG3D_OK;
   }
