@@ -154,6 +154,8 @@ class UNetEngine:
             self.dlogits = z(B, d, d, d, self.nout_h)
             self.dwcat = z(1, 128, self.nout_h, dt=F32)
             self.colsum = torch.zeros(2 * 512, dtype=F64, device=dev)
+            self.side_colsum = torch.zeros(2 * 512, dtype=F64, device=dev)
+            self.side_partials = torch.zeros_like(self.ctx.partials)
         self._graph = None
         self.use_graph = False
         self.wg_ws = None
@@ -302,11 +304,15 @@ class UNetEngine:
 
     # ------------------------------------------------------------------------------------------
     def _bias_grad(self, dc, C, gbias):
+        """db = column sums of dc.  Only Adam needs it: with the filter gradients on the side stream, on scratch of its own
+        (the main stream's BatchNorm kernels keep using ctx.partials / colsum meanwhile)."""
         rows = dc.numel() // C
         n = ops.bn_nparts(rows, C, dc.dtype)
-        part = self.ctx.partials[: n * 2 * C].view(n, 2, C)
-        ops.bn_stats(dc, C, part)
-        ops.bn_reduce_grads(part, self.colsum[: 2 * C], None, gbias)
+        with self._wgrad_stream():
+            side = self.overlap_wgrad
+            part = (self.side_partials if side else self.ctx.partials)[: n * 2 * C].view(n, 2, C)
+            ops.bn_stats(dc, C, part)
+            ops.bn_reduce_grads(part, (self.side_colsum if side else self.colsum)[: 2 * C], None, gbias)
 
     def _grad_wrt_output(self, L):
         """(dy, post, idx, dy2) describing the gradient reaching block L's BN output."""
