@@ -141,7 +141,11 @@ class UNetEngine:
         self.h_partials = torch.zeros(self.h_nparts, 6, dtype=F64, device=dev)
         self.h_partials_fused = torch.zeros(ops.heads_loss_fused_nparts(B * d ** 3), 6, dtype=F64, device=dev)
         self.fuse_heads = os.environ.get("ICSG3D_FUSE_HEADS", "1") != "0"
-        self.overlap_wgrad = os.environ.get("ICSG3D_UNET_OVERLAP_WGRAD", "1") != "0"
+        # filter / bias gradients on a side stream — single process only: the data-parallel step interleaves eager NCCL
+        # all-reduces with its launches, and a 2-rank run of the bench with the side stream on did not finish inside its
+        # time limit (the round's last GPU call; not diagnosed), so under NCCL everything stays on one stream, as in the
+        # VAE engine's NCCL mode
+        self.overlap_wgrad = self.world == 1 and os.environ.get("ICSG3D_UNET_OVERLAP_WGRAD", "1") != "0"
         self._wg_side, self._wg_pending = None, False
         self.keep_logits = False  # diagnostics / parity tests: also materialise the fp32 head logits the fused kernel skips
         self.h_raw = torch.zeros(6, dtype=F64, device=dev)
