@@ -428,7 +428,8 @@ class UNetEngine:
 
     def train_step(self):
         """train_on_batch(X, [onehot(S), S != 0]) -> metrics [loss, soft, sig, f1_m, wr_m] (device tensor)."""
-        if self.use_graph and self._graph is not None:
+        self._wfold_fresh = False  # the weights change: the inference-time folded pack is stale (a graph replay skips the
+        if self.use_graph and self._graph is not None:  # Python side of pack_weights)
             self._graph.replay()
         else:
             self._train_body()
