@@ -99,6 +99,36 @@ def upsample2(x):
     return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
 
 
+def upsample2_conv3d_same_folded(x_low, kernel, bias=None):
+    """conv3d_same(upsample2(x_low), kernel) restated on the LOW-resolution tensor (the identity behind
+    csrc/conv3d_upfold.cu, used where unet.py:309-332 and lattice_vae.py:211-217 put a Conv3D after UpSampling3D).
+    Per axis and output parity r (o = 2i + r) the three taps k = -1, 0, +1 land on low index i + floor((r + k) / 2):
+        r = 0:  {-1} -> i-1,  {0, +1} -> i          r = 1:  {-1, 0} -> i,  {+1} -> i+1
+    so every one of the 8 output phases is a 2x2x2 cross-correlation with summed taps (offsets {-1, 0} for r = 0,
+    {0, +1} for r = 1); zero padding carries over because low index -1 / D is exactly upsampled index -1 / 2D."""
+    B, D, H, W, _ = x_low.shape
+    cout = kernel.shape[-1]
+    y = x_low.new_zeros(B, 2 * D, 2 * H, 2 * W, cout)
+    sets = {0: ([0], [1, 2]), 1: ([0, 1], [2])}          # parity -> kernel indices folded onto low tap t = 0, 1
+    xp = F.pad(x_low.permute(0, 4, 1, 2, 3), (1, 1, 1, 1, 1, 1))   # one low-resolution voxel of zero padding per side
+    for rd in (0, 1):
+        for rh in (0, 1):
+            for rw in (0, 1):
+                wf = x_low.new_zeros(2, 2, 2, kernel.shape[3], cout)
+                for td in (0, 1):
+                    for th in (0, 1):
+                        for tw in (0, 1):
+                            for kd in sets[rd][td]:
+                                for kh in sets[rh][th]:
+                                    for kw in sets[rw][tw]:
+                                        wf[td, th, tw] += kernel[kd, kh, kw]
+                # low offsets t - (1 - r): the padded tensor starts at -1, so the window of phase r starts at index r
+                win = xp[:, :, rd:rd + D + 1, rh:rh + H + 1, rw:rw + W + 1]
+                ph = F.conv3d(win, wf.permute(4, 3, 0, 1, 2))
+                y[:, rd::2, rh::2, rw::2, :] = ph.permute(0, 2, 3, 4, 1)
+    return y if bias is None else y + bias
+
+
 def dense(x, kernel, bias):
     """Dense: kernel (in,out) (R8)."""
     return x @ kernel + bias

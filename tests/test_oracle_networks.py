@@ -78,3 +78,19 @@ def test_weighted_cce_reference_quirks():
     big.requires_grad_(True)
     nets.weighted_cce(big, s, 95.0).backward()
     assert float(big.grad.abs().max()) == 0.0
+
+
+def test_upsample_conv_fold_identity():
+    """SURVEY H6, the identity csrc/conv3d_upfold.cu is built on: Conv3D(3, same) after UpSampling3D(2) == per output
+    phase a 2x2x2 convolution of the low-resolution tensor with summed taps (8 of 27), borders included."""
+    import torch
+    from oracle import keras_ops as K
+    g = torch.Generator().manual_seed(3)
+    for shape, cin, cout in (((2, 4, 4, 4), 5, 3), ((1, 2, 6, 3), 2, 4)):
+        x = torch.randn(*shape, cin, generator=g, dtype=torch.float64)
+        w = torch.randn(3, 3, 3, cin, cout, generator=g, dtype=torch.float64)
+        b = torch.randn(cout, generator=g, dtype=torch.float64)
+        want = K.conv3d_same(K.upsample2(x), w, b)
+        got = K.upsample2_conv3d_same_folded(x, w, b)
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, rtol=1e-12, atol=1e-12)
